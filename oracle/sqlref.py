@@ -1,0 +1,57 @@
+"""Second opinion on the oracle: evaluate each query's *SQL* semantics directly in numpy.
+
+TEST INFRASTRUCTURE ONLY (same rules as oracle/vdl_oracle.c).  This does not interpret the
+Voodoo plan; it restates the SQL in the comment header of the reference's mplan fixtures
+(tests/tpch10noorder/06.sql.mplan:1-9, 01.sql.mplan:1-17, ...) over the same integer
+encodings the translator uses (dates as day counts Mplan.hs:46-57, decimals as scaled ints,
+dictionary codes) so integer outputs must match the plan interpreter bit for bit.
+All arithmetic is int64 with wraparound (numpy semantics), AVG is truncating integer division
+as emitted (Vlite.hs:1038-1041).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def q6(c: dict) -> dict:
+    """sum(l_extendedprice*l_discount) where 1994-01-01 <= shipdate < 1995-01-01, 0.05<=disc<=0.07, qty<24."""
+    sd, d, q, ep = (c["lineitem." + k] for k in ("l_shipdate", "l_discount", "l_quantity", "l_extendedprice"))
+    m = (sd >= 728294) & (sd < 728659) & (d >= 5) & (d <= 7) & (q < 2400)
+    if not m.any():
+        return {"revenue": np.zeros(0, np.int64)}          # G14: a fold over an empty selection has no runs
+    with np.errstate(over="ignore"):
+        return {"revenue": np.array([(ep[m].astype(np.int64) * d[m].astype(np.int64)).sum(dtype=np.int64)])}
+
+
+def q1(c: dict) -> dict:
+    """group by (returnflag, linestatus) where shipdate <= 1998-09-02 (729999)."""
+    g = lambda k: c["lineitem." + k].astype(np.int64)
+    sd, rf, ls, qty, ep, disc, tax = (g(k) for k in ("l_shipdate", "l_returnflag", "l_linestatus", "l_quantity",
+                                                     "l_extendedprice", "l_discount", "l_tax"))
+    m = sd <= 729999
+    rf, ls, qty, ep, disc, tax = (a[m] for a in (rf, ls, qty, ep, disc, tax))
+    # composite key as emitted: ((rf>>3)-2)<<2 | ((ls>>3)-2), & 31 (Vlite.hs:1123-1170; bounds.csv:67-68)
+    key = ((((rf >> 3) - 2) << 2) | ((ls >> 3) - 2)) & 31
+    names = ["l_returnflag__lineitem__l_returnflag", "l_linestatus__lineitem__l_linestatus", "sum_qty", "sum_base_price",
+             "sum_disc_price", "sum_charge", "avg_qty", "avg_price", "avg_disc", "count_order"]
+    out = {n: [] for n in names}
+    with np.errstate(over="ignore"):
+        dp = ep * (100 - disc)
+        ch = dp * (100 + tax)
+        for k in np.unique(key):
+            s = key == k
+            first = int(np.argmax(s))
+            cnt = int(s.sum())
+            vals = [rf[first], ls[first], qty[s].sum(dtype=np.int64), ep[s].sum(dtype=np.int64),
+                    dp[s].sum(dtype=np.int64), ch[s].sum(dtype=np.int64)]
+            vals += [_tdiv(vals[2], cnt), _tdiv(vals[3], cnt), _tdiv(disc[s].sum(dtype=np.int64), cnt), cnt]
+            for n, v in zip(names, vals):
+                out[n].append(int(v))
+    return {n: np.array(v, dtype=np.int64) for n, v in out.items()}
+
+
+def _tdiv(a, b) -> int:
+    """C truncating division (G4)."""
+    a, b = int(a), int(b)
+    q = abs(a) // abs(b)
+    return q if (a < 0) == (b < 0) else -q

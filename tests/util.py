@@ -1,0 +1,44 @@
+"""Shared helpers for the parity tests: host columns from the synthetic recipe, via the oracle's generator."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from mplan2vdl_b200 import synth  # noqa: E402
+from oracle.oracle import Oracle, gen_column  # noqa: E402
+
+Q6_COLS = ["l_quantity", "l_extendedprice", "l_discount", "l_shipdate"]
+Q1_COLS = Q6_COLS + ["l_tax", "l_returnflag", "l_linestatus"]
+
+
+def plan_text(name: str) -> str:
+    with open(os.path.join(ROOT, "plans", name)) as f:
+        return f.read()
+
+
+def host_columns(cat, qualified_names, rows_by_table, sf=1, seed=None, row_offset=0):
+    """{qualified: ndarray} generated on the host; rows_by_table overrides the SF cardinalities."""
+    seed = synth.seed_for(sf) if seed is None else seed
+    out = {}
+    for q in qualified_names:
+        spec = synth.column_spec(cat, q, sf)
+        t = q.split(".")[0]
+        out[q] = gen_column(spec, rows_by_table[t], row_offset, seed)
+    return out
+
+
+def run_oracle(plan, cols, threads=0):
+    o = Oracle()
+    for k, v in cols.items():
+        o.bind(k, v)
+    return o.run(plan, threads)
+
+
+def assert_same(a: dict, b: dict):
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        np.testing.assert_array_equal(np.asarray(a[k], dtype=np.int64), np.asarray(b[k], dtype=np.int64), err_msg=k)
