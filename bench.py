@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: the mplan2vdl-emitted TPC-H Q6 plan over synthetic SF100 lineitem
+columns resident in HBM (BASELINE.json north_star), executed by libvdl_cuda.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--query q06|q01] [--sf 100]
+
+One "step" = one execution of the plan over the whole (sharded) table: identity-init of the partial
+table, the fused scan-fold kernel, [all-gather of the partial tables for N>1], finalize, and the
+device->host read of the result.  Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for what each
+field means and how the roofline / cpu_baseline / e2e numbers are obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+QUERIES = {
+    # plan file, algorithmic bytes per lineitem row (SURVEY.md section 8 d: distinct base columns x stored width)
+    "q06": ("q06.vdl", 28),
+    "q01": ("q01.vdl", 52),
+}
+FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback, used only when MEASURED_PEAKS.json is absent
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_oracle_rate(cat, query: str, sf: float, target_seconds: float = 12.0, max_rows: int = 59_986_052, steps: int = 1):
+    """Time the CPU oracle (kind "port": the reference ships no executor) on a bounded sample of the same workload:
+    the first `rows` lineitem rows of the same synthetic table.  Returns (rows/s, sample rows, threads, seconds list)."""
+    from mplan2vdl_b200 import synth, tpch
+    from oracle.oracle import Oracle, gen_column, max_threads
+    text = tpch.plan_text(QUERIES[query][0])
+    names = tpch.plan_columns(text)
+    seed = synth.seed_for(sf)
+    threads = max_threads()
+
+    def run(rows, reps):
+        orc = Oracle()
+        for n in names:
+            orc.bind(n, gen_column(synth.column_spec(cat, n, sf), rows, 0, seed))
+        secs = []
+        for _ in range(reps):
+            orc.run(text)
+            secs.append(orc.seconds)
+        return secs
+
+    probe_rows = 2_000_000
+    t = min(run(probe_rows, 2))
+    rows = int(min(max_rows, max(probe_rows, probe_rows * target_seconds / max(t, 1e-6) / max(steps, 1))))
+    secs = run(rows, steps)
+    return rows / statistics.median(secs), rows, threads, secs
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  orm011/mplan2vdl ships no executor
+    (SURVEY.md section 0), so this arm times the CPU oracle -- the restatement of the Voodoo op semantics -- with all
+    host threads on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mplan2vdl_b200.meta import builtin_catalog
+    cat = builtin_catalog()
+    total = max(1, args.steps + args.warmup)
+    rate, rows, threads, secs = cpu_oracle_rate(cat, args.query, args.sf, target_seconds=60.0, steps=total)
+    timed = secs[args.warmup:] or secs
+    ms = 1e3 * statistics.mean(timed)
+    value = rows / (ms / 1e3)
+    sample = f"first {rows} lineitem rows of the synthetic SF{args.sf:g} table, {len(timed)} timed runs of the op-at-a-time CPU oracle"
+    line = {
+        "impl": "reference", "metric": f"tpch_{args.query}_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": workload_config(args, rows_total=None),
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, rows_total):
+    plan, bpr = QUERIES[args.query]
+    return {"workload": f"TPC-H {args.query.upper()} SF{args.sf:g}: plans/{plan} (mplan2vdl Voodoo plan) over synthetic lineitem columns "
+                        "generated to the reference's bounds.csv",
+            "lineitem_rows": rows_total, "algorithmic_bytes_per_row": bpr,
+            "l2": "inputs (GBs) far exceed the 126 MB L2; no flush needed between steps",
+            "parallelism": f"lineitem row-range sharded over {args.gpus} GPU(s), partial tables all-gathered"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--query", default="q06", choices=sorted(QUERIES))
+    ap.add_argument("--sf", type=float, default=100)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import __graft_entry__
+    __graft_entry__.build()
+    from mplan2vdl_b200 import synth, tpch
+    from mplan2vdl_b200.executor import Context
+    from mplan2vdl_b200.meta import builtin_catalog
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (libvdl_cuda has no CPU fallback)")
+    torch.cuda.set_device(local)
+
+    cat = builtin_catalog()
+    plan_file, bytes_per_row = QUERIES[args.query]
+    text = tpch.plan_text(plan_file)
+    names = tpch.plan_columns(text)
+    rows_total = synth.table_rows(cat, "lineitem", args.sf)
+
+    ctx = Context(local)
+    info = tpch.load_synthetic(ctx, cat, names, args.sf, rank=rank, world=world)
+    rows_here = info["rows"]["lineitem"]
+    plan = ctx.plan(text)
+    plan.set_row_base(info["row_base"])
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local)
+
+    class _View:      # library-owned device memory as a torch tensor (for NCCL)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+    gathered = []
+
+    def step():
+        plan.run_local()
+        if world > 1:
+            ptrs = []
+            with torch.cuda.stream(ext):
+                for i in range(plan.num_fused):
+                    p, n = plan.partials(i)
+                    if len(gathered) <= i:
+                        gathered.append(torch.empty(world * n, dtype=torch.int64, device=f"cuda:{local}"))
+                    dist.all_gather_into_tensor(gathered[i], torch.as_tensor(_View(p, n), device=f"cuda:{local}"))
+                    ptrs.append(gathered[i].data_ptr())
+            return plan.finish(ptrs, world)
+        return plan.finish()
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    result = None
+    for _ in range(args.warmup):
+        result = step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    kernel_ms = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(ext)
+    for _ in range(args.steps):
+        result = step()
+        kernel_ms.append(plan.kernel_ms(0))
+    ev1.record(ext)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else {}
+    if world > 1:
+        t = torch.tensor([dev_ms, statistics.mean(kernel_ms)], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, kern_ms_mean = float(t[0]), float(t[1])
+    else:
+        kern_ms_mean = statistics.mean(kernel_ms)
+    ms_per_step = dev_ms / args.steps
+    value = rows_total / (ms_per_step / 1e3)
+
+    # roofline of the dominant kernel (the fused scan): algorithmic bytes of THIS rank's shard / its mean duration
+    peak, peak_kind = measured_peak()
+    achieved = rows_here * bytes_per_row / (statistics.mean(kernel_ms) / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)" if peak_kind == "measured" else "fallback 6650 GB/s",
+                "kernel": "fused_scan_fold_kernel", "kernel_ms": statistics.mean(kernel_ms), "kernel_ms_min": min(kernel_ms),
+                "frac_of_8TBs_spec": achieved / 8000.0, "bytes_per_launch": rows_here * bytes_per_row}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f).get(f"{args.query}_sf{args.sf:g}")
+            if tr:
+                roofline["traffic"] = tr
+    except Exception:
+        pass
+
+    # end to end through the public API with HOST buffers: H2D of every column + run + D2H of the result, per step
+    e2e = None
+    if not args.no_e2e:
+        handles = [ctx.lookup(n) for n in names]
+        widths = [synth.column_spec(cat, n, args.sf).width for n in names]
+        host = []
+        for h, w in zip(handles, widths):
+            buf = torch.empty(rows_here * w, dtype=torch.uint8, pin_memory=True)
+            ctx.download_into(h, buf.data_ptr(), rows_here)
+            host.append(buf)
+        h2d = sum(b.numel() for b in host)
+
+        def e2e_step():
+            for h, b in zip(handles, host):
+                ctx.upload_into(h, b.data_ptr(), rows_here)
+            return step()
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            r2 = e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t[0])
+        for k in result:
+            assert np.array_equal(r2[k], result[k]), "e2e result differs from the device-resident result"
+        d2h = sum(8 * len(v) for v in result.values())
+        e2e = {"value": rows_total / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps, "timing": "host wall clock, barrier + synchronize both sides",
+               "h2d_gbs": h2d / e2e_s / 1e9}
+        del host
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, srows, threads, secs = cpu_oracle_rate(cat, args.query, args.sf)
+        cpu = {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"first {srows} lineitem rows of the same synthetic table; op-at-a-time CPU oracle (OpenMP), {statistics.median(secs):.2f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": f"tpch_{args.query}_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic", "config": workload_config(args, rows_total), "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "wall_ms_per_step": wall_ms / args.steps, "result": {k: [int(x) for x in v[:8]] for k, v in result.items()},
+            "plan": plan.stats(),
+        }
+        print(json.dumps(line), flush=True)
+    plan.close()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,208 @@
+/*
+ * vdl_cuda.h -- C ABI of libvdl_cuda, the B200 (sm_100a) executor for the Voodoo dataflow
+ * graphs that orm011/mplan2vdl emits.
+ *
+ * What this boundary replaces.  mplan2vdl prints the Voodoo program to stdout
+ * (MainFuns.hs:155-157) and an external Voodoo server, which is not in the reference
+ * repository, received it over HTTP and answered with JSON (eval_query.sh:18-26,
+ * resolve.py:8-32).  libvdl_cuda is that missing executor as an in-process library:
+ *   - vdl_plan_load() takes exactly the text `Vdl.vdlFromVexps` produces
+ *     (Vdl.hs:410-453 toVoodooList, 455-477 printLine, 490-495), so the existing
+ *     stdout/wire format is a valid input unchanged;
+ *   - the per-op entry points (vdl_op_*) are one call per constructor of the
+ *     emitter's op set `Vd`/`Voodop` (Vdl.hs:32-44, 110-131) -- what a Haskell
+ *     `Exec` module walking `[Vexp]` after MainFuns.hs:186 binds with
+ *     `foreign import ccall safe` (see INTEGRATION.md and hs/VdlCuda.hs);
+ *   - vdl_fused_scan_fold() is the single-launch select->map->fold kernel that the
+ *     fusion peephole (same `Vx -> Maybe Vexp` shape as Vlite.hs:1295-1340) targets.
+ *
+ * Conventions: every call returns 0 on success and a VDL_E* code otherwise and never
+ * throws or aborts across the ABI; vdl_last_error(ctx) gives the message.  Device buffers
+ * are owned by the library and referenced by opaque handles.  Calls on one context are
+ * serialised by the caller; different contexts (GPUs) may be driven from different host
+ * threads.  All calls may block: bind them as `safe` FFI calls.  Plain pointers and sizes
+ * only -- no torch or C++ types.
+ */
+#ifndef VDL_CUDA_H
+#define VDL_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDL_ABI_VERSION 1
+
+/* status codes */
+enum {
+  VDL_OK = 0,
+  VDL_EINVAL = 1,      /* bad argument / malformed plan text */
+  VDL_ECUDA = 2,       /* CUDA runtime error (message has the cudaError string) */
+  VDL_ENOTFOUND = 3,   /* Load of a column that is not registered */
+  VDL_EUNSUPPORTED = 4,/* op outside the supported vocabulary (Like, CrossProduct*, Semisort) */
+  VDL_ERANGE = 5,      /* Gather/Scatter position out of range */
+  VDL_ENOMEM = 6
+};
+
+/* storage types (reference Types.hs:66-89: SInt32 4 B; SInt64/SDecimal 8 B) */
+enum { VDL_I32 = 4, VDL_I64 = 8 };
+
+/* binary elementwise ops, in the order of `Voodop` (Vdl.hs:110-123) */
+enum {
+  VDL_LOGICAL_AND = 0, VDL_LOGICAL_OR, VDL_BITWISE_AND, VDL_BITWISE_OR, VDL_BITSHIFT, VDL_EQUALS,
+  VDL_ADD, VDL_SUBTRACT, VDL_GREATER, VDL_MULTIPLY, VDL_DIVIDE, VDL_MODULO
+};
+/* folds (Vdl.hs:124-129; FoldSelect has its own entry point) */
+enum { VDL_FOLD_SUM = 0, VDL_FOLD_MIN = 1, VDL_FOLD_MAX = 2, VDL_FOLD_CHOOSE = 3, VDL_FOLD_COUNT = 4 };
+
+/* synthetic column kinds (mplan2vdl_b200/synth.py) */
+enum { VDL_SYNTH_UNIFORM = 0, VDL_SYNTH_SEQ = 1, VDL_SYNTH_FKDENSE = 2 };
+
+typedef struct vdl_ctx vdl_ctx;     /* one per device */
+typedef struct vdl_plan vdl_plan;   /* a loaded Voodoo program */
+typedef int32_t vdl_vec;            /* handle of a device vector (>0); columns are vectors too */
+
+/* ---- context ---------------------------------------------------------------------- */
+int vdl_abi_version(void);
+/* sizeof(vdl_fused_desc) as this library was compiled, so FFI bindings can check their layout. */
+int vdl_abi_sizeof_fused_desc(void);
+int vdl_ctx_create(int device, vdl_ctx **out);
+int vdl_ctx_destroy(vdl_ctx *ctx);
+const char *vdl_last_error(vdl_ctx *ctx);
+/* The CUDA stream every kernel of this context is launched on (a cudaStream_t), so callers
+ * can time with events on the launching stream or order their own work after it. */
+void *vdl_ctx_stream(vdl_ctx *ctx);
+int vdl_ctx_synchronize(vdl_ctx *ctx);
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t vdl_ctx_launch_count(vdl_ctx *ctx);
+
+/* ---- columns: what `Load,<table>.<col>` binds (Vdl.hs:161-168, 419-420) --------------- */
+/* Allocate a named column of `rows` values of `dtype` in HBM (padded for 16-byte bulk copies). */
+int vdl_column_alloc(vdl_ctx *ctx, const char *name, int dtype, int64_t rows, vdl_vec *out);
+/* Register caller-owned device memory (e.g. a torch tensor) as a named column; the memory must
+ * stay valid while registered and be 16-byte aligned.  capacity_rows >= rows is how many rows
+ * may be read past the logical end (bulk copies round the tail up to 16 bytes). */
+int vdl_column_bind(vdl_ctx *ctx, const char *name, int dtype, int64_t rows, int64_t capacity_rows,
+                    void *device_ptr, vdl_vec *out);
+/* Host -> device copy of a whole column (pageable or pinned host memory). */
+int vdl_column_upload(vdl_ctx *ctx, vdl_vec col, const void *host, int64_t rows);
+/* Device -> host copy of a whole column in its stored type (the inverse of vdl_column_upload). */
+int vdl_column_download(vdl_ctx *ctx, vdl_vec col, void *host, int64_t rows);
+/* Fill rows [0, rows) of `col` with the counter-based synthetic recipe for global rows
+ * [row_offset, row_offset+rows): a shard generates its own row range in place. */
+int vdl_column_fill_synthetic(vdl_ctx *ctx, vdl_vec col, uint64_t seed, uint64_t stream, int kind,
+                              int64_t vmin, int64_t stride, int64_t p0, int64_t p1, int64_t row_offset);
+int vdl_column_lookup(vdl_ctx *ctx, const char *name, vdl_vec *out);
+int vdl_column_drop(vdl_ctx *ctx, const char *name);
+
+/* ---- vectors ----------------------------------------------------------------------- */
+int vdl_vec_len(vdl_ctx *ctx, vdl_vec v, int64_t *len);
+int vdl_vec_dtype(vdl_ctx *ctx, vdl_vec v, int *dtype);
+void *vdl_vec_device_ptr(vdl_ctx *ctx, vdl_vec v);
+/* Device -> host copy of v as int64 (int32 columns are sign-extended); `capacity` in elements. */
+int vdl_vec_download(vdl_ctx *ctx, vdl_vec v, int64_t *host, int64_t capacity);
+int vdl_vec_free(vdl_ctx *ctx, vdl_vec v);
+
+/* ---- per-op entry points: one per Voodoo op, explicit lengths -- */
+/* RangeV / RangeC (Vdl.hs:428-434): out[i] = from + i*step, i < len. */
+int vdl_op_range(vdl_ctx *ctx, int64_t from, int64_t step, int64_t len, vdl_vec *out);
+/* Elementwise binary op (Vdl.hs:436-439); a and b have equal length. */
+int vdl_op_binary(vdl_ctx *ctx, int op, vdl_vec a, vdl_vec b, vdl_vec *out);
+/* FoldSelect with fold = pos_ pred (Vlite.hs:721-730): ascending positions of non-zero pred. */
+int vdl_op_fold_select(vdl_ctx *ctx, vdl_vec pred, vdl_vec *out);
+/* Gather (Vdl.hs:438): out[i] = src[pos[i]]. */
+int vdl_op_gather(vdl_ctx *ctx, vdl_vec src, vdl_vec pos, vdl_vec *out);
+/* Scatter (Vdl.hs:441-442): out[pos[i]] = src[i], unwritten = 0; out_len explicit (App. G2). */
+int vdl_op_scatter(vdl_ctx *ctx, vdl_vec src, vdl_vec pos, int64_t out_len, vdl_vec *out);
+/* Partition (Vdl.hs:266-269) with pivots RangeC(pivot_from, pivot_count, pivot_step): destination
+ * positions of the stable sort of rows by bucket(data) = number of pivots below data[i]. */
+int vdl_op_partition(vdl_ctx *ctx, vdl_vec data, int64_t pivot_from, int64_t pivot_step,
+                     int64_t pivot_count, vdl_vec *out);
+/* FoldSum/Min/Max/Choose/Count (Vdl.hs:255-264): one output per run of equal consecutive groups. */
+int vdl_op_fold(vdl_ctx *ctx, int fold_op, vdl_vec groups, vdl_vec data, vdl_vec *out);
+
+/* ---- fused select -> map -> fold -------------------------------------------------------
+ * One launch that scans up to VDL_MAX_COLS columns of one table, applies a conjunction of range
+ * predicates, computes a small bit-packed group key and folds products of affine column terms
+ * per key.  This is what the fusion pass rewrites
+ *   Fold(op, groups, f(Gather(c_i, FoldSelect(pos_ p, p)) ...))            (Vlite.hs:721-730)
+ * and its Partition/Scatter-sorted grouped form (Vlite.hs:1048-1098) into. */
+#define VDL_MAX_COLS 12
+#define VDL_MAX_PREDS 8
+#define VDL_MAX_KEYS 4
+#define VDL_MAX_AGGS 10
+#define VDL_MAX_FACTORS 4
+
+typedef struct {          /* value = a + b * (column[row] >> shr); column < 0: the constant a;   */
+  int32_t column;         /* column == -2: the global row id (row_base + row)                      */
+  int32_t shr;
+  int64_t a, b;
+} vdl_affine;
+
+typedef struct { int32_t column, shr; int64_t lo, hi; } vdl_range_pred;  /* lo <= (col>>shr) <= hi */
+typedef struct { vdl_affine e; int32_t shl, pad; } vdl_key_part;         /* (e) << shl, parts OR-ed */
+typedef struct {
+  int32_t op;             /* VDL_FOLD_SUM / MIN / MAX / CHOOSE / COUNT */
+  int32_t nfactors;       /* value = product of factors (empty product = 1) */
+  vdl_affine factor[VDL_MAX_FACTORS];
+} vdl_fold_spec;
+
+typedef struct {
+  int64_t rows;                       /* rows of this shard */
+  int64_t row_base;                   /* global row id of this shard's row 0 */
+  int32_t ncolumns;
+  vdl_vec column[VDL_MAX_COLS];       /* registered columns of one table, equal length */
+  int32_t npreds;
+  vdl_range_pred pred[VDL_MAX_PREDS];
+  int32_t nkeys;                      /* 0: one group (key 0) */
+  vdl_key_part key[VDL_MAX_KEYS];
+  int64_t key_mask;                   /* key &= key_mask (Vlite.hs:1111-1115 size hint); -1: none */
+  int64_t domain;                     /* keys are in [0, domain) */
+  int32_t nfolds;
+  vdl_fold_spec fold[VDL_MAX_AGGS];
+} vdl_fused_desc;
+
+typedef struct vdl_fused vdl_fused;   /* a prepared fused scan (device tables, launch geometry) */
+
+int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_fused **out);
+/* Launch the scan over this shard; leaves the partial table [nacc][domain] of int64 in HBM. */
+int vdl_fused_launch(vdl_fused *f);
+/* The partial table for the multi-GPU combine: device pointer and its size in int64 elements. */
+int vdl_fused_partials(vdl_fused *f, void **device_ptr, int64_t *n_int64);
+/* Merge `nranks` partial tables laid out back to back at `all_partials` (an all-gather result; pass
+ * NULL and 1 to use this shard's own table), drop empty groups and produce one vector per fold,
+ * ascending key order -- the dense-model output of the Folds (G1, G14). */
+int vdl_fused_finalize(vdl_fused *f, const void *all_partials, int nranks);
+int vdl_fused_num_groups(vdl_fused *f, int64_t *ngroups);   /* synchronises */
+int vdl_fused_result(vdl_fused *f, int fold_index, vdl_vec *out);
+int vdl_fused_destroy(vdl_fused *f);
+/* Duration of the last vdl_fused_launch's scan kernel alone, CUDA events on the context stream. */
+int vdl_fused_last_kernel_ms(vdl_fused *f, float *ms);
+
+/* ---- whole plans: the text mplan2vdl prints (Vdl.hs:410-453) ---------------------------- */
+enum { VDL_PLAN_FUSE = 1 };           /* flags: run the select->map->fold fusion pass */
+int vdl_plan_load(vdl_ctx *ctx, const char *vdl_text, int flags, vdl_plan **out);
+/* Statements parsed, distinct nodes after structural CSE (App. G10), fused scans, kernel launches
+ * of the last run. */
+int vdl_plan_stats(vdl_plan *p, int *statements, int *nodes, int *fused_scans, int64_t *launches);
+/* Phase 1: everything up to and including the fused scans (local shard). */
+/* Global row id of this shard's row 0 (row-range sharding of the fact table; default 0). */
+int vdl_plan_set_row_base(vdl_plan *p, int64_t row_base);
+int vdl_plan_run_local(vdl_plan *p);
+int vdl_plan_num_fused(vdl_plan *p);
+int vdl_plan_fused(vdl_plan *p, int i, vdl_fused **out);
+/* Phase 2: finalize the fused scans (optionally from all-gathered partials, one buffer per fused scan,
+ * NULL entries / nranks 1 for single GPU), run the remaining ops, copy outputs to the host. */
+int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int nranks);
+/* vdl_plan_run_local + vdl_plan_finish for one GPU. */
+int vdl_plan_run(vdl_plan *p);
+int vdl_plan_num_outputs(vdl_plan *p);
+/* Output i in MaterializeCompact order: name (the Project's <out>, Vdl.hs:278-292), host int64 data. */
+int vdl_plan_output(vdl_plan *p, int i, const char **name, const int64_t **data, int64_t *len);
+int vdl_plan_destroy(vdl_plan *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDL_CUDA_H */

@@ -1,0 +1,338 @@
+// Context, columns and vectors of libvdl_cuda; the synthetic column generator.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "vdl_internal.h"
+
+int vdl_fail(vdl_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+int vdl_cuda_fail(vdl_ctx *ctx, cudaError_t e, const char *what) {
+  return vdl_fail(ctx, e == cudaErrorMemoryAllocation ? VDL_ENOMEM : VDL_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+static char g_noctx_err[256] = "no context";
+
+extern "C" int vdl_abi_version(void) { return VDL_ABI_VERSION; }
+extern "C" int vdl_abi_sizeof_fused_desc(void) { return (int)sizeof(vdl_fused_desc); }
+
+extern "C" int vdl_ctx_create(int device, vdl_ctx **out) {
+  if (!out) return VDL_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || device < 0 || device >= n) {
+    snprintf(g_noctx_err, sizeof g_noctx_err, "vdl_ctx_create: device %d not available (%s, %d devices)", device,
+             cudaGetErrorString(e), n);
+    return VDL_ECUDA;
+  }
+  vdl_ctx *ctx = new vdl_ctx();
+  ctx->device = device;
+  ctx->vecs.resize(1);
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMalloc(&ctx->d_errflag, sizeof(int))) != cudaSuccess || (e = cudaMemset(ctx->d_errflag, 0, sizeof(int))) != cudaSuccess) {
+    snprintf(g_noctx_err, sizeof g_noctx_err, "vdl_ctx_create: %s", cudaGetErrorString(e));
+    delete ctx;
+    return VDL_ECUDA;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  *out = ctx;
+  return VDL_OK;
+}
+
+extern "C" int vdl_ctx_destroy(vdl_ctx *ctx) {
+  if (!ctx) return VDL_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &v : ctx->vecs)
+    if (v.live && v.owned && v.ptr) cudaFree(v.ptr);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->d_errflag) cudaFree(ctx->d_errflag);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return VDL_OK;
+}
+
+extern "C" const char *vdl_last_error(vdl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_noctx_err; }
+extern "C" void *vdl_ctx_stream(vdl_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int64_t vdl_ctx_launch_count(vdl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int vdl_ctx_synchronize(vdl_ctx *ctx) {
+  if (!ctx) return VDL_EINVAL;
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- vectors
+static int vec_slot(vdl_ctx *ctx) {
+  for (size_t i = 1; i < ctx->vecs.size(); i++)
+    if (!ctx->vecs[i].live) return (int)i;
+  ctx->vecs.emplace_back();
+  return (int)ctx->vecs.size() - 1;
+}
+
+static i64 padded_bytes(int dtype, i64 rows) {
+  // Bulk (TMA) copies move whole 16-byte units and tiles of up to 2048 rows may be requested for the
+  // tail, so keep every allocation readable up to the next 256-byte boundary past the logical end.
+  i64 b = rows * (i64)dtype;
+  return ((b + 255) / 256) * 256 + 256;
+}
+
+int vec_new(vdl_ctx *ctx, int dtype, i64 len, vdl_vec *out) {
+  if (dtype != VDL_I32 && dtype != VDL_I64) return vdl_fail(ctx, VDL_EINVAL, "dtype must be VDL_I32 or VDL_I64, got %d", dtype);
+  if (len < 0) return vdl_fail(ctx, VDL_EINVAL, "negative length %lld", (long long)len);
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  void *p = nullptr;
+  i64 bytes = padded_bytes(dtype, len);
+  VDL_CUDA(ctx, cudaMalloc(&p, (size_t)bytes));
+  int h = vec_slot(ctx);
+  Vec &v = ctx->vecs[h];
+  v = Vec();
+  v.ptr = p;
+  v.dtype = dtype;
+  v.len = len;
+  v.cap_rows = bytes / dtype;
+  v.owned = true;
+  v.live = true;
+  *out = h;
+  return VDL_OK;
+}
+
+int vec_new_range(vdl_ctx *ctx, i64 from, i64 step, i64 len, vdl_vec *out) {
+  if (len < 0) return vdl_fail(ctx, VDL_EINVAL, "negative length %lld", (long long)len);
+  int h = vec_slot(ctx);
+  Vec &v = ctx->vecs[h];
+  v = Vec();
+  v.live = true;
+  v.is_range = true;
+  v.from = from;
+  v.step = step;
+  v.len = len;
+  if (from == 0 && step == 1) v.domain = len;
+  *out = h;
+  return VDL_OK;
+}
+
+Vec *vec_get(vdl_ctx *ctx, vdl_vec h) {
+  if (!ctx || h <= 0 || (size_t)h >= ctx->vecs.size() || !ctx->vecs[h].live) {
+    vdl_fail(ctx, VDL_EINVAL, "invalid vector handle %d", (int)h);
+    return nullptr;
+  }
+  return &ctx->vecs[h];
+}
+
+Operand operand_of(const Vec &v) {
+  Operand o;
+  o.p = v.ptr;
+  o.kind = v.is_range ? 2 : (v.dtype == VDL_I32 ? 1 : 0);
+  o.from = v.from;
+  o.step = v.step;
+  return o;
+}
+
+int scratch_reserve(vdl_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return VDL_OK;
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  ctx->scratch = nullptr;
+  ctx->scratch_bytes = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  VDL_CUDA(ctx, cudaMalloc(&ctx->scratch, want));
+  ctx->scratch_bytes = want;
+  return VDL_OK;
+}
+
+int check_errflag(vdl_ctx *ctx, const char *what) {
+  int flag = 0;
+  VDL_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flag) {
+    cudaMemsetAsync(ctx->d_errflag, 0, sizeof(int), ctx->stream);
+    return vdl_fail(ctx, VDL_ERANGE, "%s: %d positions out of range", what, flag);
+  }
+  return VDL_OK;
+}
+
+extern "C" int vdl_vec_len(vdl_ctx *ctx, vdl_vec h, int64_t *len) {
+  Vec *v = vec_get(ctx, h);
+  if (!v || !len) return VDL_EINVAL;
+  *len = v->len;
+  return VDL_OK;
+}
+extern "C" int vdl_vec_dtype(vdl_ctx *ctx, vdl_vec h, int *dtype) {
+  Vec *v = vec_get(ctx, h);
+  if (!v || !dtype) return VDL_EINVAL;
+  *dtype = v->dtype;
+  return VDL_OK;
+}
+extern "C" void *vdl_vec_device_ptr(vdl_ctx *ctx, vdl_vec h) {
+  Vec *v = vec_get(ctx, h);
+  return v ? v->ptr : nullptr;
+}
+extern "C" int vdl_vec_free(vdl_ctx *ctx, vdl_vec h) {
+  Vec *v = vec_get(ctx, h);
+  if (!v) return VDL_EINVAL;
+  if (!v->name.empty()) ctx->columns.erase(v->name);
+  if (v->owned && v->ptr) {
+    VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VDL_CUDA(ctx, cudaFree(v->ptr));
+  }
+  *v = Vec();
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- columns
+extern "C" int vdl_column_alloc(vdl_ctx *ctx, const char *name, int dtype, int64_t rows, vdl_vec *out) {
+  if (!ctx || !name || !out) return VDL_EINVAL;
+  if (ctx->columns.count(name)) return vdl_fail(ctx, VDL_EINVAL, "column %s already registered", name);
+  VDL_TRY(vec_new(ctx, dtype, rows, out));
+  ctx->vecs[*out].name = name;
+  ctx->columns[name] = *out;
+  return VDL_OK;
+}
+
+extern "C" int vdl_column_bind(vdl_ctx *ctx, const char *name, int dtype, int64_t rows, int64_t capacity_rows,
+                               void *device_ptr, vdl_vec *out) {
+  if (!ctx || !name || !out) return VDL_EINVAL;
+  if (dtype != VDL_I32 && dtype != VDL_I64) return vdl_fail(ctx, VDL_EINVAL, "dtype must be VDL_I32 or VDL_I64");
+  if (((uintptr_t)device_ptr & 15) != 0) return vdl_fail(ctx, VDL_EINVAL, "column %s: device pointer must be 16-byte aligned", name);
+  if (rows < 0 || capacity_rows < rows) return vdl_fail(ctx, VDL_EINVAL, "column %s: capacity %lld < rows %lld", name, (long long)capacity_rows, (long long)rows);
+  if (ctx->columns.count(name)) return vdl_fail(ctx, VDL_EINVAL, "column %s already registered", name);
+  int h = vec_slot(ctx);
+  Vec &v = ctx->vecs[h];
+  v = Vec();
+  v.ptr = device_ptr;
+  v.dtype = dtype;
+  v.len = rows;
+  v.cap_rows = capacity_rows;
+  v.live = true;
+  v.name = name;
+  ctx->columns[name] = h;
+  *out = h;
+  return VDL_OK;
+}
+
+extern "C" int vdl_column_lookup(vdl_ctx *ctx, const char *name, vdl_vec *out) {
+  if (!ctx || !name || !out) return VDL_EINVAL;
+  auto it = ctx->columns.find(name);
+  if (it == ctx->columns.end()) return vdl_fail(ctx, VDL_ENOTFOUND, "Load: column %s is not registered", name);
+  *out = it->second;
+  return VDL_OK;
+}
+
+extern "C" int vdl_column_drop(vdl_ctx *ctx, const char *name) {
+  vdl_vec h;
+  VDL_TRY(vdl_column_lookup(ctx, name, &h));
+  return vdl_vec_free(ctx, h);
+}
+
+extern "C" int vdl_column_upload(vdl_ctx *ctx, vdl_vec col, const void *host, int64_t rows) {
+  Vec *v = vec_get(ctx, col);
+  if (!v || !host) return VDL_EINVAL;
+  if (v->is_range || rows != v->len) return vdl_fail(ctx, VDL_EINVAL, "upload of %lld rows into a vector of %lld", (long long)rows, (long long)v->len);
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  VDL_CUDA(ctx, cudaMemcpyAsync(v->ptr, host, (size_t)(rows * v->dtype), cudaMemcpyHostToDevice, ctx->stream));
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VDL_OK;
+}
+
+extern "C" int vdl_column_download(vdl_ctx *ctx, vdl_vec col, void *host, int64_t rows) {
+  Vec *v = vec_get(ctx, col);
+  if (!v || !host) return VDL_EINVAL;
+  if (v->is_range || rows != v->len) return vdl_fail(ctx, VDL_EINVAL, "download of %lld rows from a vector of %lld", (long long)rows, (long long)v->len);
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  VDL_CUDA(ctx, cudaMemcpyAsync(host, v->ptr, (size_t)(rows * v->dtype), cudaMemcpyDeviceToHost, ctx->stream));
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- download
+__global__ void widen_i32_kernel(const int32_t *__restrict__ in, i64 *__restrict__ out, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+__global__ void range_fill_kernel(i64 *__restrict__ out, i64 from, i64 step, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (i64)((u64)from + (u64)i * (u64)step);
+}
+
+extern "C" int vdl_vec_download(vdl_ctx *ctx, vdl_vec h, int64_t *host, int64_t capacity) {
+  Vec *v = vec_get(ctx, h);
+  if (!v || (!host && v->len)) return VDL_EINVAL;
+  if (capacity < v->len) return vdl_fail(ctx, VDL_EINVAL, "download: capacity %lld < length %lld", (long long)capacity, (long long)v->len);
+  if (v->len == 0) return VDL_OK;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (v->is_range) {
+    for (i64 i = 0; i < v->len; i++) host[i] = (i64)((u64)v->from + (u64)i * (u64)v->step);
+    return VDL_OK;
+  }
+  const void *src = v->ptr;
+  if (v->dtype == VDL_I32) {
+    VDL_TRY(scratch_reserve(ctx, (size_t)v->len * 8));
+    unsigned blocks = (unsigned)((v->len + 255) / 256);
+    widen_i32_kernel<<<blocks, 256, 0, ctx->stream>>>((const int32_t *)v->ptr, (i64 *)ctx->scratch, v->len);
+    ctx->launches++;
+    src = ctx->scratch;
+  }
+  VDL_CUDA(ctx, cudaMemcpyAsync(host, src, (size_t)v->len * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- synthetic
+// Counter-based recipe (specification shared with the host generators; mplan2vdl_b200/synth.py).
+__device__ __forceinline__ u64 splitmix64(u64 x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  u64 z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+template <typename T>
+__global__ void synth_fill_kernel(T *__restrict__ out, i64 rows, u64 base, int kind, i64 vmin, i64 stride, u64 p0, u64 p1, u64 row_offset) {
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (i64)gridDim.x * blockDim.x) {
+    u64 row = row_offset + (u64)i;
+    u64 idx;
+    if (kind == VDL_SYNTH_UNIFORM) idx = __umul64hi(splitmix64(base + row), p0);
+    else if (kind == VDL_SYNTH_SEQ) idx = row;
+    else idx = (row * p0) / p1;
+    out[i] = (T)(i64)((u64)vmin + (u64)stride * idx);
+  }
+}
+
+static u64 host_splitmix64(u64 x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  u64 z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+extern "C" int vdl_column_fill_synthetic(vdl_ctx *ctx, vdl_vec col, uint64_t seed, uint64_t stream, int kind, int64_t vmin,
+                                         int64_t stride, int64_t p0, int64_t p1, int64_t row_offset) {
+  Vec *v = vec_get(ctx, col);
+  if (!v) return VDL_EINVAL;
+  if (v->is_range) return vdl_fail(ctx, VDL_EINVAL, "cannot fill a range vector");
+  if (kind < 0 || kind > 2 || (kind == VDL_SYNTH_FKDENSE && p1 <= 0) || (kind == VDL_SYNTH_UNIFORM && p0 <= 0))
+    return vdl_fail(ctx, VDL_EINVAL, "bad synthetic spec kind=%d p0=%lld p1=%lld", kind, (long long)p0, (long long)p1);
+  if (v->len == 0) return VDL_OK;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  u64 base = host_splitmix64(seed ^ (stream * 0x9E3779B97F4A7C15ULL));
+  int blocks = ctx->sm_count * 8;
+  if (v->dtype == VDL_I32)
+    synth_fill_kernel<int32_t><<<blocks, 256, 0, ctx->stream>>>((int32_t *)v->ptr, v->len, base, kind, vmin, stride, (u64)p0, (u64)p1, (u64)row_offset);
+  else
+    synth_fill_kernel<i64><<<blocks, 256, 0, ctx->stream>>>((i64 *)v->ptr, v->len, base, kind, vmin, stride, (u64)p0, (u64)p1, (u64)row_offset);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaGetLastError());
+  return VDL_OK;
+}

@@ -1,0 +1,643 @@
+// Fused select -> map -> fold: ONE launch that streams the columns of a table shard through shared
+// memory with TMA bulk copies and folds products of affine column terms per group key.
+//
+// What it replaces in the emitted graph (reference Vlite.hs):
+//   idx = FoldSelect(pos_ p, p); c_i @@ idx          solve' Select          Vlite.hs:721-730
+//   key = ((c >> tz) - min) << bits | ... & hint     makeCompositeKey       Vlite.hs:1123-1170, 1111-1115
+//   Partition(key) -> Scatter(x, .) -> Fold(op, ., .) solveAgg / getScatterMask Vlite.hs:1048-1098
+// In the dense model elementwise ops commute with the Gather by the selection, the
+// stable Partition+Scatter only orders rows by key, and Fold emits one row per existing key in ascending
+// order -- so the whole chain is "for every row that passes p: acc[key][j] op= value_j(row)", followed
+// by dropping the keys that saw no row.  No intermediate vector ever reaches HBM.
+//
+// Kernel shape (B200, sm_100a): persistent, one CTA per SM.  Warp 0 is the producer: one elected lane
+// issues `cp.async.bulk` (TMA, 1-D) copies of TILE rows of every column into a ring of shared-memory
+// stages, completion tracked by mbarriers (expect_tx).  The other 8 warps are consumers: they wait on
+// the stage's "full" barrier, evaluate predicate / key / products straight from shared memory (column
+// chosen by runtime index = just an address, so ONE kernel serves every plan), and release the stage
+// through its "empty" barrier.  Ungrouped folds accumulate in registers; grouped folds accumulate in
+// lane-private shared-memory tables (plain LDS/STS read-modify-write, no atomics, no bank conflicts)
+// over a per-CTA compacted slot map so that sparse key domains (Q1: 6 of 32 slots) stay small.
+// HBM traffic = the columns, once.  Roofline: HBM.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "vdl_internal.h"
+
+#define K_MAX_ACC 12
+#define K_MAX_CHOOSE 6
+#define K_CONSUMERS 256          // consumer threads per CTA (8 warps)
+#define K_THREADS (K_CONSUMERS + 32)
+
+struct KAffine { int32_t col, shr; i64 a, b; };
+struct KPred { int32_t col, shr; i64 lo; u64 span; };
+struct KKey { KAffine e; int32_t shl, pad; };
+struct KAcc { int32_t op, nfac; KAffine fac[VDL_MAX_FACTORS]; };   // op: 0 sum, 1 min, 2 max
+
+struct KDesc {
+  i64 rows, row_base, key_mask, domain, ntiles;
+  const void *col[VDL_MAX_COLS];
+  int32_t width[VDL_MAX_COLS], soff[VDL_MAX_COLS];
+  int32_t ncols, npreds, nkeys, nacc, nchoose, cnt_idx, first_idx;
+  int32_t tile_rows, stages, stage_bytes, stage_tx, gmax, grouped;
+  KPred pred[VDL_MAX_PREDS];
+  KKey key[VDL_MAX_KEYS];
+  KAcc acc[K_MAX_ACC];
+  KAcc choose[K_MAX_CHOOSE];
+  i64 *table;                    // [nacc + nchoose][domain]
+  int *errflag;
+};
+
+struct FinDesc {
+  const i64 *parts;              // nranks tables back to back, each part_stride int64
+  i64 part_stride, domain;
+  int32_t nranks, nacc, nchoose, cnt_idx, first_idx, nout;
+  int32_t acc_op[K_MAX_ACC];
+  int32_t out_kind[VDL_MAX_AGGS], out_idx[VDL_MAX_AGGS];   // kind 0: accumulator, 1: choose
+  i64 *out[VDL_MAX_AGGS];
+  i64 *ngroups;
+};
+
+// ------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier; L2 evict-first policy
+// because every byte of a scan is touched exactly once.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(K_CONSUMERS) : "memory"); }
+
+// ------------------------------------------------------------------------------ row accessors
+struct SmemRows {   // a staged tile: column c lives at base + soff[c]
+  const char *base;
+  __device__ __forceinline__ i64 ld(const KDesc &d, int c, int r) const {
+    const char *p = base + d.soff[c];
+    return d.width[c] == 4 ? (i64)((const int32_t *)p)[r] : ((const i64 *)p)[r];
+  }
+};
+struct GmemRows {   // straight from HBM (tail rows, tiny inputs, choose evaluation)
+  i64 row0;
+  __device__ __forceinline__ i64 ld(const KDesc &d, int c, i64 r) const {
+    const void *p = d.col[c];
+    return d.width[c] == 4 ? (i64)__ldg((const int32_t *)p + row0 + r) : __ldg((const i64 *)p + row0 + r);
+  }
+};
+
+template <class Rows, class Idx>
+__device__ __forceinline__ i64 eval_affine(const KDesc &d, const KAffine &A, const Rows &R, Idx r, i64 grow) {
+  if (A.col == -1) return A.a;
+  i64 leaf = (A.col == -2) ? grow : (R.ld(d, A.col, r) >> A.shr);
+  return (i64)((u64)A.a + (u64)A.b * (u64)leaf);
+}
+template <class Rows, class Idx>
+__device__ __forceinline__ i64 eval_product(const KDesc &d, const KAcc &A, const Rows &R, Idx r, i64 grow) {
+  if (A.nfac == 0) return 1;
+  i64 v = eval_affine(d, A.fac[0], R, r, grow);
+#pragma unroll
+  for (int f = 1; f < VDL_MAX_FACTORS; f++)
+    if (f < A.nfac) v = (i64)((u64)v * (u64)eval_affine(d, A.fac[f], R, r, grow));
+  return v;
+}
+template <class Rows, class Idx>
+__device__ __forceinline__ bool eval_preds(const KDesc &d, const Rows &R, Idx r) {
+  bool pass = true;
+#pragma unroll
+  for (int i = 0; i < VDL_MAX_PREDS; i++)
+    if (i < d.npreds) {
+      i64 v = R.ld(d, d.pred[i].col, r) >> d.pred[i].shr;
+      pass &= ((u64)v - (u64)d.pred[i].lo) <= d.pred[i].span;
+    }
+  return pass;
+}
+template <class Rows, class Idx>
+__device__ __forceinline__ i64 eval_key(const KDesc &d, const Rows &R, Idx r, i64 grow) {
+  i64 key = 0;
+#pragma unroll
+  for (int k = 0; k < VDL_MAX_KEYS; k++)
+    if (k < d.nkeys) key |= (i64)((u64)eval_affine(d, d.key[k].e, R, r, grow) << d.key[k].shl);
+  return key & d.key_mask;
+}
+
+__device__ __forceinline__ i64 acc_identity(int op) { return op == 0 ? 0 : (op == 1 ? INT64_MAX : INT64_MIN); }
+__device__ __forceinline__ i64 acc_combine(int op, i64 a, i64 v) {
+  return op == 0 ? (i64)((u64)a + (u64)v) : (op == 1 ? (v < a ? v : a) : (v > a ? v : a));
+}
+__device__ __forceinline__ void acc_global(int op, i64 *p, i64 v) {
+  if (op == 0) atomicAdd((unsigned long long *)p, (unsigned long long)v);
+  else if (op == 1) atomicMin((long long *)p, (long long)v);
+  else atomicMax((long long *)p, (long long)v);
+}
+__device__ __forceinline__ i64 warp_reduce(int op, i64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = acc_combine(op, v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Per-CTA group state: key -> compact slot (lane-private accumulator tables are indexed by slot).
+struct GroupState {
+  int32_t *slotmap;   // [domain]  -1 unseen, -2 being claimed, -3 overflow (stays on the global-atomic path), >=0 slot
+  int32_t *slotkey;   // [gmax]
+  int32_t *nslots;
+  i64 *tbl;           // [gmax][nacc][K_CONSUMERS]
+};
+
+template <bool GROUPED, class Rows, class Idx>
+__device__ __forceinline__ void process_row(const KDesc &d, const Rows &R, Idx r, i64 grow, i64 (&acc)[K_MAX_ACC],
+                                            const GroupState &g, int ctid) {
+  if (!eval_preds(d, R, r)) return;
+  if (!GROUPED) {
+#pragma unroll
+    for (int j = 0; j < K_MAX_ACC; j++)
+      if (j < d.nacc) acc[j] = acc_combine(d.acc[j].op, acc[j], eval_product(d, d.acc[j], R, r, grow));
+  } else {
+    i64 key = eval_key(d, R, r, grow);
+    if ((u64)key >= (u64)d.domain) {   // the planner proves key < domain (mask); never expected
+      atomicAdd(d.errflag, 1);
+      return;
+    }
+    int s = ((volatile int32_t *)g.slotmap)[key];
+    if (s >= 0) {
+      i64 *t = g.tbl + (size_t)s * d.nacc * K_CONSUMERS + ctid;
+#pragma unroll
+      for (int j = 0; j < K_MAX_ACC; j++)
+        if (j < d.nacc) {
+          i64 v = eval_product(d, d.acc[j], R, r, grow);
+          t[j * K_CONSUMERS] = acc_combine(d.acc[j].op, t[j * K_CONSUMERS], v);
+        }
+    } else {
+      // first rows of a key in this CTA: fold straight into the global table and claim a slot for the rest
+      for (int j = 0; j < d.nacc; j++) acc_global(d.acc[j].op, d.table + (size_t)j * d.domain + key, eval_product(d, d.acc[j], R, r, grow));
+      if (s == -1 && atomicCAS(&g.slotmap[key], -1, -2) == -1) {
+        int ns = atomicAdd(g.nslots, 1);
+        if (ns < d.gmax) {
+          g.slotkey[ns] = (int32_t)key;
+          __threadfence_block();
+          atomicExch(&g.slotmap[key], ns);
+        } else {
+          atomicExch(&g.slotmap[key], -3);
+        }
+      }
+    }
+  }
+}
+
+template <bool GROUPED>
+__global__ void __launch_bounds__(K_THREADS, 1) fused_scan_fold_kernel(const __grid_constant__ KDesc d) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: [ring: stages * stage_bytes][full[stages]][empty[stages]][nslots][slotkey[gmax]][slotmap[domain]][tables]
+  unsigned char *ring = smem;
+  uint64_t *full = (uint64_t *)(smem + (size_t)d.stages * d.stage_bytes);
+  uint64_t *empty = full + d.stages;
+  GroupState g;
+  g.nslots = (int32_t *)(empty + d.stages);
+  g.slotkey = g.nslots + 2;
+  g.slotmap = g.slotkey + d.gmax;
+  size_t tbl_off = (size_t)((unsigned char *)(g.slotmap + (GROUPED ? d.domain : 0)) - smem);
+  tbl_off = (tbl_off + 15) & ~(size_t)15;
+  g.tbl = (i64 *)(smem + tbl_off);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < d.stages; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], K_CONSUMERS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *g.nslots = 0;
+  }
+  if (GROUPED) {
+    for (i64 k = tid; k < d.domain; k += K_THREADS) g.slotmap[k] = -1;
+    if (tid >= 32) {
+      int ctid = tid - 32;
+      for (int s = 0; s < d.gmax; s++)
+        for (int j = 0; j < d.nacc; j++) g.tbl[((size_t)s * d.nacc + j) * K_CONSUMERS + ctid] = acc_identity(d.acc[j].op);
+    }
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      const uint64_t policy = policy_evict_first();
+      int st = 0;
+      uint32_t ph = 0;
+      for (i64 tile = blockIdx.x; tile < d.ntiles; tile += gridDim.x) {
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_expect_tx(&full[st], (uint32_t)d.stage_tx);
+        unsigned char *dst = ring + (size_t)st * d.stage_bytes;
+        for (int c = 0; c < d.ncols; c++) {
+          uint32_t bytes = (uint32_t)(d.tile_rows * d.width[c]);
+          bulk_g2s(dst + d.soff[c], (const char *)d.col[c] + (size_t)tile * bytes, bytes, &full[st], policy);
+        }
+        if (++st == d.stages) { st = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  const int ctid = tid - 32;
+  i64 acc[K_MAX_ACC];
+#pragma unroll
+  for (int j = 0; j < K_MAX_ACC; j++) acc[j] = j < d.nacc ? acc_identity(d.acc[j].op) : 0;
+
+  int st = 0;
+  uint32_t ph = 0;
+  for (i64 tile = blockIdx.x; tile < d.ntiles; tile += gridDim.x) {
+    mbar_wait(&full[st], ph);
+    SmemRows R{(const char *)ring + (size_t)st * d.stage_bytes};
+    const i64 grow0 = d.row_base + tile * d.tile_rows;
+#pragma unroll 4
+    for (int r = ctid; r < d.tile_rows; r += K_CONSUMERS) process_row<GROUPED>(d, R, r, grow0 + r, acc, g, ctid);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+    if (++st == d.stages) { st = 0; ph ^= 1; }
+  }
+  // rows past the last full tile: read straight from HBM by the CTA that would own the next tile
+  if ((i64)blockIdx.x == d.ntiles % gridDim.x) {
+    const i64 tail0 = d.ntiles * d.tile_rows;
+    GmemRows R{tail0};
+    for (i64 r = ctid; r < d.rows - tail0; r += K_CONSUMERS) process_row<GROUPED>(d, R, r, d.row_base + tail0 + r, acc, g, ctid);
+  }
+
+  if (!GROUPED) {
+    // registers -> warp shuffle -> one global atomic per warp and accumulator
+#pragma unroll
+    for (int j = 0; j < K_MAX_ACC; j++)
+      if (j < d.nacc) {
+        i64 v = warp_reduce(d.acc[j].op, acc[j]);
+        if (lane == 0) acc_global(d.acc[j].op, d.table + (size_t)j * d.domain, v);
+      }
+  } else {
+    consumer_barrier();
+    int ns = *((volatile int32_t *)g.nslots);
+    if (ns > d.gmax) ns = d.gmax;
+    const int cw = warp - 1, ncw = K_CONSUMERS / 32;
+    for (int p = cw; p < ns * d.nacc; p += ncw) {
+      int s = p / d.nacc, j = p % d.nacc, op = d.acc[j].op;
+      i64 v = acc_identity(op);
+      for (int t = lane; t < K_CONSUMERS; t += 32) v = acc_combine(op, v, g.tbl[((size_t)s * d.nacc + j) * K_CONSUMERS + t]);
+      v = warp_reduce(op, v);
+      if (lane == 0) acc_global(op, d.table + (size_t)j * d.domain + g.slotkey[s], v);
+    }
+  }
+}
+
+// identity-initialise the global table ([nacc][domain] by op, choose section zero)
+__global__ void fused_init_kernel(const __grid_constant__ KDesc d) {
+  i64 n = (i64)(d.nacc + d.nchoose) * d.domain;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    int j = (int)(i / d.domain);
+    d.table[i] = j < d.nacc ? acc_identity(d.acc[j].op) : 0;
+  }
+}
+
+// FoldChoose = first row of the run (App. G6) = the expression at the smallest selected row of the key.
+__global__ void fused_choose_kernel(const __grid_constant__ KDesc d) {
+  for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < d.domain; k += (i64)gridDim.x * blockDim.x) {
+    if (d.table[(size_t)d.cnt_idx * d.domain + k] <= 0) continue;
+    i64 grow = d.table[(size_t)d.first_idx * d.domain + k];
+    GmemRows R{0};
+    for (int c = 0; c < d.nchoose; c++)
+      d.table[(size_t)(d.nacc + c) * d.domain + k] = eval_product(d, d.choose[c], R, grow - d.row_base, grow);
+  }
+}
+
+// Merge the per-rank tables, drop empty keys, emit one dense vector per fold in ascending key order.
+__global__ void __launch_bounds__(256, 1) fused_finalize_kernel(const __grid_constant__ FinDesc f) {
+  __shared__ int warp_cnt[8];
+  __shared__ i64 running;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) running = 0;
+  __syncthreads();
+  for (i64 base = 0; base < f.domain; base += 256) {
+    i64 k = base + tid;
+    i64 cnt = 0;
+    if (k < f.domain)
+      for (int r = 0; r < f.nranks; r++) cnt += f.parts[(size_t)r * f.part_stride + (size_t)f.cnt_idx * f.domain + k];
+    bool exists = cnt > 0;
+    unsigned m = __ballot_sync(0xffffffffu, exists);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 8; w++) {
+      if (w < warp) before += warp_cnt[w];
+      total += warp_cnt[w];
+    }
+    if (exists) {
+      i64 pos = running + before + __popc(m & ((1u << lane) - 1));
+      int best = 0;   // rank holding the first row of this key
+      if (f.nchoose > 0) {
+        i64 bf = INT64_MAX;
+        for (int r = 0; r < f.nranks; r++) {
+          i64 fr = f.parts[(size_t)r * f.part_stride + (size_t)f.first_idx * f.domain + k];
+          if (fr < bf) { bf = fr; best = r; }
+        }
+      }
+      for (int o = 0; o < f.nout; o++) {
+        i64 v;
+        if (f.out_kind[o] == 1) {
+          v = f.parts[(size_t)best * f.part_stride + (size_t)(f.nacc + f.out_idx[o]) * f.domain + k];
+        } else {
+          int j = f.out_idx[o], op = f.acc_op[j];
+          v = acc_identity(op);
+          for (int r = 0; r < f.nranks; r++) v = acc_combine(op, v, f.parts[(size_t)r * f.part_stride + (size_t)j * f.domain + k]);
+        }
+        f.out[o][pos] = v;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) running += total;
+    __syncthreads();
+  }
+  if (tid == 0) *f.ngroups = running;
+}
+
+// ------------------------------------------------------------------------------ host side
+struct vdl_fused {
+  vdl_ctx *ctx = nullptr;
+  KDesc kd;
+  FinDesc fd;
+  vdl_vec table = 0;
+  vdl_vec out[VDL_MAX_AGGS] = {0};
+  int nout = 0;
+  i64 *d_ngroups = nullptr;
+  i64 ngroups = -1;
+  bool finalized = false, always_false = false;
+  size_t smem_bytes = 0;
+  int grid = 1;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+};
+
+static bool affine_ok(const vdl_affine &a, int ncols) { return a.column >= -2 && a.column < ncols && a.shr >= 0 && a.shr < 64; }
+static KAffine to_k(const vdl_affine &a) { return KAffine{a.column, a.shr, a.a, a.b}; }
+
+extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_fused **out) {
+  if (!ctx || !desc || !out) return VDL_EINVAL;
+  *out = nullptr;
+  if (desc->ncolumns < 1 || desc->ncolumns > VDL_MAX_COLS) return vdl_fail(ctx, VDL_EINVAL, "fused scan: %d columns (1..%d)", desc->ncolumns, VDL_MAX_COLS);
+  if (desc->npreds < 0 || desc->npreds > VDL_MAX_PREDS || desc->nkeys < 0 || desc->nkeys > VDL_MAX_KEYS || desc->nfolds < 1 || desc->nfolds > VDL_MAX_AGGS)
+    return vdl_fail(ctx, VDL_EINVAL, "fused scan: preds/keys/folds out of range");
+  if (desc->domain < 1 || desc->domain > (1 << 20)) return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: key domain %lld not in [1, 2^20]", (long long)desc->domain);
+  if (desc->nkeys == 0 && desc->domain != 1) return vdl_fail(ctx, VDL_EINVAL, "fused scan: no key parts but domain %lld", (long long)desc->domain);
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  vdl_fused *f = new vdl_fused();
+  f->ctx = ctx;
+  KDesc &k = f->kd;
+  memset(&k, 0, sizeof k);
+  memset(&f->fd, 0, sizeof f->fd);
+  k.rows = desc->rows;
+  k.row_base = desc->row_base;
+  k.key_mask = desc->key_mask;
+  k.domain = desc->domain;
+  k.ncols = desc->ncolumns;
+  k.errflag = ctx->d_errflag;
+  int rowbytes = 0;
+  for (int c = 0; c < desc->ncolumns; c++) {
+    Vec *v = vec_get(ctx, desc->column[c]);
+    if (!v || v->is_range) { delete f; return vdl_fail(ctx, VDL_EINVAL, "fused scan: column %d is not a stored column", c); }
+    if (v->len < desc->rows) { delete f; return vdl_fail(ctx, VDL_EINVAL, "fused scan: column %s has %lld rows < %lld", v->name.c_str(), (long long)v->len, (long long)desc->rows); }
+    k.col[c] = v->ptr;
+    k.width[c] = v->dtype;
+    rowbytes += v->dtype;
+  }
+  for (int i = 0; i < desc->npreds; i++) {
+    const vdl_range_pred &p = desc->pred[i];
+    if (p.column < 0 || p.column >= desc->ncolumns || p.shr < 0 || p.shr > 63) { delete f; return vdl_fail(ctx, VDL_EINVAL, "fused scan: bad predicate %d", i); }
+    if (p.lo > p.hi) f->always_false = true;
+    k.pred[k.npreds++] = KPred{p.column, p.shr, p.lo, (u64)p.hi - (u64)p.lo};
+  }
+  for (int i = 0; i < desc->nkeys; i++) {
+    if (!affine_ok(desc->key[i].e, desc->ncolumns) || desc->key[i].shl < 0 || desc->key[i].shl > 63) { delete f; return vdl_fail(ctx, VDL_EINVAL, "fused scan: bad key part %d", i); }
+    k.key[k.nkeys++] = KKey{to_k(desc->key[i].e), desc->key[i].shl, 0};
+  }
+  // folds -> scan-time accumulators (+ count, + first row when a FoldChoose is present)
+  f->nout = desc->nfolds;
+  for (int i = 0; i < desc->nfolds; i++) {
+    const vdl_fold_spec &s = desc->fold[i];
+    if (s.nfactors < 0 || s.nfactors > VDL_MAX_FACTORS) { delete f; return vdl_fail(ctx, VDL_EINVAL, "fused scan: fold %d has %d factors", i, s.nfactors); }
+    for (int t = 0; t < s.nfactors; t++)
+      if (!affine_ok(s.factor[t], desc->ncolumns)) { delete f; return vdl_fail(ctx, VDL_EINVAL, "fused scan: fold %d factor %d invalid", i, t); }
+    KAcc a;
+    memset(&a, 0, sizeof a);
+    a.nfac = s.nfactors;
+    for (int t = 0; t < s.nfactors; t++) a.fac[t] = to_k(s.factor[t]);
+    if (s.op == VDL_FOLD_SUM || s.op == VDL_FOLD_MIN || s.op == VDL_FOLD_MAX) {
+      a.op = s.op == VDL_FOLD_SUM ? 0 : (s.op == VDL_FOLD_MIN ? 1 : 2);
+      f->fd.out_kind[i] = 0;
+      f->fd.out_idx[i] = k.nacc;
+      k.acc[k.nacc++] = a;
+    } else if (s.op == VDL_FOLD_CHOOSE) {
+      if (k.nchoose == K_MAX_CHOOSE) { delete f; return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: more than %d FoldChoose", K_MAX_CHOOSE); }
+      f->fd.out_kind[i] = 1;
+      f->fd.out_idx[i] = k.nchoose;
+      k.choose[k.nchoose++] = a;
+    } else if (s.op == VDL_FOLD_COUNT) {
+      f->fd.out_kind[i] = 0;
+      f->fd.out_idx[i] = -1;   // patched to cnt_idx below
+    } else { delete f; return vdl_fail(ctx, VDL_EINVAL, "fused scan: fold op %d", s.op); }
+  }
+  KAcc cnt;
+  memset(&cnt, 0, sizeof cnt);
+  k.cnt_idx = k.nacc;
+  k.acc[k.nacc++] = cnt;                  // SUM of the empty product = row count per key
+  k.first_idx = -1;
+  if (k.nchoose) {
+    KAcc first;
+    memset(&first, 0, sizeof first);
+    first.op = 1;
+    first.nfac = 1;
+    first.fac[0] = KAffine{-2, 0, 0, 1};  // MIN over the global row id
+    k.first_idx = k.nacc;
+    k.acc[k.nacc++] = first;
+  }
+  for (int i = 0; i < desc->nfolds; i++)
+    if (f->fd.out_kind[i] == 0 && f->fd.out_idx[i] < 0) f->fd.out_idx[i] = k.cnt_idx;
+
+  // geometry: tile rows, ring depth, grouped tables
+  k.grouped = desc->domain > 1 || desc->nkeys > 0;
+  const int smem_max = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;
+  size_t table_bytes = 0, map_bytes = 0;
+  if (k.grouped) {
+    int gmax = 1;
+    while (gmax * 2 <= desc->domain && gmax * 2 <= 64 && (size_t)(gmax * 2) * k.nacc * K_CONSUMERS * 8 <= 120 * 1024) gmax *= 2;
+    k.gmax = gmax;
+    table_bytes = (size_t)gmax * k.nacc * K_CONSUMERS * 8;
+    map_bytes = (size_t)desc->domain * 4 + (size_t)gmax * 4;
+    if (map_bytes > 64 * 1024) { delete f; return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: key domain %lld too large for the shared-memory slot map", (long long)desc->domain); }
+  }
+  k.tile_rows = 1024;
+  size_t fixed = table_bytes + map_bytes + 16 + 2 * 8 * 16 + 256;
+  for (;;) {
+    int off = 0;
+    for (int c = 0; c < k.ncols; c++) { k.soff[c] = off; off += ((k.tile_rows * k.width[c] + 127) / 128) * 128; }
+    k.stage_bytes = off;
+    k.stage_tx = k.tile_rows * rowbytes;
+    int stages = (int)((smem_max - (long)fixed) / k.stage_bytes);
+    if (stages >= 3 || k.tile_rows <= 256) { k.stages = std::max(1, std::min(stages, 8)); break; }
+    k.tile_rows /= 2;
+  }
+  if ((size_t)k.stages * k.stage_bytes + fixed > (size_t)smem_max) { delete f; return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: does not fit shared memory"); }
+  f->smem_bytes = (size_t)k.stages * k.stage_bytes + fixed;
+  k.ntiles = desc->rows / k.tile_rows;
+  // every column must allow whole-tile bulk reads up to ntiles*tile_rows (<= rows) -- always true; tail uses plain loads
+  f->grid = (int)std::max<i64>(1, std::min<i64>(ctx->sm_count, k.ntiles));
+
+  // device buffers
+  int rc = vec_new(ctx, VDL_I64, (i64)(k.nacc + k.nchoose) * k.domain, &f->table);
+  if (rc) { delete f; return rc; }
+  k.table = (i64 *)ctx->vecs[f->table].ptr;
+  for (int i = 0; i < f->nout; i++) {
+    rc = vec_new(ctx, VDL_I64, k.domain, &f->out[i]);
+    if (rc) { vdl_fused_destroy(f); return rc; }
+    f->fd.out[i] = (i64 *)ctx->vecs[f->out[i]].ptr;
+  }
+  if (cudaMalloc(&f->d_ngroups, sizeof(i64)) != cudaSuccess) { vdl_fused_destroy(f); return vdl_fail(ctx, VDL_ENOMEM, "cudaMalloc ngroups"); }
+  cudaEventCreate(&f->ev0);
+  cudaEventCreate(&f->ev1);
+  f->fd.domain = k.domain;
+  f->fd.nacc = k.nacc;
+  f->fd.nchoose = k.nchoose;
+  f->fd.cnt_idx = k.cnt_idx;
+  f->fd.first_idx = k.first_idx;
+  f->fd.nout = f->nout;
+  f->fd.part_stride = (i64)(k.nacc + k.nchoose) * k.domain;
+  f->fd.ngroups = f->d_ngroups;
+  for (int j = 0; j < k.nacc; j++) f->fd.acc_op[j] = k.acc[j].op;
+
+  cudaError_t e = cudaFuncSetAttribute(fused_scan_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_scan_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  if (e != cudaSuccess) { vdl_fused_destroy(f); return vdl_cuda_fail(ctx, e, "cudaFuncSetAttribute(fused_scan_fold_kernel)"); }
+  *out = f;
+  return VDL_OK;
+}
+
+extern "C" int vdl_fused_launch(vdl_fused *f) {
+  if (!f) return VDL_EINVAL;
+  vdl_ctx *ctx = f->ctx;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  f->finalized = false;
+  f->ngroups = -1;
+  int nb = (int)std::min<i64>(ctx->sm_count, ((i64)(f->kd.nacc + f->kd.nchoose) * f->kd.domain + 255) / 256);
+  fused_init_kernel<<<std::max(nb, 1), 256, 0, ctx->stream>>>(f->kd);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaEventRecord(f->ev0, ctx->stream));
+  if (f->kd.rows > 0 && !f->always_false) {
+    if (f->kd.grouped) fused_scan_fold_kernel<true><<<f->grid, K_THREADS, f->smem_bytes, ctx->stream>>>(f->kd);
+    else fused_scan_fold_kernel<false><<<f->grid, K_THREADS, f->smem_bytes, ctx->stream>>>(f->kd);
+    ctx->launches++;
+  }
+  VDL_CUDA(ctx, cudaEventRecord(f->ev1, ctx->stream));
+  f->timed = true;
+  if (f->kd.nchoose && f->kd.rows > 0 && !f->always_false) {
+    int cb = (int)std::min<i64>(ctx->sm_count, (f->kd.domain + 255) / 256);
+    fused_choose_kernel<<<std::max(cb, 1), 256, 0, ctx->stream>>>(f->kd);
+    ctx->launches++;
+  }
+  VDL_CUDA(ctx, cudaGetLastError());
+  return VDL_OK;
+}
+
+extern "C" int vdl_fused_partials(vdl_fused *f, void **device_ptr, int64_t *n_int64) {
+  if (!f || !device_ptr || !n_int64) return VDL_EINVAL;
+  *device_ptr = f->kd.table;
+  *n_int64 = f->fd.part_stride;
+  return VDL_OK;
+}
+
+extern "C" int vdl_fused_finalize(vdl_fused *f, const void *all_partials, int nranks) {
+  if (!f) return VDL_EINVAL;
+  vdl_ctx *ctx = f->ctx;
+  if (nranks < 1 || (nranks > 1 && !all_partials)) return vdl_fail(ctx, VDL_EINVAL, "finalize: nranks %d without gathered partials", nranks);
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  f->fd.parts = all_partials ? (const i64 *)all_partials : f->kd.table;
+  f->fd.nranks = nranks;
+  fused_finalize_kernel<<<1, 256, 0, ctx->stream>>>(f->fd);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaGetLastError());
+  f->finalized = true;
+  f->ngroups = -1;
+  return VDL_OK;
+}
+
+extern "C" int vdl_fused_num_groups(vdl_fused *f, int64_t *ngroups) {
+  if (!f || !ngroups) return VDL_EINVAL;
+  vdl_ctx *ctx = f->ctx;
+  if (!f->finalized) return vdl_fail(ctx, VDL_EINVAL, "fused scan not finalized");
+  if (f->ngroups < 0) {
+    VDL_CUDA(ctx, cudaMemcpyAsync(&f->ngroups, f->d_ngroups, sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
+    VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VDL_TRY(check_errflag(ctx, "fused scan key"));
+    for (int i = 0; i < f->nout; i++) ctx->vecs[f->out[i]].len = f->ngroups;
+  }
+  *ngroups = f->ngroups;
+  return VDL_OK;
+}
+
+extern "C" int vdl_fused_result(vdl_fused *f, int fold_index, vdl_vec *out) {
+  if (!f || !out || fold_index < 0 || fold_index >= f->nout) return VDL_EINVAL;
+  int64_t n;
+  VDL_TRY(vdl_fused_num_groups(f, &n));
+  *out = f->out[fold_index];
+  return VDL_OK;
+}
+
+extern "C" int vdl_fused_last_kernel_ms(vdl_fused *f, float *ms) {
+  if (!f || !ms) return VDL_EINVAL;
+  if (!f->timed) return vdl_fail(f->ctx, VDL_EINVAL, "fused scan not launched yet");
+  VDL_CUDA(f->ctx, cudaEventSynchronize(f->ev1));
+  VDL_CUDA(f->ctx, cudaEventElapsedTime(ms, f->ev0, f->ev1));
+  return VDL_OK;
+}
+
+extern "C" int vdl_fused_destroy(vdl_fused *f) {
+  if (!f) return VDL_EINVAL;
+  vdl_ctx *ctx = f->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (f->table) vdl_vec_free(ctx, f->table);
+  for (int i = 0; i < f->nout; i++)
+    if (f->out[i]) vdl_vec_free(ctx, f->out[i]);
+  if (f->d_ngroups) cudaFree(f->d_ngroups);
+  if (f->ev0) cudaEventDestroy(f->ev0);
+  if (f->ev1) cudaEventDestroy(f->ev1);
+  delete f;
+  return VDL_OK;
+}

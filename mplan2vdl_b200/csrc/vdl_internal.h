@@ -1,0 +1,71 @@
+// Internal declarations shared by the translation units of libvdl_cuda (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vdl_cuda.h"
+
+typedef int64_t i64;
+typedef uint64_t u64;
+
+// A device vector.  Columns are vectors with a name.  Ranges (RangeV/RangeC) are kept virtual:
+// no HBM traffic until a consumer needs the values.
+struct Vec {
+  void *ptr = nullptr;
+  int dtype = VDL_I64;      // VDL_I32 / VDL_I64
+  i64 len = 0;
+  i64 cap_rows = 0;         // rows that may be read (>= len; bulk copies round the tail up to 16 B)
+  bool owned = false;
+  bool live = false;
+  bool is_range = false;
+  i64 from = 0, step = 0;
+  i64 domain = -1;          // length of the vector these values index into; -1 unknown (App. G2)
+  std::string name;
+};
+
+struct vdl_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int smem_optin = 0;
+  std::vector<Vec> vecs;    // handle = index, 0 unused
+  std::unordered_map<std::string, int> columns;
+  std::string err;
+  i64 launches = 0;
+  int *d_errflag = nullptr; // device-side error counter (Gather/Scatter range checks)
+  void *scratch = nullptr;  // reusable scratch for scans / histograms
+  size_t scratch_bytes = 0;
+};
+
+int vdl_fail(vdl_ctx *ctx, int code, const char *fmt, ...);
+int vdl_cuda_fail(vdl_ctx *ctx, cudaError_t e, const char *what);
+#define VDL_CUDA(ctx, call)                                       \
+  do {                                                            \
+    cudaError_t e__ = (call);                                     \
+    if (e__ != cudaSuccess) return vdl_cuda_fail(ctx, e__, #call); \
+  } while (0)
+#define VDL_TRY(call)            \
+  do {                           \
+    int rc__ = (call);           \
+    if (rc__) return rc__;       \
+  } while (0)
+
+// vector table
+int vec_new(vdl_ctx *ctx, int dtype, i64 len, vdl_vec *out);              // allocates HBM
+int vec_new_range(vdl_ctx *ctx, i64 from, i64 step, i64 len, vdl_vec *out);
+Vec *vec_get(vdl_ctx *ctx, vdl_vec v);                                    // nullptr + error if invalid
+int scratch_reserve(vdl_ctx *ctx, size_t bytes);
+int check_errflag(vdl_ctx *ctx, const char *what);                        // synchronises
+
+// Operand as the per-op kernels see it.
+struct Operand {
+  const void *p;
+  int kind;      // 0 = int64 array, 1 = int32 array, 2 = range
+  i64 from, step;
+};
+Operand operand_of(const Vec &v);

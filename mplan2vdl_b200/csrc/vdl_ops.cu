@@ -1,0 +1,483 @@
+// Per-op kernels: one entry point per Voodoo op (reference op set Vdl.hs:32-44, 110-131), so that any
+// emitted graph runs op-at-a-time when the fusion pass does not apply, and for the per-op sweep.
+// Semantics: SURVEY.md section 2.3 / Appendix G (dense vectors, int64 wraparound).
+#include <stdio.h>
+
+#include <algorithm>
+
+#include "vdl_internal.h"
+
+__device__ __forceinline__ i64 op_ld(const Operand &o, i64 i) {
+  if (o.kind == 0) return ((const i64 *)o.p)[i];
+  if (o.kind == 1) return (i64)((const int32_t *)o.p)[i];
+  return (i64)((u64)o.from + (u64)i * (u64)o.step);
+}
+
+// ---------------------------------------------------------------------------------- RangeV / RangeC
+extern "C" int vdl_op_range(vdl_ctx *ctx, int64_t from, int64_t step, int64_t len, vdl_vec *out) {
+  if (!ctx || !out) return VDL_EINVAL;
+  return vec_new_range(ctx, from, step, len, out);   // virtual: consumers read from + i*step
+}
+
+// ---------------------------------------------------------------------------------- elementwise
+// Vdl.hs:136-157, 209-231.  Comparisons / logicals give 0/1; BitShift: +k arithmetic right, -k left
+// (Vlite.hs:205-208); Divide truncates, x/0 := 0, INT64_MIN/-1 wraps; Modulo is the C remainder, x%0 := 0.
+__device__ __forceinline__ i64 binop_apply(int op, i64 a, i64 b) {
+  switch (op) {
+    case VDL_LOGICAL_AND: return (a != 0) && (b != 0);
+    case VDL_LOGICAL_OR: return (a != 0) || (b != 0);
+    case VDL_BITWISE_AND: return a & b;
+    case VDL_BITWISE_OR: return a | b;
+    case VDL_BITSHIFT:
+      if (b >= 0) return b >= 64 ? (a < 0 ? -1 : 0) : (a >> b);
+      return b <= -64 ? 0 : (i64)((u64)a << (-b));
+    case VDL_EQUALS: return a == b;
+    case VDL_ADD: return (i64)((u64)a + (u64)b);
+    case VDL_SUBTRACT: return (i64)((u64)a - (u64)b);
+    case VDL_GREATER: return a > b;
+    case VDL_MULTIPLY: return (i64)((u64)a * (u64)b);
+    case VDL_DIVIDE:
+      if (b == 0) return 0;
+      if (b == -1) return (i64)(0 - (u64)a);
+      return a / b;
+    case VDL_MODULO:
+      if (b == 0 || b == -1) return 0;
+      return a % b;
+  }
+  return 0;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) binary_kernel(Operand a, Operand b, i64 *__restrict__ out, i64 n) {
+  // two elements per thread and step: 16-byte stores, 2 x (8 or 4)-byte loads per operand in flight
+  i64 stride = (i64)gridDim.x * blockDim.x * 2;
+  for (i64 i = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride) {
+    if (i + 1 < n) {
+      longlong2 r;
+      r.x = binop_apply(OP, op_ld(a, i), op_ld(b, i));
+      r.y = binop_apply(OP, op_ld(a, i + 1), op_ld(b, i + 1));
+      *(longlong2 *)(out + i) = r;
+    } else {
+      out[i] = binop_apply(OP, op_ld(a, i), op_ld(b, i));
+    }
+  }
+}
+
+typedef void (*binary_fn)(Operand, Operand, i64 *, i64);
+static binary_fn binary_table[12] = {
+    binary_kernel<0>, binary_kernel<1>, binary_kernel<2>, binary_kernel<3>, binary_kernel<4>,  binary_kernel<5>,
+    binary_kernel<6>, binary_kernel<7>, binary_kernel<8>, binary_kernel<9>, binary_kernel<10>, binary_kernel<11>};
+
+extern "C" int vdl_op_binary(vdl_ctx *ctx, int op, vdl_vec a, vdl_vec b, vdl_vec *out) {
+  if (!ctx || !out) return VDL_EINVAL;
+  if (op < 0 || op > VDL_MODULO) return vdl_fail(ctx, VDL_EINVAL, "binary op %d unknown", op);
+  Vec *va = vec_get(ctx, a), *vb = vec_get(ctx, b);
+  if (!va || !vb) return VDL_EINVAL;
+  if (va->len != vb->len) return vdl_fail(ctx, VDL_EINVAL, "elementwise op on lengths %lld vs %lld", (long long)va->len, (long long)vb->len);
+  i64 n = va->len;
+  Operand oa = operand_of(*va), ob = operand_of(*vb);
+  VDL_TRY(vec_new(ctx, VDL_I64, n, out));
+  if (n == 0) return VDL_OK;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  i64 want = (n / 2 + 255) / 256;
+  int blocks = (int)std::max<i64>(1, std::min<i64>(want, (i64)ctx->sm_count * 16));
+  binary_table[op]<<<blocks, 256, 0, ctx->stream>>>(oa, ob, (i64 *)ctx->vecs[*out].ptr, n);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaGetLastError());
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- scan helpers
+// Exclusive scan of `n` int64 counters in place by ONE block (n is #blocks or 256 * #blocks: small next to
+// the data), total written to *total.  Warp-shuffle scan, 1024 elements per step, running carry.
+__global__ void __launch_bounds__(1024, 1) exclusive_scan_kernel(i64 *data, i64 n, i64 *total) {
+  __shared__ i64 warp_sum[32];
+  __shared__ i64 carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (i64 base = 0; base < n; base += 1024) {
+    i64 i = base + tid;
+    i64 v = i < n ? data[i] : 0, x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      i64 y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      i64 w = warp_sum[lane], s = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        i64 y = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += y;
+      }
+      warp_sum[lane] = s - w;   // exclusive prefix of the warp sums
+    }
+    __syncthreads();
+    i64 c = carry;
+    if (i < n) data[i] = c + warp_sum[warp] + x - v;
+    __syncthreads();
+    if (tid == 1023) carry = c + warp_sum[31] + x;
+    __syncthreads();
+  }
+  if (tid == 0) *total = carry;
+}
+
+#define SEL_TILE 4096   // rows per block of the flag-count / compaction kernels (16 steps of 256)
+
+// flag(i): FoldSelect -> pred[i] != 0 ; Fold head -> i == 0 || g[i] != g[i-1]
+template <bool HEADS>
+__device__ __forceinline__ bool flag_at(const Operand &o, i64 i) {
+  if (!HEADS) return op_ld(o, i) != 0;
+  return i == 0 || op_ld(o, i) != op_ld(o, i - 1);
+}
+
+template <bool HEADS>
+__global__ void __launch_bounds__(256) flag_count_kernel(Operand o, i64 n, i64 *__restrict__ block_count) {
+  __shared__ int wsum[8];
+  i64 base = (i64)blockIdx.x * SEL_TILE;
+  int c = 0;
+  for (int s = 0; s < SEL_TILE / 256; s++) {
+    i64 i = base + s * 256 + threadIdx.x;
+    c += (i < n) && flag_at<HEADS>(o, i);
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) c += __shfl_xor_sync(0xffffffffu, c, k);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; w++) t += wsum[w];
+    block_count[blockIdx.x] = t;
+  }
+}
+
+// Rank of every flagged element inside its block step, by warp ballots (stream compaction without atomics).
+struct StepRank {
+  int rank;    // number of flagged elements before this one in the block so far (valid when flagged)
+  int incl;    // flagged elements up to and including this one (valid for every element)
+};
+__device__ __forceinline__ StepRank step_rank(bool flag, int *wcnt /*[8]*/, int &run) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned m = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) wcnt[warp] = __popc(m);
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    int c = wcnt[w];
+    if (w < warp) before += c;
+    total += c;
+  }
+  StepRank r;
+  r.rank = run + before + __popc(m & ((1u << lane) - 1));
+  r.incl = r.rank + (flag ? 1 : 0);
+  run += total;
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------- FoldSelect
+// Vlite.hs:721-730: idx = Fold FSel (pos_ p) p.  Dense model: global stable compaction of positions.
+__global__ void __launch_bounds__(256) compact_kernel(Operand o, i64 n, const i64 *__restrict__ block_off, i64 *__restrict__ out) {
+  __shared__ int wcnt[8];
+  i64 base = (i64)blockIdx.x * SEL_TILE;
+  i64 off = block_off[blockIdx.x];
+  int run = 0;
+  for (int s = 0; s < SEL_TILE / 256; s++) {
+    i64 i = base + s * 256 + threadIdx.x;
+    bool f = (i < n) && op_ld(o, i) != 0;
+    StepRank r = step_rank(f, wcnt, run);
+    if (f) out[off + r.rank] = i;
+  }
+}
+
+static int flag_scan(vdl_ctx *ctx, bool heads, const Operand &o, i64 n, i64 **block_off, i64 *total) {
+  i64 nb = (n + SEL_TILE - 1) / SEL_TILE;
+  VDL_TRY(scratch_reserve(ctx, (size_t)(nb + 2) * 8));
+  i64 *cnt = (i64 *)ctx->scratch;
+  if (heads) flag_count_kernel<true><<<(unsigned)nb, 256, 0, ctx->stream>>>(o, n, cnt);
+  else flag_count_kernel<false><<<(unsigned)nb, 256, 0, ctx->stream>>>(o, n, cnt);
+  exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, nb, cnt + nb);
+  ctx->launches += 2;
+  VDL_CUDA(ctx, cudaMemcpyAsync(total, cnt + nb, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *block_off = cnt;
+  return VDL_OK;
+}
+
+extern "C" int vdl_op_fold_select(vdl_ctx *ctx, vdl_vec pred, vdl_vec *out) {
+  if (!ctx || !out) return VDL_EINVAL;
+  Vec *vp = vec_get(ctx, pred);
+  if (!vp) return VDL_EINVAL;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  i64 n = vp->len;
+  Operand o = operand_of(*vp);
+  i64 total = 0, *off = nullptr;
+  if (n > 0) VDL_TRY(flag_scan(ctx, false, o, n, &off, &total));
+  VDL_TRY(vec_new(ctx, VDL_I64, total, out));
+  ctx->vecs[*out].domain = n;   // these positions index the predicate's row space (App. G2)
+  if (total > 0) {
+    compact_kernel<<<(unsigned)((n + SEL_TILE - 1) / SEL_TILE), 256, 0, ctx->stream>>>(o, n, off, (i64 *)ctx->vecs[*out].ptr);
+    ctx->launches++;
+    VDL_CUDA(ctx, cudaGetLastError());
+  }
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- Gather / Scatter
+// Gather (Vlite.hs:86-87 `@@`, FK fetch 1264, 1276-1277): out[i] = src[pos[i]].
+__global__ void __launch_bounds__(256) gather_kernel(Operand src, i64 src_len, Operand pos, i64 n, i64 *__restrict__ out, int *errflag) {
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    i64 p = op_ld(pos, i);
+    if ((u64)p >= (u64)src_len) { atomicAdd(errflag, 1); out[i] = 0; }
+    else out[i] = op_ld(src, p);
+  }
+}
+
+extern "C" int vdl_op_gather(vdl_ctx *ctx, vdl_vec src, vdl_vec pos, vdl_vec *out) {
+  if (!ctx || !out) return VDL_EINVAL;
+  Vec *vs = vec_get(ctx, src), *vp = vec_get(ctx, pos);
+  if (!vs || !vp) return VDL_EINVAL;
+  i64 n = vp->len, m = vs->len, dom = vs->domain;
+  Operand os = operand_of(*vs), op = operand_of(*vp);
+  VDL_TRY(vec_new(ctx, VDL_I64, n, out));
+  ctx->vecs[*out].domain = dom;   // gathering positions keeps their index space
+  if (n == 0) return VDL_OK;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  int blocks = (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 16));
+  gather_kernel<<<blocks, 256, 0, ctx->stream>>>(os, m, op, n, (i64 *)ctx->vecs[*out].ptr, ctx->d_errflag);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaGetLastError());
+  return VDL_OK;
+}
+
+// Scatter (Vlite.hs:1057-1059 group sort, 1268-1275 dim validity / inverse index): out[pos[i]] = src[i],
+// unwritten slots 0.  Positions are unique in every use the translator emits (permutations, Unique masks).
+__global__ void __launch_bounds__(256) scatter_kernel(Operand src, Operand pos, i64 n, i64 *__restrict__ out, i64 out_len, int *errflag) {
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    i64 p = op_ld(pos, i);
+    if ((u64)p >= (u64)out_len) atomicAdd(errflag, 1);
+    else out[p] = op_ld(src, i);
+  }
+}
+
+extern "C" int vdl_op_scatter(vdl_ctx *ctx, vdl_vec src, vdl_vec pos, int64_t out_len, vdl_vec *out) {
+  if (!ctx || !out) return VDL_EINVAL;
+  Vec *vs = vec_get(ctx, src), *vp = vec_get(ctx, pos);
+  if (!vs || !vp) return VDL_EINVAL;
+  if (vs->len != vp->len) return vdl_fail(ctx, VDL_EINVAL, "Scatter: source length %lld != positions length %lld", (long long)vs->len, (long long)vp->len);
+  if (out_len < 0) return vdl_fail(ctx, VDL_EINVAL, "Scatter: negative output length");
+  i64 n = vs->len, dom = vs->domain;
+  Operand os = operand_of(*vs), op = operand_of(*vp);
+  VDL_TRY(vec_new(ctx, VDL_I64, out_len, out));
+  ctx->vecs[*out].domain = dom;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (out_len > 0) VDL_CUDA(ctx, cudaMemsetAsync(ctx->vecs[*out].ptr, 0, (size_t)out_len * 8, ctx->stream));
+  if (n == 0) return VDL_OK;
+  int blocks = (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 16));
+  scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(os, op, n, (i64 *)ctx->vecs[*out].ptr, out_len, ctx->d_errflag);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaGetLastError());
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- Partition
+// Vlite.hs:1082-1098 emits Partition(key, RangeC(min,1,max-min+1)); its result is the scatter position that
+// sorts rows stably by key (1057-1060, 1172).  bucket(v) = number of pivots below v (App. G3); the
+// permutation is a stable LSD radix sort of row ids by bucket, 8 bits per pass over the bits the pivot
+// count needs (Q1: 6 bits = 1 pass; Q3's 38-bit composite key = 5 passes).
+#define RDX_TILE 4096
+
+__global__ void __launch_bounds__(256) bucket_kernel(Operand data, i64 n, i64 pfrom, i64 pstep, i64 pcount, u64 *__restrict__ key, i64 *__restrict__ idx) {
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    i64 v = op_ld(data, i);
+    u64 b;
+    if (v <= pfrom) b = 0;
+    else {
+      u64 d = (u64)v - (u64)pfrom;
+      b = (d + (u64)pstep - 1) / (u64)pstep;
+      if (b > (u64)pcount) b = (u64)pcount;
+    }
+    key[i] = b;
+    idx[i] = i;
+  }
+}
+
+// digit histogram per block, stored digit-major: hist[d * nblocks + block]
+__global__ void __launch_bounds__(256) radix_hist_kernel(const u64 *__restrict__ key, i64 n, int shift, i64 nblocks, i64 *__restrict__ hist) {
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  i64 base = (i64)blockIdx.x * RDX_TILE;
+  for (int s = 0; s < RDX_TILE / 256; s++) {
+    i64 i = base + s * 256 + threadIdx.x;
+    if (i < n) atomicAdd(&h[(key[i] >> shift) & 255], 1);
+  }
+  __syncthreads();
+  hist[(i64)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// stable scatter: rank inside the block = elements with the same digit earlier in the block
+__global__ void __launch_bounds__(256) radix_scatter_kernel(const u64 *__restrict__ key_in, const i64 *__restrict__ idx_in, i64 n, int shift,
+                                                            i64 nblocks, const i64 *__restrict__ offs, u64 *__restrict__ key_out,
+                                                            i64 *__restrict__ idx_out) {
+  __shared__ int wcount[8][256];   // per-warp count of each digit in the current step
+  __shared__ int wbase[8][256];    // per-warp base of each digit in the current step
+  __shared__ int run[256];         // elements of each digit in earlier steps of this block
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int w = 0; w < 8; w++) wcount[w][tid] = 0;
+  run[tid] = 0;
+  __syncthreads();
+  i64 base = (i64)blockIdx.x * RDX_TILE;
+  for (int s = 0; s < RDX_TILE / 256; s++) {
+    i64 i = base + s * 256 + tid;
+    bool valid = i < n;
+    u64 k = valid ? key_in[i] : 0;
+    int d = valid ? (int)((k >> shift) & 255) : 256 + lane;   // invalid lanes never match anybody
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    int rank_in_warp = __popc(peers & ((1u << lane) - 1));
+    if (valid && rank_in_warp == 0) wcount[warp][d] = __popc(peers);
+    __syncthreads();
+    {   // thread `tid` owns digit `tid`: per-warp counts -> per-warp bases; counts are cleared for the next step
+      int off = run[tid];
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        int c = wcount[w][tid];
+        wcount[w][tid] = 0;
+        wbase[w][tid] = off;
+        off += c;
+      }
+      run[tid] = off;
+    }
+    __syncthreads();
+    if (valid) {
+      i64 dst = offs[(i64)d * nblocks + blockIdx.x] + wbase[warp][d] + rank_in_warp;
+      key_out[dst] = k;
+      idx_out[dst] = idx_in[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) invert_perm_kernel(const i64 *__restrict__ order, i64 n, i64 *__restrict__ out) {
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) out[order[j]] = j;
+}
+
+extern "C" int vdl_op_partition(vdl_ctx *ctx, vdl_vec data, int64_t pfrom, int64_t pstep, int64_t pcount, vdl_vec *out) {
+  if (!ctx || !out) return VDL_EINVAL;
+  Vec *vd = vec_get(ctx, data);
+  if (!vd) return VDL_EINVAL;
+  if (pcount < 1 || pstep < 1) return vdl_fail(ctx, VDL_EINVAL, "Partition: pivots must be an ascending range (count %lld step %lld)", (long long)pcount, (long long)pstep);
+  i64 n = vd->len;
+  Operand od = operand_of(*vd);
+  VDL_TRY(vec_new(ctx, VDL_I64, n, out));
+  ctx->vecs[*out].domain = n;
+  if (n == 0) return VDL_OK;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  int bits = 0;
+  while (bits < 63 && ((u64)pcount >> bits)) bits++;
+  i64 nb = (n + RDX_TILE - 1) / RDX_TILE;
+  // temporaries: key/idx ping-pong + histogram
+  vdl_vec tk[2], ti[2];
+  for (int k = 0; k < 2; k++) { VDL_TRY(vec_new(ctx, VDL_I64, n, &tk[k])); VDL_TRY(vec_new(ctx, VDL_I64, n, &ti[k])); }
+  VDL_TRY(scratch_reserve(ctx, (size_t)(256 * nb + 2) * 8));
+  i64 *hist = (i64 *)ctx->scratch;
+  u64 *key[2] = {(u64 *)ctx->vecs[tk[0]].ptr, (u64 *)ctx->vecs[tk[1]].ptr};
+  i64 *idx[2] = {(i64 *)ctx->vecs[ti[0]].ptr, (i64 *)ctx->vecs[ti[1]].ptr};
+  int grid = (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 16));
+  bucket_kernel<<<grid, 256, 0, ctx->stream>>>(od, n, pfrom, pstep, pcount, key[0], idx[0]);
+  ctx->launches++;
+  int cur = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    radix_hist_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(key[cur], n, shift, nb, hist);
+    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, 256 * nb, hist + 256 * nb);
+    radix_scatter_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(key[cur], idx[cur], n, shift, nb, hist, key[cur ^ 1], idx[cur ^ 1]);
+    ctx->launches += 3;
+    cur ^= 1;
+  }
+  invert_perm_kernel<<<grid, 256, 0, ctx->stream>>>(idx[cur], n, (i64 *)ctx->vecs[*out].ptr);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaGetLastError());
+  for (int k = 0; k < 2; k++) { VDL_TRY(vdl_vec_free(ctx, tk[k])); VDL_TRY(vdl_vec_free(ctx, ti[k])); }
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- Fold by runs
+// FoldSum/Min/Max/Choose/Count (Vlite.hs:1048-1070, 1179; Vdl.hs:255-264): one output per run of equal
+// consecutive `groups` values, in run order.  Run id = (number of run heads up to the element) - 1; inside a
+// warp equal run ids are contiguous, so a segmented shuffle reduction leaves one global atomic per
+// (warp, run) -- long runs (the common case after a Partition sort) cost almost no atomics.
+__device__ __forceinline__ i64 fold_identity(int op) { return op == VDL_FOLD_MIN ? INT64_MAX : (op == VDL_FOLD_MAX ? INT64_MIN : 0); }
+__device__ __forceinline__ i64 fold_combine(int op, i64 a, i64 b) {
+  if (op == VDL_FOLD_MIN) return b < a ? b : a;
+  if (op == VDL_FOLD_MAX) return b > a ? b : a;
+  return (i64)((u64)a + (u64)b);
+}
+
+__global__ void __launch_bounds__(256) fold_init_kernel(i64 *out, i64 n, i64 v) {
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
+}
+
+__global__ void __launch_bounds__(256) fold_runs_kernel(int op, Operand groups, Operand data, i64 n, const i64 *__restrict__ block_off, i64 *__restrict__ out) {
+  __shared__ int wcnt[8];
+  const int lane = threadIdx.x & 31;
+  i64 base = (i64)blockIdx.x * SEL_TILE;
+  i64 off = block_off[blockIdx.x];   // run heads before this block
+  int run = 0;
+  for (int s = 0; s < SEL_TILE / 256; s++) {
+    i64 i = base + s * 256 + threadIdx.x;
+    bool valid = i < n;
+    bool head = valid && flag_at<true>(groups, i);
+    StepRank r = step_rank(head, wcnt, run);
+    i64 rid = off + r.incl - 1;        // run id of this element
+    if (op == VDL_FOLD_CHOOSE) {
+      if (head) out[rid] = op_ld(data, i);
+      continue;
+    }
+    i64 v = valid ? (op == VDL_FOLD_COUNT ? 1 : op_ld(data, i)) : fold_identity(op);
+    if (!valid) rid = -1 - lane;       // never equal to a neighbour
+    // segmented inclusive scan over lanes with equal rid (contiguous)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      i64 pv = __shfl_up_sync(0xffffffffu, v, o);
+      i64 pr = __shfl_up_sync(0xffffffffu, rid, o);
+      if (lane >= o && pr == rid) v = fold_combine(op, v, pv);
+    }
+    i64 nr = __shfl_down_sync(0xffffffffu, rid, 1);
+    bool last = lane == 31 || nr != rid;
+    if (valid && last) {
+      if (op == VDL_FOLD_MIN) atomicMin((long long *)&out[rid], (long long)v);
+      else if (op == VDL_FOLD_MAX) atomicMax((long long *)&out[rid], (long long)v);
+      else atomicAdd((unsigned long long *)&out[rid], (unsigned long long)v);
+    }
+  }
+}
+
+extern "C" int vdl_op_fold(vdl_ctx *ctx, int fold_op, vdl_vec groups, vdl_vec data, vdl_vec *out) {
+  if (!ctx || !out) return VDL_EINVAL;
+  if (fold_op < VDL_FOLD_SUM || fold_op > VDL_FOLD_COUNT) return vdl_fail(ctx, VDL_EINVAL, "fold op %d unknown", fold_op);
+  Vec *vg = vec_get(ctx, groups), *vd = vec_get(ctx, data);
+  if (!vg || !vd) return VDL_EINVAL;
+  if (vg->len != vd->len) return vdl_fail(ctx, VDL_EINVAL, "Fold: groups length %lld != data length %lld", (long long)vg->len, (long long)vd->len);
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  i64 n = vd->len;
+  Operand og = operand_of(*vg), od = operand_of(*vd);
+  i64 total = 0, *off = nullptr;
+  if (n > 0) VDL_TRY(flag_scan(ctx, true, og, n, &off, &total));
+  VDL_TRY(vec_new(ctx, VDL_I64, total, out));
+  if (total == 0) return VDL_OK;
+  i64 *o = (i64 *)ctx->vecs[*out].ptr;
+  int grid = (int)std::max<i64>(1, std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16));
+  fold_init_kernel<<<grid, 256, 0, ctx->stream>>>(o, total, fold_op == VDL_FOLD_MIN ? INT64_MAX : (fold_op == VDL_FOLD_MAX ? INT64_MIN : 0));
+  fold_runs_kernel<<<(unsigned)((n + SEL_TILE - 1) / SEL_TILE), 256, 0, ctx->stream>>>(fold_op, og, od, n, off, o);
+  ctx->launches += 2;
+  VDL_CUDA(ctx, cudaGetLastError());
+  return VDL_OK;
+}

@@ -1,0 +1,781 @@
+// Plan front end of libvdl_cuda: parses the Voodoo program text mplan2vdl prints (VdlFormat,
+// reference Vdl.hs:410-453 toVoodooList / 455-477 printLine), hash-conses it (the emitter's own
+// CSE is keyed on (node, metadata) and can print duplicates: SURVEY.md App. F caveat, G10), runs the
+// select->map->fold fusion peephole, and executes what is left op-at-a-time.
+//
+// The fusion pass is the executor-side twin of the Vlite peepholes (Vlite.hs:1295-1340,
+// `Vx -> Maybe Vexp`, applied bottom-up with memoisation 1351-1417): every node is given a small
+// symbolic normal form (constant / product of affine column terms / conjunction of column ranges /
+// bit-packed key / selection / partition / sorted-by-partition) and a Fold whose operands normalise
+// is replaced by one `vdl_fused_scan_fold` launch.  Anything that does not normalise is simply not
+// fused and runs through the per-op kernels with identical results.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "vdl_internal.h"
+
+namespace {
+
+enum NodeOp { N_LOAD, N_RANGEV, N_RANGEC, N_BINARY, N_FSELECT, N_GATHER, N_SCATTER, N_PARTITION, N_FOLD };
+
+struct Node {
+  int op = 0, sub = 0;         // sub: binary op / fold op
+  int a = -1, b = -1, c = -1;  // argument node indices
+  i64 k0 = 0, k1 = 0, k2 = 0;  // RangeV: from, step; RangeC: from, count, step
+  std::string name;            // Load: "table.column"
+};
+
+struct Output { std::string name; int node; std::vector<i64> data; };
+
+// ---- symbolic normal forms ------------------------------------------------------------------
+struct Aff { int col = -1; int shr = 0; i64 a = 0, b = 0; };   // a + b*(col >> shr); col = Load node, -1: constant a
+struct RangeTerm { int col, shr; i64 lo, hi; };
+enum SymKind { S_NONE, S_VALUE, S_PRED, S_KEY, S_POS, S_SELECTION, S_PARTITION, S_SORTED };
+struct Sym {
+  int kind = S_NONE;
+  int table = -1;              // table id of the row space (-1: a constant, fits any space)
+  int sel = -1;                // node index of the predicate whose selection this lives in (-1: base rows)
+  int ref = -1;                // S_VALUE const / S_POS: node whose length it copies
+  std::vector<Aff> fac;        // S_VALUE: product of factors; S_KEY: OR of parts
+  std::vector<RangeTerm> ranges;  // S_PRED
+  bool never = false;          // S_PRED that no row satisfies
+  i64 mask = -1;               // S_KEY
+  bool masked = false;
+  int n0 = -1, n1 = -1;        // S_SELECTION: pred node; S_PARTITION: key node; S_SORTED: partition node, inner node
+  i64 lo = 0, cnt = 0;         // S_PARTITION pivots RangeC(lo, cnt, 1)
+};
+
+struct FusedFold { int node; vdl_fold_spec spec; };
+struct FusedGroup {
+  int table, sel, keynode;
+  std::vector<int> cols;                // Load node of each column slot
+  std::vector<FusedFold> folds;         // deduplicated specs
+  std::map<int, int> fold_of_node;      // Fold node -> index into folds
+  vdl_fused_desc desc;
+  vdl_fused *fused = nullptr;
+  std::vector<vdl_vec> bound;           // column handles the prepared scan was built for
+  i64 bound_rows = -1, bound_base = -1;
+};
+
+}  // namespace
+
+struct vdl_plan {
+  vdl_ctx *ctx = nullptr;
+  int flags = 0;
+  int statements = 0;
+  std::vector<Node> nodes;
+  std::vector<Output> outputs;
+  std::vector<std::string> tables;
+  std::vector<Sym> sym;
+  std::vector<char> sym_done;
+  std::vector<FusedGroup> groups;
+  std::vector<int> group_of_node;       // Fold node -> group index or -1
+  i64 row_base = 0;
+  // run state
+  std::vector<vdl_vec> val;
+  std::vector<vdl_vec> temps;
+  i64 launches_last = 0;
+  bool local_done = false;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------- parsing
+bool parse_ref(const std::string &s, int *out) {
+  if (s.compare(0, 3, "Id ") != 0) return false;
+  char *end;
+  long v = strtol(s.c_str() + 3, &end, 10);
+  if (*end || v <= 0) return false;
+  *out = (int)v;
+  return true;
+}
+bool parse_i64(const std::string &s, i64 *out) {
+  if (s.empty()) return false;
+  char *end;
+  long long v = strtoll(s.c_str(), &end, 10);
+  if (*end) return false;
+  *out = (i64)v;
+  return true;
+}
+
+const char *BINOPS[] = {"LogicalAnd", "LogicalOr", "BitwiseAnd", "BitwiseOr", "BitShift", "Equals",
+                        "Add", "Subtract", "Greater", "Multiply", "Divide", "Modulo"};
+const char *FOLDS[] = {"FoldSum", "FoldMin", "FoldMax", "FoldChoose", "FoldCount"};
+
+int parse_plan(vdl_plan *p, const char *text) {
+  vdl_ctx *ctx = p->ctx;
+  std::vector<int> canon;          // statement id -> node index (aliases resolved)
+  std::vector<std::string> outname;  // statement id -> Project out name ("" if none)
+  canon.push_back(-1);
+  outname.push_back("");
+  std::map<std::string, int> cse;
+  const char *q = text;
+  int lineno = 0;
+  while (*q) {
+    const char *eol = strchr(q, '\n');
+    std::string line = eol ? std::string(q, eol - q) : std::string(q);
+    q = eol ? eol + 1 : q + line.size();
+    lineno++;
+    size_t m = line.find(" ;; ");               // --metadata suffix (Vdl.hs:463-466)
+    if (m != std::string::npos) line.resize(m);
+    while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+    if (line.empty()) continue;
+    std::vector<std::string> f;
+    size_t pos = 0;
+    for (;;) {
+      size_t c = line.find(',', pos);
+      if (c == std::string::npos) { f.push_back(line.substr(pos)); break; }
+      f.push_back(line.substr(pos, c - pos));
+      pos = c + 1;
+    }
+    i64 id;
+    if (f.size() < 2 || !parse_i64(f[0], &id) || id != (i64)canon.size())
+      return vdl_fail(ctx, VDL_EINVAL, "plan line %d: statement ids must run 1,2,3,... (Vdl.hs:297-311)", lineno);
+    const std::string &op = f[1];
+    auto bad = [&]() { return vdl_fail(ctx, VDL_EINVAL, "plan line %d: malformed %s statement", lineno, op.c_str()); };
+    auto arg = [&](const std::string &s, int *out) {
+      int r;
+      if (!parse_ref(s, &r) || r >= (int)canon.size()) return false;
+      *out = canon[r];
+      return *out >= 0;
+    };
+    Node n;
+    std::string oname;
+    int alias = -1;
+    bool is_output = false;
+    if (op == "Load") {
+      if (f.size() != 3) return bad();
+      n.op = N_LOAD; n.name = f[2];
+    } else if (op == "Project") {           // Project,<out>,Id n,<in>: rename only
+      int r;
+      if (f.size() != 5 || !parse_ref(f[3], &r) || r >= (int)canon.size()) return bad();
+      alias = canon[r];
+      if (f[2] != "val") oname = f[2];
+    } else if (op == "Shuffle") {
+      int r;
+      if (f.size() != 3 || !parse_ref(f[2], &r) || r >= (int)canon.size()) return bad();
+      alias = canon[r];
+    } else if (op == "MaterializeCompact") {
+      int r;
+      if (f.size() != 3 || !parse_ref(f[2], &r) || r >= (int)canon.size()) return bad();
+      alias = canon[r];
+      oname = outname[r].empty() ? "val" : outname[r];
+      is_output = true;
+    } else if (op == "RangeV") {
+      if (f.size() != 6 || f[2] != "val" || !parse_i64(f[3], &n.k0) || !arg(f[4], &n.a) || !parse_i64(f[5], &n.k1)) return bad();
+      n.op = N_RANGEV;
+    } else if (op == "RangeC") {
+      if (f.size() != 6 || f[2] != "val" || !parse_i64(f[3], &n.k0) || !parse_i64(f[4], &n.k1) || !parse_i64(f[5], &n.k2)) return bad();
+      n.op = N_RANGEC;
+    } else if (op == "Gather") {
+      if (f.size() != 5 || f[4] != "val" || !arg(f[2], &n.a) || !arg(f[3], &n.b)) return bad();
+      n.op = N_GATHER;
+    } else if (op == "Scatter") {
+      if (f.size() != 7 || f[4] != "val" || f[6] != "val" || !arg(f[2], &n.a) || !arg(f[3], &n.b) || !arg(f[5], &n.c)) return bad();
+      n.op = N_SCATTER;
+    } else if (op == "Like" || op == "CrossProductOuter" || op == "CrossProductInner" || op == "Semisort") {
+      return vdl_fail(ctx, VDL_EUNSUPPORTED, "plan line %d: op %s is outside the supported vocabulary", lineno, op.c_str());
+    } else {
+      if (f.size() != 7 || f[2] != "val" || f[4] != "val" || f[6] != "val" || !arg(f[3], &n.a) || !arg(f[5], &n.b)) return bad();
+      n.op = -1;
+      for (int k = 0; k < 12; k++) if (op == BINOPS[k]) { n.op = N_BINARY; n.sub = k; }
+      for (int k = 0; k < 5; k++) if (op == FOLDS[k]) { n.op = N_FOLD; n.sub = k; }
+      if (op == "FoldSelect") n.op = N_FSELECT;
+      if (op == "Partition") n.op = N_PARTITION;
+      if (n.op < 0) return vdl_fail(ctx, VDL_EINVAL, "plan line %d: unknown op %s", lineno, op.c_str());
+    }
+    if (alias == -1 && (op == "Project" || op == "Shuffle" || op == "MaterializeCompact")) return bad();
+    int idx;
+    if (alias >= 0) {
+      idx = alias;
+    } else {
+      char key[512];
+      snprintf(key, sizeof key, "%d|%d|%d|%d|%d|%lld|%lld|%lld|%s", n.op, n.sub, n.a, n.b, n.c, (long long)n.k0, (long long)n.k1,
+               (long long)n.k2, n.name.c_str());
+      auto it = cse.find(key);
+      if (it != cse.end()) idx = it->second;
+      else {
+        idx = (int)p->nodes.size();
+        p->nodes.push_back(n);
+        cse[key] = idx;
+      }
+    }
+    canon.push_back(idx);
+    outname.push_back(oname);
+    if (is_output) p->outputs.push_back(Output{oname, idx, {}});
+  }
+  p->statements = (int)canon.size() - 1;
+  if (p->outputs.empty()) return vdl_fail(ctx, VDL_EINVAL, "plan has no MaterializeCompact output");
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- symbolic analysis
+int table_id(vdl_plan *p, const std::string &col) {
+  std::string t = col.substr(0, col.find('.'));
+  for (size_t i = 0; i < p->tables.size(); i++) if (p->tables[i] == t) return (int)i;
+  p->tables.push_back(t);
+  return (int)p->tables.size() - 1;
+}
+
+bool is_const(const Sym &s) { return s.kind == S_VALUE && s.fac.size() == 1 && s.fac[0].col < 0; }
+bool is_single(const Sym &s) { return s.kind == S_VALUE && s.fac.size() == 1; }
+bool is_leaf(const Sym &s) { return is_single(s) && s.fac[0].col >= 0 && s.fac[0].a == 0 && s.fac[0].b == 1; }
+
+// space of a binary result: constants fit anywhere; otherwise (table, sel) must agree
+bool join_space(const Sym &x, const Sym &y, Sym *r) {
+  if (x.table < 0) { r->table = y.table; r->sel = y.sel; r->ref = y.table < 0 ? x.ref : -1; return true; }
+  if (y.table < 0) { r->table = x.table; r->sel = x.sel; return true; }
+  if (x.table != y.table || x.sel != y.sel) return false;
+  r->table = x.table; r->sel = x.sel;
+  return true;
+}
+
+Sym value_const(i64 k) { Sym s; s.kind = S_VALUE; Aff a; a.a = k; s.fac.push_back(a); return s; }
+
+void add_range(Sym *s, int col, int shr, i64 lo, i64 hi) {
+  for (auto &r : s->ranges)
+    if (r.col == col && r.shr == shr) {
+      r.lo = std::max(r.lo, lo);
+      r.hi = std::min(r.hi, hi);
+      if (r.lo > r.hi) s->never = true;
+      return;
+    }
+  s->ranges.push_back(RangeTerm{col, shr, lo, hi});
+  if (lo > hi) s->never = true;
+}
+
+i64 wadd(i64 a, i64 b) { return (i64)((u64)a + (u64)b); }
+i64 wsub(i64 a, i64 b) { return (i64)((u64)a - (u64)b); }
+i64 wmul(i64 a, i64 b) { return (i64)((u64)a * (u64)b); }
+
+const Sym &analyse(vdl_plan *p, int ni);
+
+Sym analyse_binary(vdl_plan *p, const Node &n) {
+  const Sym x = analyse(p, n.a), y = analyse(p, n.b);
+  Sym r;
+  if (x.kind == S_NONE || y.kind == S_NONE) return r;
+  if (!join_space(x, y, &r)) return Sym();
+  auto none = [&]() { Sym z; z.table = r.table; z.sel = r.sel; return z; };
+  switch (n.sub) {
+    case VDL_ADD:
+    case VDL_SUBTRACT: {
+      if (!is_single(x) || !is_single(y)) return none();
+      const Aff &fx = x.fac[0], &fy = y.fac[0];
+      bool sub = n.sub == VDL_SUBTRACT;
+      Aff o;
+      if (fx.col >= 0 && fy.col >= 0) {
+        if (fx.col != fy.col || fx.shr != fy.shr) return none();
+        o = fx;
+        o.a = sub ? wsub(fx.a, fy.a) : wadd(fx.a, fy.a);
+        o.b = sub ? wsub(fx.b, fy.b) : wadd(fx.b, fy.b);
+      } else if (fx.col >= 0) {
+        o = fx;
+        o.a = sub ? wsub(fx.a, fy.a) : wadd(fx.a, fy.a);
+      } else if (fy.col >= 0) {
+        o = fy;
+        o.a = sub ? wsub(fx.a, fy.a) : wadd(fx.a, fy.a);
+        o.b = sub ? wsub(0, fy.b) : fy.b;
+      } else {
+        o.a = sub ? wsub(fx.a, fy.a) : wadd(fx.a, fy.a);
+      }
+      r.kind = S_VALUE;
+      r.fac.push_back(o);
+      return r;
+    }
+    case VDL_MULTIPLY: {
+      if (x.kind != S_VALUE || y.kind != S_VALUE) return none();
+      // constants fold into the first factor of the other operand (exact in Z/2^64)
+      const Sym *cs = is_const(x) ? &x : (is_const(y) ? &y : nullptr);
+      r.kind = S_VALUE;
+      if (cs) {
+        const Sym &o = cs == &x ? y : x;
+        r.fac = o.fac;
+        i64 k = cs->fac[0].a;
+        r.fac[0].a = wmul(r.fac[0].a, k);
+        r.fac[0].b = wmul(r.fac[0].b, k);
+        return r;
+      }
+      if (x.fac.size() + y.fac.size() > VDL_MAX_FACTORS) return none();
+      r.fac = x.fac;
+      r.fac.insert(r.fac.end(), y.fac.begin(), y.fac.end());
+      return r;
+    }
+    case VDL_BITSHIFT: {
+      if (!is_const(y) || !is_single(x)) return none();
+      i64 k = y.fac[0].a;
+      Aff o = x.fac[0];
+      if (o.col < 0) {                      // constant folding, same rule as the kernels
+        if (k >= 0) o.a = k >= 64 ? (o.a < 0 ? -1 : 0) : (o.a >> k);
+        else o.a = k <= -64 ? 0 : (i64)((u64)o.a << (-k));
+      } else if (k >= 0) {                  // (col >> s) >> k == col >> (s + k) for arithmetic shifts
+        if (o.a != 0 || o.b != 1 || o.shr + k > 63) return none();
+        o.shr += (int)k;
+      } else {                              // left shift = multiply by 2^-k, exact in Z/2^64
+        if (k <= -64) return none();
+        o.a = (i64)((u64)o.a << (-k));
+        o.b = (i64)((u64)o.b << (-k));
+      }
+      r.kind = S_VALUE;
+      r.fac.push_back(o);
+      return r;
+    }
+    case VDL_BITWISE_OR: {
+      auto parts = [](const Sym &s, std::vector<Aff> *out) {
+        if (s.kind == S_KEY && !s.masked) { out->insert(out->end(), s.fac.begin(), s.fac.end()); return true; }
+        if (is_single(s)) { out->push_back(s.fac[0]); return true; }
+        return false;
+      };
+      r.kind = S_KEY;
+      if (!parts(x, &r.fac) || !parts(y, &r.fac) || r.fac.size() > VDL_MAX_KEYS) return none();
+      return r;
+    }
+    case VDL_BITWISE_AND: {
+      const Sym *cs = is_const(y) ? &y : (is_const(x) ? &x : nullptr);
+      if (!cs) return none();
+      const Sym &o = cs == &y ? x : y;
+      i64 mk = cs->fac[0].a;
+      if (mk < 0) return none();
+      r.kind = S_KEY;
+      if (o.kind == S_KEY) { r.fac = o.fac; r.mask = o.masked ? (o.mask & mk) : mk; }
+      else if (is_single(o)) { r.fac.push_back(o.fac[0]); r.mask = mk; }
+      else return none();
+      r.masked = true;
+      return r;
+    }
+    case VDL_GREATER: {                     // column > k  or  k > column
+      r.kind = S_PRED;
+      if (is_leaf(x) && is_const(y)) {
+        i64 k = y.fac[0].a;
+        if (k == INT64_MAX) r.never = true; else add_range(&r, x.fac[0].col, x.fac[0].shr, k + 1, INT64_MAX);
+        return r;
+      }
+      if (is_const(x) && is_leaf(y)) {
+        i64 k = x.fac[0].a;
+        if (k == INT64_MIN) r.never = true; else add_range(&r, y.fac[0].col, y.fac[0].shr, INT64_MIN, k - 1);
+        return r;
+      }
+      return none();
+    }
+    case VDL_EQUALS: {
+      const Sym *cs = is_const(y) ? &y : (is_const(x) ? &x : nullptr);
+      const Sym &o = cs == &y ? x : y;
+      if (!cs || !is_leaf(o)) return none();
+      r.kind = S_PRED;
+      add_range(&r, o.fac[0].col, o.fac[0].shr, cs->fac[0].a, cs->fac[0].a);
+      return r;
+    }
+    case VDL_LOGICAL_AND: {
+      if (x.kind != S_PRED || y.kind != S_PRED) return none();
+      r.kind = S_PRED;
+      r.ranges = x.ranges;
+      r.never = x.never || y.never;
+      for (auto &t : y.ranges) add_range(&r, t.col, t.shr, t.lo, t.hi);
+      if (r.ranges.size() > VDL_MAX_PREDS) return none();
+      return r;
+    }
+    case VDL_LOGICAL_OR: {                  // union of two ranges of one column, when it is again a range
+      if (x.kind != S_PRED || y.kind != S_PRED) return none();
+      if (x.never) { Sym z = y; z.table = r.table; z.sel = r.sel; return z; }
+      if (y.never) { Sym z = x; z.table = r.table; z.sel = r.sel; return z; }
+      if (x.ranges.size() != 1 || y.ranges.size() != 1) return none();
+      const RangeTerm &s = x.ranges[0], &t = y.ranges[0];
+      if (s.col != t.col || s.shr != t.shr) return none();
+      bool touch = (s.hi == INT64_MAX || t.lo <= s.hi + 1) && (t.hi == INT64_MAX || s.lo <= t.hi + 1);
+      if (!touch) return none();
+      r.kind = S_PRED;
+      r.ranges.push_back(RangeTerm{s.col, s.shr, std::min(s.lo, t.lo), std::max(s.hi, t.hi)});
+      return r;
+    }
+  }
+  return none();
+}
+
+const Sym &analyse(vdl_plan *p, int ni) {
+  if (p->sym_done[ni]) return p->sym[ni];
+  p->sym_done[ni] = 1;
+  const Node &n = p->nodes[ni];
+  Sym r;
+  switch (n.op) {
+    case N_LOAD: {
+      r.kind = S_VALUE;
+      r.table = table_id(p, n.name);
+      Aff a; a.col = ni; a.b = 1;
+      r.fac.push_back(a);
+      break;
+    }
+    case N_RANGEV: {
+      const Sym s = analyse(p, n.a);
+      if (n.k1 == 0) { r = value_const(n.k0); }
+      else if (n.k0 == 0 && n.k1 == 1) r.kind = S_POS;
+      // constants/positions live in the row space of the vector whose length they copy
+      if (s.kind == S_SELECTION) { r.table = s.table; r.sel = s.n0; }
+      else { r.table = s.table; r.sel = s.sel; }
+      r.ref = n.a;
+      if (s.kind == S_NONE || s.kind == S_PARTITION) r.table = -2;   // unknown space: never joins
+      break;
+    }
+    case N_BINARY: r = analyse_binary(p, n); break;
+    case N_FSELECT: {
+      const Sym f = analyse(p, n.a), q = analyse(p, n.b);
+      if (f.kind == S_POS && q.kind == S_PRED && q.table >= 0 && q.sel < 0 && f.table == q.table && f.sel < 0) {
+        r.kind = S_SELECTION; r.table = q.table; r.n0 = n.b;
+      }
+      break;
+    }
+    case N_GATHER: {
+      const Sym x = analyse(p, n.a), s = analyse(p, n.b);
+      if (s.kind == S_SELECTION && (x.kind == S_VALUE || x.kind == S_KEY || x.kind == S_PRED) && x.table == s.table && x.sel < 0) {
+        r = x; r.sel = s.n0;
+      }
+      break;
+    }
+    case N_PARTITION: {
+      const Sym k = analyse(p, n.a);
+      const Node &pv = p->nodes[n.b];
+      if (pv.op == N_RANGEC && pv.k2 == 1 && (k.kind == S_KEY || is_single(k)) && k.table >= 0) {
+        r.kind = S_PARTITION; r.table = k.table; r.sel = k.sel; r.n0 = n.a; r.lo = pv.k0; r.cnt = pv.k1;
+      }
+      break;
+    }
+    case N_SCATTER: {
+      const Sym x = analyse(p, n.a), pt = analyse(p, n.c);
+      if (pt.kind == S_PARTITION && (x.kind == S_VALUE || x.kind == S_KEY)) {
+        bool same = x.table == pt.table && x.sel == pt.sel;
+        if (x.table == -1 && x.ref >= 0) {   // a constant: accept when it copies the length of a vector in the key's space
+          const Sym rs = analyse(p, x.ref);
+          same = rs.table == pt.table && rs.sel == pt.sel;
+        }
+        if (same) { r.kind = S_SORTED; r.table = pt.table; r.sel = pt.sel; r.n0 = n.c; r.n1 = n.a; }
+      }
+      break;
+    }
+    default: break;   // RangeC, Fold: opaque
+  }
+  p->sym[ni] = r;
+  return p->sym[ni];
+}
+
+// ---------------------------------------------------------------------------------- fusion
+int column_slot(FusedGroup *g, int loadnode) {
+  for (size_t i = 0; i < g->cols.size(); i++) if (g->cols[i] == loadnode) return (int)i;
+  g->cols.push_back(loadnode);
+  return (int)g->cols.size() - 1;
+}
+
+bool to_affine(FusedGroup *g, const Aff &a, vdl_affine *out) {
+  out->a = a.a; out->b = a.b; out->shr = a.shr; out->column = -1;
+  if (a.col >= 0) { out->column = column_slot(g, a.col); if (g->cols.size() > VDL_MAX_COLS) return false; }
+  return true;
+}
+
+// Try to express Fold node `ni` as a member of a fused scan.  Returns false when it does not normalise.
+bool try_fuse_fold(vdl_plan *p, int ni) {
+  const Node &n = p->nodes[ni];
+  const Sym G = analyse(p, n.a), D = analyse(p, n.b);
+  int table, sel, keynode = -1;
+  const Sym *value = nullptr;
+  Sym inner;
+  if (G.kind == S_VALUE && is_const(G) && (D.kind == S_VALUE) && D.table >= 0) {
+    // Fold over constant groups: one run (Vlite.hs:636-638 zeros_ refv for an empty group-by)
+    if (G.table != D.table || G.sel != D.sel) return false;
+    table = D.table; sel = D.sel; value = &D;
+  } else if (G.kind == S_SORTED && D.kind == S_SORTED && G.n0 == D.n0) {
+    // groups = keys sorted by Partition(keys), data = x sorted by the same partition (Vlite.hs:1057-1060)
+    const Sym P = analyse(p, G.n0);
+    if (P.kind != S_PARTITION || G.n1 != P.n0) return false;
+    inner = analyse(p, D.n1);
+    if (inner.kind != S_VALUE) return false;
+    table = P.table; sel = P.sel; keynode = P.n0; value = &inner;
+    const Sym K = analyse(p, keynode);
+    // bucket(key) = clamp(key - lo, 0, cnt); it is the key itself only when 0 <= key < cnt is proven
+    if (!(K.kind == S_KEY && K.masked && K.mask >= 0 && P.lo == 0 && P.cnt >= K.mask + 1)) return false;
+    if (K.mask + 1 > (1 << 14)) return false;
+  } else {
+    return false;
+  }
+  if (sel >= 0) {
+    const Sym Q = analyse(p, sel);
+    if (Q.kind != S_PRED || Q.table != table || Q.sel >= 0) return false;
+  }
+  if (value->fac.size() > VDL_MAX_FACTORS) return false;
+
+  int gi = -1;
+  for (size_t i = 0; i < p->groups.size(); i++)
+    if (p->groups[i].table == table && p->groups[i].sel == sel && p->groups[i].keynode == keynode) gi = (int)i;
+  if (gi < 0) {
+    FusedGroup g;
+    g.table = table; g.sel = sel; g.keynode = keynode;
+    memset(&g.desc, 0, sizeof g.desc);
+    p->groups.push_back(g);
+    gi = (int)p->groups.size() - 1;
+  }
+  FusedGroup saved = p->groups[gi];
+  FusedGroup &g = p->groups[gi];
+  vdl_fold_spec spec;
+  memset(&spec, 0, sizeof spec);
+  spec.op = n.sub;
+  if (n.sub != VDL_FOLD_COUNT) {
+    bool all_const_one = value->fac.size() == 1 && value->fac[0].col < 0 && value->fac[0].a == 1;
+    if (n.sub == VDL_FOLD_SUM && all_const_one) spec.op = VDL_FOLD_COUNT;     // COUNT(*) = FoldSum of ones (Vlite.hs:1043-1046)
+    else {
+      spec.nfactors = (int)value->fac.size();
+      for (size_t t = 0; t < value->fac.size(); t++)
+        if (!to_affine(&g, value->fac[t], &spec.factor[t])) { g = saved; return false; }
+    }
+  }
+  int fi = -1;
+  for (size_t i = 0; i < g.folds.size(); i++)
+    if (!memcmp(&g.folds[i].spec, &spec, sizeof spec)) fi = (int)i;
+  if (fi < 0) {
+    if (g.folds.size() == VDL_MAX_AGGS) { g = saved; return false; }
+    g.folds.push_back(FusedFold{ni, spec});
+    fi = (int)g.folds.size() - 1;
+  }
+  g.fold_of_node[ni] = fi;
+  p->group_of_node[ni] = gi;
+  return true;
+}
+
+// Fill the ABI descriptor of a group (predicates, key, folds); column handles are bound at run time.
+bool build_desc(vdl_plan *p, FusedGroup *g) {
+  vdl_fused_desc &d = g->desc;
+  memset(&d, 0, sizeof d);
+  d.key_mask = -1;
+  d.domain = 1;
+  if (g->sel >= 0) {
+    const Sym Q = analyse(p, g->sel);
+    if (Q.never) { d.npreds = 1; d.pred[0].column = 0; d.pred[0].lo = 1; d.pred[0].hi = 0; if (g->cols.empty()) return false; }
+    else {
+      for (auto &t : Q.ranges) {
+        if (t.lo == INT64_MIN && t.hi == INT64_MAX) continue;
+        vdl_range_pred &o = d.pred[d.npreds++];
+        o.column = column_slot(g, t.col); o.shr = t.shr; o.lo = t.lo; o.hi = t.hi;
+      }
+    }
+  }
+  if (g->keynode >= 0) {
+    const Sym K = analyse(p, g->keynode);
+    for (auto &a : K.fac) {
+      vdl_key_part &kp = d.key[d.nkeys++];
+      if (!to_affine(g, a, &kp.e)) return false;
+    }
+    d.key_mask = K.mask;
+    d.domain = K.mask + 1;
+  }
+  d.nfolds = (int)g->folds.size();
+  for (int i = 0; i < d.nfolds; i++) d.fold[i] = g->folds[i].spec;
+  if (g->cols.empty() || g->cols.size() > VDL_MAX_COLS) return false;
+  d.ncolumns = (int)g->cols.size();
+  return true;
+}
+
+int fuse(vdl_plan *p) {
+  size_t nn = p->nodes.size();
+  p->sym.assign(nn, Sym());
+  p->sym_done.assign(nn, 0);
+  p->group_of_node.assign(nn, -1);
+  if (!(p->flags & VDL_PLAN_FUSE)) return VDL_OK;
+  for (size_t i = 0; i < nn; i++)
+    if (p->nodes[i].op == N_FOLD) try_fuse_fold(p, (int)i);
+  for (size_t gi = 0; gi < p->groups.size(); gi++) {
+    if (!build_desc(p, &p->groups[gi])) {      // cannot be expressed after all: un-fuse its folds
+      for (auto &kv : p->groups[gi].fold_of_node) p->group_of_node[kv.first] = -1;
+      p->groups[gi].folds.clear();
+      p->groups[gi].fold_of_node.clear();
+    }
+  }
+  p->groups.erase(std::remove_if(p->groups.begin(), p->groups.end(), [](const FusedGroup &g) { return g.folds.empty(); }), p->groups.end());
+  // group indices may have shifted
+  std::fill(p->group_of_node.begin(), p->group_of_node.end(), -1);
+  for (size_t gi = 0; gi < p->groups.size(); gi++)
+    for (auto &kv : p->groups[gi].fold_of_node) p->group_of_node[kv.first] = (int)gi;
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- execution
+void free_temps(vdl_plan *p) {
+  for (vdl_vec v : p->temps) vdl_vec_free(p->ctx, v);
+  p->temps.clear();
+  std::fill(p->val.begin(), p->val.end(), 0);
+}
+
+int eval(vdl_plan *p, int ni, vdl_vec *out) {
+  vdl_ctx *ctx = p->ctx;
+  if (p->val[ni]) { *out = p->val[ni]; return VDL_OK; }
+  const Node &n = p->nodes[ni];
+  vdl_vec r = 0, a = 0, b = 0, c = 0;
+  bool temp = true;
+  switch (n.op) {
+    case N_LOAD: VDL_TRY(vdl_column_lookup(ctx, n.name.c_str(), &r)); temp = false; break;
+    case N_RANGEV: {
+      VDL_TRY(eval(p, n.a, &a));
+      i64 len; VDL_TRY(vdl_vec_len(ctx, a, &len));
+      VDL_TRY(vdl_op_range(ctx, n.k0, n.k1, len, &r));
+      break;
+    }
+    case N_RANGEC: VDL_TRY(vdl_op_range(ctx, n.k0, n.k2, n.k1, &r)); break;
+    case N_BINARY: VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.b, &b)); VDL_TRY(vdl_op_binary(ctx, n.sub, a, b, &r)); break;
+    case N_FSELECT: {
+      const Node &fn = p->nodes[n.a];
+      if (!(fn.op == N_RANGEV && fn.k0 == 0 && fn.k1 == 1))
+        return vdl_fail(ctx, VDL_EUNSUPPORTED, "FoldSelect: fold argument must be pos_ of the predicate (Vlite.hs:726-727)");
+      VDL_TRY(eval(p, n.b, &b));
+      VDL_TRY(vdl_op_fold_select(ctx, b, &r));
+      break;
+    }
+    case N_GATHER: VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.b, &b)); VDL_TRY(vdl_op_gather(ctx, a, b, &r)); break;
+    case N_SCATTER: {
+      VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.c, &c));
+      Vec *pv = vec_get(ctx, c);
+      if (!pv) return VDL_EINVAL;
+      if (pv->domain < 0) return vdl_fail(ctx, VDL_EUNSUPPORTED, "Scatter: output length unknown (positions carry no index space; App. G2)");
+      VDL_TRY(vdl_op_scatter(ctx, a, c, pv->domain, &r));
+      break;
+    }
+    case N_PARTITION: {
+      const Node &pv = p->nodes[n.b];
+      if (pv.op != N_RANGEC || pv.k2 <= 0) return vdl_fail(ctx, VDL_EUNSUPPORTED, "Partition: pivots must be an ascending RangeC (Vlite.hs:1088-1091)");
+      VDL_TRY(eval(p, n.a, &a));
+      VDL_TRY(vdl_op_partition(ctx, a, pv.k0, pv.k2, pv.k1, &r));
+      break;
+    }
+    case N_FOLD: {
+      int gi = p->group_of_node[ni];
+      if (gi >= 0) {
+        FusedGroup &g = p->groups[gi];
+        VDL_TRY(vdl_fused_result(g.fused, g.fold_of_node[ni], &r));
+        temp = false;
+      } else {
+        VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.b, &b));
+        VDL_TRY(vdl_op_fold(ctx, n.sub, a, b, &r));
+      }
+      break;
+    }
+  }
+  p->val[ni] = r;
+  if (temp) p->temps.push_back(r);
+  *out = r;
+  return VDL_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------- ABI
+extern "C" int vdl_plan_load(vdl_ctx *ctx, const char *vdl_text, int flags, vdl_plan **out) {
+  if (!ctx || !vdl_text || !out) return VDL_EINVAL;
+  *out = nullptr;
+  vdl_plan *p = new vdl_plan();
+  p->ctx = ctx;
+  p->flags = flags;
+  int rc = parse_plan(p, vdl_text);
+  if (!rc) rc = fuse(p);
+  if (rc) { delete p; return rc; }
+  p->val.assign(p->nodes.size(), 0);
+  *out = p;
+  return VDL_OK;
+}
+
+extern "C" int vdl_plan_stats(vdl_plan *p, int *statements, int *nodes, int *fused_scans, int64_t *launches) {
+  if (!p) return VDL_EINVAL;
+  if (statements) *statements = p->statements;
+  if (nodes) *nodes = (int)p->nodes.size();
+  if (fused_scans) *fused_scans = (int)p->groups.size();
+  if (launches) *launches = p->launches_last;
+  return VDL_OK;
+}
+
+extern "C" int vdl_plan_set_row_base(vdl_plan *p, int64_t row_base) {
+  if (!p) return VDL_EINVAL;
+  p->row_base = row_base;
+  return VDL_OK;
+}
+
+extern "C" int vdl_plan_run_local(vdl_plan *p) {
+  if (!p) return VDL_EINVAL;
+  vdl_ctx *ctx = p->ctx;
+  free_temps(p);
+  i64 l0 = ctx->launches;
+  for (auto &g : p->groups) {
+    std::vector<vdl_vec> h(g.cols.size());
+    i64 rows = -1;
+    for (size_t c = 0; c < g.cols.size(); c++) {
+      VDL_TRY(vdl_column_lookup(ctx, p->nodes[g.cols[c]].name.c_str(), &h[c]));
+      i64 len; VDL_TRY(vdl_vec_len(ctx, h[c], &len));
+      if (rows >= 0 && len != rows)
+        return vdl_fail(ctx, VDL_EINVAL, "columns of table %s differ in length (%lld vs %lld)", p->tables[g.table].c_str(), (long long)len, (long long)rows);
+      rows = len;
+    }
+    if (!g.fused || h != g.bound || rows != g.bound_rows || p->row_base != g.bound_base) {
+      if (g.fused) { vdl_fused_destroy(g.fused); g.fused = nullptr; }
+      g.desc.rows = rows;
+      g.desc.row_base = p->row_base;
+      for (size_t c = 0; c < h.size(); c++) g.desc.column[c] = h[c];
+      VDL_TRY(vdl_fused_prepare(ctx, &g.desc, &g.fused));
+      g.bound = h; g.bound_rows = rows; g.bound_base = p->row_base;
+    }
+    VDL_TRY(vdl_fused_launch(g.fused));
+  }
+  p->launches_last = ctx->launches - l0;
+  p->local_done = true;
+  return VDL_OK;
+}
+
+extern "C" int vdl_plan_num_fused(vdl_plan *p) { return p ? (int)p->groups.size() : 0; }
+extern "C" int vdl_plan_fused(vdl_plan *p, int i, vdl_fused **out) {
+  if (!p || !out || i < 0 || i >= (int)p->groups.size()) return VDL_EINVAL;
+  *out = p->groups[i].fused;
+  return *out ? VDL_OK : vdl_fail(p->ctx, VDL_EINVAL, "plan has not run yet");
+}
+
+extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int nranks) {
+  if (!p) return VDL_EINVAL;
+  vdl_ctx *ctx = p->ctx;
+  if (!p->local_done) return vdl_fail(ctx, VDL_EINVAL, "vdl_plan_finish before vdl_plan_run_local");
+  if (nranks > 1 && p->groups.empty()) return vdl_fail(ctx, VDL_EUNSUPPORTED, "plan has no fused scan: it cannot be row-sharded");
+  i64 l0 = ctx->launches;
+  for (size_t gi = 0; gi < p->groups.size(); gi++)
+    VDL_TRY(vdl_fused_finalize(p->groups[gi].fused, all_partials ? all_partials[gi] : nullptr, nranks));
+  for (auto &o : p->outputs) {
+    vdl_vec v;
+    int rc = eval(p, o.node, &v);
+    if (rc) { free_temps(p); return rc; }
+    i64 len;
+    VDL_TRY(vdl_vec_len(ctx, v, &len));
+    o.data.resize((size_t)len);
+    rc = vdl_vec_download(ctx, v, o.data.data(), len);
+    if (rc) { free_temps(p); return rc; }
+  }
+  int rc = check_errflag(ctx, "plan");
+  p->launches_last += ctx->launches - l0;
+  free_temps(p);
+  p->local_done = false;
+  return rc;
+}
+
+extern "C" int vdl_plan_run(vdl_plan *p) {
+  VDL_TRY(vdl_plan_run_local(p));
+  return vdl_plan_finish(p, nullptr, 1);
+}
+
+extern "C" int vdl_plan_num_outputs(vdl_plan *p) { return p ? (int)p->outputs.size() : 0; }
+extern "C" int vdl_plan_output(vdl_plan *p, int i, const char **name, const int64_t **data, int64_t *len) {
+  if (!p || i < 0 || i >= (int)p->outputs.size()) return VDL_EINVAL;
+  if (name) *name = p->outputs[i].name.c_str();
+  if (data) *data = p->outputs[i].data.data();
+  if (len) *len = (int64_t)p->outputs[i].data.size();
+  return VDL_OK;
+}
+
+extern "C" int vdl_plan_destroy(vdl_plan *p) {
+  if (!p) return VDL_EINVAL;
+  free_temps(p);
+  for (auto &g : p->groups) if (g.fused) vdl_fused_destroy(g.fused);
+  delete p;
+  return VDL_OK;
+}

@@ -1,0 +1,220 @@
+"""Host-side executor front end: what a caller of the missing Voodoo server would use.
+
+The reference's own pipeline (eval_query.sh:10-26) was: translate the mplan to a Voodoo program, POST
+the text to the server, get ``{"results": {tmpN: {".<outname>": [ints]}}}`` back and decode it with
+resolve.py.  Here the program text goes to ``Context.plan(text)`` and ``Plan.run()`` returns
+``{outname: int64 array}`` in MaterializeCompact order; ``mplan2vdl_b200.resolve`` decodes it.
+Everything below is a thin layer over the C ABI (include/vdl_cuda.h) -- no computation happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import VDL_I32, VDL_I64, VDL_PLAN_FUSE, VdlError
+
+
+class Context:
+    """One per GPU (vdl_ctx).  Owns the registered columns."""
+
+    def __init__(self, device: int = 0):
+        self.L = _lib.load()
+        h = C.c_void_p()
+        rc = self.L.vdl_ctx_create(device, C.byref(h))
+        if rc:
+            raise VdlError(rc, self.L.vdl_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self._keepalive = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vdl_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc:
+            raise VdlError(rc, self.L.vdl_last_error(self.h).decode())
+
+    # ---- columns -----------------------------------------------------------------------------
+    def alloc_column(self, name: str, width: int, rows: int) -> int:
+        v = C.c_int32()
+        self.check(self.L.vdl_column_alloc(self.h, name.encode(), width, rows, C.byref(v)))
+        return v.value
+
+    def upload_column(self, name: str, arr: np.ndarray) -> int:
+        """Allocate + host->device copy of an int32/int64 numpy column."""
+        if arr.dtype not in (np.int32, np.int64):
+            raise TypeError(f"{name}: columns are int32 or int64, got {arr.dtype}")
+        arr = np.ascontiguousarray(arr)
+        v = self.alloc_column(name, arr.dtype.itemsize, arr.shape[0])
+        self.check(self.L.vdl_column_upload(self.h, v, arr.ctypes.data, arr.shape[0]))
+        return v
+
+    def upload_into(self, v: int, host_ptr: int, rows: int):
+        """Host->device copy into an existing column (host memory may be pinned: then the copy is a straight DMA)."""
+        self.check(self.L.vdl_column_upload(self.h, v, host_ptr, rows))
+
+    def download_into(self, v: int, host_ptr: int, rows: int):
+        """Device->host copy of a column in its stored type."""
+        self.check(self.L.vdl_column_download(self.h, v, host_ptr, rows))
+
+    def device_ptr(self, v: int) -> int:
+        return self.L.vdl_vec_device_ptr(self.h, v) or 0
+
+    def bind_tensor(self, name: str, tensor) -> int:
+        """Register a CUDA torch tensor (int32/int64, contiguous) as a column without copying."""
+        import torch
+        if tensor.dtype not in (torch.int32, torch.int64) or not tensor.is_cuda or not tensor.is_contiguous():
+            raise TypeError(f"{name}: need a contiguous CUDA int32/int64 tensor")
+        v = C.c_int32()
+        n = tensor.numel()
+        self.check(self.L.vdl_column_bind(self.h, name.encode(), tensor.element_size(), n, n, tensor.data_ptr(), C.byref(v)))
+        self._keepalive[name] = tensor
+        return v.value
+
+    def fill_synthetic(self, name: str, spec, rows: int, seed: int, row_offset: int = 0) -> int:
+        """Allocate `rows` of column `name` and generate global rows [row_offset, row_offset+rows) in place."""
+        v = self.alloc_column(name, spec.width, rows)
+        self.check(self.L.vdl_column_fill_synthetic(self.h, v, seed & (2**64 - 1), spec.stream, spec.kind, spec.vmin,
+                                                    spec.stride, spec.p0, spec.p1, row_offset))
+        return v
+
+    def drop_column(self, name: str):
+        self.check(self.L.vdl_column_drop(self.h, name.encode()))
+        self._keepalive.pop(name, None)
+
+    def lookup(self, name: str) -> int:
+        v = C.c_int32()
+        self.check(self.L.vdl_column_lookup(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    # ---- vectors / per-op API ----------------------------------------------------------------
+    def download(self, v: int) -> np.ndarray:
+        n = C.c_int64()
+        self.check(self.L.vdl_vec_len(self.h, v, C.byref(n)))
+        out = np.empty(n.value, dtype=np.int64)
+        self.check(self.L.vdl_vec_download(self.h, v, out.ctypes.data, n.value))
+        return out
+
+    def free(self, v: int):
+        self.check(self.L.vdl_vec_free(self.h, v))
+
+    def _out(self, fn, *args) -> int:
+        v = C.c_int32()
+        self.check(fn(self.h, *args, C.byref(v)))
+        return v.value
+
+    def op_range(self, start: int, step: int, length: int) -> int:
+        return self._out(self.L.vdl_op_range, start, step, length)
+
+    def op_binary(self, op: str, a: int, b: int) -> int:
+        return self._out(self.L.vdl_op_binary, _lib.BINARY_OPS.index(op), a, b)
+
+    def op_fold_select(self, pred: int) -> int:
+        return self._out(self.L.vdl_op_fold_select, pred)
+
+    def op_gather(self, src: int, pos: int) -> int:
+        return self._out(self.L.vdl_op_gather, src, pos)
+
+    def op_scatter(self, src: int, pos: int, out_len: int) -> int:
+        return self._out(self.L.vdl_op_scatter, src, pos, out_len)
+
+    def op_partition(self, data: int, pivot_from: int, pivot_step: int, pivot_count: int) -> int:
+        return self._out(self.L.vdl_op_partition, data, pivot_from, pivot_step, pivot_count)
+
+    def op_fold(self, op: str, groups: int, data: int) -> int:
+        return self._out(self.L.vdl_op_fold, _lib.FOLD_OPS.index(op), groups, data)
+
+    # ---- misc --------------------------------------------------------------------------------
+    def synchronize(self):
+        self.check(self.L.vdl_ctx_synchronize(self.h))
+
+    @property
+    def stream(self) -> int:
+        return self.L.vdl_ctx_stream(self.h) or 0
+
+    @property
+    def launch_count(self) -> int:
+        return self.L.vdl_ctx_launch_count(self.h)
+
+    def plan(self, text: str, fuse: bool = True) -> "Plan":
+        return Plan(self, text, fuse)
+
+
+class Plan:
+    """A loaded Voodoo program (vdl_plan)."""
+
+    def __init__(self, ctx: Context, text: str, fuse: bool = True):
+        self.ctx, self.L = ctx, ctx.L
+        h = C.c_void_p()
+        ctx.check(self.L.vdl_plan_load(ctx.h, text.encode(), VDL_PLAN_FUSE if fuse else 0, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.L.vdl_plan_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self) -> dict:
+        s, n, f, l = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        self.ctx.check(self.L.vdl_plan_stats(self.h, C.byref(s), C.byref(n), C.byref(f), C.byref(l)))
+        return {"statements": s.value, "nodes": n.value, "fused_scans": f.value, "launches": l.value}
+
+    def set_row_base(self, row_base: int):
+        self.ctx.check(self.L.vdl_plan_set_row_base(self.h, row_base))
+
+    def run_local(self):
+        self.ctx.check(self.L.vdl_plan_run_local(self.h))
+
+    @property
+    def num_fused(self) -> int:
+        return self.L.vdl_plan_num_fused(self.h)
+
+    def partials(self, i: int):
+        """(device pointer, number of int64) of fused scan i's partial table."""
+        f = C.c_void_p()
+        self.ctx.check(self.L.vdl_plan_fused(self.h, i, C.byref(f)))
+        p, n = C.c_void_p(), C.c_int64()
+        self.ctx.check(self.L.vdl_fused_partials(f, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def kernel_ms(self, i: int = 0) -> float:
+        f = C.c_void_p()
+        self.ctx.check(self.L.vdl_plan_fused(self.h, i, C.byref(f)))
+        ms = C.c_float()
+        self.ctx.check(self.L.vdl_fused_last_kernel_ms(f, C.byref(ms)))
+        return ms.value
+
+    def finish(self, gathered_ptrs=None, nranks: int = 1) -> dict:
+        arr = None
+        if gathered_ptrs is not None:
+            arr = (C.c_void_p * len(gathered_ptrs))(*gathered_ptrs)
+        self.ctx.check(self.L.vdl_plan_finish(self.h, arr, nranks))
+        return self.outputs()
+
+    def run(self) -> dict:
+        self.ctx.check(self.L.vdl_plan_run(self.h))
+        return self.outputs()
+
+    def outputs(self) -> dict:
+        out = {}
+        for i in range(self.L.vdl_plan_num_outputs(self.h)):
+            name, data, n = C.c_char_p(), C.POINTER(C.c_int64)(), C.c_int64()
+            self.ctx.check(self.L.vdl_plan_output(self.h, i, C.byref(name), C.byref(data), C.byref(n)))
+            out[name.value.decode()] = np.ctypeslib.as_array(data, shape=(n.value,)).copy() if n.value else np.zeros(0, np.int64)
+        return out

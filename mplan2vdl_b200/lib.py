@@ -1,0 +1,118 @@
+"""ctypes binding of libvdl_cuda's C ABI (include/vdl_cuda.h).
+
+The product path has no CPU fallback: if the CUDA library is missing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libvdl_cuda.so")
+
+VDL_I32, VDL_I64 = 4, 8
+VDL_PLAN_FUSE = 1
+BINARY_OPS = ["LogicalAnd", "LogicalOr", "BitwiseAnd", "BitwiseOr", "BitShift", "Equals", "Add", "Subtract",
+              "Greater", "Multiply", "Divide", "Modulo"]
+FOLD_OPS = ["FoldSum", "FoldMin", "FoldMax", "FoldChoose", "FoldCount"]
+VDL_MAX_COLS, VDL_MAX_PREDS, VDL_MAX_KEYS, VDL_MAX_AGGS, VDL_MAX_FACTORS = 12, 8, 4, 10, 4
+
+
+class VdlError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libvdl_cuda error {code}: {msg}")
+        self.code = code
+
+
+class Affine(C.Structure):
+    _fields_ = [("column", C.c_int32), ("shr", C.c_int32), ("a", C.c_int64), ("b", C.c_int64)]
+
+
+class RangePred(C.Structure):
+    _fields_ = [("column", C.c_int32), ("shr", C.c_int32), ("lo", C.c_int64), ("hi", C.c_int64)]
+
+
+class KeyPart(C.Structure):
+    _fields_ = [("e", Affine), ("shl", C.c_int32), ("pad", C.c_int32)]
+
+
+class FoldSpec(C.Structure):
+    _fields_ = [("op", C.c_int32), ("nfactors", C.c_int32), ("factor", Affine * VDL_MAX_FACTORS)]
+
+
+class FusedDesc(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("row_base", C.c_int64), ("ncolumns", C.c_int32),
+                ("column", C.c_int32 * VDL_MAX_COLS), ("npreds", C.c_int32), ("pred", RangePred * VDL_MAX_PREDS),
+                ("nkeys", C.c_int32), ("key", KeyPart * VDL_MAX_KEYS), ("key_mask", C.c_int64), ("domain", C.c_int64),
+                ("nfolds", C.c_int32), ("fold", FoldSpec * VDL_MAX_AGGS)]
+
+
+# every symbol include/vdl_cuda.h declares: (name, restype, argtypes)
+_P, _I, _L = C.c_void_p, C.c_int, C.c_int64
+SYMBOLS = [
+    ("vdl_abi_version", _I, []),
+    ("vdl_abi_sizeof_fused_desc", _I, []),
+    ("vdl_ctx_create", _I, [_I, C.POINTER(_P)]),
+    ("vdl_ctx_destroy", _I, [_P]),
+    ("vdl_last_error", C.c_char_p, [_P]),
+    ("vdl_ctx_stream", _P, [_P]),
+    ("vdl_ctx_synchronize", _I, [_P]),
+    ("vdl_ctx_launch_count", _L, [_P]),
+    ("vdl_column_alloc", _I, [_P, C.c_char_p, _I, _L, C.POINTER(C.c_int32)]),
+    ("vdl_column_bind", _I, [_P, C.c_char_p, _I, _L, _L, _P, C.POINTER(C.c_int32)]),
+    ("vdl_column_upload", _I, [_P, C.c_int32, _P, _L]),
+    ("vdl_column_download", _I, [_P, C.c_int32, _P, _L]),
+    ("vdl_column_fill_synthetic", _I, [_P, C.c_int32, C.c_uint64, C.c_uint64, _I, _L, _L, _L, _L, _L]),
+    ("vdl_column_lookup", _I, [_P, C.c_char_p, C.POINTER(C.c_int32)]),
+    ("vdl_column_drop", _I, [_P, C.c_char_p]),
+    ("vdl_vec_len", _I, [_P, C.c_int32, C.POINTER(_L)]),
+    ("vdl_vec_dtype", _I, [_P, C.c_int32, C.POINTER(_I)]),
+    ("vdl_vec_device_ptr", _P, [_P, C.c_int32]),
+    ("vdl_vec_download", _I, [_P, C.c_int32, _P, _L]),
+    ("vdl_vec_free", _I, [_P, C.c_int32]),
+    ("vdl_op_range", _I, [_P, _L, _L, _L, C.POINTER(C.c_int32)]),
+    ("vdl_op_binary", _I, [_P, _I, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    ("vdl_op_fold_select", _I, [_P, C.c_int32, C.POINTER(C.c_int32)]),
+    ("vdl_op_gather", _I, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    ("vdl_op_scatter", _I, [_P, C.c_int32, C.c_int32, _L, C.POINTER(C.c_int32)]),
+    ("vdl_op_partition", _I, [_P, C.c_int32, _L, _L, _L, C.POINTER(C.c_int32)]),
+    ("vdl_op_fold", _I, [_P, _I, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    ("vdl_fused_prepare", _I, [_P, C.POINTER(FusedDesc), C.POINTER(_P)]),
+    ("vdl_fused_launch", _I, [_P]),
+    ("vdl_fused_partials", _I, [_P, C.POINTER(_P), C.POINTER(_L)]),
+    ("vdl_fused_finalize", _I, [_P, _P, _I]),
+    ("vdl_fused_num_groups", _I, [_P, C.POINTER(_L)]),
+    ("vdl_fused_result", _I, [_P, _I, C.POINTER(C.c_int32)]),
+    ("vdl_fused_destroy", _I, [_P]),
+    ("vdl_fused_last_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
+    ("vdl_plan_load", _I, [_P, C.c_char_p, _I, C.POINTER(_P)]),
+    ("vdl_plan_stats", _I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
+    ("vdl_plan_set_row_base", _I, [_P, _L]),
+    ("vdl_plan_run_local", _I, [_P]),
+    ("vdl_plan_num_fused", _I, [_P]),
+    ("vdl_plan_fused", _I, [_P, _I, C.POINTER(_P)]),
+    ("vdl_plan_finish", _I, [_P, C.POINTER(_P), _I]),
+    ("vdl_plan_run", _I, [_P]),
+    ("vdl_plan_num_outputs", _I, [_P]),
+    ("vdl_plan_output", _I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(_L)), C.POINTER(_L)]),
+    ("vdl_plan_destroy", _I, [_P]),
+]
+
+_lib = None
+
+
+def load():
+    """dlopen libvdl_cuda.so and type every entry point.  Raises if the library is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            raise ImportError(f"{SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(SO)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.vdl_abi_sizeof_fused_desc() != C.sizeof(FusedDesc):
+            raise ImportError("vdl_fused_desc layout mismatch between lib.py and libvdl_cuda.so")
+        _lib = L
+    return _lib

@@ -1,0 +1,50 @@
+"""The C-ABI library loads (no GPU needed) and exports every function include/vdl_cuda.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from util import ROOT
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "vdl_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vdl_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from mplan2vdl_b200 import lib
+    L = lib.load()
+    names = declared_functions()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/vdl_cuda.h but not exported"
+    assert sorted(s[0] for s in lib.SYMBOLS) == names, "lib.py's binding table and the header disagree"
+    assert L.vdl_abi_version() == 1
+    assert L.vdl_abi_sizeof_fused_desc() == ctypes.sizeof(lib.FusedDesc)
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mplan2vdl_b200.executor import Context
+    from mplan2vdl_b200.lib import VdlError
+    with pytest.raises(VdlError):
+        Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under mplan2vdl_b200/ may import, link or dlopen it."""
+    pkg = os.path.join(ROOT, "mplan2vdl_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                continue
+            src = open(os.path.join(dirpath, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+            assert not re.search(r"#include[^\n]*oracle|libvdl_oracle", src), f

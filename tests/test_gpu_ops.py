@@ -1,0 +1,104 @@
+"""Per-op parity on the GPU: every Voodoo op through libvdl_cuda's C ABI against the CPU oracle."""
+import numpy as np
+import pytest
+
+import test_oracle_ops as K
+from util import run_gpu, run_oracle
+
+pytestmark = pytest.mark.gpu
+I64 = np.int64
+
+
+def both(plan, **cols):
+    cols = {"t." + k: np.asarray(v) for k, v in cols.items()}
+    want = run_oracle(plan, cols)
+    for fuse in (False, True):
+        got, _ = run_gpu(plan, cols, fuse=fuse)
+        assert list(got) == list(want)
+        for k in want:
+            np.testing.assert_array_equal(got[k], want[k], err_msg=f"{k} fuse={fuse}")
+    return want
+
+
+@pytest.mark.parametrize("op", ["Add", "Subtract", "Multiply", "Divide", "Modulo", "Greater", "Equals", "LogicalAnd",
+                                "LogicalOr", "BitwiseAnd", "BitwiseOr", "BitShift"])
+def test_binary_kat_and_random(op):
+    both(K.binop_plan(op), a=K.A, b=K.B)
+    rng = np.random.default_rng(11)
+    n = 1_000_003
+    a = rng.integers(-2**62, 2**62, n).astype(I64)
+    b = rng.integers(-70, 70, n).astype(I64) if op == "BitShift" else rng.integers(-2**40, 2**40, n).astype(I64)
+    b[::97] = 0
+    both(K.binop_plan(op), a=a, b=b)
+
+
+def test_int32_columns_and_ranges():
+    both(K.binop_plan("Add"), a=np.array([-5, 7, 2**31 - 1], dtype=np.int32), b=np.array([2**40, 1, 1], dtype=I64))
+    plan = ("1,Load,t.a\n2,Project,val,Id 1,a\n3,RangeV,val,10,Id 2,3\n4,RangeC,val,-1,4,2\n"
+            "5,Project,rv,Id 3,val\n6,MaterializeCompact,Id 5\n7,Project,rc,Id 4,val\n8,MaterializeCompact,Id 7\n")
+    both(plan, a=np.zeros(3, I64))
+
+
+@pytest.mark.parametrize("n,density", [(6, 0.5), (4095, 0.3), (4096, 0.0), (4097, 1.0), (1_000_003, 0.02), (3_000_000, 0.9)])
+def test_fold_select_gather(n, density):
+    rng = np.random.default_rng(n)
+    p = (rng.random(n) < density).astype(I64) * rng.integers(1, 5, n)
+    x = rng.integers(-10**15, 10**15, n).astype(I64)
+    r = both(K.SELECT, p=p, x=x)
+    assert len(r["pos"]) == int((p != 0).sum())
+
+
+@pytest.mark.parametrize("op", ["FoldSum", "FoldMin", "FoldMax", "FoldChoose", "FoldCount"])
+def test_folds(op):
+    both(K.FOLD.format(op=op), g=np.array([5, 5, 9, 2, 2, 2, 5], I64), x=np.array([1, 2, 3, 4, 5, 6, 7], I64))
+    both(K.FOLD.format(op=op), g=np.zeros(0, I64), x=np.zeros(0, I64))
+    rng = np.random.default_rng(5)
+    for n, ngroups in ((1_000_003, 50), (300_007, 200_000), (70_001, 1)):
+        g = np.sort(rng.integers(0, ngroups, n)).astype(I64)
+        x = rng.integers(-2**62, 2**62, n).astype(I64)     # sums wrap
+        both(K.FOLD.format(op=op), g=g, x=x)
+
+
+@pytest.mark.parametrize("n,nkeys", [(7, 4), (4096, 4), (100_003, 4), (1_000_003, 4)])
+def test_partition_scatter(n, nkeys):
+    rng = np.random.default_rng(n)
+    k = rng.integers(-2, nkeys + 3, n).astype(I64)
+    r = both(K.PART, k=k)
+    assert np.all(np.diff(np.clip(r["sorted"], 0, 4)) >= 0)
+    assert sorted(r["perm"].tolist()) == list(range(n))
+
+
+def test_partition_wide_keys_multi_pass():
+    plan = K.PART.replace("3,RangeC,val,0,4,1", "3,RangeC,val,0,274877906944,1")    # 2^38 pivots (Q3's composite key)
+    rng = np.random.default_rng(3)
+    k = rng.integers(0, 2**38, 200_003).astype(I64)
+    r = both(plan, k=k)
+    np.testing.assert_array_equal(r["sorted"], np.sort(k))
+
+
+def test_scatter_index_space():
+    plan = ("1,Load,t.p\n2,Project,val,Id 1,p\n3,RangeV,val,0,Id 2,1\n4,FoldSelect,val,Id 3,val,Id 2,val\n"
+            "5,RangeV,val,1,Id 4,0\n6,RangeV,val,0,Id 5,1\n7,Scatter,Id 5,Id 6,val,Id 4,val\n"
+            "8,Project,valid,Id 7,val\n9,MaterializeCompact,Id 8\n"
+            "10,Scatter,Id 6,Id 6,val,Id 4,val\n11,Project,inv,Id 10,val\n12,MaterializeCompact,Id 11\n")
+    rng = np.random.default_rng(1)
+    both(plan, p=np.array([0, 1, 0, 0, 1, 1], I64))
+    both(plan, p=(rng.random(500_001) < 0.4).astype(I64))
+
+
+def test_errors_are_reported_not_fatal():
+    from mplan2vdl_b200.executor import Context
+    from mplan2vdl_b200.lib import VdlError
+    ctx = Context(0)
+    with pytest.raises(VdlError):
+        ctx.plan("1,Load,t.a\n2,Semisort,Id 1\n")                       # unsupported op
+    with pytest.raises(VdlError):
+        ctx.plan("1,Load,t.a\n2,Project,val,Id 1,a\n3,MaterializeCompact,Id 2\n").run()   # unbound column
+    ctx.upload_column("t.x", np.arange(3, dtype=I64))
+    ctx.upload_column("t.i", np.array([0, 3], I64))
+    with pytest.raises(VdlError):                                         # gather out of range
+        ctx.plan("1,Load,t.x\n2,Project,val,Id 1,x\n3,Load,t.i\n4,Project,val,Id 3,i\n5,Gather,Id 2,Id 4,val\n6,MaterializeCompact,Id 5\n").run()
+    # the context is still usable afterwards
+    out = ctx.plan("1,Load,t.x\n2,Project,out,Id 1,val\n3,MaterializeCompact,Id 2\n").run()
+    np.testing.assert_array_equal(out["out"], [0, 1, 2])
+    ctx.close()

@@ -42,3 +42,23 @@ def assert_same(a: dict, b: dict):
     assert list(a.keys()) == list(b.keys())
     for k in a:
         np.testing.assert_array_equal(np.asarray(a[k], dtype=np.int64), np.asarray(b[k], dtype=np.int64), err_msg=k)
+
+
+def run_gpu(plan, cols, fuse=True, ctx=None):
+    """Upload host columns, run the plan through libvdl_cuda's C ABI, return ({name: array}, stats)."""
+    from mplan2vdl_b200.executor import Context
+    own = ctx is None
+    ctx = ctx or Context(0)
+    try:
+        for k, v in cols.items():
+            ctx.upload_column(k, v)
+        p = ctx.plan(plan, fuse=fuse)
+        out = p.run()
+        stats = p.stats()
+        p.close()
+        for k in cols:
+            ctx.drop_column(k)
+        return out, stats
+    finally:
+        if own:
+            ctx.close()
