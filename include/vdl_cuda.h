@@ -131,8 +131,8 @@ int vdl_op_fold(vdl_ctx *ctx, int fold_op, vdl_vec groups, vdl_vec data, vdl_vec
 #define VDL_MAX_COLS 12
 #define VDL_MAX_PREDS 8
 #define VDL_MAX_KEYS 4
-#define VDL_MAX_AGGS 10
-#define VDL_MAX_FACTORS 4
+#define VDL_MAX_AGGS 8
+#define VDL_MAX_FACTORS 3
 
 typedef struct {          /* value = a + b * (column[row] >> shr); column < 0: the constant a;   */
   int32_t column;         /* column == -2: the global row id (row_base + row)                      */

@@ -27,15 +27,16 @@
 
 #include "vdl_internal.h"
 
-#define K_MAX_ACC 12
+#define K_MAX_ACC 10
 #define K_MAX_CHOOSE 6
-#define K_CONSUMERS 256          // consumer threads per CTA (8 warps)
-#define K_THREADS (K_CONSUMERS + 32)
 
-struct KAffine { int32_t col, shr; i64 a, b; };
-struct KPred { int32_t col, shr; i64 lo; u64 span; };
+// soff / w4 are derived by the host from col: byte offset of the column inside a staged tile, 4-byte flag.
+struct KAffine { int32_t col, shr; i64 a, b; int32_t soff, w4; };
+struct KPred { int32_t col, shr; i64 lo; u64 span; int32_t soff, w4; int32_t lo32; uint32_t span32; };
 struct KKey { KAffine e; int32_t shl, pad; };
-struct KAcc { int32_t op, nfac; KAffine fac[VDL_MAX_FACTORS]; };   // op: 0 sum, 1 min, 2 max
+// op: 0 sum, 1 min, 2 max.  chain: value = value of the previous accumulator x own factors (prefix sharing:
+// ep, ep*(100-d), ep*(100-d)*(100+t) evaluate each factor once).
+struct KAcc { int32_t op, nfac, chain, pad; KAffine fac[VDL_MAX_FACTORS]; };
 
 struct KDesc {
   i64 rows, row_base, key_mask, domain, ntiles;
@@ -98,58 +99,8 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(K_CONSUMERS) : "memory"); }
-
-// ------------------------------------------------------------------------------ row accessors
-struct SmemRows {   // a staged tile: column c lives at base + soff[c]
-  const char *base;
-  __device__ __forceinline__ i64 ld(const KDesc &d, int c, int r) const {
-    const char *p = base + d.soff[c];
-    return d.width[c] == 4 ? (i64)((const int32_t *)p)[r] : ((const i64 *)p)[r];
-  }
-};
-struct GmemRows {   // straight from HBM (tail rows, tiny inputs, choose evaluation)
-  i64 row0;
-  __device__ __forceinline__ i64 ld(const KDesc &d, int c, i64 r) const {
-    const void *p = d.col[c];
-    return d.width[c] == 4 ? (i64)__ldg((const int32_t *)p + row0 + r) : __ldg((const i64 *)p + row0 + r);
-  }
-};
-
-template <class Rows, class Idx>
-__device__ __forceinline__ i64 eval_affine(const KDesc &d, const KAffine &A, const Rows &R, Idx r, i64 grow) {
-  if (A.col == -1) return A.a;
-  i64 leaf = (A.col == -2) ? grow : (R.ld(d, A.col, r) >> A.shr);
-  return (i64)((u64)A.a + (u64)A.b * (u64)leaf);
-}
-template <class Rows, class Idx>
-__device__ __forceinline__ i64 eval_product(const KDesc &d, const KAcc &A, const Rows &R, Idx r, i64 grow) {
-  if (A.nfac == 0) return 1;
-  i64 v = eval_affine(d, A.fac[0], R, r, grow);
-#pragma unroll
-  for (int f = 1; f < VDL_MAX_FACTORS; f++)
-    if (f < A.nfac) v = (i64)((u64)v * (u64)eval_affine(d, A.fac[f], R, r, grow));
-  return v;
-}
-template <class Rows, class Idx>
-__device__ __forceinline__ bool eval_preds(const KDesc &d, const Rows &R, Idx r) {
-  bool pass = true;
-#pragma unroll
-  for (int i = 0; i < VDL_MAX_PREDS; i++)
-    if (i < d.npreds) {
-      i64 v = R.ld(d, d.pred[i].col, r) >> d.pred[i].shr;
-      pass &= ((u64)v - (u64)d.pred[i].lo) <= d.pred[i].span;
-    }
-  return pass;
-}
-template <class Rows, class Idx>
-__device__ __forceinline__ i64 eval_key(const KDesc &d, const Rows &R, Idx r, i64 grow) {
-  i64 key = 0;
-#pragma unroll
-  for (int k = 0; k < VDL_MAX_KEYS; k++)
-    if (k < d.nkeys) key |= (i64)((u64)eval_affine(d, d.key[k].e, R, r, grow) << d.key[k].shl);
-  return key & d.key_mask;
-}
+template <int NC>
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
 
 __device__ __forceinline__ i64 acc_identity(int op) { return op == 0 ? 0 : (op == 1 ? INT64_MAX : INT64_MIN); }
 __device__ __forceinline__ i64 acc_combine(int op, i64 a, i64 v) {
@@ -166,40 +117,134 @@ __device__ __forceinline__ i64 warp_reduce(int op, i64 v) {
   return v;
 }
 
+// ---- descriptor-driven evaluation over a staged tile -------------------------------------------
+// Every loop over the descriptor (predicates, key parts, accumulators, factors) is unrolled as a chain of
+// nested uniform `if (I < n)` tests, so each descriptor field is a constant-bank immediate operand of the
+// instruction that uses it (no loads, no dependent latency) and unused slots cost one uniform branch.
+__device__ __forceinline__ i64 tile_leaf(const KAffine &A, const unsigned char *tile, int r, i64 grow) {
+  if (A.col == -2) return grow;
+  i64 v = A.w4 ? (i64)((const int32_t *)(tile + A.soff))[r] : ((const i64 *)(tile + A.soff))[r];
+  if (A.shr) v >>= A.shr;
+  return v;
+}
+// a + b * leaf; col -1: the constant a; col -2: leaf = global row id
+__device__ __forceinline__ i64 tile_affine(const KAffine &A, const unsigned char *tile, int r, i64 grow) {
+  if (A.col == -1) return A.a;
+  i64 leaf = tile_leaf(A, tile, r, grow);
+  if (A.b != 1) leaf = (i64)((u64)A.b * (u64)leaf);
+  return (i64)((u64)A.a + (u64)leaf);
+}
+template <int F>
+__device__ __forceinline__ i64 factor_chain(const KAcc &A, i64 v, const unsigned char *tile, int r, i64 grow) {
+  if constexpr (F < VDL_MAX_FACTORS) {
+    if (F < A.nfac) {
+      i64 x = tile_affine(A.fac[F], tile, r, grow);
+      v = (F == 0 && !A.chain) ? x : (i64)((u64)v * (u64)x);
+      return factor_chain<F + 1>(A, v, tile, r, grow);
+    }
+  }
+  return v;
+}
+// value of accumulator A given the previous accumulator's value (used when A.chain)
+__device__ __forceinline__ i64 acc_value(const KAcc &A, i64 prev, const unsigned char *tile, int r, i64 grow) {
+  return factor_chain<0>(A, A.chain ? prev : 1, tile, r, grow);
+}
+// generic (looping) form for the rare global-atomic path
+__device__ __noinline__ i64 acc_value_slow(const KDesc &d, int j, const unsigned char *tile, int r, i64 grow) {
+  i64 v = 1;
+  int j0 = j;
+  while (d.acc[j0].chain) j0--;
+  for (int q = j0; q <= j; q++)
+    for (int f = 0; f < d.acc[q].nfac; f++) v = (i64)((u64)v * (u64)tile_affine(d.acc[q].fac[f], tile, r, grow));
+  return v;
+}
+
+template <int I, int NC, int R>
+__device__ __forceinline__ void pred_chain(const KDesc &d, const unsigned char *tile, int ctid, unsigned &pass) {
+  if constexpr (I < VDL_MAX_PREDS) {
+    if (I < d.npreds) {
+      const KPred &P = d.pred[I];
+      if (P.w4) {      // 4-byte column: compare in 32 bits against bounds clamped to int32 by the host
+        const int32_t *p = (const int32_t *)(tile + P.soff);
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+          int32_t v = p[ctid + k * NC];
+          if (P.shr) v >>= P.shr;
+          if ((uint32_t)v - (uint32_t)P.lo32 > P.span32) pass &= ~(1u << k);
+        }
+      } else {
+        const i64 *p = (const i64 *)(tile + P.soff);
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+          i64 v = p[ctid + k * NC];
+          if (P.shr) v >>= P.shr;
+          if ((u64)v - (u64)P.lo > P.span) pass &= ~(1u << k);
+        }
+      }
+      pred_chain<I + 1, NC, R>(d, tile, ctid, pass);
+    }
+  }
+}
+
+template <int Q>
+__device__ __forceinline__ i64 key_chain(const KDesc &d, i64 key, const unsigned char *tile, int r, i64 grow) {
+  if constexpr (Q < VDL_MAX_KEYS) {
+    if (Q < d.nkeys) {
+      i64 x = tile_affine(d.key[Q].e, tile, r, grow);
+      if (d.key[Q].shl) x = (i64)((u64)x << d.key[Q].shl);
+      return key_chain<Q + 1>(d, key | x, tile, r, grow);
+    }
+  }
+  return key;
+}
+
+// lane-private read-modify-write of accumulator J and all following ones
+template <int J, int NC>
+__device__ __forceinline__ void acc_chain(const KDesc &d, i64 *t, i64 prev, const unsigned char *tile, int r, i64 grow) {
+  if constexpr (J < K_MAX_ACC) {
+    if (J < d.nacc) {
+      i64 v = acc_value(d.acc[J], prev, tile, r, grow);
+      t[J * NC] = acc_combine(d.acc[J].op, t[J * NC], v);
+      acc_chain<J + 1, NC>(d, t, v, tile, r, grow);
+    }
+  }
+}
+
 // Per-CTA group state: key -> compact slot (lane-private accumulator tables are indexed by slot).
 struct GroupState {
   int32_t *slotmap;   // [domain]  -1 unseen, -2 being claimed, -3 overflow (stays on the global-atomic path), >=0 slot
   int32_t *slotkey;   // [gmax]
   int32_t *nslots;
-  i64 *tbl;           // [gmax][nacc][K_CONSUMERS]
+  i64 *tbl;           // [gmax][nacc][NC]
 };
 
-template <bool GROUPED, class Rows, class Idx>
-__device__ __forceinline__ void process_row(const KDesc &d, const Rows &R, Idx r, i64 grow, i64 (&acc)[K_MAX_ACC],
-                                            const GroupState &g, int ctid) {
-  if (!eval_preds(d, R, r)) return;
-  if (!GROUPED) {
+// Fold one staged tile.  Thread ctid owns rows ctid + k*NC, k < R; the R rows are evaluated together inside
+// each predicate (R independent shared-memory loads in flight), rows that pass are then folded one by one.
+template <int NC, int R>
+__device__ __forceinline__ void process_tile(const KDesc &d, const unsigned char *tile, i64 grow0, int nvalid, const GroupState &g, int ctid) {
+  unsigned pass = 0;
 #pragma unroll
-    for (int j = 0; j < K_MAX_ACC; j++)
-      if (j < d.nacc) acc[j] = acc_combine(d.acc[j].op, acc[j], eval_product(d, d.acc[j], R, r, grow));
-  } else {
-    i64 key = eval_key(d, R, r, grow);
+  for (int k = 0; k < R; k++)
+    if (ctid + k * NC < nvalid) pass |= 1u << k;
+  pred_chain<0, NC, R>(d, tile, ctid, pass);
+  if (!pass) return;
+#pragma unroll 1
+  for (int k = 0; k < R; k++) {
+    if (!(pass & (1u << k))) continue;
+    const int r = ctid + k * NC;
+    const i64 grow = grow0 + r;
+    i64 key = key_chain<0>(d, 0, tile, r, grow) & d.key_mask;
     if ((u64)key >= (u64)d.domain) {   // the planner proves key < domain (mask); never expected
       atomicAdd(d.errflag, 1);
-      return;
+      continue;
     }
-    int s = ((volatile int32_t *)g.slotmap)[key];
+    const int s = ((volatile int32_t *)g.slotmap)[key];
     if (s >= 0) {
-      i64 *t = g.tbl + (size_t)s * d.nacc * K_CONSUMERS + ctid;
-#pragma unroll
-      for (int j = 0; j < K_MAX_ACC; j++)
-        if (j < d.nacc) {
-          i64 v = eval_product(d, d.acc[j], R, r, grow);
-          t[j * K_CONSUMERS] = acc_combine(d.acc[j].op, t[j * K_CONSUMERS], v);
-        }
+      acc_chain<0, NC>(d, g.tbl + (size_t)s * d.nacc * NC + ctid, 1, tile, r, grow);
     } else {
       // first rows of a key in this CTA: fold straight into the global table and claim a slot for the rest
-      for (int j = 0; j < d.nacc; j++) acc_global(d.acc[j].op, d.table + (size_t)j * d.domain + key, eval_product(d, d.acc[j], R, r, grow));
+#pragma unroll 1
+      for (int j = 0; j < d.nacc; j++) acc_global(d.acc[j].op, d.table + (size_t)j * d.domain + key, acc_value_slow(d, j, tile, r, grow));
       if (s == -1 && atomicCAS(&g.slotmap[key], -1, -2) == -1) {
         int ns = atomicAdd(g.nslots, 1);
         if (ns < d.gmax) {
@@ -214,8 +259,8 @@ __device__ __forceinline__ void process_row(const KDesc &d, const Rows &R, Idx r
   }
 }
 
-template <bool GROUPED>
-__global__ void __launch_bounds__(K_THREADS, 1) fused_scan_fold_kernel(const __grid_constant__ KDesc d) {
+template <int NC, int R>
+__global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __grid_constant__ KDesc d) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: [ring: stages * stage_bytes][full[stages]][empty[stages]][nslots][slotkey[gmax]][slotmap[domain]][tables]
   unsigned char *ring = smem;
@@ -225,28 +270,28 @@ __global__ void __launch_bounds__(K_THREADS, 1) fused_scan_fold_kernel(const __g
   g.nslots = (int32_t *)(empty + d.stages);
   g.slotkey = g.nslots + 2;
   g.slotmap = g.slotkey + d.gmax;
-  size_t tbl_off = (size_t)((unsigned char *)(g.slotmap + (GROUPED ? d.domain : 0)) - smem);
+  size_t tbl_off = (size_t)((unsigned char *)(g.slotmap + d.domain) - smem);
   tbl_off = (tbl_off + 15) & ~(size_t)15;
   g.tbl = (i64 *)(smem + tbl_off);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  const bool dense = d.domain <= d.gmax;     // every key has its own slot from the start
 
   if (tid == 0) {
     for (int s = 0; s < d.stages; s++) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], K_CONSUMERS / 32);
+      mbar_init(&empty[s], NC / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    *g.nslots = 0;
+    *g.nslots = dense ? (int)d.domain : 0;
   }
-  if (GROUPED) {
-    for (i64 k = tid; k < d.domain; k += K_THREADS) g.slotmap[k] = -1;
-    if (tid >= 32) {
-      int ctid = tid - 32;
-      for (int s = 0; s < d.gmax; s++)
-        for (int j = 0; j < d.nacc; j++) g.tbl[((size_t)s * d.nacc + j) * K_CONSUMERS + ctid] = acc_identity(d.acc[j].op);
-    }
+  for (i64 k = tid; k < d.domain; k += NC + 32) g.slotmap[k] = dense ? (int32_t)k : -1;
+  if (dense && tid < d.gmax) g.slotkey[tid] = tid;
+  if (tid >= 32) {
+    const int ctid = tid - 32;
+    for (int s = 0; s < d.gmax; s++)
+      for (int j = 0; j < d.nacc; j++) g.tbl[((size_t)s * d.nacc + j) * NC + ctid] = acc_identity(d.acc[j].op);
   }
   __syncthreads();
 
@@ -260,6 +305,7 @@ __global__ void __launch_bounds__(K_THREADS, 1) fused_scan_fold_kernel(const __g
         mbar_wait(&empty[st], ph ^ 1);
         mbar_expect_tx(&full[st], (uint32_t)d.stage_tx);
         unsigned char *dst = ring + (size_t)st * d.stage_bytes;
+#pragma unroll 1
         for (int c = 0; c < d.ncols; c++) {
           uint32_t bytes = (uint32_t)(d.tile_rows * d.width[c]);
           bulk_g2s(dst + d.soff[c], (const char *)d.col[c] + (size_t)tile * bytes, bytes, &full[st], policy);
@@ -272,49 +318,49 @@ __global__ void __launch_bounds__(K_THREADS, 1) fused_scan_fold_kernel(const __g
 
   // -------------------------------------------------------------------- consumers
   const int ctid = tid - 32;
-  i64 acc[K_MAX_ACC];
-#pragma unroll
-  for (int j = 0; j < K_MAX_ACC; j++) acc[j] = j < d.nacc ? acc_identity(d.acc[j].op) : 0;
-
   int st = 0;
   uint32_t ph = 0;
-  for (i64 tile = blockIdx.x; tile < d.ntiles; tile += gridDim.x) {
-    mbar_wait(&full[st], ph);
-    SmemRows R{(const char *)ring + (size_t)st * d.stage_bytes};
-    const i64 grow0 = d.row_base + tile * d.tile_rows;
-#pragma unroll 4
-    for (int r = ctid; r < d.tile_rows; r += K_CONSUMERS) process_row<GROUPED>(d, R, r, grow0 + r, acc, g, ctid);
+  // The rows past the last full tile form one more (partial) tile, owned by the CTA next in the round-robin; it
+  // is staged with plain loads into the (by then idle) next ring stage and folded through the same code.
+  const i64 ntiles_all = d.ntiles + (d.ntiles * d.tile_rows < d.rows ? 1 : 0);
+  for (i64 tile = blockIdx.x; tile < ntiles_all; tile += gridDim.x) {
+    unsigned char *buf = ring + (size_t)st * d.stage_bytes;
+    int nvalid = d.tile_rows;
+    if (tile < d.ntiles) {
+      mbar_wait(&full[st], ph);
+    } else {
+      const i64 tail0 = d.ntiles * d.tile_rows;
+      nvalid = (int)(d.rows - tail0);
+      consumer_barrier<NC>();      // every consumer is done with the ring
+#pragma unroll 1
+      for (int c = 0; c < d.ncols; c++) {
+        if (d.width[c] == 4) {
+          const int32_t *src = (const int32_t *)d.col[c] + tail0;
+          for (int r = ctid; r < nvalid; r += NC) ((int32_t *)(buf + d.soff[c]))[r] = src[r];
+        } else {
+          const i64 *src = (const i64 *)d.col[c] + tail0;
+          for (int r = ctid; r < nvalid; r += NC) ((i64 *)(buf + d.soff[c]))[r] = src[r];
+        }
+      }
+      consumer_barrier<NC>();
+    }
+    process_tile<NC, R>(d, buf, d.row_base + tile * d.tile_rows, nvalid, g, ctid);
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);
+    if (lane == 0 && tile < d.ntiles) mbar_arrive(&empty[st]);
     if (++st == d.stages) { st = 0; ph ^= 1; }
   }
-  // rows past the last full tile: read straight from HBM by the CTA that would own the next tile
-  if ((i64)blockIdx.x == d.ntiles % gridDim.x) {
-    const i64 tail0 = d.ntiles * d.tile_rows;
-    GmemRows R{tail0};
-    for (i64 r = ctid; r < d.rows - tail0; r += K_CONSUMERS) process_row<GROUPED>(d, R, r, d.row_base + tail0 + r, acc, g, ctid);
-  }
 
-  if (!GROUPED) {
-    // registers -> warp shuffle -> one global atomic per warp and accumulator
-#pragma unroll
-    for (int j = 0; j < K_MAX_ACC; j++)
-      if (j < d.nacc) {
-        i64 v = warp_reduce(d.acc[j].op, acc[j]);
-        if (lane == 0) acc_global(d.acc[j].op, d.table + (size_t)j * d.domain, v);
-      }
-  } else {
-    consumer_barrier();
-    int ns = *((volatile int32_t *)g.nslots);
-    if (ns > d.gmax) ns = d.gmax;
-    const int cw = warp - 1, ncw = K_CONSUMERS / 32;
-    for (int p = cw; p < ns * d.nacc; p += ncw) {
-      int s = p / d.nacc, j = p % d.nacc, op = d.acc[j].op;
-      i64 v = acc_identity(op);
-      for (int t = lane; t < K_CONSUMERS; t += 32) v = acc_combine(op, v, g.tbl[((size_t)s * d.nacc + j) * K_CONSUMERS + t]);
-      v = warp_reduce(op, v);
-      if (lane == 0) acc_global(op, d.table + (size_t)j * d.domain + g.slotkey[s], v);
-    }
+  // lane-private tables -> one global atomic per (warp, slot, accumulator)
+  consumer_barrier<NC>();
+  int ns = *((volatile int32_t *)g.nslots);
+  if (ns > d.gmax) ns = d.gmax;
+  const int cw = warp - 1, ncw = NC / 32;
+  for (int p = cw; p < ns * d.nacc; p += ncw) {
+    const int s = p / d.nacc, j = p % d.nacc, op = d.acc[j].op;
+    i64 v = acc_identity(op);
+    for (int t = lane; t < NC; t += 32) v = acc_combine(op, v, g.tbl[((size_t)s * d.nacc + j) * NC + t]);
+    v = warp_reduce(op, v);
+    if (lane == 0) acc_global(op, d.table + (size_t)j * d.domain + g.slotkey[s], v);
   }
 }
 
@@ -332,9 +378,22 @@ __global__ void fused_choose_kernel(const __grid_constant__ KDesc d) {
   for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < d.domain; k += (i64)gridDim.x * blockDim.x) {
     if (d.table[(size_t)d.cnt_idx * d.domain + k] <= 0) continue;
     i64 grow = d.table[(size_t)d.first_idx * d.domain + k];
-    GmemRows R{0};
-    for (int c = 0; c < d.nchoose; c++)
-      d.table[(size_t)(d.nacc + c) * d.domain + k] = eval_product(d, d.choose[c], R, grow - d.row_base, grow);
+    i64 r = grow - d.row_base;
+    for (int c = 0; c < d.nchoose; c++) {
+      const KAcc &A = d.choose[c];
+      i64 v = 1;
+      for (int f = 0; f < A.nfac; f++) {
+        const KAffine &F = A.fac[f];
+        i64 x;
+        if (F.col == -1) x = F.a;
+        else {
+          i64 leaf = F.col == -2 ? grow : ((d.width[F.col] == 4 ? (i64)((const int32_t *)d.col[F.col])[r] : ((const i64 *)d.col[F.col])[r]) >> F.shr);
+          x = (i64)((u64)F.a + (u64)F.b * (u64)leaf);
+        }
+        v = (i64)((u64)v * (u64)x);
+      }
+      d.table[(size_t)(d.nacc + c) * d.domain + k] = v;
+    }
   }
 }
 
@@ -400,13 +459,19 @@ struct vdl_fused {
   i64 ngroups = -1;
   bool finalized = false, always_false = false;
   size_t smem_bytes = 0;
-  int grid = 1;
+  int grid = 1, nc = 256, r = 4;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
 };
 
+typedef void (*scan_kernel_fn)(const KDesc);
+static scan_kernel_fn scan_kernel_for(int nc, int r) {
+  if (nc == 512) return r == 2 ? fused_scan_fold_kernel<512, 2> : fused_scan_fold_kernel<512, 1>;
+  return r == 4 ? fused_scan_fold_kernel<256, 4> : (r == 2 ? fused_scan_fold_kernel<256, 2> : fused_scan_fold_kernel<256, 1>);
+}
+
 static bool affine_ok(const vdl_affine &a, int ncols) { return a.column >= -2 && a.column < ncols && a.shr >= 0 && a.shr < 64; }
-static KAffine to_k(const vdl_affine &a) { return KAffine{a.column, a.shr, a.a, a.b}; }
+static KAffine to_k(const vdl_affine &a) { return KAffine{a.column, a.shr, a.a, a.b, 0, 0}; }
 
 extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_fused **out) {
   if (!ctx || !desc || !out) return VDL_EINVAL;
@@ -442,7 +507,7 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     const vdl_range_pred &p = desc->pred[i];
     if (p.column < 0 || p.column >= desc->ncolumns || p.shr < 0 || p.shr > 63) { delete f; return vdl_fail(ctx, VDL_EINVAL, "fused scan: bad predicate %d", i); }
     if (p.lo > p.hi) f->always_false = true;
-    k.pred[k.npreds++] = KPred{p.column, p.shr, p.lo, (u64)p.hi - (u64)p.lo};
+    k.pred[k.npreds++] = KPred{p.column, p.shr, p.lo, (u64)p.hi - (u64)p.lo, 0, 0, 0, 0};
   }
   for (int i = 0; i < desc->nkeys; i++) {
     if (!affine_ok(desc->key[i].e, desc->ncolumns) || desc->key[i].shl < 0 || desc->key[i].shl > 63) { delete f; return vdl_fail(ctx, VDL_EINVAL, "fused scan: bad key part %d", i); }
@@ -484,41 +549,76 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     memset(&first, 0, sizeof first);
     first.op = 1;
     first.nfac = 1;
-    first.fac[0] = KAffine{-2, 0, 0, 1};  // MIN over the global row id
+    first.fac[0] = KAffine{-2, 0, 0, 1, 0, 0};  // MIN over the global row id
     k.first_idx = k.nacc;
     k.acc[k.nacc++] = first;
   }
   for (int i = 0; i < desc->nfolds; i++)
     if (f->fd.out_kind[i] == 0 && f->fd.out_idx[i] < 0) f->fd.out_idx[i] = k.cnt_idx;
 
-  // geometry: tile rows, ring depth, grouped tables
+  // geometry: consumer threads NC, rows per thread and tile R, ring depth, lane-private tables
   k.grouped = desc->domain > 1 || desc->nkeys > 0;
   const int smem_max = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;
-  size_t table_bytes = 0, map_bytes = 0;
-  if (k.grouped) {
+  if ((size_t)desc->domain * 4 > 64 * 1024) { delete f; return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: key domain %lld too large for the shared-memory slot map", (long long)desc->domain); }
+  bool placed = false;
+  for (int nc = 512; nc >= 256 && !placed; nc /= 2) {
+    // slots with lane-private tables: as many as the domain needs, up to what ~100 KB holds
     int gmax = 1;
-    while (gmax * 2 <= desc->domain && gmax * 2 <= 64 && (size_t)(gmax * 2) * k.nacc * K_CONSUMERS * 8 <= 120 * 1024) gmax *= 2;
-    k.gmax = gmax;
-    table_bytes = (size_t)gmax * k.nacc * K_CONSUMERS * 8;
-    map_bytes = (size_t)desc->domain * 4 + (size_t)gmax * 4;
-    if (map_bytes > 64 * 1024) { delete f; return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: key domain %lld too large for the shared-memory slot map", (long long)desc->domain); }
+    while (gmax < desc->domain && gmax < 64 && (size_t)(gmax * 2) * k.nacc * nc * 8 <= 120 * 1024) gmax *= 2;
+    if (nc == 512 && gmax < desc->domain && gmax < 8) continue;     // too few slots: halve the consumers instead
+    size_t fixed = (size_t)gmax * k.nacc * nc * 8 + (size_t)desc->domain * 4 + (size_t)gmax * 4 + 16 + 2 * 8 * 16 + 256;
+    for (int r = 1024 / nc; r >= 1 && !placed; r /= 2) {
+      int tile_rows = nc * r, off = 0;
+      for (int c = 0; c < k.ncols; c++) { k.soff[c] = off; off += ((tile_rows * k.width[c] + 127) / 128) * 128; }
+      int stages = (int)(((long)smem_max - (long)fixed) / off);
+      if (stages >= 3 || (r == 1 && stages >= 2 && nc == 256)) {
+        k.tile_rows = tile_rows; k.stage_bytes = off; k.stage_tx = tile_rows * rowbytes; k.stages = std::min(stages, 12);
+        k.gmax = gmax; f->nc = nc; f->r = r;
+        f->smem_bytes = (size_t)k.stages * k.stage_bytes + fixed;
+        placed = true;
+      }
+    }
   }
-  k.tile_rows = 1024;
-  size_t fixed = table_bytes + map_bytes + 16 + 2 * 8 * 16 + 256;
-  for (;;) {
-    int off = 0;
-    for (int c = 0; c < k.ncols; c++) { k.soff[c] = off; off += ((k.tile_rows * k.width[c] + 127) / 128) * 128; }
-    k.stage_bytes = off;
-    k.stage_tx = k.tile_rows * rowbytes;
-    int stages = (int)((smem_max - (long)fixed) / k.stage_bytes);
-    if (stages >= 3 || k.tile_rows <= 256) { k.stages = std::max(1, std::min(stages, 8)); break; }
-    k.tile_rows /= 2;
-  }
-  if ((size_t)k.stages * k.stage_bytes + fixed > (size_t)smem_max) { delete f; return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: does not fit shared memory"); }
-  f->smem_bytes = (size_t)k.stages * k.stage_bytes + fixed;
+  if (!placed) { delete f; return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: %d columns x %d accumulators do not fit shared memory", k.ncols, k.nacc); }
   k.ntiles = desc->rows / k.tile_rows;
-  // every column must allow whole-tile bulk reads up to ntiles*tile_rows (<= rows) -- always true; tail uses plain loads
   f->grid = (int)std::max<i64>(1, std::min<i64>(ctx->sm_count, k.ntiles));
+  // derived descriptor fields: staged offsets / width flags, 32-bit bounds for 4-byte predicate columns,
+  // prefix sharing between consecutive accumulators
+  auto place = [&](KAffine &a) { if (a.col >= 0) { a.soff = k.soff[a.col]; a.w4 = k.width[a.col] == 4; } };
+  for (int i = 0; i < k.npreds; i++) {
+    KPred &p = k.pred[i];
+    p.soff = k.soff[p.col];
+    p.w4 = k.width[p.col] == 4;
+    if (p.w4) {   // values of a 4-byte column (shifted or not) lie in int32: clamp the bounds, compare in 32 bits
+      i64 lo = std::max<i64>(p.lo, INT32_MIN), hi = std::min<i64>((i64)((u64)p.lo + p.span), INT32_MAX);
+      if (lo > hi) f->always_false = true;
+      p.lo32 = (int32_t)lo;
+      p.span32 = (uint32_t)(hi - lo);
+    }
+  }
+  for (int i = 0; i < k.nkeys; i++) place(k.key[i].e);
+  for (int j = 0; j < k.nacc; j++) {
+    KAcc &a = k.acc[j];
+    if (j > 0 && j != k.cnt_idx && j != k.first_idx) {
+      // full factor list of the previous accumulator (its own chain expanded) a prefix of this one?
+      std::vector<KAffine> prev;
+      int q = j - 1;
+      std::vector<int> chain_members;
+      while (true) { chain_members.push_back(q); if (!k.acc[q].chain) break; q--; }
+      for (int m = (int)chain_members.size() - 1; m >= 0; m--)
+        for (int t = 0; t < k.acc[chain_members[m]].nfac; t++) prev.push_back(k.acc[chain_members[m]].fac[t]);
+      bool prefix = !prev.empty() && (int)prev.size() < a.nfac && j - 1 != k.cnt_idx;
+      for (size_t t = 0; prefix && t < prev.size(); t++)
+        prefix = prev[t].col == a.fac[t].col && prev[t].shr == a.fac[t].shr && prev[t].a == a.fac[t].a && prev[t].b == a.fac[t].b;
+      if (prefix) {
+        int np = (int)prev.size();
+        for (int t = np; t < a.nfac; t++) a.fac[t - np] = a.fac[t];
+        a.nfac -= np;
+        a.chain = 1;
+      }
+    }
+    for (int t = 0; t < a.nfac; t++) place(a.fac[t]);
+  }
 
   // device buffers
   int rc = vec_new(ctx, VDL_I64, (i64)(k.nacc + k.nchoose) * k.domain, &f->table);
@@ -542,8 +642,7 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   f->fd.ngroups = f->d_ngroups;
   for (int j = 0; j < k.nacc; j++) f->fd.acc_op[j] = k.acc[j].op;
 
-  cudaError_t e = cudaFuncSetAttribute(fused_scan_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_scan_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  cudaError_t e = cudaFuncSetAttribute(scan_kernel_for(f->nc, f->r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   if (e != cudaSuccess) { vdl_fused_destroy(f); return vdl_cuda_fail(ctx, e, "cudaFuncSetAttribute(fused_scan_fold_kernel)"); }
   *out = f;
   return VDL_OK;
@@ -560,8 +659,7 @@ extern "C" int vdl_fused_launch(vdl_fused *f) {
   ctx->launches++;
   VDL_CUDA(ctx, cudaEventRecord(f->ev0, ctx->stream));
   if (f->kd.rows > 0 && !f->always_false) {
-    if (f->kd.grouped) fused_scan_fold_kernel<true><<<f->grid, K_THREADS, f->smem_bytes, ctx->stream>>>(f->kd);
-    else fused_scan_fold_kernel<false><<<f->grid, K_THREADS, f->smem_bytes, ctx->stream>>>(f->kd);
+    scan_kernel_for(f->nc, f->r)<<<f->grid, f->nc + 32, f->smem_bytes, ctx->stream>>>(f->kd);
     ctx->launches++;
   }
   VDL_CUDA(ctx, cudaEventRecord(f->ev1, ctx->stream));

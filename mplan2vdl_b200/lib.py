@@ -15,7 +15,7 @@ VDL_PLAN_FUSE = 1
 BINARY_OPS = ["LogicalAnd", "LogicalOr", "BitwiseAnd", "BitwiseOr", "BitShift", "Equals", "Add", "Subtract",
               "Greater", "Multiply", "Divide", "Modulo"]
 FOLD_OPS = ["FoldSum", "FoldMin", "FoldMax", "FoldChoose", "FoldCount"]
-VDL_MAX_COLS, VDL_MAX_PREDS, VDL_MAX_KEYS, VDL_MAX_AGGS, VDL_MAX_FACTORS = 12, 8, 4, 10, 4
+VDL_MAX_COLS, VDL_MAX_PREDS, VDL_MAX_KEYS, VDL_MAX_AGGS, VDL_MAX_FACTORS = 12, 8, 4, 8, 3
 
 
 class VdlError(RuntimeError):
