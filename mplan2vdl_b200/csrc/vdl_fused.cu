@@ -218,42 +218,53 @@ struct GroupState {
   i64 *tbl;           // [gmax][nacc][NC]
 };
 
-// Fold one staged tile.  Thread ctid owns rows ctid + k*NC, k < R; the R rows are evaluated together inside
-// each predicate (R independent shared-memory loads in flight), rows that pass are then folded one by one.
+// Phase 1 of a tile (the plan's FoldSelect, Vlite.hs:721-730, done in shared memory): thread ctid evaluates the
+// predicates of rows ctid + k*NC, k < R, together (R independent shared-memory loads in flight) and the rows
+// that pass are compacted CTA-wide into `queue` with one warp-aggregated shared atomic per warp and k.
 template <int NC, int R>
-__device__ __forceinline__ void process_tile(const KDesc &d, const unsigned char *tile, i64 grow0, int nvalid, const GroupState &g, int ctid) {
+__device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char *tile, int nvalid, int ctid, int *qcount, uint16_t *queue) {
   unsigned pass = 0;
 #pragma unroll
   for (int k = 0; k < R; k++)
     if (ctid + k * NC < nvalid) pass |= 1u << k;
   pred_chain<0, NC, R>(d, tile, ctid, pass);
-  if (!pass) return;
-#pragma unroll 1
+  const int lane = ctid & 31;
+#pragma unroll
   for (int k = 0; k < R; k++) {
-    if (!(pass & (1u << k))) continue;
-    const int r = ctid + k * NC;
-    const i64 grow = grow0 + r;
-    i64 key = key_chain<0>(d, 0, tile, r, grow) & d.key_mask;
-    if ((u64)key >= (u64)d.domain) {   // the planner proves key < domain (mask); never expected
-      atomicAdd(d.errflag, 1);
-      continue;
+    const bool p = (pass >> k) & 1;
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    if (m) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(qcount, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (p) queue[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(ctid + k * NC);
     }
-    const int s = ((volatile int32_t *)g.slotmap)[key];
-    if (s >= 0) {
-      acc_chain<0, NC>(d, g.tbl + (size_t)s * d.nacc * NC + ctid, 1, tile, r, grow);
-    } else {
-      // first rows of a key in this CTA: fold straight into the global table and claim a slot for the rest
+  }
+}
+
+// Phase 2 (the Gathers + elementwise map + Fold of the plan): fold one selected row into the lane-private tables.
+template <int NC>
+__device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *tile, int r, i64 grow, const GroupState &g, int ctid) {
+  i64 key = key_chain<0>(d, 0, tile, r, grow) & d.key_mask;
+  if ((u64)key >= (u64)d.domain) {   // the planner proves key < domain (mask); never expected
+    atomicAdd(d.errflag, 1);
+    return;
+  }
+  const int s = ((volatile int32_t *)g.slotmap)[key];
+  if (s >= 0) {
+    acc_chain<0, NC>(d, g.tbl + (size_t)s * d.nacc * NC + ctid, 1, tile, r, grow);
+  } else {
+    // first rows of a key in this CTA: fold straight into the global table and claim a slot for the rest
 #pragma unroll 1
-      for (int j = 0; j < d.nacc; j++) acc_global(d.acc[j].op, d.table + (size_t)j * d.domain + key, acc_value_slow(d, j, tile, r, grow));
-      if (s == -1 && atomicCAS(&g.slotmap[key], -1, -2) == -1) {
-        int ns = atomicAdd(g.nslots, 1);
-        if (ns < d.gmax) {
-          g.slotkey[ns] = (int32_t)key;
-          __threadfence_block();
-          atomicExch(&g.slotmap[key], ns);
-        } else {
-          atomicExch(&g.slotmap[key], -3);
-        }
+    for (int j = 0; j < d.nacc; j++) acc_global(d.acc[j].op, d.table + (size_t)j * d.domain + key, acc_value_slow(d, j, tile, r, grow));
+    if (s == -1 && atomicCAS(&g.slotmap[key], -1, -2) == -1) {
+      int ns = atomicAdd(g.nslots, 1);
+      if (ns < d.gmax) {
+        g.slotkey[ns] = (int32_t)key;
+        __threadfence_block();
+        atomicExch(&g.slotmap[key], ns);
+      } else {
+        atomicExch(&g.slotmap[key], -3);
       }
     }
   }
@@ -262,12 +273,15 @@ __device__ __forceinline__ void process_tile(const KDesc &d, const unsigned char
 template <int NC, int R>
 __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __grid_constant__ KDesc d) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: [ring: stages * stage_bytes][full[stages]][empty[stages]][nslots][slotkey[gmax]][slotmap[domain]][tables]
+  // layout: [ring: stages * stage_bytes][full[stages]][empty[stages]][qcount[4]][queue[3][tile_rows]][nslots]
+  //         [slotkey[gmax]][slotmap[domain]][tables]
   unsigned char *ring = smem;
   uint64_t *full = (uint64_t *)(smem + (size_t)d.stages * d.stage_bytes);
   uint64_t *empty = full + d.stages;
+  int *qcount = (int *)(empty + d.stages);
+  uint16_t *queue = (uint16_t *)(qcount + 4);
   GroupState g;
-  g.nslots = (int32_t *)(empty + d.stages);
+  g.nslots = (int32_t *)(queue + 3 * (NC * R));
   g.slotkey = g.nslots + 2;
   g.slotmap = g.slotkey + d.gmax;
   size_t tbl_off = (size_t)((unsigned char *)(g.slotmap + d.domain) - smem);
@@ -285,6 +299,7 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     *g.nslots = dense ? (int)d.domain : 0;
+    qcount[0] = qcount[1] = qcount[2] = 0;
   }
   for (i64 k = tid; k < d.domain; k += NC + 32) g.slotmap[k] = dense ? (int32_t)k : -1;
   if (dense && tid < d.gmax) g.slotkey[tid] = tid;
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
 
   // -------------------------------------------------------------------- consumers
   const int ctid = tid - 32;
-  int st = 0;
+  int st = 0, q = 0;
   uint32_t ph = 0;
   // The rows past the last full tile form one more (partial) tile, owned by the CTA next in the round-robin; it
   // is staged with plain loads into the (by then idle) next ring stage and folded through the same code.
@@ -344,10 +359,19 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
       }
       consumer_barrier<NC>();
     }
-    process_tile<NC, R>(d, buf, d.row_base + tile * d.tile_rows, nvalid, g, ctid);
+    select_rows<NC, R>(d, buf, nvalid, ctid, &qcount[q], queue + q * (NC * R));
+    consumer_barrier<NC>();                       // the tile's selection is complete
+    if (ctid == 0) qcount[q == 0 ? 2 : q - 1] = 0;   // the queue two tiles ahead (= the previous tile's, folded by everyone)
+    const int nsel = ((volatile int *)qcount)[q];
+    const i64 grow0 = d.row_base + tile * d.tile_rows;
+    for (int e = ctid; e < nsel; e += NC) {
+      const int r = queue[q * (NC * R) + e];
+      fold_row<NC>(d, buf, r, grow0 + r, g, ctid);
+    }
     __syncwarp();
     if (lane == 0 && tile < d.ntiles) mbar_arrive(&empty[st]);
     if (++st == d.stages) { st = 0; ph ^= 1; }
+    if (++q == 3) q = 0;
   }
 
   // lane-private tables -> one global atomic per (warp, slot, accumulator)
@@ -466,7 +490,7 @@ struct vdl_fused {
 
 typedef void (*scan_kernel_fn)(const KDesc);
 static scan_kernel_fn scan_kernel_for(int nc, int r) {
-  if (nc == 512) return r == 2 ? fused_scan_fold_kernel<512, 2> : fused_scan_fold_kernel<512, 1>;
+  if (nc == 512) return r == 4 ? fused_scan_fold_kernel<512, 4> : (r == 2 ? fused_scan_fold_kernel<512, 2> : fused_scan_fold_kernel<512, 1>);
   return r == 4 ? fused_scan_fold_kernel<256, 4> : (r == 2 ? fused_scan_fold_kernel<256, 2> : fused_scan_fold_kernel<256, 1>);
 }
 
@@ -566,9 +590,10 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     int gmax = 1;
     while (gmax < desc->domain && gmax < 64 && (size_t)(gmax * 2) * k.nacc * nc * 8 <= 120 * 1024) gmax *= 2;
     if (nc == 512 && gmax < desc->domain && gmax < 8) continue;     // too few slots: halve the consumers instead
-    size_t fixed = (size_t)gmax * k.nacc * nc * 8 + (size_t)desc->domain * 4 + (size_t)gmax * 4 + 16 + 2 * 8 * 16 + 256;
-    for (int r = 1024 / nc; r >= 1 && !placed; r /= 2) {
+    for (int r = 2048 / nc; r >= 1 && !placed; r /= 2) {
+      if (r > 4) continue;
       int tile_rows = nc * r, off = 0;
+      size_t fixed = (size_t)gmax * k.nacc * nc * 8 + (size_t)desc->domain * 4 + (size_t)gmax * 4 + 16 + 2 * 8 * 16 + 256 + 16 + 3 * 2 * (size_t)tile_rows;
       for (int c = 0; c < k.ncols; c++) { k.soff[c] = off; off += ((tile_rows * k.width[c] + 127) / 128) * 128; }
       int stages = (int)(((long)smem_max - (long)fixed) / off);
       if (stages >= 3 || (r == 1 && stages >= 2 && nc == 256)) {
