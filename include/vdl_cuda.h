@@ -81,7 +81,8 @@ int64_t vdl_ctx_launch_count(vdl_ctx *ctx);
 /* Allocate a named column of `rows` values of `dtype` in HBM (padded for 16-byte bulk copies). */
 int vdl_column_alloc(vdl_ctx *ctx, const char *name, int dtype, int64_t rows, vdl_vec *out);
 /* Register caller-owned device memory (e.g. a torch tensor) as a named column; the memory must
- * stay valid while registered and be 16-byte aligned.  capacity_rows >= rows is how many rows
+ * stay valid AND UNCHANGED while registered (the library caches column statistics; drop and re-bind after
+ * writing to it) and be 16-byte aligned.  capacity_rows >= rows is how many rows
  * may be read past the logical end (bulk copies round the tail up to 16 bytes). */
 int vdl_column_bind(vdl_ctx *ctx, const char *name, int dtype, int64_t rows, int64_t capacity_rows,
                     void *device_ptr, vdl_vec *out);
@@ -93,6 +94,10 @@ int vdl_column_download(vdl_ctx *ctx, vdl_vec col, void *host, int64_t rows);
  * [row_offset, row_offset+rows): a shard generates its own row range in place. */
 int vdl_column_fill_synthetic(vdl_ctx *ctx, vdl_vec col, uint64_t seed, uint64_t stream, int kind,
                               int64_t vmin, int64_t stride, int64_t p0, int64_t p1, int64_t row_offset);
+/* Exact minimum / maximum of a column, computed on the device once and cached until the column is written
+ * again -- the executor's own copy of what the reference reads from bounds.csv (Config.hs:57).  The fused scan
+ * uses it to compare 8-byte predicate columns in 32 bits when every value fits. */
+int vdl_column_analyze(vdl_ctx *ctx, vdl_vec col, int64_t *vmin, int64_t *vmax);
 int vdl_column_lookup(vdl_ctx *ctx, const char *name, vdl_vec *out);
 int vdl_column_drop(vdl_ctx *ctx, const char *name);
 

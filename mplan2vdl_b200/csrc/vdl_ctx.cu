@@ -239,6 +239,7 @@ extern "C" int vdl_column_upload(vdl_ctx *ctx, vdl_vec col, const void *host, in
   if (!v || !host) return VDL_EINVAL;
   if (v->is_range || rows != v->len) return vdl_fail(ctx, VDL_EINVAL, "upload of %lld rows into a vector of %lld", (long long)rows, (long long)v->len);
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  v->has_stats = false;
   VDL_CUDA(ctx, cudaMemcpyAsync(v->ptr, host, (size_t)(rows * v->dtype), cudaMemcpyHostToDevice, ctx->stream));
   VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return VDL_OK;
@@ -287,6 +288,54 @@ extern "C" int vdl_vec_download(vdl_ctx *ctx, vdl_vec h, int64_t *host, int64_t 
   return VDL_OK;
 }
 
+// ---------------------------------------------------------------------------------- column statistics
+template <typename T>
+__global__ void __launch_bounds__(256) minmax_kernel(const T *__restrict__ in, i64 n, i64 *out /* [min, max] */) {
+  i64 lo = INT64_MAX, hi = INT64_MIN;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    i64 v = (i64)in[i];
+    lo = v < lo ? v : lo;
+    hi = v > hi ? v : hi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    i64 a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = a < lo ? a : lo;
+    hi = b > hi ? b : hi;
+  }
+  if ((threadIdx.x & 31) == 0 && n > 0) {
+    atomicMin((long long *)&out[0], (long long)lo);
+    atomicMax((long long *)&out[1], (long long)hi);
+  }
+}
+
+extern "C" int vdl_column_analyze(vdl_ctx *ctx, vdl_vec col, int64_t *vmin, int64_t *vmax) {
+  Vec *v = vec_get(ctx, col);
+  if (!v) return VDL_EINVAL;
+  if (v->is_range) return vdl_fail(ctx, VDL_EINVAL, "cannot analyze a range vector");
+  if (!v->has_stats) {
+    VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+    VDL_TRY(scratch_reserve(ctx, 16));
+    v = vec_get(ctx, col);
+    i64 init[2] = {INT64_MAX, INT64_MIN}, res[2];
+    VDL_CUDA(ctx, cudaMemcpyAsync(ctx->scratch, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+    if (v->len > 0) {
+      int blocks = ctx->sm_count * 8;
+      if (v->dtype == VDL_I32) minmax_kernel<int32_t><<<blocks, 256, 0, ctx->stream>>>((const int32_t *)v->ptr, v->len, (i64 *)ctx->scratch);
+      else minmax_kernel<i64><<<blocks, 256, 0, ctx->stream>>>((const i64 *)v->ptr, v->len, (i64 *)ctx->scratch);
+      ctx->launches++;
+    }
+    VDL_CUDA(ctx, cudaMemcpyAsync(res, ctx->scratch, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    v->vmin = res[0];
+    v->vmax = res[1];
+    v->has_stats = true;
+  }
+  if (vmin) *vmin = v->vmin;
+  if (vmax) *vmax = v->vmax;
+  return VDL_OK;
+}
+
 // ---------------------------------------------------------------------------------- synthetic
 // Counter-based recipe (specification shared with the host generators; mplan2vdl_b200/synth.py).
 __device__ __forceinline__ u64 splitmix64(u64 x) {
@@ -324,6 +373,7 @@ extern "C" int vdl_column_fill_synthetic(vdl_ctx *ctx, vdl_vec col, uint64_t see
   if (v->is_range) return vdl_fail(ctx, VDL_EINVAL, "cannot fill a range vector");
   if (kind < 0 || kind > 2 || (kind == VDL_SYNTH_FKDENSE && p1 <= 0) || (kind == VDL_SYNTH_UNIFORM && p0 <= 0))
     return vdl_fail(ctx, VDL_EINVAL, "bad synthetic spec kind=%d p0=%lld p1=%lld", kind, (long long)p0, (long long)p1);
+  v->has_stats = false;
   if (v->len == 0) return VDL_OK;
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   u64 base = host_splitmix64(seed ^ (stream * 0x9E3779B97F4A7C15ULL));

@@ -164,11 +164,12 @@ __device__ __forceinline__ void pred_chain(const KDesc &d, const unsigned char *
   if constexpr (I < VDL_MAX_PREDS) {
     if (I < d.npreds) {
       const KPred &P = d.pred[I];
-      if (P.w4) {      // 4-byte column: compare in 32 bits against bounds clamped to int32 by the host
+      if (P.w4) {      // 32-bit compare against bounds clamped to int32 by the host: a 4-byte column (w4 = 1), or
+                       // the low words of an 8-byte column whose values all fit int32 per its statistics (w4 = 2)
         const int32_t *p = (const int32_t *)(tile + P.soff);
 #pragma unroll
         for (int k = 0; k < R; k++) {
-          int32_t v = p[ctid + k * NC];
+          int32_t v = p[(ctid + k * NC) * P.w4];
           if (P.shr) v >>= P.shr;
           if ((uint32_t)v - (uint32_t)P.lo32 > P.span32) pass &= ~(1u << k);
         }
@@ -229,6 +230,18 @@ __device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char 
     if (ctid + k * NC < nvalid) pass |= 1u << k;
   pred_chain<0, NC, R>(d, tile, ctid, pass);
   const int lane = ctid & 31;
+  const unsigned any = __ballot_sync(0xffffffffu, pass != 0);
+  if (!any) return;
+  if (__popc(any) <= 4) {
+    // few selected rows in this warp (selective predicates): the owning lanes append on their own
+    if (pass) {
+      int base = atomicAdd(qcount, __popc(pass));
+#pragma unroll
+      for (int k = 0; k < R; k++)
+        if ((pass >> k) & 1) queue[base++] = (uint16_t)(ctid + k * NC);
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < R; k++) {
     const bool p = (pass >> k) & 1;
@@ -273,15 +286,17 @@ __device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *ti
 template <int NC, int R>
 __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __grid_constant__ KDesc d) {
   extern __shared__ __align__(128) unsigned char smem[];
-  // layout: [ring: stages * stage_bytes][full[stages]][empty[stages]][qcount[4]][queue[3][tile_rows]][nslots]
-  //         [slotkey[gmax]][slotmap[domain]][tables]
+  // layout: [ring: stages * stage_bytes][full[stages]][empty[stages]][sel[stages]][qcount[stages]]
+  //         [queue[stages][tile_rows]][nslots][slotkey[gmax]][slotmap[domain]][tables]
+  constexpr int NW = NC / 32;                 // consumer warps
   unsigned char *ring = smem;
   uint64_t *full = (uint64_t *)(smem + (size_t)d.stages * d.stage_bytes);
   uint64_t *empty = full + d.stages;
-  int *qcount = (int *)(empty + d.stages);
-  uint16_t *queue = (uint16_t *)(qcount + 4);
+  uint64_t *sel = empty + d.stages;
+  int *qcount = (int *)(sel + d.stages);
+  uint16_t *queue = (uint16_t *)(qcount + d.stages + (d.stages & 1));
   GroupState g;
-  g.nslots = (int32_t *)(queue + 3 * (NC * R));
+  g.nslots = (int32_t *)(queue + (size_t)d.stages * (NC * R));
   g.slotkey = g.nslots + 2;
   g.slotmap = g.slotkey + d.gmax;
   size_t tbl_off = (size_t)((unsigned char *)(g.slotmap + d.domain) - smem);
@@ -295,11 +310,12 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
   if (tid == 0) {
     for (int s = 0; s < d.stages; s++) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NC / 32);
+      mbar_init(&empty[s], NW);
+      mbar_init(&sel[s], NW);
+      qcount[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     *g.nslots = dense ? (int)d.domain : 0;
-    qcount[0] = qcount[1] = qcount[2] = 0;
   }
   for (i64 k = tid; k < d.domain; k += NC + 32) g.slotmap[k] = dense ? (int32_t)k : -1;
   if (dense && tid < d.gmax) g.slotkey[tid] = tid;
@@ -317,7 +333,8 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
       int st = 0;
       uint32_t ph = 0;
       for (i64 tile = blockIdx.x; tile < d.ntiles; tile += gridDim.x) {
-        mbar_wait(&empty[st], ph ^ 1);
+        mbar_wait(&empty[st], ph ^ 1);       // every consumer warp folded the stage's previous tile
+        qcount[st] = 0;                      // (published to the consumers by the arrive below)
         mbar_expect_tx(&full[st], (uint32_t)d.stage_tx);
         unsigned char *dst = ring + (size_t)st * d.stage_bytes;
 #pragma unroll 1
@@ -332,54 +349,69 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
   }
 
   // -------------------------------------------------------------------- consumers
-  const int ctid = tid - 32;
-  int st = 0, q = 0;
-  uint32_t ph = 0;
+  // Software-pipelined by one tile and free of CTA-wide barriers in steady state: iteration `it` SELECTS tile it
+  // (predicates -> the stage's compaction queue, then a non-blocking arrive on sel[stage]) and FOLDS tile it-1
+  // (wait on its sel barrier -- normally long complete --, fold this warp's share of the queue, release the stage).
+  const int ctid = tid - 32, cw = warp - 1;
   // The rows past the last full tile form one more (partial) tile, owned by the CTA next in the round-robin; it
-  // is staged with plain loads into the (by then idle) next ring stage and folded through the same code.
+  // is staged with plain loads into the (by then idle) next ring stage and goes through the same code.
   const i64 ntiles_all = d.ntiles + (d.ntiles * d.tile_rows < d.rows ? 1 : 0);
-  for (i64 tile = blockIdx.x; tile < ntiles_all; tile += gridDim.x) {
-    unsigned char *buf = ring + (size_t)st * d.stage_bytes;
-    int nvalid = d.tile_rows;
-    if (tile < d.ntiles) {
-      mbar_wait(&full[st], ph);
-    } else {
-      const i64 tail0 = d.ntiles * d.tile_rows;
-      nvalid = (int)(d.rows - tail0);
-      consumer_barrier<NC>();      // every consumer is done with the ring
+  int st = 0, pst = 0, it = 0;
+  uint32_t ph = 0, pph = 0;
+  i64 ptile = -1;
+  for (i64 tile = blockIdx.x;; tile += gridDim.x, it++) {
+    const bool have = tile < ntiles_all;
+    if (have) {
+      unsigned char *buf = ring + (size_t)st * d.stage_bytes;
+      int nvalid = d.tile_rows;
+      if (tile < d.ntiles) {
+        mbar_wait(&full[st], ph);
+      } else {
+        const i64 tail0 = d.ntiles * d.tile_rows;
+        nvalid = (int)(d.rows - tail0);
+        consumer_barrier<NC>();      // every warp is done with this stage's previous tile (folded >= 1 iteration ago)
+        if (ctid == 0) qcount[st] = 0;
 #pragma unroll 1
-      for (int c = 0; c < d.ncols; c++) {
-        if (d.width[c] == 4) {
-          const int32_t *src = (const int32_t *)d.col[c] + tail0;
-          for (int r = ctid; r < nvalid; r += NC) ((int32_t *)(buf + d.soff[c]))[r] = src[r];
-        } else {
-          const i64 *src = (const i64 *)d.col[c] + tail0;
-          for (int r = ctid; r < nvalid; r += NC) ((i64 *)(buf + d.soff[c]))[r] = src[r];
+        for (int c = 0; c < d.ncols; c++) {
+          if (d.width[c] == 4) {
+            const int32_t *src = (const int32_t *)d.col[c] + tail0;
+            for (int r = ctid; r < nvalid; r += NC) ((int32_t *)(buf + d.soff[c]))[r] = src[r];
+          } else {
+            const i64 *src = (const i64 *)d.col[c] + tail0;
+            for (int r = ctid; r < nvalid; r += NC) ((i64 *)(buf + d.soff[c]))[r] = src[r];
+          }
         }
+        consumer_barrier<NC>();
       }
-      consumer_barrier<NC>();
+      select_rows<NC, R>(d, buf, nvalid, ctid, &qcount[st], queue + (size_t)st * (NC * R));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sel[st]);
     }
-    select_rows<NC, R>(d, buf, nvalid, ctid, &qcount[q], queue + q * (NC * R));
-    consumer_barrier<NC>();                       // the tile's selection is complete
-    if (ctid == 0) qcount[q == 0 ? 2 : q - 1] = 0;   // the queue two tiles ahead (= the previous tile's, folded by everyone)
-    const int nsel = ((volatile int *)qcount)[q];
-    const i64 grow0 = d.row_base + tile * d.tile_rows;
-    for (int e = ctid; e < nsel; e += NC) {
-      const int r = queue[q * (NC * R) + e];
-      fold_row<NC>(d, buf, r, grow0 + r, g, ctid);
+    if (ptile >= 0) {
+      mbar_wait(&sel[pst], pph);
+      const int nsel = ((volatile int *)qcount)[pst];
+      const unsigned char *buf = ring + (size_t)pst * d.stage_bytes;
+      const i64 grow0 = d.row_base + ptile * d.tile_rows;
+      // queue entries in chunks of 32, dealt to the warps starting at a warp that rotates with the tile
+      int chunk = cw - ((it - 1) % NW);
+      if (chunk < 0) chunk += NW;
+      for (int e = chunk * 32 + lane; e < nsel; e += NC) {
+        const int r = queue[(size_t)pst * (NC * R) + e];
+        fold_row<NC>(d, buf, r, grow0 + r, g, ctid);
+      }
+      __syncwarp();
+      if (lane == 0 && ptile < d.ntiles) mbar_arrive(&empty[pst]);
     }
-    __syncwarp();
-    if (lane == 0 && tile < d.ntiles) mbar_arrive(&empty[st]);
+    if (!have) break;
+    ptile = tile; pst = st; pph = ph;
     if (++st == d.stages) { st = 0; ph ^= 1; }
-    if (++q == 3) q = 0;
   }
 
   // lane-private tables -> one global atomic per (warp, slot, accumulator)
   consumer_barrier<NC>();
   int ns = *((volatile int32_t *)g.nslots);
   if (ns > d.gmax) ns = d.gmax;
-  const int cw = warp - 1, ncw = NC / 32;
-  for (int p = cw; p < ns * d.nacc; p += ncw) {
+  for (int p = cw; p < ns * d.nacc; p += NW) {
     const int s = p / d.nacc, j = p % d.nacc, op = d.acc[j].op;
     i64 v = acc_identity(op);
     for (int t = lane; t < NC; t += 32) v = acc_combine(op, v, g.tbl[((size_t)s * d.nacc + j) * NC + t]);
@@ -593,13 +625,14 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     for (int r = 2048 / nc; r >= 1 && !placed; r /= 2) {
       if (r > 4) continue;
       int tile_rows = nc * r, off = 0;
-      size_t fixed = (size_t)gmax * k.nacc * nc * 8 + (size_t)desc->domain * 4 + (size_t)gmax * 4 + 16 + 2 * 8 * 16 + 256 + 16 + 3 * 2 * (size_t)tile_rows;
+      size_t fixed = (size_t)gmax * k.nacc * nc * 8 + (size_t)desc->domain * 4 + (size_t)gmax * 4 + 16 + 256;
+      size_t per_stage = 3 * 8 + 4 + 4 + 2 * (size_t)tile_rows;   // barriers, queue count, queue
       for (int c = 0; c < k.ncols; c++) { k.soff[c] = off; off += ((tile_rows * k.width[c] + 127) / 128) * 128; }
-      int stages = (int)(((long)smem_max - (long)fixed) / off);
+      int stages = (int)(((long)smem_max - (long)fixed) / (long)(off + per_stage));
       if (stages >= 3 || (r == 1 && stages >= 2 && nc == 256)) {
         k.tile_rows = tile_rows; k.stage_bytes = off; k.stage_tx = tile_rows * rowbytes; k.stages = std::min(stages, 12);
         k.gmax = gmax; f->nc = nc; f->r = r;
-        f->smem_bytes = (size_t)k.stages * k.stage_bytes + fixed;
+        f->smem_bytes = (size_t)k.stages * (k.stage_bytes + per_stage) + fixed;
         placed = true;
       }
     }
@@ -614,6 +647,12 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     KPred &p = k.pred[i];
     p.soff = k.soff[p.col];
     p.w4 = k.width[p.col] == 4;
+    if (!p.w4) {   // 8-byte column: when the column statistics say every (shifted) value fits int32, read low words only
+      i64 cmin, cmax;
+      int rc2 = vdl_column_analyze(ctx, desc->column[p.col], &cmin, &cmax);
+      if (rc2) { vdl_fused_destroy(f); return rc2; }
+      if ((cmin >> p.shr) >= INT32_MIN && (cmax >> p.shr) <= INT32_MAX) p.w4 = 2;
+    }
     if (p.w4) {   // values of a 4-byte column (shifted or not) lie in int32: clamp the bounds, compare in 32 bits
       i64 lo = std::max<i64>(p.lo, INT32_MIN), hi = std::min<i64>((i64)((u64)p.lo + p.span), INT32_MAX);
       if (lo > hi) f->always_false = true;

@@ -25,6 +25,8 @@ struct Vec {
   bool is_range = false;
   i64 from = 0, step = 0;
   i64 domain = -1;          // length of the vector these values index into; -1 unknown (App. G2)
+  bool has_stats = false;   // vmin/vmax computed on the device by vdl_column_analyze (invalidated by writes)
+  i64 vmin = 0, vmax = 0;
   std::string name;
 };
 

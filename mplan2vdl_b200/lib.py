@@ -63,6 +63,7 @@ SYMBOLS = [
     ("vdl_column_upload", _I, [_P, C.c_int32, _P, _L]),
     ("vdl_column_download", _I, [_P, C.c_int32, _P, _L]),
     ("vdl_column_fill_synthetic", _I, [_P, C.c_int32, C.c_uint64, C.c_uint64, _I, _L, _L, _L, _L, _L]),
+    ("vdl_column_analyze", _I, [_P, C.c_int32, C.POINTER(_L), C.POINTER(_L)]),
     ("vdl_column_lookup", _I, [_P, C.c_char_p, C.POINTER(C.c_int32)]),
     ("vdl_column_drop", _I, [_P, C.c_char_p]),
     ("vdl_vec_len", _I, [_P, C.c_int32, C.POINTER(_L)]),
