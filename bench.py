@@ -117,6 +117,8 @@ def cpu_oracle_rate(cat, query: str, sf: float, target_seconds: float = 12.0, ma
     probe_rows = 2_000_000
     t = min(run(probe_rows, 2))
     rows = int(min(max_rows, max(probe_rows, probe_rows * target_seconds / max(t, 1e-6) / max(steps, 1))))
+    if steps == 1:       # bounded sample, repeated until about target_seconds of CPU work have been timed
+        steps = int(max(1, min(40, target_seconds / max(t * rows / probe_rows, 1e-6))))
     secs = run(rows, steps)
     return rows / statistics.median(secs), rows, threads, secs
 
@@ -205,28 +207,10 @@ def main():
     info = tpch.load_synthetic(ctx, cat, names, args.sf, rank=rank, world=world)
     rows_here = info["rows"]["lineitem"]
     plan = ctx.plan(text)
-    plan.set_row_base(info["row_base"])
     ext = torch.cuda.ExternalStream(ctx.stream, device=local)
-
-    class _View:      # library-owned device memory as a torch tensor (for NCCL)
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
-
-    gathered = []
-
-    def step():
-        plan.run_local()
-        if world > 1:
-            ptrs = []
-            with torch.cuda.stream(ext):
-                for i in range(plan.num_fused):
-                    p, n = plan.partials(i)
-                    if len(gathered) <= i:
-                        gathered.append(torch.empty(world * n, dtype=torch.int64, device=f"cuda:{local}"))
-                    dist.all_gather_into_tensor(gathered[i], torch.as_tensor(_View(p, n), device=f"cuda:{local}"))
-                    ptrs.append(gathered[i].data_ptr())
-            return plan.finish(ptrs, world)
-        return plan.finish()
+    from mplan2vdl_b200.dist import ShardedPlan
+    sharded = ShardedPlan(ctx, plan, rank, world, info["row_base"])
+    step = sharded.step
 
     def barrier():
         ctx.synchronize()
@@ -320,7 +304,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, srows, threads, secs = cpu_oracle_rate(cat, args.query, args.sf)
         cpu = {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
-               "sample": f"first {srows} lineitem rows of the same synthetic table; op-at-a-time CPU oracle (OpenMP), {statistics.median(secs):.2f} s"}
+               "sample": f"first {srows} lineitem rows of the same synthetic table; op-at-a-time CPU oracle (OpenMP), "
+                         f"{len(secs)} runs, median {statistics.median(secs):.2f} s, total {sum(secs):.1f} s"}
 
     if rank == 0:
         line = {

@@ -181,6 +181,9 @@ int vdl_fused_partials(vdl_fused *f, void **device_ptr, int64_t *n_int64);
 int vdl_fused_finalize(vdl_fused *f, const void *all_partials, int nranks);
 int vdl_fused_num_groups(vdl_fused *f, int64_t *ngroups);   /* synchronises */
 int vdl_fused_result(vdl_fused *f, int fold_index, vdl_vec *out);
+/* Host copy of one fold's result (pinned memory, valid until the next launch).  The group count, the error
+ * counter and all fold results of a scan come back in ONE device->host copy. */
+int vdl_fused_result_host(vdl_fused *f, int fold_index, const int64_t **data, int64_t *len);
 int vdl_fused_destroy(vdl_fused *f);
 /* Duration of the last vdl_fused_launch's scan kernel alone, CUDA events on the context stream. */
 int vdl_fused_last_kernel_ms(vdl_fused *f, float *ms);

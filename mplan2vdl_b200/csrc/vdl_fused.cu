@@ -59,7 +59,8 @@ struct FinDesc {
   int32_t acc_op[K_MAX_ACC];
   int32_t out_kind[VDL_MAX_AGGS], out_idx[VDL_MAX_AGGS];   // kind 0: accumulator, 1: choose
   i64 *out[VDL_MAX_AGGS];
-  i64 *ngroups;
+  i64 *ngroups;                  // [0] number of groups, [1] snapshot of the context's error counter
+  const int *errflag;
 };
 
 // ------------------------------------------------------------------------------ PTX helpers
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(256, 1) fused_finalize_kernel(const __grid_con
     if (tid == 0) running += total;
     __syncthreads();
   }
-  if (tid == 0) *f.ngroups = running;
+  if (tid == 0) { f.ngroups[0] = running; f.ngroups[1] = *f.errflag; }
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -511,7 +512,8 @@ struct vdl_fused {
   vdl_vec table = 0;
   vdl_vec out[VDL_MAX_AGGS] = {0};
   int nout = 0;
-  i64 *d_ngroups = nullptr;
+  i64 *d_outbuf = nullptr;       // [nout][domain] fold results, then [ngroups, errflag]: fetched with ONE copy
+  i64 *h_outbuf = nullptr;       // pinned mirror
   i64 ngroups = -1;
   bool finalized = false, always_false = false;
   size_t smem_bytes = 0;
@@ -688,12 +690,24 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   int rc = vec_new(ctx, VDL_I64, (i64)(k.nacc + k.nchoose) * k.domain, &f->table);
   if (rc) { delete f; return rc; }
   k.table = (i64 *)ctx->vecs[f->table].ptr;
-  for (int i = 0; i < f->nout; i++) {
-    rc = vec_new(ctx, VDL_I64, k.domain, &f->out[i]);
-    if (rc) { vdl_fused_destroy(f); return rc; }
-    f->fd.out[i] = (i64 *)ctx->vecs[f->out[i]].ptr;
+  {
+    size_t nb = ((size_t)f->nout * k.domain + 2) * sizeof(i64);
+    if (cudaMalloc(&f->d_outbuf, nb) != cudaSuccess || cudaMallocHost(&f->h_outbuf, nb) != cudaSuccess) {
+      vdl_fused_destroy(f);
+      return vdl_fail(ctx, VDL_ENOMEM, "fused scan: result buffers");
+    }
   }
-  if (cudaMalloc(&f->d_ngroups, sizeof(i64)) != cudaSuccess) { vdl_fused_destroy(f); return vdl_fail(ctx, VDL_ENOMEM, "cudaMalloc ngroups"); }
+  for (int i = 0; i < f->nout; i++) {   // the fold results are views into the one result buffer
+    rc = vec_new_range(ctx, 0, 0, 0, &f->out[i]);
+    if (rc) { vdl_fused_destroy(f); return rc; }
+    Vec &v = ctx->vecs[f->out[i]];
+    v.is_range = false;
+    v.ptr = f->d_outbuf + (size_t)i * k.domain;
+    v.dtype = VDL_I64;
+    v.cap_rows = k.domain;
+    v.domain = -1;
+    f->fd.out[i] = (i64 *)v.ptr;
+  }
   cudaEventCreate(&f->ev0);
   cudaEventCreate(&f->ev1);
   f->fd.domain = k.domain;
@@ -703,7 +717,8 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   f->fd.first_idx = k.first_idx;
   f->fd.nout = f->nout;
   f->fd.part_stride = (i64)(k.nacc + k.nchoose) * k.domain;
-  f->fd.ngroups = f->d_ngroups;
+  f->fd.ngroups = f->d_outbuf + (size_t)f->nout * k.domain;
+  f->fd.errflag = ctx->d_errflag;
   for (int j = 0; j < k.nacc; j++) f->fd.acc_op[j] = k.acc[j].op;
 
   cudaError_t e = cudaFuncSetAttribute(scan_kernel_for(f->nc, f->r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
@@ -759,17 +774,37 @@ extern "C" int vdl_fused_finalize(vdl_fused *f, const void *all_partials, int nr
   return VDL_OK;
 }
 
-extern "C" int vdl_fused_num_groups(vdl_fused *f, int64_t *ngroups) {
-  if (!f || !ngroups) return VDL_EINVAL;
+// One device->host copy brings the group count, the error counter and every fold result.
+static int fused_fetch(vdl_fused *f) {
   vdl_ctx *ctx = f->ctx;
   if (!f->finalized) return vdl_fail(ctx, VDL_EINVAL, "fused scan not finalized");
-  if (f->ngroups < 0) {
-    VDL_CUDA(ctx, cudaMemcpyAsync(&f->ngroups, f->d_ngroups, sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
-    VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    VDL_TRY(check_errflag(ctx, "fused scan key"));
-    for (int i = 0; i < f->nout; i++) ctx->vecs[f->out[i]].len = f->ngroups;
+  if (f->ngroups >= 0) return VDL_OK;
+  size_t n = (size_t)f->nout * f->kd.domain + 2;
+  VDL_CUDA(ctx, cudaMemcpyAsync(f->h_outbuf, f->d_outbuf, n * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  i64 ng = f->h_outbuf[n - 2], err = f->h_outbuf[n - 1];
+  if (err) {
+    cudaMemsetAsync(ctx->d_errflag, 0, sizeof(int), ctx->stream);
+    return vdl_fail(ctx, VDL_ERANGE, "fused scan: %lld rows produced a group key outside the key domain", (long long)err);
   }
+  f->ngroups = ng;
+  for (int i = 0; i < f->nout; i++) ctx->vecs[f->out[i]].len = ng;
+  return VDL_OK;
+}
+
+extern "C" int vdl_fused_num_groups(vdl_fused *f, int64_t *ngroups) {
+  if (!f || !ngroups) return VDL_EINVAL;
+  VDL_TRY(fused_fetch(f));
   *ngroups = f->ngroups;
+  return VDL_OK;
+}
+
+// Host copy of fold `fold_index`'s result (valid until the next launch); no device work beyond the one fetch.
+extern "C" int vdl_fused_result_host(vdl_fused *f, int fold_index, const int64_t **data, int64_t *len) {
+  if (!f || !data || !len || fold_index < 0 || fold_index >= f->nout) return VDL_EINVAL;
+  VDL_TRY(fused_fetch(f));
+  *data = f->h_outbuf + (size_t)fold_index * f->kd.domain;
+  *len = f->ngroups;
   return VDL_OK;
 }
 
@@ -797,7 +832,8 @@ extern "C" int vdl_fused_destroy(vdl_fused *f) {
   if (f->table) vdl_vec_free(ctx, f->table);
   for (int i = 0; i < f->nout; i++)
     if (f->out[i]) vdl_vec_free(ctx, f->out[i]);
-  if (f->d_ngroups) cudaFree(f->d_ngroups);
+  if (f->d_outbuf) cudaFree(f->d_outbuf);
+  if (f->h_outbuf) cudaFreeHost(f->h_outbuf);
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);
   delete f;

@@ -1,0 +1,70 @@
+"""Row-range sharding on the GPU: N ranks emulated on one device (one context per rank), their partial tables
+concatenated the way the NCCL all-gather lays them out, merged by the finalize kernel."""
+import numpy as np
+import pytest
+
+from mplan2vdl_b200 import tpch
+from util import Q1_COLS, Q6_COLS, assert_same, host_columns, plan_text, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("query,colnames", [("q06.vdl", Q6_COLS), ("q01.vdl", Q1_COLS)])
+@pytest.mark.parametrize("world", [2, 3])
+def test_emulated_ranks_merge_to_the_whole_table_answer(catalog, query, colnames, world):
+    import torch
+    from mplan2vdl_b200.dist import DeviceView
+    from mplan2vdl_b200.executor import Context
+    rows, text = 50_000, plan_text(query)
+    names = ["lineitem." + c for c in colnames]
+    want = run_oracle(text, host_columns(catalog, names, {"lineitem": rows}))
+    ctxs, plans, tables = [], [], []
+    for rank in range(world):
+        start, n = tpch.shard_range(rows, rank, world)
+        ctx = Context(0)
+        for k, v in host_columns(catalog, names, {"lineitem": n}, row_offset=start).items():
+            ctx.upload_column(k, v)
+        plan = ctx.plan(text)
+        plan.set_row_base(start)
+        plan.run_local()
+        assert plan.num_fused == 1
+        ptr, cnt = plan.partials(0)
+        ctx.synchronize()
+        tables.append(torch.as_tensor(DeviceView(ptr, cnt), device="cuda:0").clone())
+        ctxs.append(ctx)
+        plans.append(plan)
+    gathered = torch.cat(tables)
+    torch.cuda.synchronize()
+    for rank in range(world):          # every rank finalizes from the same gathered buffer and gets the global answer
+        got = plans[rank].finish([gathered.data_ptr()], world)
+        assert_same(got, want)
+    for p, c in zip(plans, ctxs):
+        p.close()
+        c.close()
+
+
+def test_empty_shard_is_harmless(catalog):
+    """More ranks than aligned row blocks: trailing ranks own zero rows."""
+    import torch
+    from mplan2vdl_b200.dist import DeviceView
+    from mplan2vdl_b200.executor import Context
+    rows, world, text = 5000, 3, plan_text("q06.vdl")
+    names = ["lineitem." + c for c in Q6_COLS]
+    want = run_oracle(text, host_columns(catalog, names, {"lineitem": rows}))
+    tables, keep = [], []
+    for rank in range(world):
+        start, n = tpch.shard_range(rows, rank, world)
+        ctx = Context(0)
+        for k, v in host_columns(catalog, names, {"lineitem": n}, row_offset=start).items():
+            ctx.upload_column(k, v)
+        plan = ctx.plan(text)
+        plan.set_row_base(start)
+        plan.run_local()
+        ptr, cnt = plan.partials(0)
+        ctx.synchronize()
+        tables.append(torch.as_tensor(DeviceView(ptr, cnt), device="cuda:0").clone())
+        keep.append((ctx, plan))
+    assert tpch.shard_range(rows, 2, world)[1] == 0
+    gathered = torch.cat(tables)
+    torch.cuda.synchronize()
+    assert_same(keep[0][1].finish([gathered.data_ptr()], world), want)
