@@ -184,6 +184,8 @@ int vdl_fused_result(vdl_fused *f, int fold_index, vdl_vec *out);
 /* Host copy of one fold's result (pinned memory, valid until the next launch).  The group count, the error
  * counter and all fold results of a scan come back in ONE device->host copy. */
 int vdl_fused_result_host(vdl_fused *f, int fold_index, const int64_t **data, int64_t *len);
+/* Which instantiation of the scan kernel the descriptor was matched to: "generic" or the name of a static shape. */
+const char *vdl_fused_shape_name(vdl_fused *f);
 int vdl_fused_destroy(vdl_fused *f);
 /* Duration of the last vdl_fused_launch's scan kernel alone, CUDA events on the context stream. */
 int vdl_fused_last_kernel_ms(vdl_fused *f, float *ms);

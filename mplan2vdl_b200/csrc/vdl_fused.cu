@@ -20,6 +20,7 @@
 // over a per-CTA compacted slot map so that sparse key domains (Q1: 6 of 32 slots) stay small.
 // HBM traffic = the columns, once.  Roofline: HBM.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -31,7 +32,7 @@
 #define K_MAX_CHOOSE 6
 
 // soff / w4 are derived by the host from col: byte offset of the column inside a staged tile, 4-byte flag.
-struct KAffine { int32_t col, shr; i64 a, b; int32_t soff, w4; };
+struct KAffine { int32_t col, shr; i64 a, b; int32_t soff, w4; int32_t narrow, pad; };   // narrow: host-side, see FF_NARROW
 struct KPred { int32_t col, shr; i64 lo; u64 span; int32_t soff, w4; int32_t lo32; uint32_t span32; };
 struct KKey { KAffine e; int32_t shl, pad; };
 // op: 0 sum, 1 min, 2 max.  chain: value = value of the previous accumulator x own factors (prefix sharing:
@@ -122,6 +123,35 @@ __device__ __forceinline__ i64 warp_reduce(int op, i64 v) {
 // Every loop over the descriptor (predicates, key parts, accumulators, factors) is unrolled as a chain of
 // nested uniform `if (I < n)` tests, so each descriptor field is a constant-bank immediate operand of the
 // instruction that uses it (no loads, no dependent latency) and unused slots cost one uniform branch.
+//
+// SHAPES.  The same code is instantiated over a shape-traits class S.  GenericShape answers every structural
+// question (how many predicates / key parts / accumulators / factors, 4- or 8-byte column, shift or not, b == 1,
+// a == 0, fits int32 ...) from the descriptor at run time, so one kernel runs any plan.  A static shape
+// (vdl_shapes.cuh) answers them at compile time: the uniform tests fold away and arithmetic narrows to 32 bits
+// where the column statistics allow (the executor's use of the reference's bound inference, Vlite.hs:417-467),
+// leaving straight-line code -- while every constant (bounds, offsets, a, b, shifts, masks) stays a run-time
+// descriptor field.  The host launches a static instantiation only when the prepared descriptor satisfies every
+// assumption the shape makes (shape_matches), otherwise the generic one: identical results either way.
+
+// factor flags (what the static code may assume about a KAffine)
+#define FF_W4 1        // 4-byte column (else 8-byte)
+#define FF_SHR0 2      // shr == 0
+#define FF_B1 4        // b == 1
+#define FF_BM1 8       // b == -1
+#define FF_A0 16       // a == 0
+#define FF_CONST 32    // col == -1
+#define FF_ROWID 64    // col == -2
+#define FF_NARROW 128  // leaf and a + b*leaf fit int32 (column statistics)
+
+struct GenericShape {
+  static constexpr bool kStatic = false;
+  static constexpr int NPREDS = 0, NKEYS = 0, NACC = 0, KEY32 = 0;
+  static constexpr int PRED_MODE[VDL_MAX_PREDS] = {}, PRED_SHR0[VDL_MAX_PREDS] = {};
+  static constexpr int KEY_FLAGS[VDL_MAX_KEYS] = {}, KEY_SHL0[VDL_MAX_KEYS] = {};
+  static constexpr int ACC_OP[K_MAX_ACC] = {}, ACC_CHAIN[K_MAX_ACC] = {}, ACC_NFAC[K_MAX_ACC] = {};
+  static constexpr int FAC[K_MAX_ACC][VDL_MAX_FACTORS] = {};
+};
+
 __device__ __forceinline__ i64 tile_leaf(const KAffine &A, const unsigned char *tile, int r, i64 grow) {
   if (A.col == -2) return grow;
   i64 v = A.w4 ? (i64)((const int32_t *)(tile + A.soff))[r] : ((const i64 *)(tile + A.soff))[r];
@@ -135,20 +165,52 @@ __device__ __forceinline__ i64 tile_affine(const KAffine &A, const unsigned char
   if (A.b != 1) leaf = (i64)((u64)A.b * (u64)leaf);
   return (i64)((u64)A.a + (u64)leaf);
 }
-template <int F>
+// the same with the structure known at compile time; 32-bit arithmetic when FF_NARROW
+template <int FL>
+__device__ __forceinline__ int32_t affine32(const KAffine &A, const unsigned char *tile, int r) {
+  int32_t v = ((const int32_t *)(tile + A.soff))[(FL & FF_W4) ? r : 2 * r];   // low word of an 8-byte value
+  if (!(FL & FF_SHR0)) v >>= A.shr;
+  if (FL & FF_BM1) v = -v;
+  else if (!(FL & FF_B1)) v *= (int32_t)A.b;
+  if (!(FL & FF_A0)) v += (int32_t)A.a;
+  return v;
+}
+template <int FL>
+__device__ __forceinline__ i64 affine_static(const KAffine &A, const unsigned char *tile, int r, i64 grow) {
+  if constexpr (FL & FF_CONST) return A.a;
+  else if constexpr (FL & FF_NARROW) return (i64)affine32<FL>(A, tile, r);
+  else {
+    i64 v;
+    if constexpr (FL & FF_ROWID) v = grow;
+    else {
+      v = (FL & FF_W4) ? (i64)((const int32_t *)(tile + A.soff))[r] : ((const i64 *)(tile + A.soff))[r];
+      if (!(FL & FF_SHR0)) v >>= A.shr;
+    }
+    if (FL & FF_BM1) v = (i64)(0 - (u64)v);
+    else if (!(FL & FF_B1)) v = (i64)((u64)A.b * (u64)v);
+    if (!(FL & FF_A0)) v = (i64)((u64)A.a + (u64)v);
+    return v;
+  }
+}
+
+template <class S, int J, int F>
 __device__ __forceinline__ i64 factor_chain(const KAcc &A, i64 v, const unsigned char *tile, int r, i64 grow) {
   if constexpr (F < VDL_MAX_FACTORS) {
-    if (F < A.nfac) {
-      i64 x = tile_affine(A.fac[F], tile, r, grow);
-      v = (F == 0 && !A.chain) ? x : (i64)((u64)v * (u64)x);
-      return factor_chain<F + 1>(A, v, tile, r, grow);
+    if constexpr (S::kStatic) {
+      if constexpr (F < S::ACC_NFAC[J]) {
+        i64 x = affine_static<S::FAC[J][F]>(A.fac[F], tile, r, grow);
+        v = (F == 0 && !S::ACC_CHAIN[J]) ? x : (i64)((u64)v * (u64)x);
+        return factor_chain<S, J, F + 1>(A, v, tile, r, grow);
+      }
+    } else {
+      if (F < A.nfac) {
+        i64 x = tile_affine(A.fac[F], tile, r, grow);
+        v = (F == 0 && !A.chain) ? x : (i64)((u64)v * (u64)x);
+        return factor_chain<S, J, F + 1>(A, v, tile, r, grow);
+      }
     }
   }
   return v;
-}
-// value of accumulator A given the previous accumulator's value (used when A.chain)
-__device__ __forceinline__ i64 acc_value(const KAcc &A, i64 prev, const unsigned char *tile, int r, i64 grow) {
-  return factor_chain<0>(A, A.chain ? prev : 1, tile, r, grow);
 }
 // generic (looping) form for the rare global-atomic path
 __device__ __noinline__ i64 acc_value_slow(const KDesc &d, int j, const unsigned char *tile, int r, i64 grow) {
@@ -160,18 +222,20 @@ __device__ __noinline__ i64 acc_value_slow(const KDesc &d, int j, const unsigned
   return v;
 }
 
-template <int I, int NC, int R>
+template <class S, int I, int NC, int R>
 __device__ __forceinline__ void pred_chain(const KDesc &d, const unsigned char *tile, int ctid, unsigned &pass) {
-  if constexpr (I < VDL_MAX_PREDS) {
-    if (I < d.npreds) {
+  if constexpr (I < VDL_MAX_PREDS && (!S::kStatic || I < S::NPREDS)) {
+    if (S::kStatic || I < d.npreds) {
       const KPred &P = d.pred[I];
-      if (P.w4) {      // 32-bit compare against bounds clamped to int32 by the host: a 4-byte column (w4 = 1), or
-                       // the low words of an 8-byte column whose values all fit int32 per its statistics (w4 = 2)
+      const int mode = S::kStatic ? S::PRED_MODE[I] : P.w4;
+      const bool shr0 = S::kStatic ? (bool)S::PRED_SHR0[I] : (P.shr == 0);
+      if (mode) {      // 32-bit compare against bounds clamped to int32 by the host: a 4-byte column (mode 1), or
+                       // the low words of an 8-byte column whose values all fit int32 per its statistics (mode 2)
         const int32_t *p = (const int32_t *)(tile + P.soff);
 #pragma unroll
         for (int k = 0; k < R; k++) {
-          int32_t v = p[(ctid + k * NC) * P.w4];
-          if (P.shr) v >>= P.shr;
+          int32_t v = p[(ctid + k * NC) * mode];
+          if (!shr0) v >>= P.shr;
           if ((uint32_t)v - (uint32_t)P.lo32 > P.span32) pass &= ~(1u << k);
         }
       } else {
@@ -179,35 +243,49 @@ __device__ __forceinline__ void pred_chain(const KDesc &d, const unsigned char *
 #pragma unroll
         for (int k = 0; k < R; k++) {
           i64 v = p[ctid + k * NC];
-          if (P.shr) v >>= P.shr;
+          if (!shr0) v >>= P.shr;
           if ((u64)v - (u64)P.lo > P.span) pass &= ~(1u << k);
         }
       }
-      pred_chain<I + 1, NC, R>(d, tile, ctid, pass);
+      pred_chain<S, I + 1, NC, R>(d, tile, ctid, pass);
     }
   }
 }
 
-template <int Q>
+template <class S, int Q>
 __device__ __forceinline__ i64 key_chain(const KDesc &d, i64 key, const unsigned char *tile, int r, i64 grow) {
-  if constexpr (Q < VDL_MAX_KEYS) {
-    if (Q < d.nkeys) {
-      i64 x = tile_affine(d.key[Q].e, tile, r, grow);
-      if (d.key[Q].shl) x = (i64)((u64)x << d.key[Q].shl);
-      return key_chain<Q + 1>(d, key | x, tile, r, grow);
+  if constexpr (Q < VDL_MAX_KEYS && (!S::kStatic || Q < S::NKEYS)) {
+    if (S::kStatic || Q < d.nkeys) {
+      i64 x;
+      if constexpr (S::kStatic) x = affine_static<S::KEY_FLAGS[Q]>(d.key[Q].e, tile, r, grow);
+      else x = tile_affine(d.key[Q].e, tile, r, grow);
+      if (!(S::kStatic && S::KEY_SHL0[Q]) && d.key[Q].shl) x = (i64)((u64)x << d.key[Q].shl);
+      return key_chain<S, Q + 1>(d, key | x, tile, r, grow);
     }
+  }
+  return key;
+}
+// all key parts narrow: the whole key in 32-bit arithmetic
+template <class S, int Q>
+__device__ __forceinline__ int32_t key_chain32(const KDesc &d, int32_t key, const unsigned char *tile, int r) {
+  if constexpr (Q < S::NKEYS) {
+    int32_t x = affine32<S::KEY_FLAGS[Q]>(d.key[Q].e, tile, r);
+    if (!S::KEY_SHL0[Q]) x <<= d.key[Q].shl;
+    return key_chain32<S, Q + 1>(d, key | x, tile, r);
   }
   return key;
 }
 
 // lane-private read-modify-write of accumulator J and all following ones
-template <int J, int NC>
+template <class S, int J, int NC>
 __device__ __forceinline__ void acc_chain(const KDesc &d, i64 *t, i64 prev, const unsigned char *tile, int r, i64 grow) {
-  if constexpr (J < K_MAX_ACC) {
-    if (J < d.nacc) {
-      i64 v = acc_value(d.acc[J], prev, tile, r, grow);
-      t[J * NC] = acc_combine(d.acc[J].op, t[J * NC], v);
-      acc_chain<J + 1, NC>(d, t, v, tile, r, grow);
+  if constexpr (J < K_MAX_ACC && (!S::kStatic || J < S::NACC)) {
+    if (S::kStatic || J < d.nacc) {
+      const bool chain = S::kStatic ? (bool)S::ACC_CHAIN[J] : (bool)d.acc[J].chain;
+      const int op = S::kStatic ? S::ACC_OP[J] : d.acc[J].op;
+      i64 v = factor_chain<S, J, 0>(d.acc[J], chain ? prev : 1, tile, r, grow);
+      t[J * NC] = acc_combine(op, t[J * NC], v);
+      acc_chain<S, J + 1, NC>(d, t, v, tile, r, grow);
     }
   }
 }
@@ -223,13 +301,13 @@ struct GroupState {
 // Phase 1 of a tile (the plan's FoldSelect, Vlite.hs:721-730, done in shared memory): thread ctid evaluates the
 // predicates of rows ctid + k*NC, k < R, together (R independent shared-memory loads in flight) and the rows
 // that pass are compacted CTA-wide into `queue` with one warp-aggregated shared atomic per warp and k.
-template <int NC, int R>
+template <class S, int NC, int R>
 __device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char *tile, int nvalid, int ctid, int *qcount, uint16_t *queue) {
   unsigned pass = 0;
 #pragma unroll
   for (int k = 0; k < R; k++)
     if (ctid + k * NC < nvalid) pass |= 1u << k;
-  pred_chain<0, NC, R>(d, tile, ctid, pass);
+  pred_chain<S, 0, NC, R>(d, tile, ctid, pass);
   const int lane = ctid & 31;
   const unsigned any = __ballot_sync(0xffffffffu, pass != 0);
   if (!any) return;
@@ -257,16 +335,18 @@ __device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char 
 }
 
 // Phase 2 (the Gathers + elementwise map + Fold of the plan): fold one selected row into the lane-private tables.
-template <int NC>
+template <class S, int NC>
 __device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *tile, int r, i64 grow, const GroupState &g, int ctid) {
-  i64 key = key_chain<0>(d, 0, tile, r, grow) & d.key_mask;
+  i64 key;
+  if constexpr (S::kStatic && S::KEY32) key = (i64)(key_chain32<S, 0>(d, 0, tile, r) & (int32_t)d.key_mask);
+  else key = key_chain<S, 0>(d, 0, tile, r, grow) & d.key_mask;
   if ((u64)key >= (u64)d.domain) {   // the planner proves key < domain (mask); never expected
     atomicAdd(d.errflag, 1);
     return;
   }
   const int s = ((volatile int32_t *)g.slotmap)[key];
   if (s >= 0) {
-    acc_chain<0, NC>(d, g.tbl + (size_t)s * d.nacc * NC + ctid, 1, tile, r, grow);
+    acc_chain<S, 0, NC>(d, g.tbl + (size_t)s * d.nacc * NC + ctid, 1, tile, r, grow);
   } else {
     // first rows of a key in this CTA: fold straight into the global table and claim a slot for the rest
 #pragma unroll 1
@@ -284,7 +364,7 @@ __device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *ti
   }
 }
 
-template <int NC, int R>
+template <class S, int NC, int R>
 __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __grid_constant__ KDesc d) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: [ring: stages * stage_bytes][full[stages]][empty[stages]][sel[stages]][qcount[stages]]
@@ -384,7 +464,7 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
         }
         consumer_barrier<NC>();
       }
-      select_rows<NC, R>(d, buf, nvalid, ctid, &qcount[st], queue + (size_t)st * (NC * R));
+      select_rows<S, NC, R>(d, buf, nvalid, ctid, &qcount[st], queue + (size_t)st * (NC * R));
       __syncwarp();
       if (lane == 0) mbar_arrive(&sel[st]);
     }
@@ -398,7 +478,7 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
       if (chunk < 0) chunk += NW;
       for (int e = chunk * 32 + lane; e < nsel; e += NC) {
         const int r = queue[(size_t)pst * (NC * R) + e];
-        fold_row<NC>(d, buf, r, grow0 + r, g, ctid);
+        fold_row<S, NC>(d, buf, r, grow0 + r, g, ctid);
       }
       __syncwarp();
       if (lane == 0 && ptile < d.ntiles) mbar_arrive(&empty[pst]);
@@ -505,6 +585,7 @@ __global__ void __launch_bounds__(256, 1) fused_finalize_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------ host side
+typedef void (*scan_kernel_fn)(const KDesc);
 struct vdl_fused {
   vdl_ctx *ctx = nullptr;
   KDesc kd;
@@ -518,18 +599,51 @@ struct vdl_fused {
   bool finalized = false, always_false = false;
   size_t smem_bytes = 0;
   int grid = 1, nc = 256, r = 4;
+  scan_kernel_fn kernel = nullptr;
+  const char *shape = "generic";
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
 };
 
-typedef void (*scan_kernel_fn)(const KDesc);
+#include "vdl_shapes.cuh"
+
+template <class S>
 static scan_kernel_fn scan_kernel_for(int nc, int r) {
-  if (nc == 512) return r == 4 ? fused_scan_fold_kernel<512, 4> : (r == 2 ? fused_scan_fold_kernel<512, 2> : fused_scan_fold_kernel<512, 1>);
-  return r == 4 ? fused_scan_fold_kernel<256, 4> : (r == 2 ? fused_scan_fold_kernel<256, 2> : fused_scan_fold_kernel<256, 1>);
+  if (nc == 512) return r == 4 ? fused_scan_fold_kernel<S, 512, 4> : (r == 2 ? fused_scan_fold_kernel<S, 512, 2> : fused_scan_fold_kernel<S, 512, 1>);
+  return r == 4 ? fused_scan_fold_kernel<S, 256, 4> : (r == 2 ? fused_scan_fold_kernel<S, 256, 2> : fused_scan_fold_kernel<S, 256, 1>);
+}
+
+// does the prepared descriptor satisfy every assumption static shape S compiles in?
+static bool flags_ok(int fl, const KAffine &a) {
+  if (((fl & FF_CONST) != 0) != (a.col == -1) || ((fl & FF_ROWID) != 0) != (a.col == -2)) return false;
+  if (a.col >= 0 && ((fl & FF_W4) != 0) != (a.w4 != 0)) return false;
+  if ((fl & FF_SHR0) && a.shr != 0) return false;
+  if ((fl & FF_B1) && a.b != 1) return false;
+  if ((fl & FF_BM1) && a.b != -1) return false;
+  if ((fl & FF_A0) && a.a != 0) return false;
+  if ((fl & FF_NARROW) && !a.narrow) return false;
+  return true;
+}
+template <class S>
+static bool shape_matches(const KDesc &k) {
+  if (k.npreds != S::NPREDS || k.nkeys != S::NKEYS || k.nacc != S::NACC) return false;
+  for (int i = 0; i < k.npreds; i++)
+    if (k.pred[i].w4 != S::PRED_MODE[i] || (S::PRED_SHR0[i] && k.pred[i].shr != 0)) return false;
+  for (int i = 0; i < k.nkeys; i++) {
+    if (!flags_ok(S::KEY_FLAGS[i], k.key[i].e) || (S::KEY_SHL0[i] && k.key[i].shl != 0)) return false;
+    if (S::KEY32 && !k.key[i].e.narrow) return false;
+  }
+  if (S::KEY32 && (k.key_mask < 0 || k.key_mask > INT32_MAX)) return false;
+  for (int j = 0; j < k.nacc; j++) {
+    if (k.acc[j].op != S::ACC_OP[j] || k.acc[j].chain != S::ACC_CHAIN[j] || k.acc[j].nfac != S::ACC_NFAC[j]) return false;
+    for (int t = 0; t < k.acc[j].nfac; t++)
+      if (!flags_ok(S::FAC[j][t], k.acc[j].fac[t])) return false;
+  }
+  return true;
 }
 
 static bool affine_ok(const vdl_affine &a, int ncols) { return a.column >= -2 && a.column < ncols && a.shr >= 0 && a.shr < 64; }
-static KAffine to_k(const vdl_affine &a) { return KAffine{a.column, a.shr, a.a, a.b, 0, 0}; }
+static KAffine to_k(const vdl_affine &a) { return KAffine{a.column, a.shr, a.a, a.b, 0, 0, 0, 0}; }
 
 extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_fused **out) {
   if (!ctx || !desc || !out) return VDL_EINVAL;
@@ -607,7 +721,7 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     memset(&first, 0, sizeof first);
     first.op = 1;
     first.nfac = 1;
-    first.fac[0] = KAffine{-2, 0, 0, 1, 0, 0};  // MIN over the global row id
+    first.fac[0] = KAffine{-2, 0, 0, 1, 0, 0, 0, 0};  // MIN over the global row id
     k.first_idx = k.nacc;
     k.acc[k.nacc++] = first;
   }
@@ -644,7 +758,20 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   f->grid = (int)std::max<i64>(1, std::min<i64>(ctx->sm_count, k.ntiles));
   // derived descriptor fields: staged offsets / width flags, 32-bit bounds for 4-byte predicate columns,
   // prefix sharing between consecutive accumulators
-  auto place = [&](KAffine &a) { if (a.col >= 0) { a.soff = k.soff[a.col]; a.w4 = k.width[a.col] == 4; } };
+  int place_rc = VDL_OK;
+  auto place = [&](KAffine &a) {
+    if (a.col < 0) return;
+    a.soff = k.soff[a.col];
+    a.w4 = k.width[a.col] == 4;
+    // narrow: leaf and a + b*leaf provably fit int32 given the column's exact min/max (cf. inferBounds, Vlite.hs:417-467)
+    i64 cmin, cmax;
+    int rc2 = vdl_column_analyze(ctx, desc->column[a.col], &cmin, &cmax);
+    if (rc2) { place_rc = rc2; return; }
+    __int128 l0 = cmin >> a.shr, l1 = cmax >> a.shr;
+    __int128 v0 = (__int128)a.a + (__int128)a.b * l0, v1 = (__int128)a.a + (__int128)a.b * l1;
+    auto fits = [](__int128 x) { return x >= INT32_MIN && x <= INT32_MAX; };
+    a.narrow = cmin <= cmax && fits(l0) && fits(l1) && fits(v0) && fits(v1) && fits(a.a) && fits(a.b);
+  };
   for (int i = 0; i < k.npreds; i++) {
     KPred &p = k.pred[i];
     p.soff = k.soff[p.col];
@@ -685,6 +812,23 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     }
     for (int t = 0; t < a.nfac; t++) place(a.fac[t]);
   }
+  if (place_rc) { vdl_fused_destroy(f); return place_rc; }
+  // pick the kernel: a static shape whose assumptions all hold, else the generic one
+  f->kernel = scan_kernel_for<GenericShape>(f->nc, f->r);
+  if (!getenv("VDL_GENERIC_ONLY")) {
+    if (shape_matches<ShapeSel3Sum2>(k)) { f->kernel = scan_kernel_for<ShapeSel3Sum2>(f->nc, f->r); f->shape = ShapeSel3Sum2::kName; }
+    else if (shape_matches<ShapeSel1Key2Sum5>(k)) { f->kernel = scan_kernel_for<ShapeSel1Key2Sum5>(f->nc, f->r); f->shape = ShapeSel1Key2Sum5::kName; }
+  }
+  if (getenv("VDL_DEBUG_SHAPE")) {
+    fprintf(stderr, "[vdl] fused scan: shape=%s nc=%d r=%d stages=%d gmax=%d npreds=%d nkeys=%d nacc=%d\n", f->shape, f->nc, f->r, k.stages, k.gmax, k.npreds, k.nkeys, k.nacc);
+    for (int i = 0; i < k.npreds; i++) fprintf(stderr, "[vdl]   pred %d: mode=%d shr=%d\n", i, k.pred[i].w4, k.pred[i].shr);
+    for (int i = 0; i < k.nkeys; i++) fprintf(stderr, "[vdl]   key %d: col=%d w4=%d shr=%d a=%lld b=%lld shl=%d narrow=%d\n", i, k.key[i].e.col, k.key[i].e.w4, k.key[i].e.shr, (long long)k.key[i].e.a, (long long)k.key[i].e.b, k.key[i].shl, k.key[i].e.narrow);
+    for (int j = 0; j < k.nacc; j++) {
+      fprintf(stderr, "[vdl]   acc %d: op=%d chain=%d nfac=%d", j, k.acc[j].op, k.acc[j].chain, k.acc[j].nfac);
+      for (int t = 0; t < k.acc[j].nfac; t++) fprintf(stderr, " [col=%d w4=%d shr=%d a=%lld b=%lld narrow=%d]", k.acc[j].fac[t].col, k.acc[j].fac[t].w4, k.acc[j].fac[t].shr, (long long)k.acc[j].fac[t].a, (long long)k.acc[j].fac[t].b, k.acc[j].fac[t].narrow);
+      fprintf(stderr, "\n");
+    }
+  }
 
   // device buffers
   int rc = vec_new(ctx, VDL_I64, (i64)(k.nacc + k.nchoose) * k.domain, &f->table);
@@ -721,7 +865,7 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   f->fd.errflag = ctx->d_errflag;
   for (int j = 0; j < k.nacc; j++) f->fd.acc_op[j] = k.acc[j].op;
 
-  cudaError_t e = cudaFuncSetAttribute(scan_kernel_for(f->nc, f->r), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+  cudaError_t e = cudaFuncSetAttribute(f->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   if (e != cudaSuccess) { vdl_fused_destroy(f); return vdl_cuda_fail(ctx, e, "cudaFuncSetAttribute(fused_scan_fold_kernel)"); }
   *out = f;
   return VDL_OK;
@@ -738,7 +882,7 @@ extern "C" int vdl_fused_launch(vdl_fused *f) {
   ctx->launches++;
   VDL_CUDA(ctx, cudaEventRecord(f->ev0, ctx->stream));
   if (f->kd.rows > 0 && !f->always_false) {
-    scan_kernel_for(f->nc, f->r)<<<f->grid, f->nc + 32, f->smem_bytes, ctx->stream>>>(f->kd);
+    f->kernel<<<f->grid, f->nc + 32, f->smem_bytes, ctx->stream>>>(f->kd);
     ctx->launches++;
   }
   VDL_CUDA(ctx, cudaEventRecord(f->ev1, ctx->stream));
@@ -823,6 +967,8 @@ extern "C" int vdl_fused_last_kernel_ms(vdl_fused *f, float *ms) {
   VDL_CUDA(f->ctx, cudaEventElapsedTime(ms, f->ev0, f->ev1));
   return VDL_OK;
 }
+
+extern "C" const char *vdl_fused_shape_name(vdl_fused *f) { return f ? f->shape : ""; }
 
 extern "C" int vdl_fused_destroy(vdl_fused *f) {
   if (!f) return VDL_EINVAL;

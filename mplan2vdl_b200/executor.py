@@ -193,6 +193,12 @@ class Plan:
         self.ctx.check(self.L.vdl_fused_partials(f, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def shape(self, i: int = 0) -> str:
+        """Which scan-kernel instantiation fused scan i uses: "generic" or a static shape name."""
+        f = C.c_void_p()
+        self.ctx.check(self.L.vdl_plan_fused(self.h, i, C.byref(f)))
+        return self.L.vdl_fused_shape_name(f).decode()
+
     def kernel_ms(self, i: int = 0) -> float:
         f = C.c_void_p()
         self.ctx.check(self.L.vdl_plan_fused(self.h, i, C.byref(f)))

@@ -85,6 +85,7 @@ SYMBOLS = [
     ("vdl_fused_num_groups", _I, [_P, C.POINTER(_L)]),
     ("vdl_fused_result", _I, [_P, _I, C.POINTER(C.c_int32)]),
     ("vdl_fused_result_host", _I, [_P, _I, C.POINTER(C.POINTER(_L)), C.POINTER(_L)]),
+    ("vdl_fused_shape_name", C.c_char_p, [_P]),
     ("vdl_fused_destroy", _I, [_P]),
     ("vdl_fused_last_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
     ("vdl_plan_load", _I, [_P, C.c_char_p, _I, C.POINTER(_P)]),

@@ -23,6 +23,30 @@ def test_q6_parity(catalog, rows):
         assert_same(got_u, want)
 
 
+@pytest.mark.parametrize("query,colnames,shape", [("q06.vdl", Q6_COLS, "sel3_sum2"), ("q01.vdl", Q1_COLS, "sel1_key2_sum5")])
+def test_static_shape_and_generic_kernel_agree(catalog, query, colnames, shape, monkeypatch):
+    """The static-shape instantiation is what runs on TPC-H-shaped data; forcing the generic kernel gives the same bits."""
+    cols = host_columns(catalog, ["lineitem." + c for c in colnames], {"lineitem": 700_001})
+    want = run_oracle(plan_text(query), cols)
+    got, stats = run_gpu(plan_text(query), cols)
+    assert stats["shape"] == shape
+    assert_same(got, want)
+    monkeypatch.setenv("VDL_GENERIC_ONLY", "1")
+    got_g, stats_g = run_gpu(plan_text(query), cols)
+    assert stats_g["shape"] == "generic"
+    assert_same(got_g, want)
+
+
+def test_wide_values_fall_back_to_the_generic_kernel(catalog):
+    """Values that do not fit int32 break the static shape's narrowing assumption: the generic kernel must be chosen."""
+    cols = host_columns(catalog, ["lineitem." + c for c in Q6_COLS], {"lineitem": 100_000})
+    cols["lineitem.l_extendedprice"] = cols["lineitem.l_extendedprice"] * 1_000_003   # ~1e13: wraps in the sum, exactly as the oracle
+    want = run_oracle(plan_text("q06.vdl"), cols)
+    got, stats = run_gpu(plan_text("q06.vdl"), cols)
+    assert stats["shape"] == "generic"
+    assert_same(got, want)
+
+
 def test_q6_empty_selection(catalog):
     cols = host_columns(catalog, ["lineitem." + c for c in Q6_COLS], {"lineitem": 5000})
     cols["lineitem.l_quantity"][:] = 5000

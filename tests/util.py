@@ -55,6 +55,7 @@ def run_gpu(plan, cols, fuse=True, ctx=None):
         p = ctx.plan(plan, fuse=fuse)
         out = p.run()
         stats = p.stats()
+        stats["shape"] = p.shape(0) if stats["fused_scans"] else None
         p.close()
         for k in cols:
             ctx.drop_column(k)
