@@ -298,42 +298,6 @@ struct GroupState {
   i64 *tbl;           // [gmax][nacc][NC]
 };
 
-// Phase 1 of a tile (the plan's FoldSelect, Vlite.hs:721-730, done in shared memory): thread ctid evaluates the
-// predicates of rows ctid + k*NC, k < R, together (R independent shared-memory loads in flight) and the rows
-// that pass are compacted CTA-wide into `queue` with one warp-aggregated shared atomic per warp and k.
-template <class S, int NC, int R>
-__device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char *tile, int nvalid, int ctid, int *qcount, uint16_t *queue) {
-  unsigned pass = 0;
-#pragma unroll
-  for (int k = 0; k < R; k++)
-    if (ctid + k * NC < nvalid) pass |= 1u << k;
-  pred_chain<S, 0, NC, R>(d, tile, ctid, pass);
-  const int lane = ctid & 31;
-  const unsigned any = __ballot_sync(0xffffffffu, pass != 0);
-  if (!any) return;
-  if (__popc(any) <= 4) {
-    // few selected rows in this warp (selective predicates): the owning lanes append on their own
-    if (pass) {
-      int base = atomicAdd(qcount, __popc(pass));
-#pragma unroll
-      for (int k = 0; k < R; k++)
-        if ((pass >> k) & 1) queue[base++] = (uint16_t)(ctid + k * NC);
-    }
-    return;
-  }
-#pragma unroll
-  for (int k = 0; k < R; k++) {
-    const bool p = (pass >> k) & 1;
-    const unsigned m = __ballot_sync(0xffffffffu, p);
-    if (m) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(qcount, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (p) queue[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(ctid + k * NC);
-    }
-  }
-}
-
 // Phase 2 (the Gathers + elementwise map + Fold of the plan): fold one selected row into the lane-private tables.
 template <class S, int NC>
 __device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *tile, int r, i64 grow, const GroupState &g, int ctid) {
@@ -360,6 +324,50 @@ __device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *ti
       } else {
         atomicExch(&g.slotmap[key], -3);
       }
+    }
+  }
+}
+
+// Phase 1 of a tile (the plan's FoldSelect, Vlite.hs:721-730, done in shared memory): thread ctid evaluates the
+// predicates of rows ctid + k*NC, k < R, together (R independent shared-memory loads in flight) and the rows
+// that pass are compacted CTA-wide into `queue` with one warp-aggregated shared atomic per warp and k.
+template <class S, int NC, int R>
+__device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char *tile, int nvalid, int ctid, int *qcount, uint16_t *queue,
+                                            i64 grow0, const GroupState &g) {
+  unsigned pass = 0;
+#pragma unroll
+  for (int k = 0; k < R; k++)
+    if (ctid + k * NC < nvalid) pass |= 1u << k;
+  pred_chain<S, 0, NC, R>(d, tile, ctid, pass);
+  const int lane = ctid & 31;
+  const unsigned any = __ballot_sync(0xffffffffu, pass != 0);
+  if (!any) return;
+  if (__popc(any) >= 24) {
+    // dense selection (most lanes own a selected row): compaction would buy nothing, fold the rows where they are
+#pragma unroll 1
+    for (int k = 0; k < R; k++)
+      if ((pass >> k) & 1) fold_row<S, NC>(d, tile, ctid + k * NC, grow0 + ctid + k * NC, g, ctid);
+    return;
+  }
+  if (__popc(any) <= 4) {
+    // few selected rows in this warp (selective predicates): the owning lanes append on their own
+    if (pass) {
+      int base = atomicAdd(qcount, __popc(pass));
+#pragma unroll
+      for (int k = 0; k < R; k++)
+        if ((pass >> k) & 1) queue[base++] = (uint16_t)(ctid + k * NC);
+    }
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    const bool p = (pass >> k) & 1;
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    if (m) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(qcount, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (p) queue[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(ctid + k * NC);
     }
   }
 }
@@ -464,7 +472,7 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
         }
         consumer_barrier<NC>();
       }
-      select_rows<S, NC, R>(d, buf, nvalid, ctid, &qcount[st], queue + (size_t)st * (NC * R));
+      select_rows<S, NC, R>(d, buf, nvalid, ctid, &qcount[st], queue + (size_t)st * (NC * R), d.row_base + tile * d.tile_rows, g);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sel[st]);
     }
