@@ -55,3 +55,42 @@ def _tdiv(a, b) -> int:
     a, b = int(a), int(b)
     q = abs(a) // abs(b)
     return q if (a < 0) == (b < 0) else -q
+
+
+def q3(c: dict) -> dict:
+    """03.sql.mplan: orders[o_orderdate < 1995-03-15] x customer[BUILDING] x lineitem[l_shipdate > 1995-03-15],
+    group by (l_orderkey, o_shippriority, o_orderdate); groups in ascending composite-key order."""
+    d = 728732
+    cust_ok = c["customer.c_mktsegment"] == 16
+    ord_ok = (c["orders.o_orderdate"] < d) & cust_ok[c["orders.orders_customer"]]
+    fk = c["lineitem.lineitem_orders"]
+    m = (c["lineitem.l_shipdate"] > d) & ord_ok[fk]
+    ok = c["lineitem.l_orderkey"][m].astype(np.int64)
+    od = c["orders.o_orderdate"][fk[m]].astype(np.int64)
+    sp = c["orders.o_shippriority"][fk[m]].astype(np.int64)
+    with np.errstate(over="ignore"):
+        rev = c["lineitem.l_extendedprice"][m] * (100 - c["lineitem.l_discount"][m])
+    key = ((((ok - 1) << 0) | (sp >> 33)) << 12) | (od - 727563)
+    order = np.argsort(key, kind="stable")
+    key, ok, od, sp, rev = key[order], ok[order], od[order], sp[order], rev[order]
+    heads = np.r_[True, key[1:] != key[:-1]] if len(key) else np.zeros(0, bool)
+    starts = np.nonzero(heads)[0]
+    sums = np.add.reduceat(rev, starts) if len(starts) else np.zeros(0, np.int64)
+    return {"l_orderkey__lineitem__l_orderkey": ok[starts], "revenue": sums.astype(np.int64),
+            "o_orderdate__orders__o_orderdate": od[starts], "o_shippriority__orders__o_shippriority": sp[starts]}
+
+
+def q5(c: dict) -> dict:
+    """05.sql.mplan: revenue per nation for ASIA, orders of 1994, customer and supplier in the same nation."""
+    o_ok = (c["orders.o_orderdate"] >= 728294) & (c["orders.o_orderdate"] < 728659)
+    lo, ls = c["lineitem.lineitem_orders"], c["lineitem.lineitem_supplier"]
+    cust_nation = c["customer.c_nationkey"][c["orders.orders_customer"][lo]]
+    supp_nation_key = c["supplier.s_nationkey"][ls]
+    nation_row = c["supplier.supplier_nation"][ls]
+    region_ok = c["region.r_name"] == 64
+    m = o_ok[lo] & (cust_nation == supp_nation_key) & region_ok[c["nation.nation_region"][nation_row]]
+    name = c["nation.n_name"][nation_row[m]].astype(np.int64)
+    with np.errstate(over="ignore"):
+        rev = c["lineitem.l_extendedprice"][m] * (100 - c["lineitem.l_discount"][m])
+    names = np.unique(name)
+    return {"n_name__nation__n_name": names, "revenue": np.array([rev[name == n].sum(dtype=np.int64) for n in names], dtype=np.int64)}

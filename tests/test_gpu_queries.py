@@ -123,3 +123,17 @@ def test_q6_full_size_linearity(catalog):
                 ctx.drop_column(n)
     assert whole.shape == (1,) and whole[0] == total
     ctx.close()
+
+
+@pytest.mark.parametrize("q", ["q03.vdl", "q05.vdl"])
+@pytest.mark.parametrize("sf", [0.002, 0.02])
+def test_fk_join_plans_parity(catalog, q, sf):
+    """BASELINE config 3: the FK-join plans (Gather through join-index columns, Scatter-built validity / inverse
+    index over the dimension, FoldSelect compaction, radix Partition on the composite key) op-at-a-time on the GPU."""
+    text = plan_text(q)
+    rows = {t: synth.table_rows(catalog, t, sf) for t in catalog.tables}
+    cols = host_columns(catalog, tpch.plan_columns(text), rows, sf=sf)
+    want = run_oracle(text, cols)
+    got, stats = run_gpu(text, cols)
+    assert_same(got, want)
+    assert len(next(iter(want.values()))) > 0
