@@ -24,10 +24,25 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 QUERIES = {
-    # plan file, algorithmic bytes per lineitem row (SURVEY.md section 8 d: distinct base columns x stored width)
+    # plan file, algorithmic bytes per lineitem row for the single-table plans (SURVEY.md section 8 d: distinct base
+    # columns x stored width); for the join plans the bytes are summed over every table the plan loads
     "q06": ("q06.vdl", 28),
     "q01": ("q01.vdl", 52),
+    "q03": ("q03.vdl", None),
+    "q05": ("q05.vdl", None),
 }
+
+
+def algorithmic_bytes(cat, names, rows_of, rows_fact_here):
+    """Sum over the distinct base columns the plan Loads of rows x stored width; pkey pseudo-columns only give a length."""
+    from mplan2vdl_b200 import tpch
+    total = 0
+    for n in names:
+        t, c = n.split(".", 1)
+        if c == cat.tables[t].pkey_name:
+            continue
+        total += (rows_fact_here if t == tpch.FACT_TABLE else rows_of(t)) * cat.column(n).width
+    return total
 FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback, used only when MEASURED_PEAKS.json is absent
 
 
@@ -154,7 +169,7 @@ def workload_config(args, rows_total):
     plan, bpr = QUERIES[args.query]
     return {"workload": f"TPC-H {args.query.upper()} SF{args.sf:g}: plans/{plan} (mplan2vdl Voodoo plan) over synthetic lineitem columns "
                         "generated to the reference's bounds.csv",
-            "lineitem_rows": rows_total, "algorithmic_bytes_per_row": bpr,
+            "lineitem_rows": rows_total, "algorithmic_bytes_per_lineitem_row": bpr,
             "l2": "inputs (GBs) far exceed the 126 MB L2; no flush needed between steps",
             "parallelism": f"lineitem row-range sharded over {args.gpus} GPU(s), partial tables all-gathered"}
 
@@ -206,6 +221,7 @@ def main():
     ctx = Context(local)
     info = tpch.load_synthetic(ctx, cat, names, args.sf, rank=rank, world=world)
     rows_here = info["rows"]["lineitem"]
+    bytes_here = algorithmic_bytes(cat, names, lambda t: synth.table_rows(cat, t, args.sf), rows_here)
     plan = ctx.plan(text)
     ext = torch.cuda.ExternalStream(ctx.stream, device=local)
     from mplan2vdl_b200.dist import ShardedPlan
@@ -233,7 +249,7 @@ def main():
     ev0.record(ext)
     for _ in range(args.steps):
         result = step()
-        kernel_ms.append(plan.kernel_ms(0))
+        kernel_ms.append(plan.kernel_ms(0) if plan.num_fused else float("nan"))
     ev1.record(ext)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -248,14 +264,19 @@ def main():
         kern_ms_mean = statistics.mean(kernel_ms)
     ms_per_step = dev_ms / args.steps
     value = rows_total / (ms_per_step / 1e3)
+    fused = plan.num_fused > 0
+    if not fused:          # op-at-a-time plan (FK joins): the "kernel" is the whole chain of per-op launches
+        kernel_ms = [ms_per_step] * args.steps
+        kern_ms_mean = ms_per_step
 
     # roofline of the dominant kernel (the fused scan): algorithmic bytes of THIS rank's shard / its mean duration
     peak, peak_kind = measured_peak()
-    achieved = rows_here * bytes_per_row / (statistics.mean(kernel_ms) / 1e3) / 1e9
+    achieved = bytes_here / (statistics.mean(kernel_ms) / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)" if peak_kind == "measured" else "fallback 6650 GB/s",
-                "kernel": "fused_scan_fold_kernel", "kernel_ms": statistics.mean(kernel_ms), "kernel_ms_min": min(kernel_ms),
-                "frac_of_8TBs_spec": achieved / 8000.0, "bytes_per_launch": rows_here * bytes_per_row}
+                "kernel": f"fused_scan_fold_kernel<{plan.shape(0)}>" if fused else "op-at-a-time plan (all per-op kernels of one step)",
+                "kernel_ms": statistics.mean(kernel_ms), "kernel_ms_min": min(kernel_ms),
+                "frac_of_8TBs_spec": achieved / 8000.0, "bytes_per_launch": bytes_here}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f).get(f"{args.query}_sf{args.sf:g}")
@@ -269,16 +290,17 @@ def main():
     if not args.no_e2e:
         handles = [ctx.lookup(n) for n in names]
         widths = [synth.column_spec(cat, n, args.sf).width for n in names]
+        nrows = [info["rows"][n.split(".")[0]] for n in names]
         host = []
-        for h, w in zip(handles, widths):
-            buf = torch.empty(rows_here * w, dtype=torch.uint8, pin_memory=True)
-            ctx.download_into(h, buf.data_ptr(), rows_here)
+        for h, w, nr in zip(handles, widths, nrows):
+            buf = torch.empty(nr * w, dtype=torch.uint8, pin_memory=True)
+            ctx.download_into(h, buf.data_ptr(), nr)
             host.append(buf)
         h2d = sum(b.numel() for b in host)
 
         def e2e_step():
-            for h, b in zip(handles, host):
-                ctx.upload_into(h, b.data_ptr(), rows_here)
+            for h, b, nr in zip(handles, host, nrows):
+                ctx.upload_into(h, b.data_ptr(), nr)
             return step()
 
         e2e_step()
