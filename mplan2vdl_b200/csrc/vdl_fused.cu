@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <vector>
 
 #include "vdl_internal.h"
@@ -142,6 +143,11 @@ __device__ __forceinline__ i64 warp_reduce(int op, i64 v) {
 #define FF_CONST 32    // col == -1
 #define FF_ROWID 64    // col == -2
 #define FF_NARROW 128  // leaf and a + b*leaf fit int32 (column statistics)
+// how a register-slot kernel keeps an accumulator per thread (see vdl_shapes.cuh)
+#define RK_WIDE 0
+#define RK_N32 1
+#define RK_FIRST 2
+#define RK_MADW 3
 
 struct GenericShape {
   static constexpr bool kStatic = false;
@@ -150,6 +156,8 @@ struct GenericShape {
   static constexpr int KEY_FLAGS[VDL_MAX_KEYS] = {}, KEY_SHL0[VDL_MAX_KEYS] = {};
   static constexpr int ACC_OP[K_MAX_ACC] = {}, ACC_CHAIN[K_MAX_ACC] = {}, ACC_NFAC[K_MAX_ACC] = {};
   static constexpr int FAC[K_MAX_ACC][VDL_MAX_FACTORS] = {};
+  static constexpr int RS_G = 0;
+  static constexpr int ACC_RK[K_MAX_ACC] = {};
 };
 
 __device__ __forceinline__ i64 tile_leaf(const KAffine &A, const unsigned char *tile, int r, i64 grow) {
@@ -290,6 +298,134 @@ __device__ __forceinline__ void acc_chain(const KDesc &d, i64 *t, i64 prev, cons
   }
 }
 
+// ---- register slots (G > 0): per-thread accumulators of the first G keys of the CTA live in registers ----------
+// All indexing below is static after unrolling, so the arrays are plain registers and entries of the kind an
+// accumulator does not use are never materialised.
+template <class S, int G>
+struct RegAcc {
+  static constexpr int NA = (S::kStatic && S::NACC > 0) ? S::NACC : 1;
+  static constexpr int NG = G > 0 ? G : 1;
+  i64 w[NG][NA];
+  int32_t n[NG][NA];
+};
+template <class S, int G, int J>
+__device__ __forceinline__ void rs_init(RegAcc<S, G> &ra) {
+  if constexpr (G > 0 && J < S::NACC) {
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      constexpr int op = S::ACC_OP[J];
+      if constexpr (S::ACC_RK[J] == RK_WIDE || S::ACC_RK[J] == RK_MADW) ra.w[g][J] = acc_identity(op);
+      else if constexpr (S::ACC_RK[J] == RK_N32) ra.n[g][J] = 0;
+      else ra.n[g][J] = INT32_MAX;
+    }
+    rs_init<S, G, J + 1>(ra);
+  }
+}
+// product of own factors F0 .. F1-1 of accumulator J onto v
+template <class S, int J, int F, int F1>
+__device__ __forceinline__ i64 factor_range(const KAcc &A, i64 v, bool have, const unsigned char *tile, int r, i64 grow) {
+  if constexpr (F < F1) {
+    i64 x = affine_static<S::FAC[J][F]>(A.fac[F], tile, r, grow);
+    return factor_range<S, J, F + 1, F1>(A, have ? (i64)((u64)v * (u64)x) : x, true, tile, r, grow);
+  }
+  return v;
+}
+// values of every accumulator for one row (prefix-shared exactly like acc_chain).  RK_MADW accumulators are kept as
+// the pair (a, b) with value a * b, both int32 by the host's proof, so that the update is one `mad.wide.s32`.
+template <class S, int J>
+__device__ __forceinline__ void rs_values(const KDesc &d, i64 *v, int32_t *va, int32_t *vb, i64 prev, const unsigned char *tile, int r, i64 grow) {
+  if constexpr (J < S::NACC) {
+    constexpr bool chain = (bool)S::ACC_CHAIN[J];
+    constexpr int nfac = S::ACC_NFAC[J];
+    if constexpr (S::ACC_RK[J] == RK_FIRST) {
+      v[J] = 0;   // the CTA-local row index is supplied by the caller
+      rs_values<S, J + 1>(d, v, va, vb, prev, tile, r, grow);
+    } else if constexpr (S::ACC_RK[J] == RK_MADW) {
+      i64 a = factor_range<S, J, 0, nfac - 1>(d.acc[J], chain ? prev : 1, chain, tile, r, grow);
+      va[J] = (int32_t)a;
+      vb[J] = (int32_t)affine_static<S::FAC[J][nfac - 1]>(d.acc[J].fac[nfac - 1], tile, r, grow);
+      v[J] = (i64)va[J] * (i64)vb[J];
+      rs_values<S, J + 1>(d, v, va, vb, v[J], tile, r, grow);
+    } else {
+      v[J] = factor_chain<S, J, 0>(d.acc[J], chain ? prev : 1, tile, r, grow);
+      rs_values<S, J + 1>(d, v, va, vb, v[J], tile, r, grow);
+    }
+  }
+}
+// Predicated updates (`@p add` / `@p min`): the slot test never branches, so a warp whose 32 rows hit 6 different
+// slots runs ONE straight instruction stream instead of 6 divergent switch arms (the compiler turns an if-chain
+// over `slot == g` into a jump table, which serialises the arms and stalls on every indirect branch).
+__device__ __forceinline__ void pred_add64(i64 &acc, i64 v, int s, int g) {
+  // split add with carry: ptxas keeps the low add predicated (a predicated add.s64 / mad.wide becomes add + 2 SEL)
+  uint32_t lo = (uint32_t)acc, hi = (uint32_t)((u64)acc >> 32);
+  asm("{\n .reg .pred p;\n setp.eq.s32 p, %4, %5;\n @p add.cc.u32 %0, %0, %2;\n @p addc.u32 %1, %1, %3;\n}"
+      : "+r"(lo), "+r"(hi) : "r"((uint32_t)v), "r"((uint32_t)((u64)v >> 32)), "r"(s), "r"(g));
+  acc = (i64)(((u64)hi << 32) | lo);
+}
+__device__ __forceinline__ void pred_min64(i64 &acc, i64 v, int s, int g) {
+  asm("{\n .reg .pred p;\n setp.eq.s32 p, %2, %3;\n @p min.s64 %0, %0, %1;\n}" : "+l"(acc) : "l"(v), "r"(s), "r"(g));
+}
+__device__ __forceinline__ void pred_max64(i64 &acc, i64 v, int s, int g) {
+  asm("{\n .reg .pred p;\n setp.eq.s32 p, %2, %3;\n @p max.s64 %0, %0, %1;\n}" : "+l"(acc) : "l"(v), "r"(s), "r"(g));
+}
+__device__ __forceinline__ void pred_madw(i64 &acc, int32_t a, int32_t b, int s, int g) {
+  asm("{\n .reg .pred p;\n setp.eq.s32 p, %3, %4;\n @p mad.wide.s32 %0, %1, %2, %0;\n}" : "+l"(acc) : "r"(a), "r"(b), "r"(s), "r"(g));
+}
+__device__ __forceinline__ void pred_add32(int32_t &acc, int32_t v, int s, int g) {
+  asm("{\n .reg .pred p;\n setp.eq.s32 p, %2, %3;\n @p add.s32 %0, %0, %1;\n}" : "+r"(acc) : "r"(v), "r"(s), "r"(g));
+}
+__device__ __forceinline__ void pred_min32(int32_t &acc, int32_t v, int s, int g) {
+  asm("{\n .reg .pred p;\n setp.eq.s32 p, %2, %3;\n @p min.s32 %0, %0, %1;\n}" : "+r"(acc) : "r"(v), "r"(s), "r"(g));
+}
+// slot Q's accumulators take the row's values iff s == Q
+template <class S, int G, int Q, int J>
+__device__ __forceinline__ void rs_apply(RegAcc<S, G> &ra, int s, const i64 *v, const int32_t *va, const int32_t *vb, int lrow) {
+  if constexpr (J < S::NACC) {
+    constexpr int op = S::ACC_OP[J];
+    if constexpr (S::ACC_RK[J] == RK_MADW) pred_add64(ra.w[Q][J], v[J], s, Q);
+    else if constexpr (S::ACC_RK[J] == RK_WIDE) {
+      if constexpr (op == 0) pred_add64(ra.w[Q][J], v[J], s, Q);
+      else if constexpr (op == 1) pred_min64(ra.w[Q][J], v[J], s, Q);
+      else pred_max64(ra.w[Q][J], v[J], s, Q);
+    } else if constexpr (S::ACC_RK[J] == RK_N32) pred_add32(ra.n[Q][J], (int32_t)v[J], s, Q);
+    else pred_min32(ra.n[Q][J], lrow, s, Q);
+    rs_apply<S, G, Q, J + 1>(ra, s, v, va, vb, lrow);
+  }
+}
+template <class S, int G, int Q>
+__device__ __forceinline__ void rs_apply_slots(RegAcc<S, G> &ra, int s, const i64 *v, const int32_t *va, const int32_t *vb, int lrow) {
+  if constexpr (Q < G) {
+    rs_apply<S, G, Q, 0>(ra, s, v, va, vb, lrow);
+    rs_apply_slots<S, G, Q + 1>(ra, s, v, va, vb, lrow);
+  }
+}
+
+// end of kernel: warp-reduce every (slot, accumulator) and let lane 0 store it at out[g * NACC + J]
+template <class S, int G, int J>
+__device__ __forceinline__ void rs_flush(const KDesc &d, const RegAcc<S, G> &ra, i64 *out, int lane) {
+  if constexpr (G > 0 && J < S::NACC) {
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      i64 v;
+      if constexpr (S::ACC_RK[J] == RK_WIDE || S::ACC_RK[J] == RK_MADW) v = ra.w[g][J];
+      else if constexpr (S::ACC_RK[J] == RK_N32) v = (i64)ra.n[g][J];
+      else {
+        // CTA-local row index (iteration * tile_rows + row in tile) -> global row id; monotonic within the CTA
+        const int idx = ra.n[g][J];
+        v = INT64_MAX;
+        if (idx != INT32_MAX) {
+          const i64 tile = (i64)blockIdx.x + (i64)(idx / d.tile_rows) * gridDim.x;
+          v = d.row_base + tile * d.tile_rows + idx % d.tile_rows;
+        }
+      }
+      constexpr int op = S::ACC_OP[J];
+      v = warp_reduce(op, v);
+      if (lane == 0) out[g * S::NACC + J] = v;
+    }
+    rs_flush<S, G, J + 1>(d, ra, out, lane);
+  }
+}
+
 // Per-CTA group state: key -> compact slot (lane-private accumulator tables are indexed by slot).
 struct GroupState {
   int32_t *slotmap;   // [domain]  -1 unseen, -2 being claimed, -3 overflow (stays on the global-atomic path), >=0 slot
@@ -299,8 +435,9 @@ struct GroupState {
 };
 
 // Phase 2 (the Gathers + elementwise map + Fold of the plan): fold one selected row into the lane-private tables.
-template <class S, int NC>
-__device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *tile, int r, i64 grow, const GroupState &g, int ctid) {
+template <class S, int NC, int G>
+__device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *tile, int r, i64 grow, const GroupState &g, int ctid,
+                                         RegAcc<S, G> &ra, int lrow) {
   i64 key;
   if constexpr (S::kStatic && S::KEY32) key = (i64)(key_chain32<S, 0>(d, 0, tile, r) & (int32_t)d.key_mask);
   else key = key_chain<S, 0>(d, 0, tile, r, grow) & d.key_mask;
@@ -309,8 +446,14 @@ __device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *ti
     return;
   }
   const int s = ((volatile int32_t *)g.slotmap)[key];
+  if constexpr (G > 0) {
+    i64 v[RegAcc<S, G>::NA];
+    int32_t va[RegAcc<S, G>::NA], vb[RegAcc<S, G>::NA];
+    rs_values<S, 0>(d, v, va, vb, 1, tile, r, grow);
+    rs_apply_slots<S, G, 0>(ra, s, v, va, vb, lrow);     // s < 0 (key without a slot yet) matches none
+  }
   if (s >= 0) {
-    acc_chain<S, 0, NC>(d, g.tbl + (size_t)s * d.nacc * NC + ctid, 1, tile, r, grow);
+    if constexpr (G == 0) acc_chain<S, 0, NC>(d, g.tbl + (size_t)s * d.nacc * NC + ctid, 1, tile, r, grow);
   } else {
     // first rows of a key in this CTA: fold straight into the global table and claim a slot for the rest
 #pragma unroll 1
@@ -331,9 +474,9 @@ __device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *ti
 // Phase 1 of a tile (the plan's FoldSelect, Vlite.hs:721-730, done in shared memory): thread ctid evaluates the
 // predicates of rows ctid + k*NC, k < R, together (R independent shared-memory loads in flight) and the rows
 // that pass are compacted CTA-wide into `queue` with one warp-aggregated shared atomic per warp and k.
-template <class S, int NC, int R>
+template <class S, int NC, int R, int G>
 __device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char *tile, int nvalid, int ctid, int *qcount, uint16_t *queue,
-                                            i64 grow0, const GroupState &g) {
+                                            i64 grow0, const GroupState &g, RegAcc<S, G> &ra, int lrow0) {
   unsigned pass = 0;
 #pragma unroll
   for (int k = 0; k < R; k++)
@@ -344,9 +487,15 @@ __device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char 
   if (!any) return;
   if (__popc(any) >= 24) {
     // dense selection (most lanes own a selected row): compaction would buy nothing, fold the rows where they are
+    if constexpr (G > 0) {   // straight-line predicated code: let the R rows of a thread overlap
+#pragma unroll
+      for (int k = 0; k < R; k++)
+        if ((pass >> k) & 1) fold_row<S, NC, G>(d, tile, ctid + k * NC, grow0 + ctid + k * NC, g, ctid, ra, lrow0 + ctid + k * NC);
+    } else {
 #pragma unroll 1
-    for (int k = 0; k < R; k++)
-      if ((pass >> k) & 1) fold_row<S, NC>(d, tile, ctid + k * NC, grow0 + ctid + k * NC, g, ctid);
+      for (int k = 0; k < R; k++)
+        if ((pass >> k) & 1) fold_row<S, NC, G>(d, tile, ctid + k * NC, grow0 + ctid + k * NC, g, ctid, ra, lrow0 + ctid + k * NC);
+    }
     return;
   }
   if (__popc(any) <= 4) {
@@ -372,7 +521,7 @@ __device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char 
   }
 }
 
-template <class S, int NC, int R>
+template <class S, int NC, int R, int G>
 __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __grid_constant__ KDesc d) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: [ring: stages * stage_bytes][full[stages]][empty[stages]][sel[stages]][qcount[stages]]
@@ -408,7 +557,7 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
   }
   for (i64 k = tid; k < d.domain; k += NC + 32) g.slotmap[k] = dense ? (int32_t)k : -1;
   if (dense && tid < d.gmax) g.slotkey[tid] = tid;
-  if (tid >= 32) {
+  if (G == 0 && tid >= 32) {
     const int ctid = tid - 32;
     for (int s = 0; s < d.gmax; s++)
       for (int j = 0; j < d.nacc; j++) g.tbl[((size_t)s * d.nacc + j) * NC + ctid] = acc_identity(d.acc[j].op);
@@ -442,6 +591,8 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
   // (predicates -> the stage's compaction queue, then a non-blocking arrive on sel[stage]) and FOLDS tile it-1
   // (wait on its sel barrier -- normally long complete --, fold this warp's share of the queue, release the stage).
   const int ctid = tid - 32, cw = warp - 1;
+  RegAcc<S, G> ra;
+  rs_init<S, G, 0>(ra);
   // The rows past the last full tile form one more (partial) tile, owned by the CTA next in the round-robin; it
   // is staged with plain loads into the (by then idle) next ring stage and goes through the same code.
   const i64 ntiles_all = d.ntiles + (d.ntiles * d.tile_rows < d.rows ? 1 : 0);
@@ -472,7 +623,8 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
         }
         consumer_barrier<NC>();
       }
-      select_rows<S, NC, R>(d, buf, nvalid, ctid, &qcount[st], queue + (size_t)st * (NC * R), d.row_base + tile * d.tile_rows, g);
+      select_rows<S, NC, R, G>(d, buf, nvalid, ctid, &qcount[st], queue + (size_t)st * (NC * R), d.row_base + tile * d.tile_rows, g, ra,
+                               it * d.tile_rows);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sel[st]);
     }
@@ -486,7 +638,7 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
       if (chunk < 0) chunk += NW;
       for (int e = chunk * 32 + lane; e < nsel; e += NC) {
         const int r = queue[(size_t)pst * (NC * R) + e];
-        fold_row<S, NC>(d, buf, r, grow0 + r, g, ctid);
+        fold_row<S, NC, G>(d, buf, r, grow0 + r, g, ctid, ra, (it - 1) * d.tile_rows + r);
       }
       __syncwarp();
       if (lane == 0 && ptile < d.ntiles) mbar_arrive(&empty[pst]);
@@ -496,10 +648,23 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
     if (++st == d.stages) { st = 0; ph ^= 1; }
   }
 
-  // lane-private tables -> one global atomic per (warp, slot, accumulator)
   consumer_barrier<NC>();
   int ns = *((volatile int32_t *)g.nslots);
   if (ns > d.gmax) ns = d.gmax;
+  if constexpr (G > 0) {
+    // register slots -> warp shuffles -> one row per warp in the (now idle) ring -> one global atomic per (CTA, slot, accumulator)
+    i64 *red = (i64 *)ring;                   // [NW][G * NACC]
+    rs_flush<S, G, 0>(d, ra, red + (size_t)cw * (G * S::NACC), lane);
+    consumer_barrier<NC>();
+    for (int p = ctid; p < ns * S::NACC; p += NC) {
+      const int j = p % S::NACC, op = d.acc[j].op;
+      i64 v = acc_identity(op);
+      for (int w = 0; w < NW; w++) v = acc_combine(op, v, red[(size_t)w * (G * S::NACC) + p]);
+      if (v != acc_identity(op)) acc_global(op, d.table + (size_t)j * d.domain + g.slotkey[p / S::NACC], v);
+    }
+    return;
+  }
+  // lane-private tables -> one global atomic per (warp, slot, accumulator)
   for (int p = cw; p < ns * d.nacc; p += NW) {
     const int s = p / d.nacc, j = p % d.nacc, op = d.acc[j].op;
     i64 v = acc_identity(op);
@@ -604,7 +769,7 @@ struct vdl_fused {
   i64 *d_outbuf = nullptr;       // [nout][domain] fold results, then [ngroups, errflag]: fetched with ONE copy
   i64 *h_outbuf = nullptr;       // pinned mirror
   i64 ngroups = -1;
-  bool finalized = false, always_false = false;
+  bool finalized = false, always_false = false, rs = false;
   size_t smem_bytes = 0;
   int grid = 1, nc = 256, r = 4;
   scan_kernel_fn kernel = nullptr;
@@ -617,9 +782,24 @@ struct vdl_fused {
 
 template <class S>
 static scan_kernel_fn scan_kernel_for(int nc, int r) {
-  if (nc == 512) return r == 4 ? fused_scan_fold_kernel<S, 512, 4> : (r == 2 ? fused_scan_fold_kernel<S, 512, 2> : fused_scan_fold_kernel<S, 512, 1>);
-  return r == 4 ? fused_scan_fold_kernel<S, 256, 4> : (r == 2 ? fused_scan_fold_kernel<S, 256, 2> : fused_scan_fold_kernel<S, 256, 1>);
+  if (nc == 512) return r == 4 ? fused_scan_fold_kernel<S, 512, 4, 0> : (r == 2 ? fused_scan_fold_kernel<S, 512, 2, 0> : fused_scan_fold_kernel<S, 512, 1, 0>);
+  return r == 4 ? fused_scan_fold_kernel<S, 256, 4, 0> : (r == 2 ? fused_scan_fold_kernel<S, 256, 2, 0> : fused_scan_fold_kernel<S, 256, 1, 0>);
 }
+// register-slot instantiations (geometries: rs_geometries)
+template <class S>
+static scan_kernel_fn rs_kernel_for(int nc, int r) {
+  if constexpr (S::RS_G > 0) {
+    // consumer warps + the producer warp are dealt round-robin to the 4 SM sub-partitions (16 K registers each):
+    // 11 + 1 warps -> 3 per sub-partition -> 168 registers per thread; 15 + 1 -> 4 -> 128; 7 + 1 -> 2 -> 255
+    if (nc == 352 && r == 2) return fused_scan_fold_kernel<S, 352, 2, S::RS_G>;
+    if (nc == 352 && r == 4) return fused_scan_fold_kernel<S, 352, 4, S::RS_G>;
+    if (nc == 352 && r == 3) return fused_scan_fold_kernel<S, 352, 3, S::RS_G>;
+    if (nc == 480 && r == 2) return fused_scan_fold_kernel<S, 480, 2, S::RS_G>;
+    if (nc == 224 && r == 4) return fused_scan_fold_kernel<S, 224, 4, S::RS_G>;
+  }
+  return nullptr;
+}
+static const int rs_geometries[][2] = {{352, 4}, {352, 3}, {352, 2}, {480, 2}, {224, 4}};
 
 // does the prepared descriptor satisfy every assumption static shape S compiles in?
 static bool flags_ok(int fl, const KAffine &a) {
@@ -736,39 +916,73 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   for (int i = 0; i < desc->nfolds; i++)
     if (f->fd.out_kind[i] == 0 && f->fd.out_idx[i] < 0) f->fd.out_idx[i] = k.cnt_idx;
 
-  // geometry: consumer threads NC, rows per thread and tile R, ring depth, lane-private tables
+  // geometry: consumer threads NC, rows per thread and tile R, ring depth, lane-private tables (or none: register slots)
   k.grouped = desc->domain > 1 || desc->nkeys > 0;
   const int smem_max = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;
   if ((size_t)desc->domain * 4 > 64 * 1024) { delete f; return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: key domain %lld too large for the shared-memory slot map", (long long)desc->domain); }
-  bool placed = false;
-  for (int nc = 512; nc >= 256 && !placed; nc /= 2) {
-    // slots with lane-private tables: as many as the domain needs, up to what ~100 KB holds
-    int gmax = 1;
-    while (gmax < desc->domain && gmax < 64 && (size_t)(gmax * 2) * k.nacc * nc * 8 <= 120 * 1024) gmax *= 2;
-    if (nc == 512 && gmax < desc->domain && gmax < 8) continue;     // too few slots: halve the consumers instead
-    for (int r = 2048 / nc; r >= 1 && !placed; r /= 2) {
-      if (r > 4) continue;
-      int tile_rows = nc * r, off = 0;
-      size_t fixed = (size_t)gmax * k.nacc * nc * 8 + (size_t)desc->domain * 4 + (size_t)gmax * 4 + 16 + 256;
-      size_t per_stage = 3 * 8 + 4 + 4 + 2 * (size_t)tile_rows;   // barriers, queue count, queue
-      for (int c = 0; c < k.ncols; c++) { k.soff[c] = off; off += ((tile_rows * k.width[c] + 127) / 128) * 128; }
-      int stages = (int)(((long)smem_max - (long)fixed) / (long)(off + per_stage));
-      if (stages >= 3 || (r == 1 && stages >= 2 && nc == 256)) {
-        k.tile_rows = tile_rows; k.stage_bytes = off; k.stage_tx = tile_rows * rowbytes; k.stages = std::min(stages, 12);
-        k.gmax = gmax; f->nc = nc; f->r = r;
-        f->smem_bytes = (size_t)k.stages * (k.stage_bytes + per_stage) + fixed;
-        placed = true;
+  auto set_geometry = [&](int nc, int r, int gmax, bool tables, int min_stages) -> bool {
+    int tile_rows = nc * r, off = 0;
+    size_t fixed = (tables ? (size_t)gmax * k.nacc * nc * 8 : 0) + (size_t)desc->domain * 4 + (size_t)gmax * 4 + 16 + 256;
+    size_t per_stage = 3 * 8 + 4 + 4 + 2 * (size_t)tile_rows;   // barriers, queue count, queue
+    for (int c = 0; c < k.ncols; c++) { k.soff[c] = off; off += ((tile_rows * k.width[c] + 127) / 128) * 128; }
+    int stages = (int)(((long)smem_max - (long)fixed) / (long)(off + per_stage));
+    if (stages < min_stages) return false;
+    k.tile_rows = tile_rows; k.stage_bytes = off; k.stage_tx = tile_rows * rowbytes; k.stages = std::min(stages, 12);
+    k.gmax = gmax; f->nc = nc; f->r = r;
+    f->smem_bytes = (size_t)k.stages * (k.stage_bytes + per_stage) + fixed;
+    k.ntiles = desc->rows / k.tile_rows;
+    f->grid = (int)std::max<i64>(1, std::min<i64>(ctx->sm_count, k.ntiles));
+    return true;
+  };
+  auto default_geometry = [&]() -> bool {
+    for (int nc = 512; nc >= 256; nc /= 2) {
+      // slots with lane-private tables: as many as the domain needs, up to what ~100 KB holds
+      int gmax = 1;
+      while (gmax < desc->domain && gmax < 64 && (size_t)(gmax * 2) * k.nacc * nc * 8 <= 120 * 1024) gmax *= 2;
+      if (nc == 512 && gmax < desc->domain && gmax < 8) continue;     // too few slots: halve the consumers instead
+      for (int r = 2048 / nc; r >= 1; r /= 2) {
+        if (r > 4) continue;
+        if (set_geometry(nc, r, gmax, true, (r == 1 && nc == 256) ? 2 : 3)) return true;
       }
     }
+    return false;
+  };
+  if (!default_geometry()) { delete f; return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: %d columns x %d accumulators do not fit shared memory", k.ncols, k.nacc); }
+
+  // prefix sharing between consecutive accumulators (ep, ep*(100-d), ep*(100-d)*(100+t) evaluate each factor once)
+  for (int j = 1; j < k.nacc; j++) {
+    KAcc &a = k.acc[j];
+    if (j == k.cnt_idx || j == k.first_idx || j - 1 == k.cnt_idx) continue;
+    // full factor list of the previous accumulator (its own chain expanded) a prefix of this one?
+    std::vector<KAffine> prev;
+    int q = j - 1;
+    std::vector<int> chain_members;
+    while (true) { chain_members.push_back(q); if (!k.acc[q].chain) break; q--; }
+    for (int m = (int)chain_members.size() - 1; m >= 0; m--)
+      for (int t = 0; t < k.acc[chain_members[m]].nfac; t++) prev.push_back(k.acc[chain_members[m]].fac[t]);
+    bool prefix = !prev.empty() && (int)prev.size() < a.nfac;
+    for (size_t t = 0; prefix && t < prev.size(); t++)
+      prefix = prev[t].col == a.fac[t].col && prev[t].shr == a.fac[t].shr && prev[t].a == a.fac[t].a && prev[t].b == a.fac[t].b;
+    if (prefix) {
+      int np = (int)prev.size();
+      for (int t = np; t < a.nfac; t++) a.fac[t - np] = a.fac[t];
+      a.nfac -= np;
+      a.chain = 1;
+    }
   }
-  if (!placed) { delete f; return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: %d columns x %d accumulators do not fit shared memory", k.ncols, k.nacc); }
-  k.ntiles = desc->rows / k.tile_rows;
-  f->grid = (int)std::max<i64>(1, std::min<i64>(ctx->sm_count, k.ntiles));
-  // derived descriptor fields: staged offsets / width flags, 32-bit bounds for 4-byte predicate columns,
-  // prefix sharing between consecutive accumulators
+
+  // derived descriptor fields (depend on the geometry): staged offsets / width flags, 32-bit bounds for 4-byte
+  // predicate columns, value bounds of every affine term from the column statistics
+  struct Bound { __int128 lo, hi; };
+  std::map<const KAffine *, Bound> bound;
   int place_rc = VDL_OK;
   auto place = [&](KAffine &a) {
-    if (a.col < 0) return;
+    if (a.col == -1) { bound[&a] = Bound{a.a, a.a}; return; }
+    if (a.col == -2) {
+      __int128 v0 = (__int128)a.a + (__int128)a.b * k.row_base, v1 = (__int128)a.a + (__int128)a.b * (k.row_base + k.rows);
+      bound[&a] = Bound{std::min(v0, v1), std::max(v0, v1)};
+      return;
+    }
     a.soff = k.soff[a.col];
     a.w4 = k.width[a.col] == 4;
     // narrow: leaf and a + b*leaf provably fit int32 given the column's exact min/max (cf. inferBounds, Vlite.hs:417-467)
@@ -779,56 +993,102 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     __int128 v0 = (__int128)a.a + (__int128)a.b * l0, v1 = (__int128)a.a + (__int128)a.b * l1;
     auto fits = [](__int128 x) { return x >= INT32_MIN && x <= INT32_MAX; };
     a.narrow = cmin <= cmax && fits(l0) && fits(l1) && fits(v0) && fits(v1) && fits(a.a) && fits(a.b);
+    bound[&a] = Bound{std::min(v0, v1), std::max(v0, v1)};
   };
-  for (int i = 0; i < k.npreds; i++) {
-    KPred &p = k.pred[i];
-    p.soff = k.soff[p.col];
-    p.w4 = k.width[p.col] == 4;
-    if (!p.w4) {   // 8-byte column: when the column statistics say every (shifted) value fits int32, read low words only
-      i64 cmin, cmax;
-      int rc2 = vdl_column_analyze(ctx, desc->column[p.col], &cmin, &cmax);
-      if (rc2) { vdl_fused_destroy(f); return rc2; }
-      if ((cmin >> p.shr) >= INT32_MIN && (cmax >> p.shr) <= INT32_MAX) p.w4 = 2;
-    }
-    if (p.w4) {   // values of a 4-byte column (shifted or not) lie in int32: clamp the bounds, compare in 32 bits
-      i64 lo = std::max<i64>(p.lo, INT32_MIN), hi = std::min<i64>((i64)((u64)p.lo + p.span), INT32_MAX);
-      if (lo > hi) f->always_false = true;
-      p.lo32 = (int32_t)lo;
-      p.span32 = (uint32_t)(hi - lo);
-    }
-  }
-  for (int i = 0; i < k.nkeys; i++) place(k.key[i].e);
-  for (int j = 0; j < k.nacc; j++) {
-    KAcc &a = k.acc[j];
-    if (j > 0 && j != k.cnt_idx && j != k.first_idx) {
-      // full factor list of the previous accumulator (its own chain expanded) a prefix of this one?
-      std::vector<KAffine> prev;
-      int q = j - 1;
-      std::vector<int> chain_members;
-      while (true) { chain_members.push_back(q); if (!k.acc[q].chain) break; q--; }
-      for (int m = (int)chain_members.size() - 1; m >= 0; m--)
-        for (int t = 0; t < k.acc[chain_members[m]].nfac; t++) prev.push_back(k.acc[chain_members[m]].fac[t]);
-      bool prefix = !prev.empty() && (int)prev.size() < a.nfac && j - 1 != k.cnt_idx;
-      for (size_t t = 0; prefix && t < prev.size(); t++)
-        prefix = prev[t].col == a.fac[t].col && prev[t].shr == a.fac[t].shr && prev[t].a == a.fac[t].a && prev[t].b == a.fac[t].b;
-      if (prefix) {
-        int np = (int)prev.size();
-        for (int t = np; t < a.nfac; t++) a.fac[t - np] = a.fac[t];
-        a.nfac -= np;
-        a.chain = 1;
+  auto derive = [&]() -> int {
+    for (int i = 0; i < k.npreds; i++) {
+      KPred &p = k.pred[i];
+      p.soff = k.soff[p.col];
+      p.w4 = k.width[p.col] == 4;
+      if (!p.w4) {   // 8-byte column: when the column statistics say every (shifted) value fits int32, read low words only
+        i64 cmin, cmax;
+        int rc2 = vdl_column_analyze(ctx, desc->column[p.col], &cmin, &cmax);
+        if (rc2) return rc2;
+        if ((cmin >> p.shr) >= INT32_MIN && (cmax >> p.shr) <= INT32_MAX) p.w4 = 2;
+      }
+      if (p.w4) {   // values of a 4-byte column (shifted or not) lie in int32: clamp the bounds, compare in 32 bits
+        i64 lo = std::max<i64>(p.lo, INT32_MIN), hi = std::min<i64>((i64)((u64)p.lo + p.span), INT32_MAX);
+        if (lo > hi) f->always_false = true;
+        p.lo32 = (int32_t)lo;
+        p.span32 = (uint32_t)(hi - lo);
       }
     }
-    for (int t = 0; t < a.nfac; t++) place(a.fac[t]);
-  }
-  if (place_rc) { vdl_fused_destroy(f); return place_rc; }
-  // pick the kernel: a static shape whose assumptions all hold, else the generic one
+    for (int i = 0; i < k.nkeys; i++) place(k.key[i].e);
+    for (int j = 0; j < k.nacc; j++)
+      for (int t = 0; t < k.acc[j].nfac; t++) place(k.acc[j].fac[t]);
+    return place_rc;
+  };
+  { int rc2 = derive(); if (rc2) { vdl_fused_destroy(f); return rc2; } }
+
+  // largest |value| accumulator j can take on one row (chain expanded), saturating
+  auto acc_maxabs = [&](int j) -> __int128 {
+    __int128 m = 1;
+    const __int128 cap = (__int128)1 << 100;
+    for (int q = j;; q--) {
+      for (int t = 0; t < k.acc[q].nfac; t++) {
+        const Bound &b = bound[&k.acc[q].fac[t]];
+        __int128 x = std::max(b.lo < 0 ? -b.lo : b.lo, b.hi < 0 ? -b.hi : b.hi);
+        m = m * x;
+        if (m > cap) m = cap;
+      }
+      if (!k.acc[q].chain) break;
+    }
+    return m;
+  };
+  // the proofs a register-slot instantiation of shape S needs under the CURRENT geometry (vdl_shapes.cuh)
+  auto rs_proofs_hold = [&](const int *rk) -> bool {
+    const i64 ntiles_all = k.ntiles + (k.ntiles * k.tile_rows < k.rows ? 1 : 0);
+    const i64 tiles_per_cta = (ntiles_all + f->grid - 1) / f->grid;
+    const __int128 rows_per_thread = (__int128)tiles_per_cta * 2 * f->r;   // own rows of a dense tile + a share of the queue
+    for (int j = 0; j < k.nacc; j++) {
+      if (rk[j] == RK_N32 && (k.acc[j].op != 0 || rows_per_thread * acc_maxabs(j) > INT32_MAX)) return false;
+      if (rk[j] == RK_MADW) {          // value = a * b with a = everything but the last own factor, b = that factor
+        if (k.acc[j].op != 0 || k.acc[j].nfac < 1) return false;
+        const Bound &bb = bound[&k.acc[j].fac[k.acc[j].nfac - 1]];
+        __int128 bmax = std::max(bb.lo < 0 ? -bb.lo : bb.lo, bb.hi < 0 ? -bb.hi : bb.hi);
+        if (bmax > INT32_MAX || (bmax > 0 && acc_maxabs(j) / bmax > INT32_MAX) || acc_maxabs(j) >= ((__int128)1 << 100)) return false;
+      }
+      if (rk[j] == RK_FIRST && (k.acc[j].op != 1 || (__int128)tiles_per_cta * k.tile_rows >= INT32_MAX)) return false;
+    }
+    return true;
+  };
+
+  // pick the kernel: a static shape whose assumptions all hold, else the generic one; a shape with register slots
+  // runs in that mode when the key domain's slots and the 32-bit proofs allow it
   f->kernel = scan_kernel_for<GenericShape>(f->nc, f->r);
+  auto try_shape = [&](auto shape_tag) -> int {
+    using S = decltype(shape_tag);
+    if (!shape_matches<S>(k)) return 0;
+    f->kernel = scan_kernel_for<S>(f->nc, f->r);
+    f->shape = S::kName;
+    if constexpr (S::RS_G > 0) {
+      if (getenv("VDL_NO_REGISTER_SLOTS")) return 1;
+      int want_nc = 0, want_r = 0;
+      if (const char *e = getenv("VDL_RS_GEOMETRY")) sscanf(e, "%d,%d", &want_nc, &want_r);
+      for (auto &geo : rs_geometries) {
+        if (want_nc && (geo[0] != want_nc || geo[1] != want_r)) continue;
+        if (!rs_kernel_for<S>(geo[0], geo[1]) || !set_geometry(geo[0], geo[1], S::RS_G, false, 3)) continue;
+        int rc2 = derive();
+        if (rc2) return -rc2;
+        if (shape_matches<S>(k) && rs_proofs_hold(S::ACC_RK)) {
+          f->kernel = rs_kernel_for<S>(geo[0], geo[1]);
+          f->rs = true;
+          return 1;
+        }
+      }
+      default_geometry();               // no register-slot geometry qualified: back to the shared-memory tables
+      int rc2 = derive();
+      if (rc2) return -rc2;
+    }
+    return 1;
+  };
   if (!getenv("VDL_GENERIC_ONLY")) {
-    if (shape_matches<ShapeSel3Sum2>(k)) { f->kernel = scan_kernel_for<ShapeSel3Sum2>(f->nc, f->r); f->shape = ShapeSel3Sum2::kName; }
-    else if (shape_matches<ShapeSel1Key2Sum5>(k)) { f->kernel = scan_kernel_for<ShapeSel1Key2Sum5>(f->nc, f->r); f->shape = ShapeSel1Key2Sum5::kName; }
+    int m = try_shape(ShapeSel3Sum2{});
+    if (m == 0) m = try_shape(ShapeSel1Key2Sum5{});
+    if (m < 0) { vdl_fused_destroy(f); return -m; }
   }
   if (getenv("VDL_DEBUG_SHAPE")) {
-    fprintf(stderr, "[vdl] fused scan: shape=%s nc=%d r=%d stages=%d gmax=%d npreds=%d nkeys=%d nacc=%d\n", f->shape, f->nc, f->r, k.stages, k.gmax, k.npreds, k.nkeys, k.nacc);
+    fprintf(stderr, "[vdl] fused scan: shape=%s%s nc=%d r=%d stages=%d gmax=%d npreds=%d nkeys=%d nacc=%d smem=%zu\n", f->shape, f->rs ? " (register slots)" : "", f->nc, f->r, k.stages, k.gmax, k.npreds, k.nkeys, k.nacc, f->smem_bytes);
     for (int i = 0; i < k.npreds; i++) fprintf(stderr, "[vdl]   pred %d: mode=%d shr=%d\n", i, k.pred[i].w4, k.pred[i].shr);
     for (int i = 0; i < k.nkeys; i++) fprintf(stderr, "[vdl]   key %d: col=%d w4=%d shr=%d a=%lld b=%lld shl=%d narrow=%d\n", i, k.key[i].e.col, k.key[i].e.w4, k.key[i].e.shr, (long long)k.key[i].e.a, (long long)k.key[i].e.b, k.key[i].shl, k.key[i].e.narrow);
     for (int j = 0; j < k.nacc; j++) {

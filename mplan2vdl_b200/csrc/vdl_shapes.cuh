@@ -9,6 +9,14 @@
 
 #define FF_COLN (FF_SHR0 | FF_B1 | FF_A0 | FF_NARROW)      /* a plain 8-byte column whose values fit int32 */
 
+// REGISTER SLOTS.  A grouped shape may declare RS_G > 0: the first RS_G keys a CTA meets get their accumulators in
+// the REGISTERS of every consumer thread (updated under `slot == g` predicates: no shared-memory read-modify-write
+// at all), reduced once at the end of the kernel.  ACC_RK says how accumulator J is kept per thread:
+//   RK_WIDE  64-bit;  RK_MADW  64-bit SUM of a product a x b with |a|, |b| < 2^31 proved from the statistics (the
+//   update is one predicated mad.wide.s32);  RK_N32  32-bit SUM -- the host proves from the column statistics and the launch geometry that
+//   rows-per-thread x max|value| < 2^31;  RK_FIRST  MIN(row id) kept as a 32-bit CTA-local row index.
+// The host falls back to the shared-memory tables (same shape, G = 0) when a proof fails.
+
 // select(3 ranges: int32 col, 2 x narrow 8-byte col) -> SUM(col * col), COUNT          [TPC-H Q6, Vlite.hs:721-730]
 struct ShapeSel3Sum2 {
   static constexpr bool kStatic = true;
@@ -18,6 +26,8 @@ struct ShapeSel3Sum2 {
   static constexpr int KEY_FLAGS[VDL_MAX_KEYS] = {}, KEY_SHL0[VDL_MAX_KEYS] = {};
   static constexpr int ACC_OP[K_MAX_ACC] = {0, 0}, ACC_CHAIN[K_MAX_ACC] = {0, 0}, ACC_NFAC[K_MAX_ACC] = {2, 0};
   static constexpr int FAC[K_MAX_ACC][VDL_MAX_FACTORS] = {{FF_COLN, FF_COLN}, {}};
+  static constexpr int RS_G = 0;
+  static constexpr int ACC_RK[K_MAX_ACC] = {};
 };
 
 // select(1 range on an int32 col) -> group by a 2-part narrow key -> SUM c, SUM c, SUM c*(k-c), chain*(k+c), SUM c,
@@ -34,4 +44,6 @@ struct ShapeSel1Key2Sum5 {
   static constexpr int FAC[K_MAX_ACC][VDL_MAX_FACTORS] = {
       {FF_COLN}, {FF_COLN}, {FF_SHR0 | FF_BM1 | FF_NARROW}, {FF_SHR0 | FF_B1 | FF_NARROW}, {FF_COLN}, {},
       {FF_ROWID | FF_SHR0 | FF_B1 | FF_A0}};
+  static constexpr int RS_G = 8;
+  static constexpr int ACC_RK[K_MAX_ACC] = {RK_N32, RK_MADW, RK_MADW, RK_MADW, RK_N32, RK_N32, RK_FIRST};
 };
