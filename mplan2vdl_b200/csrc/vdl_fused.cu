@@ -45,7 +45,7 @@ struct KDesc {
   const void *col[VDL_MAX_COLS];
   int32_t width[VDL_MAX_COLS], soff[VDL_MAX_COLS];
   int32_t ncols, npreds, nkeys, nacc, nchoose, cnt_idx, first_idx;
-  int32_t tile_rows, stages, stage_bytes, stage_tx, gmax, grouped;
+  int32_t tile_rows, stages, stage_bytes, stage_tx, gmax, pad0;
   KPred pred[VDL_MAX_PREDS];
   KKey key[VDL_MAX_KEYS];
   KAcc acc[K_MAX_ACC];
@@ -382,7 +382,12 @@ template <class S, int G, int Q, int J>
 __device__ __forceinline__ void rs_apply(RegAcc<S, G> &ra, int s, const i64 *v, const int32_t *va, const int32_t *vb, int lrow) {
   if constexpr (J < S::NACC) {
     constexpr int op = S::ACC_OP[J];
-    if constexpr (S::ACC_RK[J] == RK_MADW) pred_add64(ra.w[Q][J], v[J], s, Q);
+    if constexpr (S::ACC_RK[J] == RK_MADW) {
+      // acc += (slot matches ? a : 0) * b as ONE 32x32+64 multiply-add (IMAD.WIDE.U32, fma pipe) after one select that
+      // accumulators sharing `a` share; 0 <= a, b < 2^31 by the host's proof.  (A predicated 64-bit add costs 3.)
+      const uint32_t am = (s == Q) ? (uint32_t)va[J] : 0u;
+      ra.w[Q][J] = (i64)((u64)ra.w[Q][J] + (u64)am * (u64)(uint32_t)vb[J]);
+    }
     else if constexpr (S::ACC_RK[J] == RK_WIDE) {
       if constexpr (op == 0) pred_add64(ra.w[Q][J], v[J], s, Q);
       else if constexpr (op == 1) pred_min64(ra.w[Q][J], v[J], s, Q);
@@ -392,11 +397,11 @@ __device__ __forceinline__ void rs_apply(RegAcc<S, G> &ra, int s, const i64 *v, 
     rs_apply<S, G, Q, J + 1>(ra, s, v, va, vb, lrow);
   }
 }
-template <class S, int G, int Q>
+template <class S, int G, int GL, int Q>
 __device__ __forceinline__ void rs_apply_slots(RegAcc<S, G> &ra, int s, const i64 *v, const int32_t *va, const int32_t *vb, int lrow) {
-  if constexpr (Q < G) {
+  if constexpr (Q < GL) {
     rs_apply<S, G, Q, 0>(ra, s, v, va, vb, lrow);
-    rs_apply_slots<S, G, Q + 1>(ra, s, v, va, vb, lrow);
+    rs_apply_slots<S, G, GL, Q + 1>(ra, s, v, va, vb, lrow);
   }
 }
 
@@ -435,7 +440,8 @@ struct GroupState {
 };
 
 // Phase 2 (the Gathers + elementwise map + Fold of the plan): fold one selected row into the lane-private tables.
-template <class S, int NC, int G>
+// GL (register slots only): the slot tests cover slots 0 .. GL-1 (= G today; a slot >= GL takes the global-atomic path).
+template <class S, int NC, int G, int GL>
 __device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *tile, int r, i64 grow, const GroupState &g, int ctid,
                                          RegAcc<S, G> &ra, int lrow) {
   i64 key;
@@ -450,9 +456,9 @@ __device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *ti
     i64 v[RegAcc<S, G>::NA];
     int32_t va[RegAcc<S, G>::NA], vb[RegAcc<S, G>::NA];
     rs_values<S, 0>(d, v, va, vb, 1, tile, r, grow);
-    rs_apply_slots<S, G, 0>(ra, s, v, va, vb, lrow);     // s < 0 (key without a slot yet) matches none
+    rs_apply_slots<S, G, GL, 0>(ra, s, v, va, vb, lrow);     // s < 0 (key without a slot yet) matches none
   }
-  if (s >= 0) {
+  if (s >= 0 && (G == 0 || s < GL)) {
     if constexpr (G == 0) acc_chain<S, 0, NC>(d, g.tbl + (size_t)s * d.nacc * NC + ctid, 1, tile, r, grow);
   } else {
     // first rows of a key in this CTA: fold straight into the global table and claim a slot for the rest
@@ -468,6 +474,52 @@ __device__ __forceinline__ void fold_row(const KDesc &d, const unsigned char *ti
         atomicExch(&g.slotmap[key], -3);
       }
     }
+  }
+}
+
+// Dense tile, register slots: the R rows of a thread as ONE branch-free block so that their shared-memory loads and
+// dependent chains overlap.  A row that did not pass the selection, or whose key has no register slot yet, gets
+// slot -1 (matches no predicate); the latter rows are then redone by fold_row, which owns the claim / global path.
+template <class S, int NC, int R, int G, int GL>
+__device__ __forceinline__ void fold_dense(const KDesc &d, const unsigned char *tile, unsigned pass, int ctid, i64 grow0, const GroupState &g,
+                                           RegAcc<S, G> &ra, int lrow0) {
+  if constexpr (S::kStatic && S::KEY32) {
+    int sl[R];
+    unsigned redo = 0;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      // the host checked 0 <= key_mask < domain for a KEY32 shape: the masked key needs no range test
+      const int key = key_chain32<S, 0>(d, 0, tile, ctid + k * NC) & (int32_t)d.key_mask;
+      const int s = ((volatile int32_t *)g.slotmap)[key];
+      const bool on = (pass >> k) & 1, have = (unsigned)s < (unsigned)GL;
+      sl[k] = (on && have) ? s : -1;
+      if (on && !have) redo |= 1u << k;
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      const int r = ctid + k * NC;
+      i64 v[RegAcc<S, G>::NA];
+      int32_t va[RegAcc<S, G>::NA], vb[RegAcc<S, G>::NA];
+      rs_values<S, 0>(d, v, va, vb, 1, tile, r, grow0 + r);
+      rs_apply_slots<S, G, GL, 0>(ra, sl[k], v, va, vb, lrow0 + r);
+    }
+    if (redo) {
+#pragma unroll 1
+      for (int k = 0; k < R; k++)
+        if ((redo >> k) & 1) fold_row<S, NC, G, GL>(d, tile, ctid + k * NC, grow0 + ctid + k * NC, g, ctid, ra, lrow0 + ctid + k * NC);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < R; k++)
+      if ((pass >> k) & 1) fold_row<S, NC, G, GL>(d, tile, ctid + k * NC, grow0 + ctid + k * NC, g, ctid, ra, lrow0 + ctid + k * NC);
+  }
+}
+template <class S, int NC, int R, int G, int GL>
+__device__ __forceinline__ void fold_queue(const KDesc &d, const unsigned char *buf, const uint16_t *queue, int e0, int nsel, i64 grow0,
+                                           const GroupState &g, int ctid, RegAcc<S, G> &ra, int lrow0) {
+  for (int e = e0; e < nsel; e += NC) {
+    const int r = queue[e];
+    fold_row<S, NC, G, GL>(d, buf, r, grow0 + r, g, ctid, ra, lrow0 + r);
   }
 }
 
@@ -488,13 +540,11 @@ __device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char 
   if (__popc(any) >= 24) {
     // dense selection (most lanes own a selected row): compaction would buy nothing, fold the rows where they are
     if constexpr (G > 0) {   // straight-line predicated code: let the R rows of a thread overlap
-#pragma unroll
-      for (int k = 0; k < R; k++)
-        if ((pass >> k) & 1) fold_row<S, NC, G>(d, tile, ctid + k * NC, grow0 + ctid + k * NC, g, ctid, ra, lrow0 + ctid + k * NC);
+      fold_dense<S, NC, R, G, G>(d, tile, pass, ctid, grow0, g, ra, lrow0);
     } else {
 #pragma unroll 1
       for (int k = 0; k < R; k++)
-        if ((pass >> k) & 1) fold_row<S, NC, G>(d, tile, ctid + k * NC, grow0 + ctid + k * NC, g, ctid, ra, lrow0 + ctid + k * NC);
+        if ((pass >> k) & 1) fold_row<S, NC, G, 0>(d, tile, ctid + k * NC, grow0 + ctid + k * NC, g, ctid, ra, lrow0 + ctid + k * NC);
     }
     return;
   }
@@ -636,10 +686,9 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
       // queue entries in chunks of 32, dealt to the warps starting at a warp that rotates with the tile
       int chunk = cw - ((it - 1) % NW);
       if (chunk < 0) chunk += NW;
-      for (int e = chunk * 32 + lane; e < nsel; e += NC) {
-        const int r = queue[(size_t)pst * (NC * R) + e];
-        fold_row<S, NC, G>(d, buf, r, grow0 + r, g, ctid, ra, (it - 1) * d.tile_rows + r);
-      }
+      const uint16_t *q = queue + (size_t)pst * (NC * R);
+      const int e0 = chunk * 32 + lane, lrow0 = (it - 1) * d.tile_rows;
+      fold_queue<S, NC, R, G, G>(d, buf, q, e0, nsel, grow0, g, ctid, ra, lrow0);
       __syncwarp();
       if (lane == 0 && ptile < d.ntiles) mbar_arrive(&empty[pst]);
     }
@@ -770,6 +819,11 @@ struct vdl_fused {
   i64 *h_outbuf = nullptr;       // pinned mirror
   i64 ngroups = -1;
   bool finalized = false, always_false = false, rs = false;
+  // register slots: kernels by slot count; the launch picks the smallest count that covers the groups the previous
+  // run of this scan produced (more slots = more predicated work per row; too few = keys on the slow global path)
+  scan_kernel_fn rs_kernel[9] = {nullptr};
+  int rs_gmax = 0;
+  i64 groups_seen = -1;
   size_t smem_bytes = 0;
   int grid = 1, nc = 256, r = 4;
   scan_kernel_fn kernel = nullptr;
@@ -785,21 +839,28 @@ static scan_kernel_fn scan_kernel_for(int nc, int r) {
   if (nc == 512) return r == 4 ? fused_scan_fold_kernel<S, 512, 4, 0> : (r == 2 ? fused_scan_fold_kernel<S, 512, 2, 0> : fused_scan_fold_kernel<S, 512, 1, 0>);
   return r == 4 ? fused_scan_fold_kernel<S, 256, 4, 0> : (r == 2 ? fused_scan_fold_kernel<S, 256, 2, 0> : fused_scan_fold_kernel<S, 256, 1, 0>);
 }
-// register-slot instantiations (geometries: rs_geometries)
+// register-slot instantiations (geometries: rs_geometries) for g of the shape's RS_G slots in registers
+template <class S, int G>
+static scan_kernel_fn rs_kernel_for_g(int nc, int r) {
+  // consumer warps + the producer warp are dealt round-robin to the 4 SM sub-partitions (16 K registers each):
+  // 11 + 1 warps -> 3 per sub-partition -> 168 registers per thread; 15 + 1 -> 4 -> 128; 7 + 1 -> 2 -> 255
+  if (nc == 352 && r == 4) return fused_scan_fold_kernel<S, 352, 4, G>;
+  if (nc == 352 && r == 2) return fused_scan_fold_kernel<S, 352, 2, G>;
+  if (nc == 480 && r == 2) return fused_scan_fold_kernel<S, 480, 2, G>;
+  return nullptr;
+}
 template <class S>
-static scan_kernel_fn rs_kernel_for(int nc, int r) {
+static scan_kernel_fn rs_kernel_for(int nc, int r, int g) {
   if constexpr (S::RS_G > 0) {
-    // consumer warps + the producer warp are dealt round-robin to the 4 SM sub-partitions (16 K registers each):
-    // 11 + 1 warps -> 3 per sub-partition -> 168 registers per thread; 15 + 1 -> 4 -> 128; 7 + 1 -> 2 -> 255
-    if (nc == 352 && r == 2) return fused_scan_fold_kernel<S, 352, 2, S::RS_G>;
-    if (nc == 352 && r == 4) return fused_scan_fold_kernel<S, 352, 4, S::RS_G>;
-    if (nc == 352 && r == 3) return fused_scan_fold_kernel<S, 352, 3, S::RS_G>;
-    if (nc == 480 && r == 2) return fused_scan_fold_kernel<S, 480, 2, S::RS_G>;
-    if (nc == 224 && r == 4) return fused_scan_fold_kernel<S, 224, 4, S::RS_G>;
+    static_assert(S::RS_G == 8, "instantiate the slot counts this shape allows");
+    if (g == 8) return rs_kernel_for_g<S, 8>(nc, r);
+    if (g == 6) return rs_kernel_for_g<S, 6>(nc, r);
+    if (g == 4) return rs_kernel_for_g<S, 4>(nc, r);
   }
   return nullptr;
 }
-static const int rs_geometries[][2] = {{352, 4}, {352, 3}, {352, 2}, {480, 2}, {224, 4}};
+static const int rs_slot_counts[] = {4, 6, 8};
+static const int rs_geometries[][2] = {{352, 4}, {352, 2}, {480, 2}};
 
 // does the prepared descriptor satisfy every assumption static shape S compiles in?
 static bool flags_ok(int fl, const KAffine &a) {
@@ -821,7 +882,7 @@ static bool shape_matches(const KDesc &k) {
     if (!flags_ok(S::KEY_FLAGS[i], k.key[i].e) || (S::KEY_SHL0[i] && k.key[i].shl != 0)) return false;
     if (S::KEY32 && !k.key[i].e.narrow) return false;
   }
-  if (S::KEY32 && (k.key_mask < 0 || k.key_mask > INT32_MAX)) return false;
+  if (S::KEY32 && (k.key_mask < 0 || k.key_mask > INT32_MAX || k.key_mask >= k.domain)) return false;
   for (int j = 0; j < k.nacc; j++) {
     if (k.acc[j].op != S::ACC_OP[j] || k.acc[j].chain != S::ACC_CHAIN[j] || k.acc[j].nfac != S::ACC_NFAC[j]) return false;
     for (int t = 0; t < k.acc[j].nfac; t++)
@@ -917,7 +978,6 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     if (f->fd.out_kind[i] == 0 && f->fd.out_idx[i] < 0) f->fd.out_idx[i] = k.cnt_idx;
 
   // geometry: consumer threads NC, rows per thread and tile R, ring depth, lane-private tables (or none: register slots)
-  k.grouped = desc->domain > 1 || desc->nkeys > 0;
   const int smem_max = ctx->smem_optin > 0 ? ctx->smem_optin : 232448;
   if ((size_t)desc->domain * 4 > 64 * 1024) { delete f; return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: key domain %lld too large for the shared-memory slot map", (long long)desc->domain); }
   auto set_geometry = [&](int nc, int r, int gmax, bool tables, int min_stages) -> bool {
@@ -1047,6 +1107,11 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
         const Bound &bb = bound[&k.acc[j].fac[k.acc[j].nfac - 1]];
         __int128 bmax = std::max(bb.lo < 0 ? -bb.lo : bb.lo, bb.hi < 0 ? -bb.hi : bb.hi);
         if (bmax > INT32_MAX || (bmax > 0 && acc_maxabs(j) / bmax > INT32_MAX) || acc_maxabs(j) >= ((__int128)1 << 100)) return false;
+        for (int q = j;; q--) {        // every factor nonnegative: the multiply-add is unsigned
+          for (int t = 0; t < k.acc[q].nfac; t++)
+            if (bound[&k.acc[q].fac[t]].lo < 0) return false;
+          if (!k.acc[q].chain) break;
+        }
       }
       if (rk[j] == RK_FIRST && (k.acc[j].op != 1 || (__int128)tiles_per_cta * k.tile_rows >= INT32_MAX)) return false;
     }
@@ -1067,12 +1132,14 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
       if (const char *e = getenv("VDL_RS_GEOMETRY")) sscanf(e, "%d,%d", &want_nc, &want_r);
       for (auto &geo : rs_geometries) {
         if (want_nc && (geo[0] != want_nc || geo[1] != want_r)) continue;
-        if (!rs_kernel_for<S>(geo[0], geo[1]) || !set_geometry(geo[0], geo[1], S::RS_G, false, 3)) continue;
+        if (!rs_kernel_for<S>(geo[0], geo[1], S::RS_G) || !set_geometry(geo[0], geo[1], S::RS_G, false, 3)) continue;
         int rc2 = derive();
         if (rc2) return -rc2;
         if (shape_matches<S>(k) && rs_proofs_hold(S::ACC_RK)) {
-          f->kernel = rs_kernel_for<S>(geo[0], geo[1]);
+          for (int g : rs_slot_counts) f->rs_kernel[g] = rs_kernel_for<S>(geo[0], geo[1], g);
+          f->kernel = f->rs_kernel[S::RS_G];
           f->rs = true;
+          f->rs_gmax = S::RS_G;
           return 1;
         }
       }
@@ -1135,6 +1202,11 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
 
   cudaError_t e = cudaFuncSetAttribute(f->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   if (e != cudaSuccess) { vdl_fused_destroy(f); return vdl_cuda_fail(ctx, e, "cudaFuncSetAttribute(fused_scan_fold_kernel)"); }
+  for (int g : rs_slot_counts)
+    if (f->rs && f->rs_kernel[g] && (e = cudaFuncSetAttribute(f->rs_kernel[g], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max)) != cudaSuccess) {
+      vdl_fused_destroy(f);
+      return vdl_cuda_fail(ctx, e, "cudaFuncSetAttribute(fused_scan_fold_kernel, register slots)");
+    }
   *out = f;
   return VDL_OK;
 }
@@ -1149,6 +1221,14 @@ extern "C" int vdl_fused_launch(vdl_fused *f) {
   fused_init_kernel<<<std::max(nb, 1), 256, 0, ctx->stream>>>(f->kd);
   ctx->launches++;
   VDL_CUDA(ctx, cudaEventRecord(f->ev0, ctx->stream));
+  if (f->rs) {
+    int g = f->rs_gmax;
+    if (f->groups_seen >= 0 && !getenv("VDL_RS_ALL_SLOTS"))
+      for (int c : rs_slot_counts)
+        if (c >= f->groups_seen && c < g && f->rs_kernel[c]) g = c;
+    f->kernel = f->rs_kernel[g];
+    f->kd.gmax = g;
+  }
   if (f->kd.rows > 0 && !f->always_false) {
     f->kernel<<<f->grid, f->nc + 32, f->smem_bytes, ctx->stream>>>(f->kd);
     ctx->launches++;
@@ -1200,6 +1280,7 @@ static int fused_fetch(vdl_fused *f) {
     return vdl_fail(ctx, VDL_ERANGE, "fused scan: %lld rows produced a group key outside the key domain", (long long)err);
   }
   f->ngroups = ng;
+  f->groups_seen = ng;
   for (int i = 0; i < f->nout; i++) ctx->vecs[f->out[i]].len = ng;
   return VDL_OK;
 }

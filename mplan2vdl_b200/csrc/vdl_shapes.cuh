@@ -12,8 +12,8 @@
 // REGISTER SLOTS.  A grouped shape may declare RS_G > 0: the first RS_G keys a CTA meets get their accumulators in
 // the REGISTERS of every consumer thread (updated under `slot == g` predicates: no shared-memory read-modify-write
 // at all), reduced once at the end of the kernel.  ACC_RK says how accumulator J is kept per thread:
-//   RK_WIDE  64-bit;  RK_MADW  64-bit SUM of a product a x b with |a|, |b| < 2^31 proved from the statistics (the
-//   update is one predicated mad.wide.s32);  RK_N32  32-bit SUM -- the host proves from the column statistics and the launch geometry that
+//   RK_WIDE  64-bit;  RK_MADW  64-bit SUM of a product a x b with 0 <= a, b < 2^31 proved from the statistics (the
+//   update is one select + one 32x32+64 multiply-add);  RK_N32  32-bit SUM -- the host proves from the column statistics and the launch geometry that
 //   rows-per-thread x max|value| < 2^31;  RK_FIRST  MIN(row id) kept as a 32-bit CTA-local row index.
 // The host falls back to the shared-memory tables (same shape, G = 0) when a proof fails.
 
