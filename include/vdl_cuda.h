@@ -138,6 +138,7 @@ int vdl_op_fold(vdl_ctx *ctx, int fold_op, vdl_vec groups, vdl_vec data, vdl_vec
 #define VDL_MAX_KEYS 4
 #define VDL_MAX_AGGS 8
 #define VDL_MAX_FACTORS 3
+#define VDL_MAX_POSTS 8
 
 typedef struct {          /* value = a + b * (column[row] >> shr); column < 0: the constant a;   */
   int32_t column;         /* column == -2: the global row id (row_base + row)                      */
@@ -153,6 +154,12 @@ typedef struct {
   vdl_affine factor[VDL_MAX_FACTORS];
 } vdl_fold_spec;
 
+/* Elementwise epilogue over the fold results (AVG = Divide(FoldSum x, FoldSum 1), Vlite.hs:1038-1041): post op i
+ * = op(a, b) per group, evaluated inside the finalize kernel; an operand is a fold's result, an earlier post op's
+ * result, or a constant. */
+enum { VDL_POST_FOLD = 0, VDL_POST_POST = 1, VDL_POST_CONST = 2 };
+typedef struct { int32_t op, a_kind, b_kind, pad; int64_t a, b; } vdl_post_op;   /* op: a VDL_* binary op */
+
 typedef struct {
   int64_t rows;                       /* rows of this shard */
   int64_t row_base;                   /* global row id of this shard's row 0 */
@@ -166,6 +173,8 @@ typedef struct {
   int64_t domain;                     /* keys are in [0, domain) */
   int32_t nfolds;
   vdl_fold_spec fold[VDL_MAX_AGGS];
+  int32_t nposts;
+  vdl_post_op post[VDL_MAX_POSTS];
 } vdl_fused_desc;
 
 typedef struct vdl_fused vdl_fused;   /* a prepared fused scan (device tables, launch geometry) */
@@ -173,6 +182,9 @@ typedef struct vdl_fused vdl_fused;   /* a prepared fused scan (device tables, l
 int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_fused **out);
 /* Launch the scan over this shard; leaves the partial table [nacc][domain] of int64 in HBM. */
 int vdl_fused_launch(vdl_fused *f);
+/* self_finalize != 0 (single GPU): the scan kernel's last thread block also finalizes (as vdl_fused_finalize(f, NULL, 1)
+ * would), so a step is one launch; 0 = vdl_fused_launch. */
+int vdl_fused_launch_ex(vdl_fused *f, int self_finalize);
 /* The partial table for the multi-GPU combine: device pointer and its size in int64 elements. */
 int vdl_fused_partials(vdl_fused *f, void **device_ptr, int64_t *n_int64);
 /* Merge `nranks` partial tables laid out back to back at `all_partials` (an all-gather result; pass
@@ -184,6 +196,8 @@ int vdl_fused_result(vdl_fused *f, int fold_index, vdl_vec *out);
 /* Host copy of one fold's result (pinned memory, valid until the next launch).  The group count, the error
  * counter and all fold results of a scan come back in ONE device->host copy. */
 int vdl_fused_result_host(vdl_fused *f, int fold_index, const int64_t **data, int64_t *len);
+/* The same for post op `post_index` of the descriptor. */
+int vdl_fused_post_host(vdl_fused *f, int post_index, const int64_t **data, int64_t *len);
 /* Which instantiation of the scan kernel the descriptor was matched to: "generic" or the name of a static shape. */
 const char *vdl_fused_shape_name(vdl_fused *f);
 int vdl_fused_destroy(vdl_fused *f);

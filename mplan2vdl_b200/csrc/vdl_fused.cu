@@ -52,6 +52,11 @@ struct KDesc {
   KAcc choose[K_MAX_CHOOSE];
   i64 *table;                    // [nacc + nchoose][domain]
   int *errflag;
+  // Epilogue run by the LAST CTA to finish (ticket counter `done`): 0 none, 1 FoldChoose values only (the partial
+  // table is then complete for an external all-gather), 2 FoldChoose + finalize + table reset (single GPU: the scan
+  // is the only launch of a step).
+  unsigned int *done;
+  int32_t epilogue, pad1;
 };
 
 struct FinDesc {
@@ -61,8 +66,13 @@ struct FinDesc {
   int32_t acc_op[K_MAX_ACC];
   int32_t out_kind[VDL_MAX_AGGS], out_idx[VDL_MAX_AGGS];   // kind 0: accumulator, 1: choose
   i64 *out[VDL_MAX_AGGS];
+  int32_t npost, pad;
+  vdl_post_op post[VDL_MAX_POSTS];
+  i64 *post_out[VDL_MAX_POSTS];
   i64 *ngroups;                  // [0] number of groups, [1] snapshot of the context's error counter
   const int *errflag;
+  i64 *hmirror;                  // mapped pinned host copy of the whole result buffer (same layout as out[0]...), or null
+  i64 *reset_table;              // this rank's partial table, re-initialised for the next launch after the merge, or null
 };
 
 // ------------------------------------------------------------------------------ PTX helpers
@@ -571,8 +581,12 @@ __device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char 
   }
 }
 
+__device__ __forceinline__ void choose_keys(const KDesc &d, i64 k0, i64 kstride);
+template <int NT>
+__device__ __forceinline__ void finalize_block(const FinDesc &f, int tid, int *warp_cnt, i64 *running);
+
 template <class S, int NC, int R, int G>
-__global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __grid_constant__ KDesc d) {
+__global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __grid_constant__ KDesc d, const __grid_constant__ FinDesc fd) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: [ring: stages * stage_bytes][full[stages]][empty[stages]][sel[stages]][qcount[stages]]
   //         [queue[stages][tile_rows]][nslots][slotkey[gmax]][slotmap[domain]][tables]
@@ -711,15 +725,34 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
       for (int w = 0; w < NW; w++) v = acc_combine(op, v, red[(size_t)w * (G * S::NACC) + p]);
       if (v != acc_identity(op)) acc_global(op, d.table + (size_t)j * d.domain + g.slotkey[p / S::NACC], v);
     }
-    return;
+  } else {
+    // lane-private tables -> one global atomic per (warp, slot, accumulator)
+    for (int p = cw; p < ns * d.nacc; p += NW) {
+      const int s = p / d.nacc, j = p % d.nacc, op = d.acc[j].op;
+      i64 v = acc_identity(op);
+      for (int t = lane; t < NC; t += 32) v = acc_combine(op, v, g.tbl[((size_t)s * d.nacc + j) * NC + t]);
+      v = warp_reduce(op, v);
+      if (lane == 0) acc_global(op, d.table + (size_t)j * d.domain + g.slotkey[s], v);
+    }
   }
-  // lane-private tables -> one global atomic per (warp, slot, accumulator)
-  for (int p = cw; p < ns * d.nacc; p += NW) {
-    const int s = p / d.nacc, j = p % d.nacc, op = d.acc[j].op;
-    i64 v = acc_identity(op);
-    for (int t = lane; t < NC; t += 32) v = acc_combine(op, v, g.tbl[((size_t)s * d.nacc + j) * NC + t]);
-    v = warp_reduce(op, v);
-    if (lane == 0) acc_global(op, d.table + (size_t)j * d.domain + g.slotkey[s], v);
+
+  // ---- epilogue by the last CTA to get here: the table is complete, finish the step without another launch
+  if (d.epilogue) {
+    __threadfence();                       // this CTA's atomics are ordered before its ticket
+    consumer_barrier<NC>();
+    if (ctid == 0) g.nslots[1] = atomicAdd(d.done, 1u) == gridDim.x - 1;
+    consumer_barrier<NC>();
+    if (g.nslots[1]) {
+      __threadfence();
+      if (d.nchoose) choose_keys(d, ctid, NC);
+      if (d.epilogue == 2) {
+        __threadfence();
+        consumer_barrier<NC>();
+        // scratch in the idle ring: [running][warp counts]
+        finalize_block<NC>(fd, ctid, (int *)(ring + 16), (i64 *)ring);
+      }
+      if (ctid == 0) *d.done = 0;
+    }
   }
 }
 
@@ -733,10 +766,11 @@ __global__ void fused_init_kernel(const __grid_constant__ KDesc d) {
 }
 
 // FoldChoose = first row of the run (App. G6) = the expression at the smallest selected row of the key.
-__global__ void fused_choose_kernel(const __grid_constant__ KDesc d) {
-  for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < d.domain; k += (i64)gridDim.x * blockDim.x) {
-    if (d.table[(size_t)d.cnt_idx * d.domain + k] <= 0) continue;
-    i64 grow = d.table[(size_t)d.first_idx * d.domain + k];
+// Reads the table with cache-global loads: other CTAs built it with atomics at L2.
+__device__ __forceinline__ void choose_keys(const KDesc &d, i64 k0, i64 kstride) {
+  for (i64 k = k0; k < d.domain; k += kstride) {
+    if (__ldcg(&d.table[(size_t)d.cnt_idx * d.domain + k]) <= 0) continue;
+    i64 grow = __ldcg(&d.table[(size_t)d.first_idx * d.domain + k]);
     i64 r = grow - d.row_base;
     for (int c = 0; c < d.nchoose; c++) {
       const KAcc &A = d.choose[c];
@@ -755,59 +789,96 @@ __global__ void fused_choose_kernel(const __grid_constant__ KDesc d) {
     }
   }
 }
+__global__ void fused_choose_kernel(const __grid_constant__ KDesc d) {
+  choose_keys(d, (i64)blockIdx.x * blockDim.x + threadIdx.x, (i64)gridDim.x * blockDim.x);
+}
 
-// Merge the per-rank tables, drop empty keys, emit one dense vector per fold in ascending key order.
-__global__ void __launch_bounds__(256, 1) fused_finalize_kernel(const __grid_constant__ FinDesc f) {
-  __shared__ int warp_cnt[8];
-  __shared__ i64 running;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) running = 0;
-  __syncthreads();
-  for (i64 base = 0; base < f.domain; base += 256) {
+// Merge the per-rank tables, drop empty keys, emit one dense vector per fold in ascending key order, run the post
+// ops, optionally re-initialise this rank's table.  One thread block of NT threads (threads tid 0..NT-1; the
+// barrier is the named barrier 2 so that the scan kernel's consumer warps can run it without the producer warp).
+template <int NT>
+__device__ __forceinline__ void finalize_block(const FinDesc &f, int tid, int *warp_cnt, i64 *running) {
+  constexpr int NWF = NT / 32;
+  auto bar = []() { asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory"); };
+  const int lane = tid & 31, warp = tid >> 5;
+  // out[] / post_out[] / ngroups live in one device buffer that starts at out[0]; hmirror has the same layout
+  auto mirror = [&](i64 *dev) { return f.hmirror + (dev - f.out[0]); };
+  if (tid == 0) *running = 0;
+  bar();
+  for (i64 base = 0; base < f.domain; base += NT) {
     i64 k = base + tid;
     i64 cnt = 0;
     if (k < f.domain)
-      for (int r = 0; r < f.nranks; r++) cnt += f.parts[(size_t)r * f.part_stride + (size_t)f.cnt_idx * f.domain + k];
+      for (int r = 0; r < f.nranks; r++) cnt += __ldcg(&f.parts[(size_t)r * f.part_stride + (size_t)f.cnt_idx * f.domain + k]);
     bool exists = cnt > 0;
     unsigned m = __ballot_sync(0xffffffffu, exists);
     if (lane == 0) warp_cnt[warp] = __popc(m);
-    __syncthreads();
+    bar();
     int before = 0, total = 0;
-    for (int w = 0; w < 8; w++) {
+    for (int w = 0; w < NWF; w++) {
       if (w < warp) before += warp_cnt[w];
       total += warp_cnt[w];
     }
     if (exists) {
-      i64 pos = running + before + __popc(m & ((1u << lane) - 1));
+      i64 pos = *running + before + __popc(m & ((1u << lane) - 1));
       int best = 0;   // rank holding the first row of this key
       if (f.nchoose > 0) {
         i64 bf = INT64_MAX;
         for (int r = 0; r < f.nranks; r++) {
-          i64 fr = f.parts[(size_t)r * f.part_stride + (size_t)f.first_idx * f.domain + k];
+          i64 fr = __ldcg(&f.parts[(size_t)r * f.part_stride + (size_t)f.first_idx * f.domain + k]);
           if (fr < bf) { bf = fr; best = r; }
         }
       }
+      i64 ov[VDL_MAX_AGGS], pv[VDL_MAX_POSTS];
       for (int o = 0; o < f.nout; o++) {
         i64 v;
         if (f.out_kind[o] == 1) {
-          v = f.parts[(size_t)best * f.part_stride + (size_t)(f.nacc + f.out_idx[o]) * f.domain + k];
+          v = __ldcg(&f.parts[(size_t)best * f.part_stride + (size_t)(f.nacc + f.out_idx[o]) * f.domain + k]);
         } else {
           int j = f.out_idx[o], op = f.acc_op[j];
           v = acc_identity(op);
-          for (int r = 0; r < f.nranks; r++) v = acc_combine(op, v, f.parts[(size_t)r * f.part_stride + (size_t)j * f.domain + k]);
+          for (int r = 0; r < f.nranks; r++) v = acc_combine(op, v, __ldcg(&f.parts[(size_t)r * f.part_stride + (size_t)j * f.domain + k]));
         }
         f.out[o][pos] = v;
+        if (f.hmirror) mirror(f.out[o])[pos] = v;
+        ov[o] = v;
+      }
+      // elementwise epilogue over the fold results (AVG's Divide, ...)
+      for (int q = 0; q < f.npost; q++) {
+        const vdl_post_op &P = f.post[q];
+        i64 a = P.a_kind == VDL_POST_CONST ? P.a : (P.a_kind == VDL_POST_FOLD ? ov[P.a] : pv[P.a]);
+        i64 b = P.b_kind == VDL_POST_CONST ? P.b : (P.b_kind == VDL_POST_FOLD ? ov[P.b] : pv[P.b]);
+        pv[q] = binop_apply(P.op, a, b);
+        f.post_out[q][pos] = pv[q];
+        if (f.hmirror) mirror(f.post_out[q])[pos] = pv[q];
       }
     }
-    __syncthreads();
-    if (tid == 0) running += total;
-    __syncthreads();
+    bar();
+    if (tid == 0) *running += total;
+    bar();
   }
-  if (tid == 0) { f.ngroups[0] = running; f.ngroups[1] = *f.errflag; }
+  if (tid == 0) {
+    const i64 ng = *running, err = *f.errflag;
+    f.ngroups[0] = ng; f.ngroups[1] = err;
+    if (f.hmirror) { mirror(f.ngroups)[0] = ng; mirror(f.ngroups)[1] = err; }
+  }
+  if (f.reset_table) {      // every thread has read what it needed (barriers above): identity-initialise for the next launch
+    const i64 n = (i64)(f.nacc + f.nchoose) * f.domain;
+    for (i64 i = tid; i < n; i += NT) {
+      int j = (int)(i / f.domain);
+      f.reset_table[i] = j < f.nacc ? acc_identity(f.acc_op[j]) : 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) fused_finalize_kernel(const __grid_constant__ FinDesc f) {
+  __shared__ int warp_cnt[8];
+  __shared__ i64 running;
+  finalize_block<256>(f, threadIdx.x, warp_cnt, &running);
 }
 
 // ------------------------------------------------------------------------------ host side
-typedef void (*scan_kernel_fn)(const KDesc);
+typedef void (*scan_kernel_fn)(const KDesc, const FinDesc);
 struct vdl_fused {
   vdl_ctx *ctx = nullptr;
   KDesc kd;
@@ -819,6 +890,9 @@ struct vdl_fused {
   i64 *h_outbuf = nullptr;       // pinned mirror
   i64 ngroups = -1;
   bool finalized = false, always_false = false, rs = false;
+  bool table_clean = false;       // the partial table holds the fold identities (init kernel or a finalize that reset it)
+  unsigned int *d_done = nullptr; // ticket counter of the scan kernel's last-CTA epilogue
+  i64 *h_mapped = nullptr;        // device address of h_outbuf (mapped pinned memory)
   // register slots: kernels by slot count; the launch picks the smallest count that covers the groups the previous
   // run of this scan produced (more slots = more predicated work per row; too few = keys on the slow global path)
   scan_kernel_fn rs_kernel[9] = {nullptr};
@@ -902,6 +976,12 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     return vdl_fail(ctx, VDL_EINVAL, "fused scan: preds/keys/folds out of range");
   if (desc->domain < 1 || desc->domain > (1 << 20)) return vdl_fail(ctx, VDL_EUNSUPPORTED, "fused scan: key domain %lld not in [1, 2^20]", (long long)desc->domain);
   if (desc->nkeys == 0 && desc->domain != 1) return vdl_fail(ctx, VDL_EINVAL, "fused scan: no key parts but domain %lld", (long long)desc->domain);
+  if (desc->nposts < 0 || desc->nposts > VDL_MAX_POSTS) return vdl_fail(ctx, VDL_EINVAL, "fused scan: %d post ops (0..%d)", desc->nposts, VDL_MAX_POSTS);
+  for (int q = 0; q < desc->nposts; q++) {
+    const vdl_post_op &P = desc->post[q];
+    auto ok = [&](int kind, i64 v) { return kind == VDL_POST_CONST || (kind == VDL_POST_FOLD && v >= 0 && v < desc->nfolds) || (kind == VDL_POST_POST && v >= 0 && v < q); };
+    if (P.op < 0 || P.op > VDL_MODULO || !ok(P.a_kind, P.a) || !ok(P.b_kind, P.b)) return vdl_fail(ctx, VDL_EINVAL, "fused scan: bad post op %d", q);
+  }
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
 
   vdl_fused *f = new vdl_fused();
@@ -1170,11 +1250,14 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   if (rc) { delete f; return rc; }
   k.table = (i64 *)ctx->vecs[f->table].ptr;
   {
-    size_t nb = ((size_t)f->nout * k.domain + 2) * sizeof(i64);
-    if (cudaMalloc(&f->d_outbuf, nb) != cudaSuccess || cudaMallocHost(&f->h_outbuf, nb) != cudaSuccess) {
+    size_t nb = ((size_t)(f->nout + desc->nposts) * k.domain + 2) * sizeof(i64);
+    if (cudaMalloc(&f->d_outbuf, nb) != cudaSuccess || cudaHostAlloc(&f->h_outbuf, nb, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&f->h_mapped, f->h_outbuf, 0) != cudaSuccess || cudaMalloc(&f->d_done, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemsetAsync(f->d_done, 0, sizeof(unsigned int), ctx->stream) != cudaSuccess) {
       vdl_fused_destroy(f);
       return vdl_fail(ctx, VDL_ENOMEM, "fused scan: result buffers");
     }
+    k.done = f->d_done;
   }
   for (int i = 0; i < f->nout; i++) {   // the fold results are views into the one result buffer
     rc = vec_new_range(ctx, 0, 0, 0, &f->out[i]);
@@ -1196,8 +1279,14 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   f->fd.first_idx = k.first_idx;
   f->fd.nout = f->nout;
   f->fd.part_stride = (i64)(k.nacc + k.nchoose) * k.domain;
-  f->fd.ngroups = f->d_outbuf + (size_t)f->nout * k.domain;
+  f->fd.npost = desc->nposts;
+  for (int q = 0; q < desc->nposts; q++) {
+    f->fd.post[q] = desc->post[q];
+    f->fd.post_out[q] = f->d_outbuf + (size_t)(f->nout + q) * k.domain;
+  }
+  f->fd.ngroups = f->d_outbuf + (size_t)(f->nout + desc->nposts) * k.domain;
   f->fd.errflag = ctx->d_errflag;
+  f->fd.hmirror = f->h_mapped;
   for (int j = 0; j < k.nacc; j++) f->fd.acc_op[j] = k.acc[j].op;
 
   cudaError_t e = cudaFuncSetAttribute(f->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
@@ -1211,15 +1300,22 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   return VDL_OK;
 }
 
-extern "C" int vdl_fused_launch(vdl_fused *f) {
+// self_finalize != 0: single-GPU step -- the scan kernel's last CTA also runs FoldChoose, the finalize and the table
+// reset, so a step is ONE launch and the results are on the host (mapped pinned memory) when the stream drains.
+// self_finalize == 0: the scan leaves the complete partial table (FoldChoose values included) for an external
+// combine across ranks; vdl_fused_finalize() then merges the gathered tables.
+extern "C" int vdl_fused_launch_ex(vdl_fused *f, int self_finalize) {
   if (!f) return VDL_EINVAL;
   vdl_ctx *ctx = f->ctx;
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   f->finalized = false;
   f->ngroups = -1;
-  int nb = (int)std::min<i64>(ctx->sm_count, ((i64)(f->kd.nacc + f->kd.nchoose) * f->kd.domain + 255) / 256);
-  fused_init_kernel<<<std::max(nb, 1), 256, 0, ctx->stream>>>(f->kd);
-  ctx->launches++;
+  if (!f->table_clean) {
+    int nb = (int)std::min<i64>(ctx->sm_count, ((i64)(f->kd.nacc + f->kd.nchoose) * f->kd.domain + 255) / 256);
+    fused_init_kernel<<<std::max(nb, 1), 256, 0, ctx->stream>>>(f->kd);
+    ctx->launches++;
+    f->table_clean = true;
+  }
   VDL_CUDA(ctx, cudaEventRecord(f->ev0, ctx->stream));
   if (f->rs) {
     int g = f->rs_gmax;
@@ -1229,20 +1325,27 @@ extern "C" int vdl_fused_launch(vdl_fused *f) {
     f->kernel = f->rs_kernel[g];
     f->kd.gmax = g;
   }
-  if (f->kd.rows > 0 && !f->always_false) {
-    f->kernel<<<f->grid, f->nc + 32, f->smem_bytes, ctx->stream>>>(f->kd);
+  const bool scan = f->kd.rows > 0 && !f->always_false;
+  f->fd.parts = f->kd.table;
+  f->fd.nranks = 1;
+  f->fd.reset_table = f->kd.table;
+  if (scan) {
+    f->kd.epilogue = self_finalize ? 2 : 1;
+    f->kernel<<<f->grid, f->nc + 32, f->smem_bytes, ctx->stream>>>(f->kd, f->fd);
+    ctx->launches++;
+    f->table_clean = self_finalize != 0;
+  } else if (self_finalize) {            // nothing to scan: the (identity) table finalizes to zero groups
+    fused_finalize_kernel<<<1, 256, 0, ctx->stream>>>(f->fd);
     ctx->launches++;
   }
   VDL_CUDA(ctx, cudaEventRecord(f->ev1, ctx->stream));
   f->timed = true;
-  if (f->kd.nchoose && f->kd.rows > 0 && !f->always_false) {
-    int cb = (int)std::min<i64>(ctx->sm_count, (f->kd.domain + 255) / 256);
-    fused_choose_kernel<<<std::max(cb, 1), 256, 0, ctx->stream>>>(f->kd);
-    ctx->launches++;
-  }
   VDL_CUDA(ctx, cudaGetLastError());
+  if (self_finalize) f->finalized = true;
   return VDL_OK;
 }
+
+extern "C" int vdl_fused_launch(vdl_fused *f) { return vdl_fused_launch_ex(f, 0); }
 
 extern "C" int vdl_fused_partials(vdl_fused *f, void **device_ptr, int64_t *n_int64) {
   if (!f || !device_ptr || !n_int64) return VDL_EINVAL;
@@ -1258,9 +1361,11 @@ extern "C" int vdl_fused_finalize(vdl_fused *f, const void *all_partials, int nr
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   f->fd.parts = all_partials ? (const i64 *)all_partials : f->kd.table;
   f->fd.nranks = nranks;
+  f->fd.reset_table = f->kd.table;      // the gathered copies (or this one launch) are the last readers of the table
   fused_finalize_kernel<<<1, 256, 0, ctx->stream>>>(f->fd);
   ctx->launches++;
   VDL_CUDA(ctx, cudaGetLastError());
+  f->table_clean = true;
   f->finalized = true;
   f->ngroups = -1;
   return VDL_OK;
@@ -1271,9 +1376,8 @@ static int fused_fetch(vdl_fused *f) {
   vdl_ctx *ctx = f->ctx;
   if (!f->finalized) return vdl_fail(ctx, VDL_EINVAL, "fused scan not finalized");
   if (f->ngroups >= 0) return VDL_OK;
-  size_t n = (size_t)f->nout * f->kd.domain + 2;
-  VDL_CUDA(ctx, cudaMemcpyAsync(f->h_outbuf, f->d_outbuf, n * sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
-  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  size_t n = (size_t)(f->nout + f->fd.npost) * f->kd.domain + 2;
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // the finalize wrote the results straight into h_outbuf (mapped)
   i64 ng = f->h_outbuf[n - 2], err = f->h_outbuf[n - 1];
   if (err) {
     cudaMemsetAsync(ctx->d_errflag, 0, sizeof(int), ctx->stream);
@@ -1297,6 +1401,14 @@ extern "C" int vdl_fused_result_host(vdl_fused *f, int fold_index, const int64_t
   if (!f || !data || !len || fold_index < 0 || fold_index >= f->nout) return VDL_EINVAL;
   VDL_TRY(fused_fetch(f));
   *data = f->h_outbuf + (size_t)fold_index * f->kd.domain;
+  *len = f->ngroups;
+  return VDL_OK;
+}
+
+extern "C" int vdl_fused_post_host(vdl_fused *f, int post_index, const int64_t **data, int64_t *len) {
+  if (!f || !data || !len || post_index < 0 || post_index >= f->fd.npost) return VDL_EINVAL;
+  VDL_TRY(fused_fetch(f));
+  *data = f->h_outbuf + (size_t)(f->nout + post_index) * f->kd.domain;
   *len = f->ngroups;
   return VDL_OK;
 }
@@ -1328,6 +1440,7 @@ extern "C" int vdl_fused_destroy(vdl_fused *f) {
   for (int i = 0; i < f->nout; i++)
     if (f->out[i]) vdl_vec_free(ctx, f->out[i]);
   if (f->d_outbuf) cudaFree(f->d_outbuf);
+  if (f->d_done) cudaFree(f->d_done);
   if (f->h_outbuf) cudaFreeHost(f->h_outbuf);
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);

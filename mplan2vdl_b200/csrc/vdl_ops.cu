@@ -20,33 +20,7 @@ extern "C" int vdl_op_range(vdl_ctx *ctx, int64_t from, int64_t step, int64_t le
 }
 
 // ---------------------------------------------------------------------------------- elementwise
-// Vdl.hs:136-157, 209-231.  Comparisons / logicals give 0/1; BitShift: +k arithmetic right, -k left
-// (Vlite.hs:205-208); Divide truncates, x/0 := 0, INT64_MIN/-1 wraps; Modulo is the C remainder, x%0 := 0.
-__device__ __forceinline__ i64 binop_apply(int op, i64 a, i64 b) {
-  switch (op) {
-    case VDL_LOGICAL_AND: return (a != 0) && (b != 0);
-    case VDL_LOGICAL_OR: return (a != 0) || (b != 0);
-    case VDL_BITWISE_AND: return a & b;
-    case VDL_BITWISE_OR: return a | b;
-    case VDL_BITSHIFT:
-      if (b >= 0) return b >= 64 ? (a < 0 ? -1 : 0) : (a >> b);
-      return b <= -64 ? 0 : (i64)((u64)a << (-b));
-    case VDL_EQUALS: return a == b;
-    case VDL_ADD: return (i64)((u64)a + (u64)b);
-    case VDL_SUBTRACT: return (i64)((u64)a - (u64)b);
-    case VDL_GREATER: return a > b;
-    case VDL_MULTIPLY: return (i64)((u64)a * (u64)b);
-    case VDL_DIVIDE:
-      if (b == 0) return 0;
-      if (b == -1) return (i64)(0 - (u64)a);
-      return a / b;
-    case VDL_MODULO:
-      if (b == 0 || b == -1) return 0;
-      return a % b;
-  }
-  return 0;
-}
-
+// op semantics: binop_apply in vdl_internal.h
 template <int OP>
 __global__ void __launch_bounds__(256) binary_kernel(Operand a, Operand b, i64 *__restrict__ out, i64 n) {
   // two elements per thread and step: 16-byte stores, 2 x (8 or 4)-byte loads per operand in flight

@@ -57,6 +57,8 @@ struct FusedGroup {
   std::vector<int> cols;                // Load node of each column slot
   std::vector<FusedFold> folds;         // deduplicated specs
   std::map<int, int> fold_of_node;      // Fold node -> index into folds
+  std::vector<vdl_post_op> posts;       // elementwise epilogue over the fold results, run by the finalize kernel
+  std::map<int, int> post_of_node;      // Binary node -> index into posts
   vdl_fused_desc desc;
   vdl_fused *fused = nullptr;
   std::vector<vdl_vec> bound;           // column handles the prepared scan was built for
@@ -75,13 +77,13 @@ struct vdl_plan {
   std::vector<Sym> sym;
   std::vector<char> sym_done;
   std::vector<FusedGroup> groups;
-  std::vector<int> group_of_node;       // Fold node -> group index or -1
+  std::vector<int> group_of_node;       // Fold node (or Binary node computed as a post op) -> group index or -1
   i64 row_base = 0;
   // run state
   std::vector<vdl_vec> val;
   std::vector<vdl_vec> temps;
   i64 launches_last = 0;
-  bool local_done = false;
+  bool local_done = false, self_finalized = false;
 };
 
 namespace {
@@ -570,9 +572,56 @@ bool build_desc(vdl_plan *p, FusedGroup *g) {
   }
   d.nfolds = (int)g->folds.size();
   for (int i = 0; i < d.nfolds; i++) d.fold[i] = g->folds[i].spec;
+  d.nposts = (int)g->posts.size();
+  for (int i = 0; i < d.nposts; i++) d.post[i] = g->posts[i];
   if (g->cols.empty() || g->cols.size() > VDL_MAX_COLS) return false;
   d.ncolumns = (int)g->cols.size();
   return true;
+}
+
+// An output that is an elementwise expression over the Folds of ONE fused scan (AVG = Divide(FoldSum x, FoldSum 1),
+// Vlite.hs:1038-1041) becomes a post op of that scan: evaluated per group inside the finalize kernel and returned by
+// the scan's single result copy, instead of op-at-a-time launches over a handful of elements.
+// Returns the operand kind (VDL_POST_*) or -1 when `ni` is not such an expression.
+int post_operand(vdl_plan *p, int ni, int *gi, i64 *val) {
+  const Node &n = p->nodes[ni];
+  if (n.op == N_FOLD) {
+    int g = p->group_of_node[ni];
+    if (g < 0 || (*gi >= 0 && *gi != g)) return -1;
+    *gi = g;
+    *val = p->groups[g].fold_of_node[ni];
+    return VDL_POST_FOLD;
+  }
+  if (n.op == N_RANGEV && n.k1 == 0) {             // a constant as long as a vector of the same scan's results
+    i64 dummy;
+    if (post_operand(p, n.a, gi, &dummy) < 0) return -1;
+    *val = n.k0;
+    return VDL_POST_CONST;
+  }
+  if (n.op == N_BINARY) {
+    int g0 = *gi;
+    if (g0 >= 0) {
+      auto it = p->groups[g0].post_of_node.find(ni);
+      if (it != p->groups[g0].post_of_node.end()) { *val = it->second; return VDL_POST_POST; }
+    }
+    vdl_post_op op;
+    memset(&op, 0, sizeof op);
+    op.op = n.sub;
+    int ka = post_operand(p, n.a, gi, &op.a);
+    if (ka < 0) return -1;
+    int kb = post_operand(p, n.b, gi, &op.b);
+    if (kb < 0 || *gi < 0) return -1;
+    op.a_kind = ka; op.b_kind = kb;
+    FusedGroup &g = p->groups[*gi];
+    auto it = g.post_of_node.find(ni);           // the group may only have become known through the operands
+    if (it != g.post_of_node.end()) { *val = it->second; return VDL_POST_POST; }
+    if (g.posts.size() == VDL_MAX_POSTS) return -1;
+    g.posts.push_back(op);
+    g.post_of_node[ni] = (int)g.posts.size() - 1;
+    *val = (i64)g.posts.size() - 1;
+    return VDL_POST_POST;
+  }
+  return -1;
 }
 
 int fuse(vdl_plan *p) {
@@ -583,18 +632,35 @@ int fuse(vdl_plan *p) {
   if (!(p->flags & VDL_PLAN_FUSE)) return VDL_OK;
   for (size_t i = 0; i < nn; i++)
     if (p->nodes[i].op == N_FOLD) try_fuse_fold(p, (int)i);
+  for (auto &o : p->outputs) {
+    if (p->nodes[o.node].op != N_BINARY) continue;
+    std::vector<size_t> mark;
+    for (auto &g : p->groups) mark.push_back(g.posts.size());
+    int gi = -1;
+    i64 v;
+    if (post_operand(p, o.node, &gi, &v) != VDL_POST_POST)      // roll back partial registrations
+      for (size_t g = 0; g < p->groups.size(); g++) {
+        FusedGroup &G = p->groups[g];
+        for (auto it = G.post_of_node.begin(); it != G.post_of_node.end();)
+          it = it->second >= (int)mark[g] ? G.post_of_node.erase(it) : std::next(it);
+        G.posts.resize(mark[g]);
+      }
+  }
   for (size_t gi = 0; gi < p->groups.size(); gi++) {
     if (!build_desc(p, &p->groups[gi])) {      // cannot be expressed after all: un-fuse its folds
       for (auto &kv : p->groups[gi].fold_of_node) p->group_of_node[kv.first] = -1;
       p->groups[gi].folds.clear();
       p->groups[gi].fold_of_node.clear();
+      p->groups[gi].post_of_node.clear();
     }
   }
   p->groups.erase(std::remove_if(p->groups.begin(), p->groups.end(), [](const FusedGroup &g) { return g.folds.empty(); }), p->groups.end());
   // group indices may have shifted
   std::fill(p->group_of_node.begin(), p->group_of_node.end(), -1);
-  for (size_t gi = 0; gi < p->groups.size(); gi++)
+  for (size_t gi = 0; gi < p->groups.size(); gi++) {
     for (auto &kv : p->groups[gi].fold_of_node) p->group_of_node[kv.first] = (int)gi;
+    for (auto &kv : p->groups[gi].post_of_node) p->group_of_node[kv.first] = (int)gi;
+  }
   return VDL_OK;
 }
 
@@ -696,7 +762,7 @@ extern "C" int vdl_plan_set_row_base(vdl_plan *p, int64_t row_base) {
   return VDL_OK;
 }
 
-extern "C" int vdl_plan_run_local(vdl_plan *p) {
+static int plan_run_local(vdl_plan *p, int self_finalize) {
   if (!p) return VDL_EINVAL;
   vdl_ctx *ctx = p->ctx;
   free_temps(p);
@@ -719,12 +785,15 @@ extern "C" int vdl_plan_run_local(vdl_plan *p) {
       VDL_TRY(vdl_fused_prepare(ctx, &g.desc, &g.fused));
       g.bound = h; g.bound_rows = rows; g.bound_base = p->row_base;
     }
-    VDL_TRY(vdl_fused_launch(g.fused));
+    VDL_TRY(vdl_fused_launch_ex(g.fused, self_finalize));
   }
   p->launches_last = ctx->launches - l0;
   p->local_done = true;
+  p->self_finalized = self_finalize != 0;
   return VDL_OK;
 }
+
+extern "C" int vdl_plan_run_local(vdl_plan *p) { return plan_run_local(p, 0); }
 
 extern "C" int vdl_plan_num_fused(vdl_plan *p) { return p ? (int)p->groups.size() : 0; }
 extern "C" int vdl_plan_fused(vdl_plan *p, int i, vdl_fused **out) {
@@ -739,14 +808,16 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
   if (!p->local_done) return vdl_fail(ctx, VDL_EINVAL, "vdl_plan_finish before vdl_plan_run_local");
   if (nranks > 1 && p->groups.empty()) return vdl_fail(ctx, VDL_EUNSUPPORTED, "plan has no fused scan: it cannot be row-sharded");
   i64 l0 = ctx->launches;
-  for (size_t gi = 0; gi < p->groups.size(); gi++)
-    VDL_TRY(vdl_fused_finalize(p->groups[gi].fused, all_partials ? all_partials[gi] : nullptr, nranks));
+  if (!(p->self_finalized && nranks == 1 && !all_partials))
+    for (size_t gi = 0; gi < p->groups.size(); gi++)
+      VDL_TRY(vdl_fused_finalize(p->groups[gi].fused, all_partials ? all_partials[gi] : nullptr, nranks));
   bool ran_ops = false;
   for (auto &o : p->outputs) {
-    int gi = p->nodes[o.node].op == N_FOLD ? p->group_of_node[o.node] : -1;
-    if (gi >= 0) {   // the output IS a fused fold: it arrived with the scan's single result copy
+    int gi = p->group_of_node[o.node];
+    if (gi >= 0) {   // the output IS a fused fold or a post op of one: it arrived with the scan's single result copy
       const int64_t *data; int64_t len;
-      VDL_TRY(vdl_fused_result_host(p->groups[gi].fused, p->groups[gi].fold_of_node[o.node], &data, &len));
+      if (p->nodes[o.node].op == N_FOLD) VDL_TRY(vdl_fused_result_host(p->groups[gi].fused, p->groups[gi].fold_of_node[o.node], &data, &len));
+      else VDL_TRY(vdl_fused_post_host(p->groups[gi].fused, p->groups[gi].post_of_node[o.node], &data, &len));
       o.data.assign(data, data + len);
       continue;
     }
@@ -768,7 +839,7 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
 }
 
 extern "C" int vdl_plan_run(vdl_plan *p) {
-  VDL_TRY(vdl_plan_run_local(p));
+  VDL_TRY(plan_run_local(p, 1));        // single GPU: every fused scan finalizes itself (one launch per scan)
   return vdl_plan_finish(p, nullptr, 1);
 }
 

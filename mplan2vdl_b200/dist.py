@@ -41,9 +41,9 @@ class ShardedPlan:
         self._gathered = []
 
     def step(self) -> dict:
-        self.plan.run_local()
         if self.world == 1:
-            return self.plan.finish()
+            return self.plan.run()                      # one launch per fused scan: its last thread block finalizes
+        self.plan.run_local()
         ptrs = []
         with torch.cuda.stream(self._stream):           # NCCL is ordered after the scan on the library's stream
             for i in range(self.plan.num_fused):

@@ -15,7 +15,8 @@ VDL_PLAN_FUSE = 1
 BINARY_OPS = ["LogicalAnd", "LogicalOr", "BitwiseAnd", "BitwiseOr", "BitShift", "Equals", "Add", "Subtract",
               "Greater", "Multiply", "Divide", "Modulo"]
 FOLD_OPS = ["FoldSum", "FoldMin", "FoldMax", "FoldChoose", "FoldCount"]
-VDL_MAX_COLS, VDL_MAX_PREDS, VDL_MAX_KEYS, VDL_MAX_AGGS, VDL_MAX_FACTORS = 12, 8, 4, 8, 3
+VDL_MAX_COLS, VDL_MAX_PREDS, VDL_MAX_KEYS, VDL_MAX_AGGS, VDL_MAX_FACTORS, VDL_MAX_POSTS = 12, 8, 4, 8, 3, 8
+VDL_POST_FOLD, VDL_POST_POST, VDL_POST_CONST = 0, 1, 2
 
 
 class VdlError(RuntimeError):
@@ -40,11 +41,17 @@ class FoldSpec(C.Structure):
     _fields_ = [("op", C.c_int32), ("nfactors", C.c_int32), ("factor", Affine * VDL_MAX_FACTORS)]
 
 
+class PostOp(C.Structure):
+    _fields_ = [("op", C.c_int32), ("a_kind", C.c_int32), ("b_kind", C.c_int32), ("pad", C.c_int32),
+                ("a", C.c_int64), ("b", C.c_int64)]
+
+
 class FusedDesc(C.Structure):
     _fields_ = [("rows", C.c_int64), ("row_base", C.c_int64), ("ncolumns", C.c_int32),
                 ("column", C.c_int32 * VDL_MAX_COLS), ("npreds", C.c_int32), ("pred", RangePred * VDL_MAX_PREDS),
                 ("nkeys", C.c_int32), ("key", KeyPart * VDL_MAX_KEYS), ("key_mask", C.c_int64), ("domain", C.c_int64),
-                ("nfolds", C.c_int32), ("fold", FoldSpec * VDL_MAX_AGGS)]
+                ("nfolds", C.c_int32), ("fold", FoldSpec * VDL_MAX_AGGS),
+                ("nposts", C.c_int32), ("post", PostOp * VDL_MAX_POSTS)]
 
 
 # every symbol include/vdl_cuda.h declares: (name, restype, argtypes)
@@ -84,7 +91,9 @@ SYMBOLS = [
     ("vdl_fused_finalize", _I, [_P, _P, _I]),
     ("vdl_fused_num_groups", _I, [_P, C.POINTER(_L)]),
     ("vdl_fused_result", _I, [_P, _I, C.POINTER(C.c_int32)]),
+    ("vdl_fused_launch_ex", _I, [_P, _I]),
     ("vdl_fused_result_host", _I, [_P, _I, C.POINTER(C.POINTER(_L)), C.POINTER(_L)]),
+    ("vdl_fused_post_host", _I, [_P, _I, C.POINTER(C.POINTER(_L)), C.POINTER(_L)]),
     ("vdl_fused_shape_name", C.c_char_p, [_P]),
     ("vdl_fused_destroy", _I, [_P]),
     ("vdl_fused_last_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
