@@ -4,9 +4,9 @@ columns resident in HBM (BASELINE.json north_star), executed by libvdl_cuda.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--query q06|q01] [--sf 100]
 
-One "step" = one execution of the plan over the whole (sharded) table: identity-init of the partial
-table, the fused scan-fold kernel, [all-gather of the partial tables for N>1], finalize, and the
-device->host read of the result.  Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for what each
+One "step" = one execution of the plan over the whole (sharded) table: ONE launch of the fused scan-fold
+kernel per GPU, whose last thread block [exchanges the partial tables with the other GPUs through peer memory
+for N>1,] finalizes and writes the result to mapped host memory, and the host's wait for it.  Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for what each
 field means and how the roofline / cpu_baseline / e2e numbers are obtained.
 """
 from __future__ import annotations
@@ -165,13 +165,13 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, rows_total):
+def workload_config(args, rows_total, combine="all-gather of the partial tables"):
     plan, bpr = QUERIES[args.query]
     return {"workload": f"TPC-H {args.query.upper()} SF{args.sf:g}: plans/{plan} (mplan2vdl Voodoo plan) over synthetic lineitem columns "
                         "generated to the reference's bounds.csv",
             "lineitem_rows": rows_total, "algorithmic_bytes_per_lineitem_row": bpr,
             "l2": "inputs (GBs) far exceed the 126 MB L2; no flush needed between steps",
-            "parallelism": f"lineitem row-range sharded over {args.gpus} GPU(s), partial tables all-gathered"}
+            "parallelism": f"lineitem row-range sharded over {args.gpus} GPU(s); combine: {combine}"}
 
 
 def main():
@@ -333,7 +333,9 @@ def main():
         line = {
             "metric": f"tpch_{args.query}_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "int64", "data": "synthetic", "config": workload_config(args, rows_total), "roofline": roofline,
+            "dtype": "int64", "data": "synthetic", "config": workload_config(args, rows_total, "none (single GPU)" if world == 1 else ("peer-memory exchange fused into the scan kernel's last thread block (NVLink stores + epoch flags), no collective"
+                                                                   if sharded.peer_mode else "NCCL all-gather of the partial tables + finalize kernel")),
+            "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "wall_ms_per_step": wall_ms / args.steps, "result": {k: [int(x) for x in v[:8]] for k, v in result.items()},
             "plan": plan.stats(),

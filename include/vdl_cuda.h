@@ -182,8 +182,8 @@ typedef struct vdl_fused vdl_fused;   /* a prepared fused scan (device tables, l
 int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_fused **out);
 /* Launch the scan over this shard; leaves the partial table [nacc][domain] of int64 in HBM. */
 int vdl_fused_launch(vdl_fused *f);
-/* self_finalize != 0 (single GPU): the scan kernel's last thread block also finalizes (as vdl_fused_finalize(f, NULL, 1)
- * would), so a step is one launch; 0 = vdl_fused_launch. */
+/* mode 1 (single GPU): the scan kernel's last thread block also finalizes (as vdl_fused_finalize(f, NULL, 1) would),
+ * so a step is one launch; mode 2: the same after the peer-memory exchange below; mode 0 = vdl_fused_launch. */
 int vdl_fused_launch_ex(vdl_fused *f, int self_finalize);
 /* The partial table for the multi-GPU combine: device pointer and its size in int64 elements. */
 int vdl_fused_partials(vdl_fused *f, void **device_ptr, int64_t *n_int64);
@@ -201,6 +201,23 @@ int vdl_fused_post_host(vdl_fused *f, int post_index, const int64_t **data, int6
 /* Which instantiation of the scan kernel the descriptor was matched to: "generic" or the name of a static shape. */
 const char *vdl_fused_shape_name(vdl_fused *f);
 int vdl_fused_destroy(vdl_fused *f);
+/* ---- multi-GPU combine over peer memory (NVLink / NVSwitch), no collective library on the data path -------------
+ * Every rank owns an exchange buffer of vdl_fused_exchange_bytes() in device memory that its peers can address
+ * (same process: the pointer itself; one process per GPU: vdl_ipc_export on the owner, vdl_ipc_open on the peers).
+ * After vdl_fused_set_peers(), vdl_fused_launch_ex(f, 2) runs the whole step as ONE kernel per GPU: the last thread
+ * block of the scan stores this rank's partial table into every peer's buffer, publishes a per-rank epoch flag
+ * (release, system scope), waits for the flags of all ranks, merges the tables and finalizes -- every rank ends up
+ * with the global result.  All ranks must launch the same steps in the same order. */
+#define VDL_MAX_RANKS 16
+#define VDL_IPC_HANDLE_BYTES 64
+int vdl_fused_exchange_bytes(vdl_fused *f, int world, int64_t *bytes);
+int vdl_fused_set_peers(vdl_fused *f, int rank, int world, void *const *peer_buffers);
+int vdl_ipc_alloc(vdl_ctx *ctx, int64_t bytes, void **device_ptr);            /* zero-filled cudaMalloc memory */
+int vdl_ipc_export(vdl_ctx *ctx, void *device_ptr, unsigned char handle[VDL_IPC_HANDLE_BYTES]);
+int vdl_ipc_open(vdl_ctx *ctx, const unsigned char handle[VDL_IPC_HANDLE_BYTES], void **device_ptr);
+int vdl_ipc_close(vdl_ctx *ctx, void *device_ptr);
+int vdl_ipc_free(vdl_ctx *ctx, void *device_ptr);
+
 /* Duration of the last vdl_fused_launch's scan kernel alone, CUDA events on the context stream. */
 int vdl_fused_last_kernel_ms(vdl_fused *f, float *ms);
 
@@ -215,6 +232,11 @@ int vdl_plan_stats(vdl_plan *p, int *statements, int *nodes, int *fused_scans, i
 int vdl_plan_set_row_base(vdl_plan *p, int64_t row_base);
 int vdl_plan_run_local(vdl_plan *p);
 int vdl_plan_num_fused(vdl_plan *p);
+/* Sharded execution without a collective library: exchange buffers of fused scan `fused_index` on every rank (see
+ * vdl_fused_set_peers); afterwards vdl_plan_run() returns the GLOBAL result on every rank.  The size comes from
+ * vdl_plan_exchange_bytes() once the plan has run at least once (vdl_plan_run_local). */
+int vdl_plan_exchange_bytes(vdl_plan *p, int fused_index, int world, int64_t *bytes);
+int vdl_plan_set_peers(vdl_plan *p, int fused_index, int rank, int world, void *const *peer_buffers);
 int vdl_plan_fused(vdl_plan *p, int i, vdl_fused **out);
 /* Phase 2: finalize the fused scans (optionally from all-gathered partials, one buffer per fused scan,
  * NULL entries / nranks 1 for single GPU), run the remaining ops, copy outputs to the host. */

@@ -386,3 +386,41 @@ extern "C" int vdl_column_fill_synthetic(vdl_ctx *ctx, vdl_vec col, uint64_t see
   VDL_CUDA(ctx, cudaGetLastError());
   return VDL_OK;
 }
+
+// ---------------------------------------------------------------------------------- peer-addressable buffers
+extern "C" int vdl_ipc_alloc(vdl_ctx *ctx, int64_t bytes, void **device_ptr) {
+  if (!ctx || !device_ptr || bytes <= 0) return VDL_EINVAL;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  VDL_CUDA(ctx, cudaMalloc(device_ptr, (size_t)bytes));
+  VDL_CUDA(ctx, cudaMemset(*device_ptr, 0, (size_t)bytes));
+  return VDL_OK;
+}
+extern "C" int vdl_ipc_export(vdl_ctx *ctx, void *device_ptr, unsigned char handle[VDL_IPC_HANDLE_BYTES]) {
+  if (!ctx || !device_ptr || !handle) return VDL_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == VDL_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  VDL_CUDA(ctx, cudaIpcGetMemHandle(&h, device_ptr));
+  memcpy(handle, &h, sizeof h);
+  return VDL_OK;
+}
+extern "C" int vdl_ipc_open(vdl_ctx *ctx, const unsigned char handle[VDL_IPC_HANDLE_BYTES], void **device_ptr) {
+  if (!ctx || !device_ptr || !handle) return VDL_EINVAL;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  VDL_CUDA(ctx, cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return VDL_OK;
+}
+extern "C" int vdl_ipc_close(vdl_ctx *ctx, void *device_ptr) {
+  if (!ctx || !device_ptr) return VDL_EINVAL;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  VDL_CUDA(ctx, cudaIpcCloseMemHandle(device_ptr));
+  return VDL_OK;
+}
+extern "C" int vdl_ipc_free(vdl_ctx *ctx, void *device_ptr) {
+  if (!ctx || !device_ptr) return VDL_EINVAL;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  VDL_CUDA(ctx, cudaFree(device_ptr));
+  return VDL_OK;
+}

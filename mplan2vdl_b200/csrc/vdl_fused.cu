@@ -54,7 +54,7 @@ struct KDesc {
   int *errflag;
   // Epilogue run by the LAST CTA to finish (ticket counter `done`): 0 none, 1 FoldChoose values only (the partial
   // table is then complete for an external all-gather), 2 FoldChoose + finalize + table reset (single GPU: the scan
-  // is the only launch of a step).
+  // is the only launch of a step), 3 the same with the peer-memory exchange of the tables before the finalize.
   unsigned int *done;
   int32_t epilogue, pad1;
 };
@@ -73,6 +73,16 @@ struct FinDesc {
   const int *errflag;
   i64 *hmirror;                  // mapped pinned host copy of the whole result buffer (same layout as out[0]...), or null
   i64 *reset_table;              // this rank's partial table, re-initialised for the next launch after the merge, or null
+};
+
+// Peer-memory exchange of the partial tables (one buffer per rank, addressable by all ranks):
+//   data  [2 (epoch parity)][world][stride] int64   rank r's table of the step lands in slot [parity][r] of EVERY buffer
+//   flags [2][world] uint64                         epoch of the last step whose table rank r has fully stored
+struct XDesc {
+  int32_t rank, world;
+  u64 epoch;                      // this step's number (1, 2, ...); parity double-buffers against a rank running ahead
+  i64 stride;                     // int64 per table
+  i64 *peer[VDL_MAX_RANKS];       // base of every rank's buffer as seen from this GPU
 };
 
 // ------------------------------------------------------------------------------ PTX helpers
@@ -111,6 +121,17 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
+}
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) {
+  u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ u64 global_timer_ns() {
+  u64 t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 template <int NC>
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
@@ -583,10 +604,12 @@ __device__ __forceinline__ void select_rows(const KDesc &d, const unsigned char 
 
 __device__ __forceinline__ void choose_keys(const KDesc &d, i64 k0, i64 kstride);
 template <int NT>
-__device__ __forceinline__ void finalize_block(const FinDesc &f, int tid, int *warp_cnt, i64 *running);
+__device__ __forceinline__ void finalize_block(const FinDesc &f, const i64 *parts, int nranks, int tid, int *warp_cnt, i64 *running);
+template <int NT>
+__device__ __forceinline__ const i64 *exchange_block(const XDesc &x, const i64 *table, int *errflag, int tid);
 
 template <class S, int NC, int R, int G>
-__global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __grid_constant__ KDesc d, const __grid_constant__ FinDesc fd) {
+__global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __grid_constant__ KDesc d, const __grid_constant__ FinDesc fd, const __grid_constant__ XDesc xd) {
   extern __shared__ __align__(128) unsigned char smem[];
   // layout: [ring: stages * stage_bytes][full[stages]][empty[stages]][sel[stages]][qcount[stages]]
   //         [queue[stages][tile_rows]][nslots][slotkey[gmax]][slotmap[domain]][tables]
@@ -745,11 +768,17 @@ __global__ void __launch_bounds__(NC + 32, 1) fused_scan_fold_kernel(const __gri
     if (g.nslots[1]) {
       __threadfence();
       if (d.nchoose) choose_keys(d, ctid, NC);
-      if (d.epilogue == 2) {
+      if (d.epilogue >= 2) {
         __threadfence();
         consumer_barrier<NC>();
+        const i64 *parts = fd.parts;
+        int nranks = 1;
+        if (d.epilogue == 3) {             // combine across GPUs through peer memory first
+          parts = exchange_block<NC>(xd, d.table, d.errflag, ctid);
+          nranks = xd.world;
+        }
         // scratch in the idle ring: [running][warp counts]
-        finalize_block<NC>(fd, ctid, (int *)(ring + 16), (i64 *)ring);
+        finalize_block<NC>(fd, parts, nranks, ctid, (int *)(ring + 16), (i64 *)ring);
       }
       if (ctid == 0) *d.done = 0;
     }
@@ -796,8 +825,34 @@ __global__ void fused_choose_kernel(const __grid_constant__ KDesc d) {
 // Merge the per-rank tables, drop empty keys, emit one dense vector per fold in ascending key order, run the post
 // ops, optionally re-initialise this rank's table.  One thread block of NT threads (threads tid 0..NT-1; the
 // barrier is the named barrier 2 so that the scan kernel's consumer warps can run it without the producer warp).
+// Store this rank's table into every rank's exchange buffer, publish the epoch, wait for every rank's epoch.
+// Returns the [world][stride] block of this rank's own buffer that now holds all tables of the step.
 template <int NT>
-__device__ __forceinline__ void finalize_block(const FinDesc &f, int tid, int *warp_cnt, i64 *running) {
+__device__ __forceinline__ const i64 *exchange_block(const XDesc &x, const i64 *table, int *errflag, int tid) {
+  auto bar = []() { asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory"); };
+  const int par = (int)(x.epoch & 1);
+  const size_t slot = ((size_t)par * x.world + x.rank) * x.stride, flags = (size_t)2 * x.world * x.stride;
+  for (int p = 0; p < x.world; p++) {                // NVLink stores (plain st.global to the peer mapping)
+    i64 *dst = x.peer[p] + slot;
+    for (i64 i = tid; i < x.stride; i += NT) dst[i] = __ldcg(&table[i]);
+  }
+  __threadfence_system();
+  bar();
+  if (tid < x.world) {
+    st_release_sys((u64 *)(x.peer[tid] + flags) + (size_t)par * x.world + x.rank, x.epoch);
+    const u64 *mine = (const u64 *)(x.peer[x.rank] + flags) + (size_t)par * x.world + tid;
+    const u64 t0 = global_timer_ns();
+    while (ld_acquire_sys(mine) < x.epoch) {
+      if (global_timer_ns() - t0 > 10000000000ull) { atomicAdd(errflag, 1 << 20); break; }   // a peer never arrived: fail, do not hang
+      __nanosleep(64);
+    }
+  }
+  bar();
+  return x.peer[x.rank] + (size_t)par * x.world * x.stride;
+}
+
+template <int NT>
+__device__ __forceinline__ void finalize_block(const FinDesc &f, const i64 *parts, int nranks, int tid, int *warp_cnt, i64 *running) {
   constexpr int NWF = NT / 32;
   auto bar = []() { asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory"); };
   const int lane = tid & 31, warp = tid >> 5;
@@ -809,7 +864,7 @@ __device__ __forceinline__ void finalize_block(const FinDesc &f, int tid, int *w
     i64 k = base + tid;
     i64 cnt = 0;
     if (k < f.domain)
-      for (int r = 0; r < f.nranks; r++) cnt += __ldcg(&f.parts[(size_t)r * f.part_stride + (size_t)f.cnt_idx * f.domain + k]);
+      for (int r = 0; r < nranks; r++) cnt += __ldcg(&parts[(size_t)r * f.part_stride + (size_t)f.cnt_idx * f.domain + k]);
     bool exists = cnt > 0;
     unsigned m = __ballot_sync(0xffffffffu, exists);
     if (lane == 0) warp_cnt[warp] = __popc(m);
@@ -824,8 +879,8 @@ __device__ __forceinline__ void finalize_block(const FinDesc &f, int tid, int *w
       int best = 0;   // rank holding the first row of this key
       if (f.nchoose > 0) {
         i64 bf = INT64_MAX;
-        for (int r = 0; r < f.nranks; r++) {
-          i64 fr = __ldcg(&f.parts[(size_t)r * f.part_stride + (size_t)f.first_idx * f.domain + k]);
+        for (int r = 0; r < nranks; r++) {
+          i64 fr = __ldcg(&parts[(size_t)r * f.part_stride + (size_t)f.first_idx * f.domain + k]);
           if (fr < bf) { bf = fr; best = r; }
         }
       }
@@ -833,11 +888,11 @@ __device__ __forceinline__ void finalize_block(const FinDesc &f, int tid, int *w
       for (int o = 0; o < f.nout; o++) {
         i64 v;
         if (f.out_kind[o] == 1) {
-          v = __ldcg(&f.parts[(size_t)best * f.part_stride + (size_t)(f.nacc + f.out_idx[o]) * f.domain + k]);
+          v = __ldcg(&parts[(size_t)best * f.part_stride + (size_t)(f.nacc + f.out_idx[o]) * f.domain + k]);
         } else {
           int j = f.out_idx[o], op = f.acc_op[j];
           v = acc_identity(op);
-          for (int r = 0; r < f.nranks; r++) v = acc_combine(op, v, __ldcg(&f.parts[(size_t)r * f.part_stride + (size_t)j * f.domain + k]));
+          for (int r = 0; r < nranks; r++) v = acc_combine(op, v, __ldcg(&parts[(size_t)r * f.part_stride + (size_t)j * f.domain + k]));
         }
         f.out[o][pos] = v;
         if (f.hmirror) mirror(f.out[o])[pos] = v;
@@ -874,11 +929,19 @@ __device__ __forceinline__ void finalize_block(const FinDesc &f, int tid, int *w
 __global__ void __launch_bounds__(256, 1) fused_finalize_kernel(const __grid_constant__ FinDesc f) {
   __shared__ int warp_cnt[8];
   __shared__ i64 running;
-  finalize_block<256>(f, threadIdx.x, warp_cnt, &running);
+  finalize_block<256>(f, f.parts, f.nranks, threadIdx.x, warp_cnt, &running);
+}
+
+// A rank with nothing to scan still takes part in the exchange: its (identity) table, then the common finalize.
+__global__ void __launch_bounds__(256, 1) fused_exchange_kernel(const __grid_constant__ KDesc d, const __grid_constant__ FinDesc f, const __grid_constant__ XDesc x) {
+  __shared__ int warp_cnt[8];
+  __shared__ i64 running;
+  const i64 *parts = exchange_block<256>(x, d.table, d.errflag, threadIdx.x);
+  finalize_block<256>(f, parts, x.world, threadIdx.x, warp_cnt, &running);
 }
 
 // ------------------------------------------------------------------------------ host side
-typedef void (*scan_kernel_fn)(const KDesc, const FinDesc);
+typedef void (*scan_kernel_fn)(const KDesc, const FinDesc, const XDesc);
 struct vdl_fused {
   vdl_ctx *ctx = nullptr;
   KDesc kd;
@@ -893,6 +956,7 @@ struct vdl_fused {
   bool table_clean = false;       // the partial table holds the fold identities (init kernel or a finalize that reset it)
   unsigned int *d_done = nullptr; // ticket counter of the scan kernel's last-CTA epilogue
   i64 *h_mapped = nullptr;        // device address of h_outbuf (mapped pinned memory)
+  XDesc xd;                       // peer exchange (world == 0: not configured)
   // register slots: kernels by slot count; the launch picks the smallest count that covers the groups the previous
   // run of this scan produced (more slots = more predicated work per row; too few = keys on the slow global path)
   scan_kernel_fn rs_kernel[9] = {nullptr};
@@ -989,6 +1053,7 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   KDesc &k = f->kd;
   memset(&k, 0, sizeof k);
   memset(&f->fd, 0, sizeof f->fd);
+  memset(&f->xd, 0, sizeof f->xd);
   k.rows = desc->rows;
   k.row_base = desc->row_base;
   k.key_mask = desc->key_mask;
@@ -1326,14 +1391,21 @@ extern "C" int vdl_fused_launch_ex(vdl_fused *f, int self_finalize) {
     f->kd.gmax = g;
   }
   const bool scan = f->kd.rows > 0 && !f->always_false;
+  if (self_finalize == 2) {
+    if (f->xd.world < 1) return vdl_fail(ctx, VDL_EINVAL, "fused scan: peer exchange requested before vdl_fused_set_peers");
+    f->xd.epoch++;
+  }
   f->fd.parts = f->kd.table;
   f->fd.nranks = 1;
   f->fd.reset_table = f->kd.table;
   if (scan) {
-    f->kd.epilogue = self_finalize ? 2 : 1;
-    f->kernel<<<f->grid, f->nc + 32, f->smem_bytes, ctx->stream>>>(f->kd, f->fd);
+    f->kd.epilogue = self_finalize == 2 ? 3 : (self_finalize ? 2 : 1);
+    f->kernel<<<f->grid, f->nc + 32, f->smem_bytes, ctx->stream>>>(f->kd, f->fd, f->xd);
     ctx->launches++;
     f->table_clean = self_finalize != 0;
+  } else if (self_finalize == 2) {       // nothing to scan here, but the other ranks wait for this rank's table
+    fused_exchange_kernel<<<1, 256, 0, ctx->stream>>>(f->kd, f->fd, f->xd);
+    ctx->launches++;
   } else if (self_finalize) {            // nothing to scan: the (identity) table finalizes to zero groups
     fused_finalize_kernel<<<1, 256, 0, ctx->stream>>>(f->fd);
     ctx->launches++;
@@ -1342,6 +1414,29 @@ extern "C" int vdl_fused_launch_ex(vdl_fused *f, int self_finalize) {
   f->timed = true;
   VDL_CUDA(ctx, cudaGetLastError());
   if (self_finalize) f->finalized = true;
+  return VDL_OK;
+}
+
+// step counter of the peer exchange; the plan carries it over when a scan is re-prepared on the same buffers
+u64 vdl_fused_epoch(vdl_fused *f) { return f->xd.epoch; }
+void vdl_fused_set_epoch(vdl_fused *f, u64 e) { f->xd.epoch = e; }
+
+extern "C" int vdl_fused_exchange_bytes(vdl_fused *f, int world, int64_t *bytes) {
+  if (!f || !bytes || world < 1 || world > VDL_MAX_RANKS) return VDL_EINVAL;
+  *bytes = ((int64_t)2 * world * f->fd.part_stride + 2 * world) * (int64_t)sizeof(i64);
+  return VDL_OK;
+}
+
+extern "C" int vdl_fused_set_peers(vdl_fused *f, int rank, int world, void *const *peer_buffers) {
+  if (!f || !peer_buffers || world < 1 || world > VDL_MAX_RANKS || rank < 0 || rank >= world) return VDL_EINVAL;
+  memset(&f->xd, 0, sizeof f->xd);
+  f->xd.rank = rank;
+  f->xd.world = world;
+  f->xd.stride = f->fd.part_stride;
+  for (int r = 0; r < world; r++) {
+    if (!peer_buffers[r]) return vdl_fail(f->ctx, VDL_EINVAL, "set_peers: buffer of rank %d is null", r);
+    f->xd.peer[r] = (i64 *)peer_buffers[r];
+  }
   return VDL_OK;
 }
 

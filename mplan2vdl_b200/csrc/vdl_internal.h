@@ -72,6 +72,9 @@ struct Operand {
 };
 Operand operand_of(const Vec &v);
 
+u64 vdl_fused_epoch(vdl_fused *f);
+void vdl_fused_set_epoch(vdl_fused *f, u64 e);
+
 #ifdef __CUDACC__
 // Elementwise op semantics (Vdl.hs:136-157, 209-231).  Comparisons / logicals give 0/1; BitShift: +k arithmetic right,
 // -k left (Vlite.hs:205-208); Divide truncates, x/0 := 0, INT64_MIN/-1 wraps; Modulo is the C remainder, x%0 := 0.

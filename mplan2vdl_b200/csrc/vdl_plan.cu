@@ -63,6 +63,10 @@ struct FusedGroup {
   vdl_fused *fused = nullptr;
   std::vector<vdl_vec> bound;           // column handles the prepared scan was built for
   i64 bound_rows = -1, bound_base = -1;
+  // peer-memory combine (vdl_plan_set_peers): re-applied whenever the scan is re-prepared
+  int peer_rank = -1, peer_world = 0;
+  std::vector<void *> peers;
+  u64 epoch = 0;
 };
 
 }  // namespace
@@ -778,14 +782,18 @@ static int plan_run_local(vdl_plan *p, int self_finalize) {
       rows = len;
     }
     if (!g.fused || h != g.bound || rows != g.bound_rows || p->row_base != g.bound_base) {
-      if (g.fused) { vdl_fused_destroy(g.fused); g.fused = nullptr; }
+      if (g.fused) { g.epoch = vdl_fused_epoch(g.fused); vdl_fused_destroy(g.fused); g.fused = nullptr; }
       g.desc.rows = rows;
       g.desc.row_base = p->row_base;
       for (size_t c = 0; c < h.size(); c++) g.desc.column[c] = h[c];
       VDL_TRY(vdl_fused_prepare(ctx, &g.desc, &g.fused));
       g.bound = h; g.bound_rows = rows; g.bound_base = p->row_base;
+      if (g.peer_world > 0) {
+        VDL_TRY(vdl_fused_set_peers(g.fused, g.peer_rank, g.peer_world, g.peers.data()));
+        vdl_fused_set_epoch(g.fused, g.epoch);
+      }
     }
-    VDL_TRY(vdl_fused_launch_ex(g.fused, self_finalize));
+    VDL_TRY(vdl_fused_launch_ex(g.fused, self_finalize && g.peer_world > 0 ? 2 : self_finalize));
   }
   p->launches_last = ctx->launches - l0;
   p->local_done = true;
@@ -800,6 +808,22 @@ extern "C" int vdl_plan_fused(vdl_plan *p, int i, vdl_fused **out) {
   if (!p || !out || i < 0 || i >= (int)p->groups.size()) return VDL_EINVAL;
   *out = p->groups[i].fused;
   return *out ? VDL_OK : vdl_fail(p->ctx, VDL_EINVAL, "plan has not run yet");
+}
+
+extern "C" int vdl_plan_exchange_bytes(vdl_plan *p, int fused_index, int world, int64_t *bytes) {
+  if (!p || fused_index < 0 || fused_index >= (int)p->groups.size()) return VDL_EINVAL;
+  if (!p->groups[fused_index].fused) return vdl_fail(p->ctx, VDL_EINVAL, "plan has not run yet");
+  return vdl_fused_exchange_bytes(p->groups[fused_index].fused, world, bytes);
+}
+
+extern "C" int vdl_plan_set_peers(vdl_plan *p, int fused_index, int rank, int world, void *const *peer_buffers) {
+  if (!p || fused_index < 0 || fused_index >= (int)p->groups.size() || !peer_buffers || world < 1 || world > VDL_MAX_RANKS) return VDL_EINVAL;
+  FusedGroup &g = p->groups[fused_index];
+  g.peer_rank = rank; g.peer_world = world;
+  g.peers.assign(peer_buffers, peer_buffers + world);
+  g.epoch = 0;
+  if (g.fused) VDL_TRY(vdl_fused_set_peers(g.fused, rank, world, g.peers.data()));
+  return VDL_OK;
 }
 
 extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int nranks) {

@@ -1,5 +1,12 @@
 """Row-range sharded execution: one process per GPU, torch.distributed for the plumbing.
 
+Two ways to combine the per-rank partial aggregate tables:
+* peer memory (default on GPUs): every rank owns a small exchange buffer that all ranks map (CUDA IPC); the LAST
+  thread block of each rank's scan kernel stores its table into every peer's buffer over NVLink, publishes an epoch
+  flag, waits for the other ranks' flags, merges and finalizes.  One kernel launch per GPU and step, no collective
+  library on the data path (include/vdl_cuda.h, "multi-GPU combine over peer memory").
+* all-gather (gloo on CPUs in the tests, NCCL if peer mapping is unavailable or VDL_NO_PEER is set), described next.
+
 The fact table is split by contiguous row range (tpch.shard_range), dimension tables are replicated, every rank
 runs the same plan on its shard (vdl_plan_run_local), the per-rank partial aggregate tables -- [accumulators x key
 domain] int64, a few bytes to a few KB -- are all-gathered (NCCL over NVLink on GPUs), and every rank merges them in
@@ -34,15 +41,56 @@ def gather_partial_tables(local: torch.Tensor, world: int, group=None) -> torch.
 class ShardedPlan:
     """A plan executed over this rank's shard; step() returns the global result on every rank."""
 
-    def __init__(self, ctx, plan, rank: int, world: int, row_base: int, group=None):
+    def __init__(self, ctx, plan, rank: int, world: int, row_base: int, group=None, peer: bool | None = None):
+        import os
         self.ctx, self.plan, self.rank, self.world, self.group = ctx, plan, rank, world, group
         plan.set_row_base(row_base)
         self._stream = torch.cuda.ExternalStream(ctx.stream, device=ctx.device) if world > 1 else None
         self._gathered = []
+        self._want_peer = world > 1 and (peer if peer is not None else not os.environ.get("VDL_NO_PEER"))
+        self.peer_mode = False
+        self._mine, self._opened = [], []
+
+    def _setup_peers(self) -> bool:
+        """Allocate / exchange / map the exchange buffers (after the scans exist, i.e. after one step).  Collective."""
+        import torch.distributed as dist
+        ok, ptr_lists = 1, []
+        try:
+            for i in range(self.plan.num_fused):
+                mine = self.ctx.ipc_alloc(self.plan.exchange_bytes(i, self.world))
+                self._mine.append(mine)
+                handles = [None] * self.world
+                dist.all_gather_object(handles, self.ctx.ipc_export(mine), group=self.group)
+                ptrs = []
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        ptrs.append(mine)
+                    else:
+                        ptrs.append(self.ctx.ipc_open(h))
+                        self._opened.append(ptrs[-1])
+                ptr_lists.append(ptrs)
+        except Exception as e:                      # no peer mapping on this box: every rank falls back together
+            print(f"[vdl] rank {self.rank}: peer-memory exchange unavailable ({e}); using the all-gather path", flush=True)
+            ok = 0
+        flag = torch.tensor([ok], device=f"cuda:{self.ctx.device}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            return False
+        for i, ptrs in enumerate(ptr_lists):
+            self.plan.set_peers(i, self.rank, self.world, ptrs)
+        dist.barrier(group=self.group)
+        return True
 
     def step(self) -> dict:
-        if self.world == 1:
+        if self.world == 1 or self.peer_mode:
             return self.plan.run()                      # one launch per fused scan: its last thread block finalizes
+        out = self._step_all_gather()
+        if self._want_peer:                             # the scans exist now: switch to the peer-memory combine
+            self._want_peer = False
+            self.peer_mode = self._setup_peers()
+        return out
+
+    def _step_all_gather(self) -> dict:
         self.plan.run_local()
         ptrs = []
         with torch.cuda.stream(self._stream):           # NCCL is ordered after the scan on the library's stream
@@ -55,3 +103,16 @@ class ShardedPlan:
                 self._gathered[i] = g                   # keep alive until finish() has consumed it
                 ptrs.append(g.data_ptr())
         return self.plan.finish(ptrs, self.world)
+
+    def close(self):
+        for p in self._opened:
+            try:
+                self.ctx.ipc_close(p)
+            except Exception:
+                pass
+        for p in self._mine:
+            try:
+                self.ctx.ipc_free(p)
+            except Exception:
+                pass
+        self._opened, self._mine = [], []

@@ -134,6 +134,28 @@ class Context:
     def op_fold(self, op: str, groups: int, data: int) -> int:
         return self._out(self.L.vdl_op_fold, _lib.FOLD_OPS.index(op), groups, data)
 
+    # ---- peer-addressable buffers (multi-GPU combine without a collective library) ------------
+    def ipc_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self.check(self.L.vdl_ipc_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self.check(self.L.vdl_ipc_export(self.h, C.c_void_p(ptr), buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self.check(self.L.vdl_ipc_open(self.h, handle, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr: int):
+        self.check(self.L.vdl_ipc_close(self.h, C.c_void_p(ptr)))
+
+    def ipc_free(self, ptr: int):
+        self.check(self.L.vdl_ipc_free(self.h, C.c_void_p(ptr)))
+
     # ---- misc --------------------------------------------------------------------------------
     def synchronize(self):
         self.check(self.L.vdl_ctx_synchronize(self.h))
@@ -177,6 +199,17 @@ class Plan:
 
     def set_row_base(self, row_base: int):
         self.ctx.check(self.L.vdl_plan_set_row_base(self.h, row_base))
+
+    def exchange_bytes(self, i: int, world: int) -> int:
+        n = C.c_int64()
+        self.ctx.check(self.L.vdl_plan_exchange_bytes(self.h, i, world, C.byref(n)))
+        return n.value
+
+    def set_peers(self, i: int, rank: int, world: int, ptrs):
+        """Exchange buffers (device pointers valid on THIS GPU) of all ranks for fused scan i; run() then returns the
+        global result on every rank with one kernel launch per GPU."""
+        arr = (C.c_void_p * world)(*ptrs)
+        self.ctx.check(self.L.vdl_plan_set_peers(self.h, i, rank, world, arr))
 
     def run_local(self):
         self.ctx.check(self.L.vdl_plan_run_local(self.h))

@@ -100,6 +100,15 @@ SYMBOLS = [
     ("vdl_plan_load", _I, [_P, C.c_char_p, _I, C.POINTER(_P)]),
     ("vdl_plan_stats", _I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
     ("vdl_plan_set_row_base", _I, [_P, _L]),
+    ("vdl_plan_exchange_bytes", _I, [_P, _I, _I, C.POINTER(_L)]),
+    ("vdl_plan_set_peers", _I, [_P, _I, _I, _I, C.POINTER(_P)]),
+    ("vdl_fused_exchange_bytes", _I, [_P, _I, C.POINTER(_L)]),
+    ("vdl_fused_set_peers", _I, [_P, _I, _I, C.POINTER(_P)]),
+    ("vdl_ipc_alloc", _I, [_P, _L, C.POINTER(_P)]),
+    ("vdl_ipc_export", _I, [_P, _P, C.c_char_p]),
+    ("vdl_ipc_open", _I, [_P, C.c_char_p, C.POINTER(_P)]),
+    ("vdl_ipc_close", _I, [_P, _P]),
+    ("vdl_ipc_free", _I, [_P, _P]),
     ("vdl_plan_run_local", _I, [_P]),
     ("vdl_plan_num_fused", _I, [_P]),
     ("vdl_plan_fused", _I, [_P, _I, C.POINTER(_P)]),

@@ -68,3 +68,52 @@ def test_empty_shard_is_harmless(catalog):
     gathered = torch.cat(tables)
     torch.cuda.synchronize()
     assert_same(keep[0][1].finish([gathered.data_ptr()], world), want)
+
+
+@pytest.mark.parametrize("query,colnames", [("q06.vdl", Q6_COLS), ("q01.vdl", Q1_COLS)])
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_memory_exchange_emulated_ranks(catalog, query, colnames, world):
+    """The fused combine: every rank's scan kernel stores its partial table into all ranks' exchange buffers, waits
+    for the others' epoch flags and finalizes -- one launch per rank and step, no collective.  Ranks are emulated by
+    one context (stream) each on the same GPU, driven from one host thread each; several steps to cover both buffer
+    parities; the last rank owns an empty shard when the rows do not split."""
+    import threading
+    from mplan2vdl_b200.executor import Context
+    rows, text = 40_000, plan_text(query)
+    names = ["lineitem." + c for c in colnames]
+    want = run_oracle(text, host_columns(catalog, names, {"lineitem": rows}))
+    ctxs, plans = [], []
+    for rank in range(world):
+        start, n = tpch.shard_range(rows, rank, world)
+        ctx = Context(0)
+        for k, v in host_columns(catalog, names, {"lineitem": n}, row_offset=start).items():
+            ctx.upload_column(k, v)
+        plan = ctx.plan(text)
+        plan.set_row_base(start)
+        plan.run_local()                    # prepares the scan (all allocations happen here, none while peers spin)
+        ctx.synchronize()
+        ctxs.append(ctx)
+        plans.append(plan)
+    bufs = [ctxs[r].ipc_alloc(plans[r].exchange_bytes(0, world)) for r in range(world)]
+    for r in range(world):
+        plans[r].set_peers(0, r, world, bufs)
+    for step in range(3):
+        results, errors = [None] * world, []
+
+        def work(r):
+            try:
+                results[r] = plans[r].run()
+            except Exception as e:          # pragma: no cover
+                errors.append(e)
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(60)
+        assert not errors, errors
+        for r in range(world):
+            assert_same(results[r], want)
+    for r in range(world):
+        plans[r].close()
+        ctxs[r].ipc_free(bufs[r])
+        ctxs[r].close()
