@@ -221,6 +221,48 @@ int vdl_ipc_free(vdl_ctx *ctx, void *device_ptr);
 /* Duration of the last vdl_fused_launch's scan kernel alone, CUDA events on the context stream. */
 int vdl_fused_last_kernel_ms(vdl_fused *f, float *ms);
 
+/* ---- fused FK-join probe ----------------------------------------------------------------
+ * One pass over a fact-table shard that follows foreign-key index columns into dimension columns, applies
+ * the predicates of the whole join chain (handleGatherJoin / deduceMasks, Vlite.hs:1199-1280) and either
+ * folds per group key or emits the surviving rows' expressions as dense vectors in row order.
+ *   leaf       value(row) = column[ parent < 0 ? row : value of leaf `parent` (row) ]   (parent precedes the leaf)
+ *   term       a + b * (leaf >> shr);  leaf -1: the constant a;  leaf -2: the global row id
+ *   predicate  kind 0: lo <= t <= hi;  kind 1: t == u;  evaluated in order, the first failure rejects the row */
+#define VDL_MAX_LEAVES 24
+#define VDL_MAX_PROBE_PREDS 12
+#define VDL_MAX_EMITS 8
+typedef struct { vdl_vec column; int32_t parent; } vdl_leaf;
+typedef struct { int32_t leaf, shr; int64_t a, b; } vdl_term;
+typedef struct { int32_t kind, pad; vdl_term t, u; int64_t lo, hi; } vdl_probe_pred;
+typedef struct { int32_t nfactors, pad; vdl_term factor[VDL_MAX_FACTORS]; } vdl_product;
+typedef struct { int32_t op, pad; vdl_product value; } vdl_probe_fold;       /* op: VDL_FOLD_* */
+typedef struct {
+  int64_t rows, row_base;
+  int32_t nleaves, npreds;
+  vdl_leaf leaf[VDL_MAX_LEAVES];
+  vdl_probe_pred pred[VDL_MAX_PROBE_PREDS];
+  /* fold mode (nfolds > 0): key = OR of (term << shl) & key_mask in [0, domain); nkeys == 0: one group */
+  int32_t nkeys, nfolds;
+  vdl_term key[VDL_MAX_KEYS];
+  int32_t key_shl[VDL_MAX_KEYS];
+  int64_t key_mask, domain;
+  vdl_probe_fold fold[VDL_MAX_AGGS];
+  int32_t nposts, nemits;
+  vdl_post_op post[VDL_MAX_POSTS];
+  /* emit mode (nemits > 0): one dense int64 vector per expression, surviving rows in ascending row order */
+  vdl_product emit[VDL_MAX_EMITS];
+} vdl_probe_desc;
+typedef struct vdl_probe vdl_probe;
+int vdl_abi_sizeof_probe_desc(void);
+int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_probe **out);
+int vdl_probe_run(vdl_probe *p);                 /* asynchronous on the context stream */
+/* fold mode: host copy of fold `index` (0..nfolds-1) or post op (nfolds..); one vector entry per existing key */
+int vdl_probe_result_host(vdl_probe *p, int index, const int64_t **data, int64_t *len);
+/* emit mode: take ownership of the k-th emitted vector (synchronises for its length) */
+int vdl_probe_emit_take(vdl_probe *p, int k, vdl_vec *out);
+int vdl_probe_last_kernel_ms(vdl_probe *p, float *ms);
+int vdl_probe_destroy(vdl_probe *p);
+
 /* ---- whole plans: the text mplan2vdl prints (Vdl.hs:410-453) ---------------------------- */
 enum { VDL_PLAN_FUSE = 1 };           /* flags: run the select->map->fold fusion pass */
 int vdl_plan_load(vdl_ctx *ctx, const char *vdl_text, int flags, vdl_plan **out);

@@ -43,6 +43,14 @@ extern "C" int vdl_ctx_create(int device, vdl_ctx **out) {
     delete ctx;
     return VDL_ECUDA;
   }
+  {   // vectors come from the device's stream-ordered pool (cudaMallocAsync): allocation and release are stream operations,
+      // never a device synchronisation; keep freed memory in the pool instead of returning it to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   *out = ctx;
@@ -54,7 +62,8 @@ extern "C" int vdl_ctx_destroy(vdl_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto &v : ctx->vecs)
-    if (v.live && v.owned && v.ptr) cudaFree(v.ptr);
+    if (v.live && v.owned && v.ptr) cudaFreeAsync(v.ptr, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->d_errflag) cudaFree(ctx->d_errflag);
   cudaStreamDestroy(ctx->stream);
@@ -92,7 +101,7 @@ int vec_new(vdl_ctx *ctx, int dtype, i64 len, vdl_vec *out) {
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   void *p = nullptr;
   i64 bytes = padded_bytes(dtype, len);
-  VDL_CUDA(ctx, cudaMalloc(&p, (size_t)bytes));
+  VDL_CUDA(ctx, cudaMallocAsync(&p, (size_t)bytes, ctx->stream));
   int h = vec_slot(ctx);
   Vec &v = ctx->vecs[h];
   v = Vec();
@@ -181,10 +190,7 @@ extern "C" int vdl_vec_free(vdl_ctx *ctx, vdl_vec h) {
   Vec *v = vec_get(ctx, h);
   if (!v) return VDL_EINVAL;
   if (!v->name.empty()) ctx->columns.erase(v->name);
-  if (v->owned && v->ptr) {
-    VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    VDL_CUDA(ctx, cudaFree(v->ptr));
-  }
+  if (v->owned && v->ptr) VDL_CUDA(ctx, cudaFreeAsync(v->ptr, ctx->stream));   // ordered after the stream's pending readers
   *v = Vec();
   return VDL_OK;
 }

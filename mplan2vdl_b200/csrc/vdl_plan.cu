@@ -20,6 +20,9 @@
 
 #include "vdl_internal.h"
 
+#include <chrono>
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 namespace {
 
 enum NodeOp { N_LOAD, N_RANGEV, N_RANGEC, N_BINARY, N_FSELECT, N_GATHER, N_SCATTER, N_PARTITION, N_FOLD };
@@ -88,6 +91,8 @@ struct vdl_plan {
   std::vector<vdl_vec> temps;
   i64 launches_last = 0;
   bool local_done = false, self_finalized = false;
+  bool trace = false;
+  double trace_t0 = 0, trace_last = 0;
 };
 
 namespace {
@@ -731,6 +736,16 @@ int eval(vdl_plan *p, int ni, vdl_vec *out) {
   p->val[ni] = r;
   if (temp) p->temps.push_back(r);
   *out = r;
+  if (p->trace) {      // VDL_TRACE: host wall time per node, synchronised (debugging aid: serialises the plan)
+    cudaStreamSynchronize(ctx->stream);
+    double t1 = now_ms();
+    i64 len = 0;
+    vdl_vec_len(ctx, r, &len);
+    static const char *OPN[] = {"Load", "RangeV", "RangeC", "Binary", "FoldSelect", "Gather", "Scatter", "Partition", "Fold"};
+    fprintf(stderr, "[vdl trace] node %3d %-10s sub %2d len %10lld  %8.3f ms (cumulative since plan start %8.3f)\n", ni, OPN[n.op], n.sub, (long long)len,
+            t1 - p->trace_last, t1 - p->trace_t0);
+    p->trace_last = now_ms();
+  }
   return VDL_OK;
 }
 
@@ -830,6 +845,8 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
   if (!p) return VDL_EINVAL;
   vdl_ctx *ctx = p->ctx;
   if (!p->local_done) return vdl_fail(ctx, VDL_EINVAL, "vdl_plan_finish before vdl_plan_run_local");
+  p->trace = getenv("VDL_TRACE") != nullptr;
+  if (p->trace) p->trace_t0 = p->trace_last = now_ms();
   if (nranks > 1 && p->groups.empty()) return vdl_fail(ctx, VDL_EUNSUPPORTED, "plan has no fused scan: it cannot be row-sharded");
   i64 l0 = ctx->launches;
   if (!(p->self_finalized && nranks == 1 && !all_partials))

@@ -1,0 +1,529 @@
+// Fused FK-join probe: ONE pass over a fact-table shard that follows foreign-key index columns into
+// dimension columns (replicated in HBM, mostly L2-resident), applies the selection predicates of the whole
+// join chain, and either folds per group key (Q5-class plans) or emits the surviving rows' expressions as
+// dense vectors in row order (Q3-class plans, whose high-cardinality group-by continues op-at-a-time on the
+// few surviving rows).
+//
+// What it replaces in the emitted graph (reference Vlite.hs): handleGatherJoin / deduceMasks
+// (Vlite.hs:1199-1232, 1248-1280; diagram 1420-1447) lower an FK join to
+//     fk'      = Gather(Load fact.fk_idx, factmask)
+//     valid    = Scatter(ones -> dimmask positions)         inv = Scatter(pos -> dimmask positions)
+//     boolean  = Gather(valid, fk')                         gmask = Gather(inv, fk')
+//     selmask  = FoldSelect(pos_ boolean, boolean)
+//     fact cols, gmask <- Gather(., selmask)                dim cols <- Gather(Gather(col, dimmask), gmask)
+// and chain that per join.  In the dense model every vector of the joined row space is a
+// function of the underlying fact row i:  dim column e -> e[fk(i)],  nested joins -> e[fk2[fk1(i)]], and the
+// selection is the conjunction of the fact predicates and the dimension predicates evaluated at fk(i).  The
+// planner (vdl_plan.cu, analyse) proves that normal form; this kernel evaluates it:
+//   leaf      value(i) = column[ parent leaf's value(i) ]   (parent < 0: column[i] of the fact table)
+//   term      a + b * (leaf >> shr), or a constant, or the row id
+//   predicate lo <= term <= hi, or term == term; evaluated in chain order, first failure rejects the row
+// No validity vector, inverse index, position vector or gathered copy is ever materialised.
+//
+// Kernel shape: persistent thread blocks take 1024-row tiles in order from a ticket counter; a thread owns
+// rows tid + k*256 of the tile (coalesced fact-column loads; the lineitem->orders index is clustered, so the
+// first dimension gather is nearly sequential too).  Fold mode accumulates into a shared-memory table per block
+// (flushed with global atomics); emit mode orders the survivors with ballots inside the tile and a decoupled
+// look-back across tiles (one 64-bit status word per tile), so the output vectors are exactly the dense
+// FoldSelect order.  Bound: HBM for the fact columns + L2 latency for the dimension gathers.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "vdl_internal.h"
+
+#define P_TILE 1024
+#define P_THREADS 256
+#define P_R (P_TILE / P_THREADS)
+#define P_MAX_DEPTH 6
+#define P_SMEM_TABLE_BYTES (40 * 1024)
+
+struct PLeaf { const void *ptr; i64 len; int32_t w4, parent; };
+struct PTerm { int32_t leaf, shr; i64 a, b; };             // leaf -1: constant a; -2: global row id
+struct PPred { int32_t kind, pad; PTerm t, u; i64 lo; u64 span; };
+struct PProd { int32_t nfac, pad; PTerm f[VDL_MAX_FACTORS]; };
+
+struct PDesc {
+  i64 rows, row_base, key_mask, domain, ntiles;
+  int32_t nleaves, npreds, nkeys, nfolds, nemits, smem_table, pad0, pad1;
+  PLeaf leaf[VDL_MAX_LEAVES];
+  PPred pred[VDL_MAX_PROBE_PREDS];
+  PTerm key[VDL_MAX_KEYS];
+  int32_t key_shl[VDL_MAX_KEYS];
+  int32_t fold_op[VDL_MAX_AGGS];
+  PProd fold[VDL_MAX_AGGS];
+  PProd emit[VDL_MAX_EMITS];
+  i64 *table;                       // fold mode: [nfolds + 2][domain]: fold accumulators, row count, first row
+  i64 *emit_out[VDL_MAX_EMITS];     // emit mode: dense output vectors (capacity rows)
+  unsigned long long *tile_state;   // emit mode look-back: (status << 62) | count; status 1 = tile aggregate, 2 = inclusive prefix
+  unsigned int *ticket;
+  i64 *total;                       // emit mode: number of surviving rows
+  int *errflag;
+};
+
+struct PFin {
+  i64 domain;
+  int32_t nfolds, npost;
+  int32_t fold_op[VDL_MAX_AGGS];
+  vdl_post_op post[VDL_MAX_POSTS];
+  const i64 *table;
+  i64 *out;                         // [(nfolds + npost)][domain] then [ngroups, errors]
+  i64 *hmirror;
+  const int *errflag;
+};
+
+__device__ __forceinline__ i64 p_identity(int op) { return op == VDL_FOLD_MIN ? INT64_MAX : (op == VDL_FOLD_MAX ? INT64_MIN : 0); }
+
+// value of leaf l at fact row `row` (local to the shard): walk the parent chain, then load top-down
+__device__ __forceinline__ i64 leaf_value(const PDesc &d, int l, i64 row, bool &ok) {
+  int chain[P_MAX_DEPTH];
+  int n = 0;
+#pragma unroll
+  for (int k = 0; k < P_MAX_DEPTH; k++)
+    if (l >= 0) { chain[k] = l; n = k + 1; l = d.leaf[l].parent; }
+  i64 idx = row;
+#pragma unroll
+  for (int k = P_MAX_DEPTH - 1; k >= 0; k--) {
+    if (k < n) {
+      const PLeaf &L = d.leaf[chain[k]];
+      if ((u64)idx >= (u64)L.len) { ok = false; return 0; }
+      idx = L.w4 ? (i64)__ldg((const int32_t *)L.ptr + idx) : __ldg((const i64 *)L.ptr + idx);
+    }
+  }
+  return idx;
+}
+__device__ __forceinline__ i64 term_value(const PDesc &d, const PTerm &t, i64 row, bool &ok) {
+  if (t.leaf == -1) return t.a;
+  i64 v = t.leaf == -2 ? d.row_base + row : leaf_value(d, t.leaf, row, ok);
+  if (t.shr) v >>= t.shr;
+  return (i64)((u64)t.a + (u64)t.b * (u64)v);
+}
+__device__ __forceinline__ i64 prod_value(const PDesc &d, const PProd &p, i64 row, bool &ok) {
+  i64 v = 1;
+  for (int f = 0; f < p.nfac; f++) v = (i64)((u64)v * (u64)term_value(d, p.f[f], row, ok));
+  return v;
+}
+__device__ __forceinline__ bool row_passes(const PDesc &d, i64 row, bool &ok) {
+  for (int q = 0; q < d.npreds; q++) {
+    const PPred &P = d.pred[q];
+    i64 t = term_value(d, P.t, row, ok);
+    if (!ok) return false;
+    if (P.kind == 0) {
+      if ((u64)t - (u64)P.lo > P.span) return false;
+    } else {
+      i64 u = term_value(d, P.u, row, ok);
+      if (!ok || t != u) return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void table_update(int op, i64 *p, i64 v) {
+  if (op == VDL_FOLD_MIN) atomicMin((long long *)p, (long long)v);
+  else if (op == VDL_FOLD_MAX) atomicMax((long long *)p, (long long)v);
+  else atomicAdd((unsigned long long *)p, (unsigned long long)v);
+}
+
+__global__ void __launch_bounds__(P_THREADS, 4) probe_kernel(const __grid_constant__ PDesc d) {
+  extern __shared__ __align__(16) unsigned char psm[];
+  __shared__ int wcnt[P_THREADS / 32];
+  __shared__ i64 s_off;
+  __shared__ unsigned int s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool folding = d.nemits == 0;
+  const int nacc = d.nfolds + 2;
+  i64 *stab = (i64 *)psm;                         // [nacc][domain] when smem_table
+  if (folding && d.smem_table) {
+    for (i64 i = tid; i < (i64)nacc * d.domain; i += P_THREADS) {
+      int j = (int)(i / d.domain);
+      stab[i] = j < d.nfolds ? p_identity(d.fold_op[j]) : (j == d.nfolds ? 0 : INT64_MAX);
+    }
+  }
+  __syncthreads();
+  i64 *tab = (folding && d.smem_table) ? stab : d.table;
+
+  for (;;) {
+    if (tid == 0) s_tile = atomicAdd(d.ticket, 1u);
+    __syncthreads();
+    const i64 tile = s_tile;
+    if (tile >= d.ntiles) break;
+    const i64 base = tile * P_TILE;
+    bool pass[P_R];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < P_R; k++) {
+      const i64 row = base + k * P_THREADS + tid;
+      pass[k] = row < d.rows && row_passes(d, row, ok);
+    }
+    if (folding) {
+#pragma unroll 1
+      for (int k = 0; k < P_R; k++) {
+        if (!pass[k]) continue;
+        const i64 row = base + k * P_THREADS + tid;
+        i64 key = 0;
+        for (int q = 0; q < d.nkeys; q++) key |= (i64)((u64)term_value(d, d.key[q], row, ok) << d.key_shl[q]);
+        key &= d.key_mask;
+        if ((u64)key >= (u64)d.domain) { ok = false; continue; }
+        for (int j = 0; j < d.nfolds; j++) {
+          const int op = d.fold_op[j];
+          if (op == VDL_FOLD_CHOOSE || op == VDL_FOLD_COUNT) continue;     // from the first row / the row count
+          table_update(op, tab + (size_t)j * d.domain + key, prod_value(d, d.fold[j], row, ok));
+        }
+        atomicAdd((unsigned long long *)(tab + (size_t)d.nfolds * d.domain + key), 1ull);
+        atomicMin((long long *)(tab + (size_t)(d.nfolds + 1) * d.domain + key), (long long)(d.row_base + row));
+      }
+    } else {
+      // ---- ordered emission: rank inside the tile by ballots per step, tile offset by decoupled look-back
+      int before_step[P_R], rank[P_R], run = 0;
+#pragma unroll
+      for (int k = 0; k < P_R; k++) {
+        unsigned m = __ballot_sync(0xffffffffu, pass[k]);
+        if (lane == 0) wcnt[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < P_THREADS / 32; w++) { int c = wcnt[w]; if (w < warp) before += c; total += c; }
+        rank[k] = run + before + __popc(m & ((1u << lane) - 1));
+        before_step[k] = run;
+        run += total;
+        __syncthreads();
+      }
+      (void)before_step;
+      if (tid == 0) {
+        const unsigned long long T = (unsigned long long)run;
+        i64 excl = 0;
+        if (tile == 0) {
+          atomicExch(d.tile_state, (2ull << 62) | T);
+        } else {
+          atomicExch(d.tile_state + tile, (1ull << 62) | T);
+          for (i64 j = tile - 1;; j--) {
+            unsigned long long s;
+            do { s = *((volatile unsigned long long *)(d.tile_state + j)); } while ((s >> 62) == 0);
+            excl += (i64)(s & ((1ull << 62) - 1));
+            if ((s >> 62) == 2) break;
+          }
+          atomicExch(d.tile_state + tile, (2ull << 62) | (unsigned long long)(excl + (i64)T));
+        }
+        s_off = excl;
+        if (tile == d.ntiles - 1) *d.total = excl + (i64)T;
+      }
+      __syncthreads();
+      const i64 off = s_off;
+#pragma unroll 1
+      for (int k = 0; k < P_R; k++) {
+        if (!pass[k]) continue;
+        const i64 row = base + k * P_THREADS + tid;
+        for (int e = 0; e < d.nemits; e++) d.emit_out[e][off + rank[k]] = prod_value(d, d.emit[e], row, ok);
+      }
+    }
+    if (!ok) atomicAdd(d.errflag, 1);
+    __syncthreads();
+  }
+  if (folding && d.smem_table) {
+    __syncthreads();
+    for (i64 i = tid; i < (i64)nacc * d.domain; i += P_THREADS) {
+      int j = (int)(i / d.domain);
+      const i64 v = stab[i];
+      if (j < d.nfolds) { if (v != p_identity(d.fold_op[j])) table_update(d.fold_op[j], d.table + i, v); }
+      else if (j == d.nfolds) { if (v) atomicAdd((unsigned long long *)(d.table + i), (unsigned long long)v); }
+      else if (v != INT64_MAX) atomicMin((long long *)(d.table + i), (long long)v);
+    }
+  }
+}
+
+__global__ void probe_init_kernel(const __grid_constant__ PDesc d) {
+  const i64 n = (i64)(d.nfolds + 2) * d.domain;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    int j = (int)(i / d.domain);
+    d.table[i] = j < d.nfolds ? p_identity(d.fold_op[j]) : (j == d.nfolds ? 0 : INT64_MAX);
+  }
+}
+
+// One dense vector per fold in ascending key order (keys without rows dropped: G14), FoldChoose evaluated at the
+// key's first row, then the post ops; results mirrored into mapped host memory.
+__global__ void __launch_bounds__(256, 1) probe_finalize_kernel(const __grid_constant__ PDesc d, const __grid_constant__ PFin f) {
+  __shared__ int warp_cnt[8];
+  __shared__ i64 running;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) running = 0;
+  __syncthreads();
+  for (i64 base = 0; base < f.domain; base += 256) {
+    const i64 k = base + tid;
+    const i64 cnt = k < f.domain ? f.table[(size_t)f.nfolds * f.domain + k] : 0;
+    const bool exists = cnt > 0;
+    unsigned m = __ballot_sync(0xffffffffu, exists);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 8; w++) { if (w < warp) before += warp_cnt[w]; total += warp_cnt[w]; }
+    if (exists) {
+      const i64 pos = running + before + __popc(m & ((1u << lane) - 1));
+      const i64 first = f.table[(size_t)(f.nfolds + 1) * f.domain + k] - d.row_base;
+      i64 ov[VDL_MAX_AGGS], pv[VDL_MAX_POSTS];
+      bool ok = true;
+      for (int j = 0; j < f.nfolds; j++) {
+        i64 v;
+        if (f.fold_op[j] == VDL_FOLD_COUNT) v = cnt;
+        else if (f.fold_op[j] == VDL_FOLD_CHOOSE) v = prod_value(d, d.fold[j], first, ok);
+        else v = f.table[(size_t)j * f.domain + k];
+        ov[j] = v;
+        f.out[(size_t)j * f.domain + pos] = v;
+        if (f.hmirror) f.hmirror[(size_t)j * f.domain + pos] = v;
+      }
+      for (int q = 0; q < f.npost; q++) {
+        const vdl_post_op &P = f.post[q];
+        i64 a = P.a_kind == VDL_POST_CONST ? P.a : (P.a_kind == VDL_POST_FOLD ? ov[P.a] : pv[P.a]);
+        i64 b = P.b_kind == VDL_POST_CONST ? P.b : (P.b_kind == VDL_POST_FOLD ? ov[P.b] : pv[P.b]);
+        pv[q] = binop_apply(P.op, a, b);
+        f.out[(size_t)(f.nfolds + q) * f.domain + pos] = pv[q];
+        if (f.hmirror) f.hmirror[(size_t)(f.nfolds + q) * f.domain + pos] = pv[q];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) running += total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const size_t tail = (size_t)(f.nfolds + f.npost) * f.domain;
+    const i64 ng = running, err = *f.errflag;
+    f.out[tail] = ng; f.out[tail + 1] = err;
+    if (f.hmirror) { f.hmirror[tail] = ng; f.hmirror[tail + 1] = err; }
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+struct vdl_probe {
+  vdl_ctx *ctx = nullptr;
+  PDesc pd;
+  PFin pf;
+  bool folding = true, ran = false, fetched = false;
+  vdl_vec table = 0;
+  i64 *d_out = nullptr, *h_out = nullptr, *h_mapped = nullptr;
+  i64 *d_total = nullptr;              // [0] survivors (emit mode)
+  unsigned int *d_ticket = nullptr;
+  unsigned long long *d_state = nullptr;
+  vdl_vec emit_vec[VDL_MAX_EMITS] = {0};
+  i64 ngroups = -1, nselected = -1;
+  int grid = 1;
+  size_t smem = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static bool term_ok(const vdl_term &t, int nleaves) { return t.leaf >= -2 && t.leaf < nleaves && t.shr >= 0 && t.shr < 64; }
+static PTerm to_p(const vdl_term &t) { return PTerm{t.leaf, t.shr, t.a, t.b}; }
+
+extern "C" int vdl_abi_sizeof_probe_desc(void) { return (int)sizeof(vdl_probe_desc); }
+
+extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_probe **out) {
+  if (!ctx || !desc || !out) return VDL_EINVAL;
+  *out = nullptr;
+  if (desc->nleaves < 1 || desc->nleaves > VDL_MAX_LEAVES || desc->npreds < 0 || desc->npreds > VDL_MAX_PROBE_PREDS ||
+      desc->nkeys < 0 || desc->nkeys > VDL_MAX_KEYS || desc->nfolds < 0 || desc->nfolds > VDL_MAX_AGGS || desc->nemits < 0 ||
+      desc->nemits > VDL_MAX_EMITS || desc->nposts < 0 || desc->nposts > VDL_MAX_POSTS)
+    return vdl_fail(ctx, VDL_EINVAL, "probe: descriptor counts out of range");
+  if ((desc->nfolds > 0) == (desc->nemits > 0)) return vdl_fail(ctx, VDL_EINVAL, "probe: exactly one of folds / emits must be given");
+  if (desc->rows < 0) return vdl_fail(ctx, VDL_EINVAL, "probe: negative row count");
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  vdl_probe *p = new vdl_probe();
+  p->ctx = ctx;
+  PDesc &d = p->pd;
+  memset(&d, 0, sizeof d);
+  memset(&p->pf, 0, sizeof p->pf);
+  auto fail = [&](int rc) { vdl_probe_destroy(p); return rc; };
+  d.rows = desc->rows;
+  d.row_base = desc->row_base;
+  d.nleaves = desc->nleaves;
+  for (int l = 0; l < desc->nleaves; l++) {
+    Vec *v = vec_get(ctx, desc->leaf[l].column);
+    if (!v || v->is_range) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: leaf %d is not a stored vector", l));
+    int par = desc->leaf[l].parent;
+    if (par >= l || par < -1) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: leaf %d has parent %d (must precede it)", l, par));
+    if (par < 0 && v->len < desc->rows) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: fact column %s has %lld rows < %lld", v->name.c_str(), (long long)v->len, (long long)desc->rows));
+    int depth = 1;
+    for (int q = par; q >= 0; q = desc->leaf[q].parent) depth++;
+    if (depth > P_MAX_DEPTH) return fail(vdl_fail(ctx, VDL_EUNSUPPORTED, "probe: lookup chain deeper than %d", P_MAX_DEPTH));
+    d.leaf[l] = PLeaf{v->ptr, v->len, v->dtype == VDL_I32, par};
+  }
+  d.npreds = desc->npreds;
+  for (int q = 0; q < desc->npreds; q++) {
+    const vdl_probe_pred &s = desc->pred[q];
+    if (!term_ok(s.t, desc->nleaves) || (s.kind == 1 && !term_ok(s.u, desc->nleaves)) || (s.kind != 0 && s.kind != 1))
+      return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad predicate %d", q));
+    PPred &o = d.pred[q];
+    o.kind = s.kind; o.t = to_p(s.t); o.u = to_p(s.u);
+    if (s.kind == 0 && s.lo > s.hi) { o.lo = 1; o.span = 0; o.t = PTerm{-1, 0, 0, 0}; }    // never true: 0 in [1, 1]
+    else { o.lo = s.lo; o.span = (u64)s.hi - (u64)s.lo; }
+  }
+  d.nkeys = desc->nkeys;
+  for (int q = 0; q < desc->nkeys; q++) {
+    if (!term_ok(desc->key[q], desc->nleaves) || desc->key_shl[q] < 0 || desc->key_shl[q] > 63) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad key part %d", q));
+    d.key[q] = to_p(desc->key[q]);
+    d.key_shl[q] = desc->key_shl[q];
+  }
+  auto prod = [&](const vdl_product &s, PProd *o) {
+    if (s.nfactors < 0 || s.nfactors > VDL_MAX_FACTORS) return false;
+    o->nfac = s.nfactors;
+    for (int t = 0; t < s.nfactors; t++) { if (!term_ok(s.factor[t], desc->nleaves)) return false; o->f[t] = to_p(s.factor[t]); }
+    return true;
+  };
+  p->folding = desc->nfolds > 0;
+  d.nfolds = desc->nfolds;
+  d.nemits = desc->nemits;
+  d.ntiles = (desc->rows + P_TILE - 1) / P_TILE;
+  d.errflag = ctx->d_errflag;
+  if (cudaMalloc(&p->d_ticket, sizeof(unsigned int)) != cudaSuccess || cudaMalloc(&p->d_total, 2 * sizeof(i64)) != cudaSuccess)
+    return fail(vdl_fail(ctx, VDL_ENOMEM, "probe: counters"));
+  d.ticket = p->d_ticket;
+  d.total = p->d_total;
+  if (p->folding) {
+    if (desc->nkeys == 0 ? desc->domain != 1 : (desc->domain < 1 || desc->domain > (1 << 22)))
+      return fail(vdl_fail(ctx, VDL_EUNSUPPORTED, "probe: key domain %lld not supported", (long long)desc->domain));
+    d.key_mask = desc->key_mask;
+    d.domain = desc->domain;
+    for (int j = 0; j < desc->nfolds; j++) {
+      int op = desc->fold[j].op;
+      if (op < VDL_FOLD_SUM || op > VDL_FOLD_COUNT || !prod(desc->fold[j].value, &d.fold[j])) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad fold %d", j));
+      d.fold_op[j] = op;
+    }
+    int rc = vec_new(ctx, VDL_I64, (i64)(d.nfolds + 2) * d.domain, &p->table);
+    if (rc) return fail(rc);
+    d.table = (i64 *)ctx->vecs[p->table].ptr;
+    size_t tb = (size_t)(d.nfolds + 2) * d.domain * 8;
+    d.smem_table = tb <= P_SMEM_TABLE_BYTES;
+    p->smem = d.smem_table ? tb : 0;
+    for (int q = 0; q < desc->nposts; q++) {
+      const vdl_post_op &P = desc->post[q];
+      auto okk = [&](int kind, i64 v) { return kind == VDL_POST_CONST || (kind == VDL_POST_FOLD && v >= 0 && v < desc->nfolds) || (kind == VDL_POST_POST && v >= 0 && v < q); };
+      if (P.op < 0 || P.op > VDL_MODULO || !okk(P.a_kind, P.a) || !okk(P.b_kind, P.b)) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad post op %d", q));
+      p->pf.post[q] = P;
+    }
+    size_t nb = ((size_t)(d.nfolds + desc->nposts) * d.domain + 2) * sizeof(i64);
+    if (cudaMalloc(&p->d_out, nb) != cudaSuccess || cudaHostAlloc(&p->h_out, nb, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&p->h_mapped, p->h_out, 0) != cudaSuccess)
+      return fail(vdl_fail(ctx, VDL_ENOMEM, "probe: result buffers"));
+    p->pf.domain = d.domain; p->pf.nfolds = d.nfolds; p->pf.npost = desc->nposts;
+    for (int j = 0; j < d.nfolds; j++) p->pf.fold_op[j] = d.fold_op[j];
+    p->pf.table = d.table; p->pf.out = p->d_out; p->pf.hmirror = p->h_mapped; p->pf.errflag = ctx->d_errflag;
+  } else {
+    for (int e = 0; e < desc->nemits; e++)
+      if (!prod(desc->emit[e], &d.emit[e])) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad emit %d", e));
+    if (cudaMalloc(&p->d_state, (size_t)std::max<i64>(1, d.ntiles) * 8) != cudaSuccess) return fail(vdl_fail(ctx, VDL_ENOMEM, "probe: tile states"));
+    d.tile_state = p->d_state;
+    if (cudaHostAlloc(&p->h_out, 2 * sizeof(i64), cudaHostAllocDefault) != cudaSuccess) return fail(vdl_fail(ctx, VDL_ENOMEM, "probe: host counter"));
+  }
+  cudaEventCreate(&p->ev0);
+  cudaEventCreate(&p->ev1);
+  int per_sm = 4;
+  p->grid = (int)std::max<i64>(1, std::min<i64>((i64)ctx->sm_count * per_sm, d.ntiles));
+  if (p->smem > 48 * 1024) cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+  *out = p;
+  return VDL_OK;
+}
+
+extern "C" int vdl_probe_run(vdl_probe *p) {
+  if (!p) return VDL_EINVAL;
+  vdl_ctx *ctx = p->ctx;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  PDesc &d = p->pd;
+  p->fetched = false;
+  p->ngroups = p->nselected = -1;
+  VDL_CUDA(ctx, cudaMemsetAsync(p->d_ticket, 0, sizeof(unsigned int), ctx->stream));
+  if (p->folding) {
+    int nb = (int)std::min<i64>(ctx->sm_count, ((i64)(d.nfolds + 2) * d.domain + 255) / 256);
+    probe_init_kernel<<<std::max(nb, 1), 256, 0, ctx->stream>>>(d);
+    ctx->launches++;
+  } else {
+    VDL_CUDA(ctx, cudaMemsetAsync(p->d_state, 0, (size_t)std::max<i64>(1, d.ntiles) * 8, ctx->stream));
+    VDL_CUDA(ctx, cudaMemsetAsync(p->d_total, 0, 2 * sizeof(i64), ctx->stream));
+    // emit capacity: one vector of `rows` int64 per emitted expression (the survivors are usually far fewer; the
+    // pool keeps the pages), released by the caller through the vector handles
+    for (int e = 0; e < d.nemits; e++) {
+      if (p->emit_vec[e]) { vdl_vec_free(ctx, p->emit_vec[e]); p->emit_vec[e] = 0; }
+      VDL_TRY(vec_new(ctx, VDL_I64, d.rows, &p->emit_vec[e]));
+      d.emit_out[e] = (i64 *)ctx->vecs[p->emit_vec[e]].ptr;
+    }
+  }
+  VDL_CUDA(ctx, cudaEventRecord(p->ev0, ctx->stream));
+  if (d.rows > 0) {
+    probe_kernel<<<p->grid, P_THREADS, p->smem, ctx->stream>>>(d);
+    ctx->launches++;
+  }
+  VDL_CUDA(ctx, cudaEventRecord(p->ev1, ctx->stream));
+  if (p->folding) {
+    probe_finalize_kernel<<<1, 256, 0, ctx->stream>>>(d, p->pf);
+    ctx->launches++;
+  } else {
+    VDL_CUDA(ctx, cudaMemcpyAsync(p->h_out, p->d_total, sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  VDL_CUDA(ctx, cudaGetLastError());
+  p->ran = true;
+  return VDL_OK;
+}
+
+static int probe_fetch(vdl_probe *p) {
+  vdl_ctx *ctx = p->ctx;
+  if (!p->ran) return vdl_fail(ctx, VDL_EINVAL, "probe has not run");
+  if (p->fetched) return VDL_OK;
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (p->folding) {
+    size_t tail = (size_t)(p->pd.nfolds + p->pf.npost) * p->pd.domain;
+    i64 err = p->h_out[tail + 1];
+    if (err) {
+      cudaMemsetAsync(ctx->d_errflag, 0, sizeof(int), ctx->stream);
+      return vdl_fail(ctx, VDL_ERANGE, "probe: %lld rows had a lookup index or group key out of range", (long long)err);
+    }
+    p->ngroups = p->h_out[tail];
+  } else {
+    p->nselected = p->h_out[0];
+    for (int e = 0; e < p->pd.nemits; e++) {
+      Vec &v = ctx->vecs[p->emit_vec[e]];
+      v.len = p->nselected;
+    }
+  }
+  p->fetched = true;
+  return VDL_OK;
+}
+
+extern "C" int vdl_probe_result_host(vdl_probe *p, int index, const int64_t **data, int64_t *len) {
+  if (!p || !data || !len || !p->folding || index < 0 || index >= p->pd.nfolds + p->pf.npost) return VDL_EINVAL;
+  VDL_TRY(probe_fetch(p));
+  *data = p->h_out + (size_t)index * p->pd.domain;
+  *len = p->ngroups;
+  return VDL_OK;
+}
+
+// Emit mode: the k-th emitted vector (length = number of surviving rows).  Ownership passes to the caller.
+extern "C" int vdl_probe_emit_take(vdl_probe *p, int k, vdl_vec *out) {
+  if (!p || !out || p->folding || k < 0 || k >= p->pd.nemits) return VDL_EINVAL;
+  VDL_TRY(probe_fetch(p));
+  if (!p->emit_vec[k]) return vdl_fail(p->ctx, VDL_EINVAL, "probe: emitted vector %d already taken", k);
+  *out = p->emit_vec[k];
+  p->emit_vec[k] = 0;
+  return VDL_OK;
+}
+
+extern "C" int vdl_probe_last_kernel_ms(vdl_probe *p, float *ms) {
+  if (!p || !ms || !p->ran) return VDL_EINVAL;
+  VDL_CUDA(p->ctx, cudaEventSynchronize(p->ev1));
+  VDL_CUDA(p->ctx, cudaEventElapsedTime(ms, p->ev0, p->ev1));
+  return VDL_OK;
+}
+
+extern "C" int vdl_probe_destroy(vdl_probe *p) {
+  if (!p) return VDL_EINVAL;
+  vdl_ctx *ctx = p->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (p->table) vdl_vec_free(ctx, p->table);
+  for (int e = 0; e < VDL_MAX_EMITS; e++)
+    if (p->emit_vec[e]) vdl_vec_free(ctx, p->emit_vec[e]);
+  if (p->d_out) cudaFree(p->d_out);
+  if (p->h_out) cudaFreeHost(p->h_out);
+  if (p->d_total) cudaFree(p->d_total);
+  if (p->d_ticket) cudaFree(p->d_ticket);
+  if (p->d_state) cudaFree(p->d_state);
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
+  delete p;
+  return VDL_OK;
+}

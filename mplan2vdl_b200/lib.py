@@ -54,6 +54,37 @@ class FusedDesc(C.Structure):
                 ("nposts", C.c_int32), ("post", PostOp * VDL_MAX_POSTS)]
 
 
+VDL_MAX_LEAVES, VDL_MAX_PROBE_PREDS, VDL_MAX_EMITS = 24, 12, 8
+
+
+class Leaf(C.Structure):
+    _fields_ = [("column", C.c_int32), ("parent", C.c_int32)]
+
+
+class Term(C.Structure):
+    _fields_ = [("leaf", C.c_int32), ("shr", C.c_int32), ("a", C.c_int64), ("b", C.c_int64)]
+
+
+class ProbePred(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("pad", C.c_int32), ("t", Term), ("u", Term), ("lo", C.c_int64), ("hi", C.c_int64)]
+
+
+class Product(C.Structure):
+    _fields_ = [("nfactors", C.c_int32), ("pad", C.c_int32), ("factor", Term * VDL_MAX_FACTORS)]
+
+
+class ProbeFold(C.Structure):
+    _fields_ = [("op", C.c_int32), ("pad", C.c_int32), ("value", Product)]
+
+
+class ProbeDesc(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("row_base", C.c_int64), ("nleaves", C.c_int32), ("npreds", C.c_int32),
+                ("leaf", Leaf * VDL_MAX_LEAVES), ("pred", ProbePred * VDL_MAX_PROBE_PREDS),
+                ("nkeys", C.c_int32), ("nfolds", C.c_int32), ("key", Term * VDL_MAX_KEYS), ("key_shl", C.c_int32 * VDL_MAX_KEYS),
+                ("key_mask", C.c_int64), ("domain", C.c_int64), ("fold", ProbeFold * VDL_MAX_AGGS),
+                ("nposts", C.c_int32), ("nemits", C.c_int32), ("post", PostOp * VDL_MAX_POSTS), ("emit", Product * VDL_MAX_EMITS)]
+
+
 # every symbol include/vdl_cuda.h declares: (name, restype, argtypes)
 _P, _I, _L = C.c_void_p, C.c_int, C.c_int64
 SYMBOLS = [
@@ -99,6 +130,13 @@ SYMBOLS = [
     ("vdl_fused_last_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
     ("vdl_plan_load", _I, [_P, C.c_char_p, _I, C.POINTER(_P)]),
     ("vdl_plan_stats", _I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
+    ("vdl_abi_sizeof_probe_desc", _I, []),
+    ("vdl_probe_prepare", _I, [_P, C.POINTER(ProbeDesc), C.POINTER(_P)]),
+    ("vdl_probe_run", _I, [_P]),
+    ("vdl_probe_result_host", _I, [_P, _I, C.POINTER(C.POINTER(_L)), C.POINTER(_L)]),
+    ("vdl_probe_emit_take", _I, [_P, _I, C.POINTER(C.c_int32)]),
+    ("vdl_probe_last_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
+    ("vdl_probe_destroy", _I, [_P]),
     ("vdl_plan_set_row_base", _I, [_P, _L]),
     ("vdl_plan_exchange_bytes", _I, [_P, _I, _I, C.POINTER(_L)]),
     ("vdl_plan_set_peers", _I, [_P, _I, _I, _I, C.POINTER(_P)]),
@@ -133,6 +171,8 @@ def load():
         for name, res, args in SYMBOLS:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
+        if L.vdl_abi_sizeof_probe_desc() != C.sizeof(ProbeDesc):
+            raise RuntimeError("vdl_probe_desc layout mismatch between lib.py and libvdl_cuda.so")
         if L.vdl_abi_sizeof_fused_desc() != C.sizeof(FusedDesc):
             raise ImportError("vdl_fused_desc layout mismatch between lib.py and libvdl_cuda.so")
         _lib = L
