@@ -249,7 +249,7 @@ def main():
     ev0.record(ext)
     for _ in range(args.steps):
         result = step()
-        kernel_ms.append(plan.kernel_ms(0) if plan.num_fused else float("nan"))
+        kernel_ms.append(plan.kernel_ms(0) if plan.num_fused else plan.probe_kernel_ms())
     ev1.record(ext)
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -265,7 +265,9 @@ def main():
     ms_per_step = dev_ms / args.steps
     value = rows_total / (ms_per_step / 1e3)
     fused = plan.num_fused > 0
-    if not fused:          # op-at-a-time plan (FK joins): the "kernel" is the whole chain of per-op launches
+    pstats = plan.stats()
+    probed = pstats["probe_folds"] + pstats["probe_emits"] > 0
+    if not fused and not probed:   # op-at-a-time plan: the "kernel" is the whole chain of per-op launches
         kernel_ms = [ms_per_step] * args.steps
         kern_ms_mean = ms_per_step
 
@@ -274,7 +276,7 @@ def main():
     achieved = bytes_here / (statistics.mean(kernel_ms) / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json)" if peak_kind == "measured" else "fallback 6650 GB/s",
-                "kernel": f"fused_scan_fold_kernel<{plan.shape(0)}>" if fused else "op-at-a-time plan (all per-op kernels of one step)",
+                "kernel": f"fused_scan_fold_kernel<{plan.shape(0)}>" if fused else ("probe_kernel (fused FK-join probe)" if probed else "op-at-a-time plan (all per-op kernels of one step)"),
                 "kernel_ms": statistics.mean(kernel_ms), "kernel_ms_min": min(kernel_ms),
                 "frac_of_8TBs_spec": achieved / 8000.0, "bytes_per_launch": bytes_here}
     try:

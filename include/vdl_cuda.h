@@ -269,6 +269,9 @@ int vdl_plan_load(vdl_ctx *ctx, const char *vdl_text, int flags, vdl_plan **out)
 /* Statements parsed, distinct nodes after structural CSE (App. G10), fused scans, kernel launches
  * of the last run. */
 int vdl_plan_stats(vdl_plan *p, int *statements, int *nodes, int *fused_scans, int64_t *launches);
+/* FK-join plans: Folds run by the probe kernel, probe passes in emit mode, vectors those materialise. */
+int vdl_plan_probe_stats(vdl_plan *p, int *fold_groups, int *emit_groups, int *emitted_vectors);
+int vdl_plan_probe_kernel_ms(vdl_plan *p, float *ms);   /* sum over the probe passes of the last run; synchronises */
 /* Phase 1: everything up to and including the fused scans (local shard). */
 /* Global row id of this shard's row 0 (row-range sharding of the fact table; default 0). */
 int vdl_plan_set_row_base(vdl_plan *p, int64_t row_base);

@@ -74,6 +74,12 @@ struct FusedGroup {
 
 }  // namespace
 
+namespace {
+struct JoinAnalysis;
+struct ProbeFoldGroup;
+struct EmitGroup;
+}  // namespace
+
 struct vdl_plan {
   vdl_ctx *ctx = nullptr;
   int flags = 0;
@@ -85,6 +91,12 @@ struct vdl_plan {
   std::vector<char> sym_done;
   std::vector<FusedGroup> groups;
   std::vector<int> group_of_node;       // Fold node (or Binary node computed as a post op) -> group index or -1
+  // FK-join plans (vdl_plan_join.inc): join-aware normal forms, Folds run by the probe kernel, vectors it emits
+  JoinAnalysis *join = nullptr;
+  std::vector<ProbeFoldGroup *> pgroups;
+  std::vector<int> pgroup_of_node;      // Fold node -> probe fold group or -1
+  std::vector<EmitGroup *> egroups;
+  std::vector<int> egroup_of_node, eslot_of_node;   // node materialised by a probe in emit mode -> group, slot
   i64 row_base = 0;
   // run state
   std::vector<vdl_vec> val;
@@ -588,6 +600,139 @@ bool build_desc(vdl_plan *p, FusedGroup *g) {
   return true;
 }
 
+#include "vdl_plan_join.inc"
+
+struct ProbeFoldGroup {
+  int space = -1, keynode = -1;
+  ProbeBuild b;
+  std::map<int, int> fold_of_node;
+  vdl_probe *probe = nullptr;
+  std::vector<vdl_vec> bound;
+  i64 bound_rows = -1, bound_base = -1;
+};
+struct EmitGroup {
+  int space = -1;
+  std::vector<int> nodes;
+  ProbeBuild b;
+  vdl_probe *probe = nullptr;
+  std::vector<vdl_vec> bound;
+  i64 bound_rows = -1, bound_base = -1;
+  bool ran = false;
+};
+
+// Fold node `ni` over a joined space with a small key domain -> member of a probe fold group (Q5-class).
+bool try_probe_fold(vdl_plan *p, int ni) {
+  JoinAnalysis &J = *p->join;
+  const Node &n = p->nodes[ni];
+  const JSym G = janalyse(p, J, n.a), D = janalyse(p, J, n.b);
+  int space, keynode = -1;
+  JSym value;
+  if (G.kind == Z_SORTED && D.kind == Z_SORTED && G.n0 == D.n0) {
+    const JSym P = janalyse(p, J, G.n0);
+    if (P.kind != Z_PART || G.n1 != P.n0) return false;
+    value = janalyse(p, J, D.n1);
+    if (value.kind != Z_VALUE) return false;
+    space = P.space; keynode = P.n0;
+    const JSym K = janalyse(p, J, keynode);
+    if (!(K.kind == Z_KEY && K.masked && K.mask >= 0 && P.lo == 0 && P.cnt >= K.mask + 1) || K.mask + 1 > (1 << 20)) return false;
+  } else if (j_is_const(G) && D.kind == Z_VALUE && D.space >= 0 && (G.space == D.space || G.space < 0)) {
+    space = D.space; value = D;                        // one group (empty group-by, Vlite.hs:636-638)
+  } else {
+    return false;
+  }
+  if (space < 0 || j_is_base(J, space)) return false;  // single-table scans belong to the TMA-staged fused scan
+  ProbeFoldGroup *g = nullptr;
+  for (auto *q : p->pgroups) if (q->space == space && q->keynode == keynode) g = q;
+  bool fresh = !g;
+  if (fresh) {
+    g = new ProbeFoldGroup();
+    g->space = space; g->keynode = keynode;
+    if (!pb_init(p, J, space, &g->b)) { delete g; return false; }
+    if (keynode >= 0) {
+      const JSym K = janalyse(p, J, keynode);
+      g->b.desc.nkeys = (int)K.fac.size();
+      for (size_t i = 0; i < K.fac.size(); i++) {
+        if (K.fac[i].leaf >= 0 && !pb_rooted(p, J, K.fac[i].leaf, J.spaces[space].table)) { delete g; return false; }
+        if (!pb_term(J, &g->b, K.fac[i], &g->b.desc.key[i])) { delete g; return false; }
+      }
+      g->b.desc.key_mask = K.mask;
+      g->b.desc.domain = K.mask + 1;
+    }
+  }
+  ProbeBuild saved = g->b;
+  vdl_probe_fold spec;
+  memset(&spec, 0, sizeof spec);
+  spec.op = n.sub;
+  bool ok = true;
+  if (n.sub != VDL_FOLD_COUNT) {
+    bool ones = value.fac.size() == 1 && value.fac[0].leaf == -1 && value.fac[0].a == 1;
+    if (n.sub == VDL_FOLD_SUM && ones) spec.op = VDL_FOLD_COUNT;
+    else {
+      for (auto &t : value.fac) if (t.leaf >= 0 && !pb_rooted(p, J, t.leaf, J.spaces[space].table)) ok = false;
+      ok = ok && pb_product(J, &g->b, value.fac, &spec.value);
+    }
+  }
+  int fi = -1;
+  if (ok) {
+    for (int i = 0; i < g->b.desc.nfolds; i++) if (!memcmp(&g->b.desc.fold[i], &spec, sizeof spec)) fi = i;
+    if (fi < 0) {
+      if (g->b.desc.nfolds == VDL_MAX_AGGS) ok = false;
+      else { fi = g->b.desc.nfolds; g->b.desc.fold[g->b.desc.nfolds++] = spec; }
+    }
+  }
+  if (!ok) {
+    g->b = saved;
+    if (fresh) delete g;
+    return false;
+  }
+  if (fresh) p->pgroups.push_back(g);
+  g->fold_of_node[ni] = fi;
+  for (size_t i = 0; i < p->pgroups.size(); i++) if (p->pgroups[i] == g) p->pgroup_of_node[ni] = (int)i;
+  return true;
+}
+
+// Which nodes does an op-at-a-time evaluation of the outputs touch?  A Gather / elementwise node whose normal form is
+// a product of leaf terms over a joined space is cut off there and materialised by a probe in emit mode.
+void mark_emits(vdl_plan *p, int ni, std::vector<char> &seen) {
+  if (seen[ni]) return;
+  seen[ni] = 1;
+  JoinAnalysis &J = *p->join;
+  const Node &n = p->nodes[ni];
+  if (n.op == N_FOLD && (p->group_of_node[ni] >= 0 || p->pgroup_of_node[ni] >= 0)) return;
+  if (n.op == N_BINARY && p->group_of_node[ni] >= 0) return;
+  const JSym &z = janalyse(p, J, ni);
+  if ((n.op == N_GATHER || n.op == N_BINARY) && z.kind == Z_VALUE && z.space >= 0 && !j_is_base(J, z.space) && !j_is_const(z)) {
+    bool rooted = true;
+    for (auto &t : z.fac) if (t.leaf >= 0 && !pb_rooted(p, J, t.leaf, J.spaces[z.space].table)) rooted = false;
+    if (rooted) {
+      EmitGroup *g = nullptr;
+      for (auto *q : p->egroups) if (q->space == z.space && q->b.desc.nemits < VDL_MAX_EMITS) g = q;
+      bool fresh = !g;
+      if (fresh) { g = new EmitGroup(); g->space = z.space; if (!pb_init(p, J, z.space, &g->b)) { delete g; g = nullptr; } }
+      if (g) {
+        ProbeBuild saved = g->b;
+        if (pb_product(J, &g->b, z.fac, &g->b.desc.emit[g->b.desc.nemits])) {
+          if (fresh) p->egroups.push_back(g);
+          for (size_t i = 0; i < p->egroups.size(); i++) if (p->egroups[i] == g) p->egroup_of_node[ni] = (int)i;
+          p->eslot_of_node[ni] = g->b.desc.nemits++;
+          g->nodes.push_back(ni);
+          return;
+        }
+        g->b = saved;
+        if (fresh) delete g;
+      }
+    }
+  }
+  switch (n.op) {
+    case N_RANGEV: mark_emits(p, n.a, seen); break;
+    case N_BINARY: case N_GATHER: case N_FOLD: mark_emits(p, n.a, seen); mark_emits(p, n.b, seen); break;
+    case N_FSELECT: mark_emits(p, n.b, seen); break;
+    case N_SCATTER: mark_emits(p, n.a, seen); mark_emits(p, n.c, seen); break;
+    case N_PARTITION: mark_emits(p, n.a, seen); break;
+    default: break;
+  }
+}
+
 // An output that is an elementwise expression over the Folds of ONE fused scan (AVG = Divide(FoldSum x, FoldSum 1),
 // Vlite.hs:1038-1041) becomes a post op of that scan: evaluated per group inside the finalize kernel and returned by
 // the scan's single result copy, instead of op-at-a-time launches over a handful of elements.
@@ -638,6 +783,9 @@ int fuse(vdl_plan *p) {
   p->sym.assign(nn, Sym());
   p->sym_done.assign(nn, 0);
   p->group_of_node.assign(nn, -1);
+  p->pgroup_of_node.assign(nn, -1);
+  p->egroup_of_node.assign(nn, -1);
+  p->eslot_of_node.assign(nn, -1);
   if (!(p->flags & VDL_PLAN_FUSE)) return VDL_OK;
   for (size_t i = 0; i < nn; i++)
     if (p->nodes[i].op == N_FOLD) try_fuse_fold(p, (int)i);
@@ -670,6 +818,19 @@ int fuse(vdl_plan *p) {
     for (auto &kv : p->groups[gi].fold_of_node) p->group_of_node[kv.first] = (int)gi;
     for (auto &kv : p->groups[gi].post_of_node) p->group_of_node[kv.first] = (int)gi;
   }
+  // FK-join plans: Folds over a joined space -> probe fold groups; vectors of joined spaces that op-at-a-time
+  // consumers need -> probe emit groups
+  if (!getenv("VDL_NO_PROBE")) {
+    p->join = new JoinAnalysis();
+    p->join->sym.assign(nn, JSym());
+    p->join->done.assign(nn, 0);
+    std::vector<int> uses(nn, 0);
+    for (auto &n : p->nodes) for (int a : {n.a, n.b, n.c}) if (a >= 0) uses[a]++;
+    for (size_t i = 0; i < nn; i++)
+      if (p->nodes[i].op == N_FOLD && p->group_of_node[i] < 0 && uses[i] == 0) try_probe_fold(p, (int)i);
+    std::vector<char> seen(nn, 0);
+    for (auto &o : p->outputs) mark_emits(p, o.node, seen);
+  }
   return VDL_OK;
 }
 
@@ -677,12 +838,54 @@ int fuse(vdl_plan *p) {
 void free_temps(vdl_plan *p) {
   for (vdl_vec v : p->temps) vdl_vec_free(p->ctx, v);
   p->temps.clear();
+  for (auto *g : p->egroups) g->ran = false;
   std::fill(p->val.begin(), p->val.end(), 0);
+}
+
+// Bind a probe descriptor's leaves to the registered columns and (re)prepare it when the binding changed.
+int bind_probe(vdl_plan *p, ProbeBuild *b, vdl_probe **probe, std::vector<vdl_vec> *bound, i64 *bound_rows, i64 *bound_base) {
+  vdl_ctx *ctx = p->ctx;
+  std::vector<vdl_vec> h(b->loadnode.size());
+  i64 rows = -1;
+  for (size_t l = 0; l < h.size(); l++) {
+    VDL_TRY(vdl_column_lookup(ctx, p->nodes[b->loadnode[l]].name.c_str(), &h[l]));
+    if (b->desc.leaf[l].parent < 0) {
+      i64 len; VDL_TRY(vdl_vec_len(ctx, h[l], &len));
+      if (rows >= 0 && len != rows) return vdl_fail(ctx, VDL_EINVAL, "probe: fact columns differ in length (%lld vs %lld)", (long long)len, (long long)rows);
+      rows = len;
+    }
+  }
+  if (rows < 0) return vdl_fail(ctx, VDL_EUNSUPPORTED, "probe: no fact column among the leaves");
+  if (!*probe || h != *bound || rows != *bound_rows || p->row_base != *bound_base) {
+    if (*probe) { vdl_probe_destroy(*probe); *probe = nullptr; }
+    b->desc.rows = rows;
+    b->desc.row_base = p->row_base;
+    for (size_t l = 0; l < h.size(); l++) b->desc.leaf[l].column = h[l];
+    VDL_TRY(vdl_probe_prepare(ctx, &b->desc, probe));
+    *bound = h; *bound_rows = rows; *bound_base = p->row_base;
+  }
+  return VDL_OK;
 }
 
 int eval(vdl_plan *p, int ni, vdl_vec *out) {
   vdl_ctx *ctx = p->ctx;
   if (p->val[ni]) { *out = p->val[ni]; return VDL_OK; }
+  if (p->egroup_of_node[ni] >= 0) {        // materialised by one probe pass together with its siblings of the same space
+    EmitGroup &g = *p->egroups[p->egroup_of_node[ni]];
+    if (!g.ran) {
+      VDL_TRY(bind_probe(p, &g.b, &g.probe, &g.bound, &g.bound_rows, &g.bound_base));
+      VDL_TRY(vdl_probe_run(g.probe));
+      for (size_t k = 0; k < g.nodes.size(); k++) {
+        vdl_vec v;
+        VDL_TRY(vdl_probe_emit_take(g.probe, (int)k, &v));
+        p->val[g.nodes[k]] = v;
+        p->temps.push_back(v);
+      }
+      g.ran = true;
+    }
+    *out = p->val[ni];
+    return VDL_OK;
+  }
   const Node &n = p->nodes[ni];
   vdl_vec r = 0, a = 0, b = 0, c = 0;
   bool temp = true;
@@ -722,6 +925,7 @@ int eval(vdl_plan *p, int ni, vdl_vec *out) {
     }
     case N_FOLD: {
       int gi = p->group_of_node[ni];
+      if (p->pgroup_of_node[ni] >= 0) return vdl_fail(ctx, VDL_EUNSUPPORTED, "a Fold run by the probe kernel has no device vector (it is only fused when nothing consumes it)");
       if (gi >= 0) {
         FusedGroup &g = p->groups[gi];
         VDL_TRY(vdl_fused_result(g.fused, g.fold_of_node[ni], &r));
@@ -762,6 +966,28 @@ extern "C" int vdl_plan_load(vdl_ctx *ctx, const char *vdl_text, int flags, vdl_
   if (!rc) rc = fuse(p);
   if (rc) { delete p; return rc; }
   p->val.assign(p->nodes.size(), 0);
+  if (getenv("VDL_DEBUG_PLAN")) {
+    fprintf(stderr, "[vdl plan] %d statements, %zu nodes: %zu fused scans, %zu probe fold groups, %zu probe emit groups\n", p->statements, p->nodes.size(),
+            p->groups.size(), p->pgroups.size(), p->egroups.size());
+    for (auto *g : p->pgroups)
+      fprintf(stderr, "[vdl plan]   probe fold: table %s, %d leaves, %d predicates, %d key parts (domain %lld), %d folds\n", p->tables[p->join->spaces[g->space].table].c_str(),
+              g->b.desc.nleaves, g->b.desc.npreds, g->b.desc.nkeys, (long long)g->b.desc.domain, g->b.desc.nfolds);
+    for (auto *g : p->pgroups) {
+      const vdl_probe_desc &d = g->b.desc;
+      for (int l = 0; l < d.nleaves; l++) fprintf(stderr, "[vdl plan]     leaf %d: %s parent %d\n", l, p->nodes[g->b.loadnode[l]].name.c_str(), d.leaf[l].parent);
+      for (int q = 0; q < d.npreds; q++) fprintf(stderr, "[vdl plan]     pred %d: kind %d t(leaf %d shr %d a %lld b %lld) u(leaf %d) [%lld, %lld]\n", q, d.pred[q].kind, d.pred[q].t.leaf, d.pred[q].t.shr, (long long)d.pred[q].t.a, (long long)d.pred[q].t.b, d.pred[q].u.leaf, (long long)d.pred[q].lo, (long long)d.pred[q].hi);
+      for (int j = 0; j < d.nfolds; j++) {
+        fprintf(stderr, "[vdl plan]     fold %d: op %d nfactors %d", j, d.fold[j].op, d.fold[j].value.nfactors);
+        for (int t = 0; t < d.fold[j].value.nfactors; t++) fprintf(stderr, " (leaf %d shr %d a %lld b %lld)", d.fold[j].value.factor[t].leaf, d.fold[j].value.factor[t].shr, (long long)d.fold[j].value.factor[t].a, (long long)d.fold[j].value.factor[t].b);
+        fprintf(stderr, "\n");
+      }
+    }
+    for (auto *g : p->egroups) {
+      fprintf(stderr, "[vdl plan]   probe emit: table %s, %d leaves, %d predicates, nodes", p->tables[p->join->spaces[g->space].table].c_str(), g->b.desc.nleaves, g->b.desc.npreds);
+      for (int n : g->nodes) fprintf(stderr, " %d", n);
+      fprintf(stderr, "\n");
+    }
+  }
   *out = p;
   return VDL_OK;
 }
@@ -772,6 +998,25 @@ extern "C" int vdl_plan_stats(vdl_plan *p, int *statements, int *nodes, int *fus
   if (nodes) *nodes = (int)p->nodes.size();
   if (fused_scans) *fused_scans = (int)p->groups.size();
   if (launches) *launches = p->launches_last;
+  return VDL_OK;
+}
+
+extern "C" int vdl_plan_probe_stats(vdl_plan *p, int *fold_groups, int *emit_groups, int *emitted_vectors) {
+  if (!p) return VDL_EINVAL;
+  if (fold_groups) *fold_groups = (int)p->pgroups.size();
+  if (emit_groups) *emit_groups = (int)p->egroups.size();
+  int n = 0;
+  for (auto *g : p->egroups) n += (int)g->nodes.size();
+  if (emitted_vectors) *emitted_vectors = n;
+  return VDL_OK;
+}
+
+// Sum of the probe kernels' durations in the last run (CUDA events on the context stream); synchronises.
+extern "C" int vdl_plan_probe_kernel_ms(vdl_plan *p, float *ms) {
+  if (!p || !ms) return VDL_EINVAL;
+  *ms = 0;
+  for (auto *g : p->pgroups) if (g->probe) { float t = 0; VDL_TRY(vdl_probe_last_kernel_ms(g->probe, &t)); *ms += t; }
+  for (auto *g : p->egroups) if (g->probe) { float t = 0; VDL_TRY(vdl_probe_last_kernel_ms(g->probe, &t)); *ms += t; }
   return VDL_OK;
 }
 
@@ -810,6 +1055,10 @@ static int plan_run_local(vdl_plan *p, int self_finalize) {
     }
     VDL_TRY(vdl_fused_launch_ex(g.fused, self_finalize && g.peer_world > 0 ? 2 : self_finalize));
   }
+  for (auto *g : p->pgroups) {
+    VDL_TRY(bind_probe(p, &g->b, &g->probe, &g->bound, &g->bound_rows, &g->bound_base));
+    VDL_TRY(vdl_probe_run(g->probe));
+  }
   p->launches_last = ctx->launches - l0;
   p->local_done = true;
   p->self_finalized = self_finalize != 0;
@@ -847,7 +1096,8 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
   if (!p->local_done) return vdl_fail(ctx, VDL_EINVAL, "vdl_plan_finish before vdl_plan_run_local");
   p->trace = getenv("VDL_TRACE") != nullptr;
   if (p->trace) p->trace_t0 = p->trace_last = now_ms();
-  if (nranks > 1 && p->groups.empty()) return vdl_fail(ctx, VDL_EUNSUPPORTED, "plan has no fused scan: it cannot be row-sharded");
+  if (nranks > 1 && (p->groups.empty() || !p->pgroups.empty() || !p->egroups.empty()))
+    return vdl_fail(ctx, VDL_EUNSUPPORTED, "only plans made of fused single-table scans can be row-sharded so far");
   i64 l0 = ctx->launches;
   if (!(p->self_finalized && nranks == 1 && !all_partials))
     for (size_t gi = 0; gi < p->groups.size(); gi++)
@@ -855,6 +1105,13 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
   bool ran_ops = false;
   for (auto &o : p->outputs) {
     int gi = p->group_of_node[o.node];
+    if (p->pgroup_of_node[o.node] >= 0) {   // a Fold over a joined space: the probe's result buffer is already on its way
+      ProbeFoldGroup &g = *p->pgroups[p->pgroup_of_node[o.node]];
+      const int64_t *data; int64_t len;
+      VDL_TRY(vdl_probe_result_host(g.probe, g.fold_of_node[o.node], &data, &len));
+      o.data.assign(data, data + len);
+      continue;
+    }
     if (gi >= 0) {   // the output IS a fused fold or a post op of one: it arrived with the scan's single result copy
       const int64_t *data; int64_t len;
       if (p->nodes[o.node].op == N_FOLD) VDL_TRY(vdl_fused_result_host(p->groups[gi].fused, p->groups[gi].fold_of_node[o.node], &data, &len));
@@ -897,6 +1154,9 @@ extern "C" int vdl_plan_destroy(vdl_plan *p) {
   if (!p) return VDL_EINVAL;
   free_temps(p);
   for (auto &g : p->groups) if (g.fused) vdl_fused_destroy(g.fused);
+  for (auto *g : p->pgroups) { if (g->probe) vdl_probe_destroy(g->probe); delete g; }
+  for (auto *g : p->egroups) { if (g->probe) vdl_probe_destroy(g->probe); delete g; }
+  delete p->join;
   delete p;
   return VDL_OK;
 }

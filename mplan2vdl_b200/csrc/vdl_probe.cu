@@ -20,12 +20,12 @@
 //   predicate lo <= term <= hi, or term == term; evaluated in chain order, first failure rejects the row
 // No validity vector, inverse index, position vector or gathered copy is ever materialised.
 //
-// Kernel shape: persistent thread blocks take 1024-row tiles in order from a ticket counter; a thread owns
-// rows tid + k*256 of the tile (coalesced fact-column loads; the lineitem->orders index is clustered, so the
-// first dimension gather is nearly sequential too).  Fold mode accumulates into a shared-memory table per block
-// (flushed with global atomics); emit mode orders the survivors with ballots inside the tile and a decoupled
-// look-back across tiles (one 64-bit status word per tile), so the output vectors are exactly the dense
-// FoldSelect order.  Bound: HBM for the fact columns + L2 latency for the dimension gathers.
+// Kernel shape: persistent thread blocks take 2048-row tiles in order from a ticket counter and evaluate the
+// predicates stage by stage, compacting the survivors in row order after each (see "staged evaluation" below; the
+// fact-column loads of a stage are coalesced, and the lineitem->orders index is clustered, so the first dimension
+// gather is nearly sequential too).  Fold mode accumulates into a shared-memory table per block (flushed with
+// global atomics); emit mode places a tile's survivors with a decoupled look-back across tiles (one 64-bit
+// status word per tile), so the output vectors are exactly the dense FoldSelect order.  Bound: HBM for the fact columns + L2 latency for the dimension gathers.
 #include <stdio.h>
 #include <string.h>
 
@@ -33,9 +33,8 @@
 
 #include "vdl_internal.h"
 
-#define P_TILE 1024
-#define P_THREADS 256
-#define P_R (P_TILE / P_THREADS)
+#define P_TILE 2048
+#define P_THREADS 128
 #define P_MAX_DEPTH 6
 #define P_SMEM_TABLE_BYTES (40 * 1024)
 
@@ -124,9 +123,36 @@ __device__ __forceinline__ void table_update(int op, i64 *p, i64 v) {
   else atomicAdd((unsigned long long *)p, (unsigned long long)v);
 }
 
-__global__ void __launch_bounds__(P_THREADS, 4) probe_kernel(const __grid_constant__ PDesc d) {
+// ---- staged evaluation ---------------------------------------------------------------------------------------------
+// A tile goes through the predicates one STAGE at a time; after every stage the surviving rows are compacted (in row
+// order) into a shared-memory queue, so the next stage runs with full warps on survivors only and its lookups are
+// independent loads of different rows (memory-level parallelism instead of divergent lanes waiting on a long
+// dependent chain).  A range predicate on a lookup chain of depth <= 4 -- every predicate the FK-join lowering
+// produces -- runs as straight-line code: the chain (pointers, lengths, widths) is read from the descriptor once per
+// tile and stage, not per row.
+struct StageRegs { const void *ptr[4]; i64 len[4]; int w4mask, shr, depth; i64 a, b, lo; u64 span; };
+
+// S.ptr[0] is the leaf's own column (the LAST load), S.ptr[D-1] the fact column (the first): all indexing static.
+template <int D>
+__device__ __forceinline__ bool chain_test(const StageRegs &S, i64 row, i64 row_base, bool &ok) {
+  i64 v = row;
+  if (D == 0) v = row_base + row;
+#pragma unroll
+  for (int k = D - 1; k >= 0; k--) {
+    if ((u64)v >= (u64)S.len[k]) { ok = false; return false; }
+    v = ((S.w4mask >> k) & 1) ? (i64)__ldg((const int32_t *)S.ptr[k] + v) : __ldg((const i64 *)S.ptr[k] + v);
+  }
+  v >>= S.shr;
+  v = (i64)((u64)S.a + (u64)S.b * (u64)v);
+  return (u64)v - (u64)S.lo <= S.span;
+}
+
+#define P_SUB 8      // rows per thread and round of a stage
+
+__global__ void __launch_bounds__(P_THREADS, 8) probe_kernel(const __grid_constant__ PDesc d) {
   extern __shared__ __align__(16) unsigned char psm[];
-  __shared__ int wcnt[P_THREADS / 32];
+  __shared__ uint16_t queue[2][P_TILE];
+  __shared__ int wcnt[P_SUB][P_THREADS / 32];
   __shared__ i64 s_off;
   __shared__ unsigned int s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -148,59 +174,120 @@ __global__ void __launch_bounds__(P_THREADS, 4) probe_kernel(const __grid_consta
     const i64 tile = s_tile;
     if (tile >= d.ntiles) break;
     const i64 base = tile * P_TILE;
-    bool pass[P_R];
     bool ok = true;
+    int n_in = (int)min((i64)P_TILE, d.rows - base);      // stage input: all rows of the tile, then the previous stage's survivors
+    int cur = 0;
+    for (int q = 0; q < d.npreds && n_in > 0; q++) {
+      const PPred &P = d.pred[q];
+      // the chain of this stage's term, if it has the fast form
+      StageRegs S;
+      S.depth = -1;
+      if (P.kind == 0 && P.t.leaf != -1) {
+        int l = P.t.leaf, n = 0;
+        S.w4mask = 0;
 #pragma unroll
-    for (int k = 0; k < P_R; k++) {
-      const i64 row = base + k * P_THREADS + tid;
-      pass[k] = row < d.rows && row_passes(d, row, ok);
-    }
-    if (folding) {
+        for (int k = 0; k < 4; k++) {
+          S.ptr[k] = nullptr; S.len[k] = 0;
+          if (l >= 0) {
+            const PLeaf &L = d.leaf[l];
+            S.ptr[k] = L.ptr; S.len[k] = L.len; S.w4mask |= (L.w4 ? 1 : 0) << k;
+            l = L.parent; n = k + 1;
+          }
+        }
+        if (l < 0) { S.depth = n; S.shr = P.t.shr; S.a = P.t.a; S.b = P.t.b; S.lo = P.lo; S.span = P.span; }
+      }
+      int n_out = 0;
+      for (int j0 = 0; j0 < n_in; j0 += P_SUB * P_THREADS) {
+        bool f[P_SUB];
+        int r[P_SUB];
+#pragma unroll
+        for (int k = 0; k < P_SUB; k++) {
+          const int j = j0 + k * P_THREADS + tid;
+          r[k] = j < n_in ? (q == 0 ? j : (int)queue[cur][j]) : -1;
+        }
+        if (S.depth == 1) {
+#pragma unroll
+          for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && chain_test<1>(S, base + r[k], d.row_base, ok);
+        } else if (S.depth == 2) {
+#pragma unroll
+          for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && chain_test<2>(S, base + r[k], d.row_base, ok);
+        } else if (S.depth == 3) {
+#pragma unroll
+          for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && chain_test<3>(S, base + r[k], d.row_base, ok);
+        } else if (S.depth == 4) {
+#pragma unroll
+          for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && chain_test<4>(S, base + r[k], d.row_base, ok);
+        } else if (S.depth == 0) {
+#pragma unroll
+          for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && chain_test<0>(S, base + r[k], d.row_base, ok);
+        } else {      // generic: constants, column == column, deeper chains
 #pragma unroll 1
-      for (int k = 0; k < P_R; k++) {
-        if (!pass[k]) continue;
-        const i64 row = base + k * P_THREADS + tid;
+          for (int k = 0; k < P_SUB; k++) {
+            f[k] = false;
+            if (r[k] < 0) continue;
+            const i64 row = base + r[k];
+            i64 t = term_value(d, P.t, row, ok);
+            if (P.kind == 0) f[k] = (u64)t - (u64)P.lo <= P.span;
+            else f[k] = t == term_value(d, P.u, row, ok);
+          }
+        }
+        // ordered append of the survivors of this round: (sub-round, warp, lane) order = queue order.  The P_SUB x 8
+        // per-warp counts are scanned by every warp for itself with shuffles (lane = sub-round * 8 + warp).
+        unsigned m[P_SUB];
+#pragma unroll
+        for (int k = 0; k < P_SUB; k++) {
+          m[k] = __ballot_sync(0xffffffffu, f[k]);
+          if (lane == 0) wcnt[k][warp] = __popc(m[k]);
+        }
+        __syncthreads();
+        static_assert(P_SUB * (P_THREADS / 32) == 32, "one counter per lane");
+        const int c = (&wcnt[0][0])[lane];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int excl = incl - c, total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+        for (int k = 0; k < P_SUB; k++) {
+          const int mine = n_out + __shfl_sync(0xffffffffu, excl, k * (P_THREADS / 32) + warp);
+          if (f[k]) queue[cur ^ 1][mine + __popc(m[k] & ((1u << lane) - 1))] = (uint16_t)r[k];
+        }
+        n_out += total;
+        __syncthreads();
+      }
+      n_in = n_out;
+      cur ^= 1;
+    }
+    const bool implicit = d.npreds == 0;            // no predicate at all: every row of the tile survives
+    // ---- survivors: fold into the table, or emit in order
+    if (folding) {
+      for (int j = tid; j < n_in; j += P_THREADS) {
+        const i64 row = base + (implicit ? j : (int)queue[cur][j]);
         i64 key = 0;
         for (int q = 0; q < d.nkeys; q++) key |= (i64)((u64)term_value(d, d.key[q], row, ok) << d.key_shl[q]);
         key &= d.key_mask;
         if ((u64)key >= (u64)d.domain) { ok = false; continue; }
-        for (int j = 0; j < d.nfolds; j++) {
-          const int op = d.fold_op[j];
+        for (int j2 = 0; j2 < d.nfolds; j2++) {
+          const int op = d.fold_op[j2];
           if (op == VDL_FOLD_CHOOSE || op == VDL_FOLD_COUNT) continue;     // from the first row / the row count
-          table_update(op, tab + (size_t)j * d.domain + key, prod_value(d, d.fold[j], row, ok));
+          table_update(op, tab + (size_t)j2 * d.domain + key, prod_value(d, d.fold[j2], row, ok));
         }
         atomicAdd((unsigned long long *)(tab + (size_t)d.nfolds * d.domain + key), 1ull);
         atomicMin((long long *)(tab + (size_t)(d.nfolds + 1) * d.domain + key), (long long)(d.row_base + row));
       }
     } else {
-      // ---- ordered emission: rank inside the tile by ballots per step, tile offset by decoupled look-back
-      int before_step[P_R], rank[P_R], run = 0;
-#pragma unroll
-      for (int k = 0; k < P_R; k++) {
-        unsigned m = __ballot_sync(0xffffffffu, pass[k]);
-        if (lane == 0) wcnt[warp] = __popc(m);
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < P_THREADS / 32; w++) { int c = wcnt[w]; if (w < warp) before += c; total += c; }
-        rank[k] = run + before + __popc(m & ((1u << lane) - 1));
-        before_step[k] = run;
-        run += total;
-        __syncthreads();
-      }
-      (void)before_step;
+      // tile offset by decoupled look-back over the tiles before this one
       if (tid == 0) {
-        const unsigned long long T = (unsigned long long)run;
+        const unsigned long long T = (unsigned long long)n_in;
         i64 excl = 0;
         if (tile == 0) {
           atomicExch(d.tile_state, (2ull << 62) | T);
         } else {
           atomicExch(d.tile_state + tile, (1ull << 62) | T);
           for (i64 j = tile - 1;; j--) {
-            unsigned long long s;
-            do { s = *((volatile unsigned long long *)(d.tile_state + j)); } while ((s >> 62) == 0);
-            excl += (i64)(s & ((1ull << 62) - 1));
-            if ((s >> 62) == 2) break;
+            unsigned long long st;
+            do { st = *((volatile unsigned long long *)(d.tile_state + j)); } while ((st >> 62) == 0);
+            excl += (i64)(st & ((1ull << 62) - 1));
+            if ((st >> 62) == 2) break;
           }
           atomicExch(d.tile_state + tile, (2ull << 62) | (unsigned long long)(excl + (i64)T));
         }
@@ -209,11 +296,9 @@ __global__ void __launch_bounds__(P_THREADS, 4) probe_kernel(const __grid_consta
       }
       __syncthreads();
       const i64 off = s_off;
-#pragma unroll 1
-      for (int k = 0; k < P_R; k++) {
-        if (!pass[k]) continue;
-        const i64 row = base + k * P_THREADS + tid;
-        for (int e = 0; e < d.nemits; e++) d.emit_out[e][off + rank[k]] = prod_value(d, d.emit[e], row, ok);
+      for (int j = tid; j < n_in; j += P_THREADS) {
+        const i64 row = base + (implicit ? j : (int)queue[cur][j]);
+        for (int e = 0; e < d.nemits; e++) d.emit_out[e][off + j] = prod_value(d, d.emit[e], row, ok);
       }
     }
     if (!ok) atomicAdd(d.errflag, 1);
@@ -413,7 +498,7 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
   }
   cudaEventCreate(&p->ev0);
   cudaEventCreate(&p->ev1);
-  int per_sm = 4;
+  int per_sm = 8;
   p->grid = (int)std::max<i64>(1, std::min<i64>((i64)ctx->sm_count * per_sm, d.ntiles));
   if (p->smem > 48 * 1024) cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
   *out = p;

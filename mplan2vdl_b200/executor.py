@@ -195,7 +195,10 @@ class Plan:
     def stats(self) -> dict:
         s, n, f, l = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
         self.ctx.check(self.L.vdl_plan_stats(self.h, C.byref(s), C.byref(n), C.byref(f), C.byref(l)))
-        return {"statements": s.value, "nodes": n.value, "fused_scans": f.value, "launches": l.value}
+        pf, pe, pv = C.c_int(), C.c_int(), C.c_int()
+        self.ctx.check(self.L.vdl_plan_probe_stats(self.h, C.byref(pf), C.byref(pe), C.byref(pv)))
+        return {"statements": s.value, "nodes": n.value, "fused_scans": f.value, "launches": l.value,
+                "probe_folds": pf.value, "probe_emits": pe.value, "emitted_vectors": pv.value}
 
     def set_row_base(self, row_base: int):
         self.ctx.check(self.L.vdl_plan_set_row_base(self.h, row_base))
@@ -237,6 +240,11 @@ class Plan:
         self.ctx.check(self.L.vdl_plan_fused(self.h, i, C.byref(f)))
         ms = C.c_float()
         self.ctx.check(self.L.vdl_fused_last_kernel_ms(f, C.byref(ms)))
+        return ms.value
+
+    def probe_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self.ctx.check(self.L.vdl_plan_probe_kernel_ms(self.h, C.byref(ms)))
         return ms.value
 
     def finish(self, gathered_ptrs=None, nranks: int = 1) -> dict:

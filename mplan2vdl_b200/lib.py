@@ -137,6 +137,8 @@ SYMBOLS = [
     ("vdl_probe_emit_take", _I, [_P, _I, C.POINTER(C.c_int32)]),
     ("vdl_probe_last_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
     ("vdl_probe_destroy", _I, [_P]),
+    ("vdl_plan_probe_stats", _I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    ("vdl_plan_probe_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
     ("vdl_plan_set_row_base", _I, [_P, _L]),
     ("vdl_plan_exchange_bytes", _I, [_P, _I, _I, C.POINTER(_L)]),
     ("vdl_plan_set_peers", _I, [_P, _I, _I, _I, C.POINTER(_P)]),
