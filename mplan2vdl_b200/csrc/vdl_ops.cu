@@ -343,6 +343,21 @@ __global__ void __launch_bounds__(256) invert_perm_kernel(const i64 *__restrict_
   for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) out[order[j]] = j;
 }
 
+__device__ __forceinline__ u64 bucket_of(i64 v, i64 pfrom, i64 pstep, i64 pcount) {
+  if (v <= pfrom) return 0;
+  u64 d = (u64)v - (u64)pfrom;
+  u64 b = (d + (u64)pstep - 1) / (u64)pstep;
+  return b > (u64)pcount ? (u64)pcount : b;
+}
+// rows already ordered by bucket (e.g. lineitem clustered on l_orderkey, storage.csv `sorted`)?  counts the descents
+__global__ void __launch_bounds__(256) descents_kernel(Operand data, i64 n, i64 pfrom, i64 pstep, i64 pcount, int *descents) {
+  i64 stride = (i64)gridDim.x * blockDim.x;
+  int bad = 0;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += stride)
+    bad |= bucket_of(op_ld(data, i), pfrom, pstep, pcount) > bucket_of(op_ld(data, i + 1), pfrom, pstep, pcount);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAdd(descents, 1);
+}
+
 extern "C" int vdl_op_partition(vdl_ctx *ctx, vdl_vec data, int64_t pfrom, int64_t pstep, int64_t pcount, vdl_vec *out) {
   if (!ctx || !out) return VDL_EINVAL;
   Vec *vd = vec_get(ctx, data);
@@ -350,10 +365,23 @@ extern "C" int vdl_op_partition(vdl_ctx *ctx, vdl_vec data, int64_t pfrom, int64
   if (pcount < 1 || pstep < 1) return vdl_fail(ctx, VDL_EINVAL, "Partition: pivots must be an ascending range (count %lld step %lld)", (long long)pcount, (long long)pstep);
   i64 n = vd->len;
   Operand od = operand_of(*vd);
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n > 0) {
+    // one cheap pass first: keys that are already in bucket order sort to the identity permutation, which stays a
+    // virtual range -- no radix passes, and a Scatter by it is the source vector itself
+    VDL_TRY(scratch_reserve(ctx, 64));
+    int *d_desc = (int *)ctx->scratch, h_desc = 1;
+    VDL_CUDA(ctx, cudaMemsetAsync(d_desc, 0, sizeof(int), ctx->stream));
+    int g0 = (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 16));
+    descents_kernel<<<g0, 256, 0, ctx->stream>>>(od, n, pfrom, pstep, pcount, d_desc);
+    ctx->launches++;
+    VDL_CUDA(ctx, cudaMemcpyAsync(&h_desc, d_desc, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_desc == 0) return vec_new_range(ctx, 0, 1, n, out);      // (its domain is n: positions 0..n-1)
+  }
   VDL_TRY(vec_new(ctx, VDL_I64, n, out));
   ctx->vecs[*out].domain = n;
   if (n == 0) return VDL_OK;
-  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   int bits = 0;
   while (bits < 63 && ((u64)pcount >> bits)) bits++;
   i64 nb = (n + RDX_TILE - 1) / RDX_TILE;

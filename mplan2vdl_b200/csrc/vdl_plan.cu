@@ -34,7 +34,8 @@ struct Node {
   std::string name;            // Load: "table.column"
 };
 
-struct Output { std::string name; int node; std::vector<i64> data; };
+// data points at the result's host copy: the fused scan's / probe's mapped result buffer, or this output's own pinned buffer
+struct Output { std::string name; int node; const i64 *data = nullptr; i64 len = 0; i64 *pinned = nullptr; size_t cap = 0; };
 
 // ---- symbolic normal forms ------------------------------------------------------------------
 struct Aff { int col = -1; int shr = 0; i64 a = 0, b = 0; };   // a + b*(col >> shr); col = Load node, -1: constant a
@@ -231,7 +232,7 @@ int parse_plan(vdl_plan *p, const char *text) {
     }
     canon.push_back(idx);
     outname.push_back(oname);
-    if (is_output) p->outputs.push_back(Output{oname, idx, {}});
+    if (is_output) { Output o; o.name = oname; o.node = idx; p->outputs.push_back(o); }
   }
   p->statements = (int)canon.size() - 1;
   if (p->outputs.empty()) return vdl_fail(ctx, VDL_EINVAL, "plan has no MaterializeCompact output");
@@ -910,9 +911,13 @@ int eval(vdl_plan *p, int ni, vdl_vec *out) {
     case N_GATHER: VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.b, &b)); VDL_TRY(vdl_op_gather(ctx, a, b, &r)); break;
     case N_SCATTER: {
       VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.c, &c));
-      Vec *pv = vec_get(ctx, c);
-      if (!pv) return VDL_EINVAL;
+      Vec *pv = vec_get(ctx, c), *sv = vec_get(ctx, a);
+      if (!pv || !sv) return VDL_EINVAL;
       if (pv->domain < 0) return vdl_fail(ctx, VDL_EUNSUPPORTED, "Scatter: output length unknown (positions carry no index space; App. G2)");
+      if (pv->is_range && pv->from == 0 && pv->step == 1 && pv->len == pv->domain && sv->len == pv->len && !sv->is_range && sv->dtype == VDL_I64) {
+        r = a; temp = false;       // scattering by the identity permutation (Partition of keys already in order): the source itself
+        break;
+      }
       VDL_TRY(vdl_op_scatter(ctx, a, c, pv->domain, &r));
       break;
     }
@@ -1109,14 +1114,14 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
       ProbeFoldGroup &g = *p->pgroups[p->pgroup_of_node[o.node]];
       const int64_t *data; int64_t len;
       VDL_TRY(vdl_probe_result_host(g.probe, g.fold_of_node[o.node], &data, &len));
-      o.data.assign(data, data + len);
+      o.data = data; o.len = len;
       continue;
     }
     if (gi >= 0) {   // the output IS a fused fold or a post op of one: it arrived with the scan's single result copy
       const int64_t *data; int64_t len;
       if (p->nodes[o.node].op == N_FOLD) VDL_TRY(vdl_fused_result_host(p->groups[gi].fused, p->groups[gi].fold_of_node[o.node], &data, &len));
       else VDL_TRY(vdl_fused_post_host(p->groups[gi].fused, p->groups[gi].post_of_node[o.node], &data, &len));
-      o.data.assign(data, data + len);
+      o.data = data; o.len = len;
       continue;
     }
     ran_ops = true;
@@ -1125,9 +1130,16 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
     if (rc) { free_temps(p); return rc; }
     i64 len;
     VDL_TRY(vdl_vec_len(ctx, v, &len));
-    o.data.resize((size_t)len);
-    rc = vdl_vec_download(ctx, v, o.data.data(), len);
+    if ((size_t)len > o.cap) {              // pinned, so the copy is one DMA at PCIe rate
+      if (o.pinned) cudaFreeHost(o.pinned);
+      o.pinned = nullptr; o.cap = 0;
+      size_t want = (size_t)len + (size_t)len / 4 + 16;
+      if (cudaHostAlloc(&o.pinned, want * sizeof(i64), cudaHostAllocDefault) != cudaSuccess) { free_temps(p); return vdl_fail(ctx, VDL_ENOMEM, "output buffer of %lld values", (long long)len); }
+      o.cap = want;
+    }
+    rc = vdl_vec_download(ctx, v, o.pinned, len);
     if (rc) { free_temps(p); return rc; }
+    o.data = o.pinned; o.len = len;
   }
   int rc = ran_ops ? check_errflag(ctx, "plan") : VDL_OK;
   p->launches_last += ctx->launches - l0;
@@ -1145,8 +1157,8 @@ extern "C" int vdl_plan_num_outputs(vdl_plan *p) { return p ? (int)p->outputs.si
 extern "C" int vdl_plan_output(vdl_plan *p, int i, const char **name, const int64_t **data, int64_t *len) {
   if (!p || i < 0 || i >= (int)p->outputs.size()) return VDL_EINVAL;
   if (name) *name = p->outputs[i].name.c_str();
-  if (data) *data = p->outputs[i].data.data();
-  if (len) *len = (int64_t)p->outputs[i].data.size();
+  if (data) *data = p->outputs[i].data;
+  if (len) *len = (int64_t)p->outputs[i].len;
   return VDL_OK;
 }
 
@@ -1154,6 +1166,7 @@ extern "C" int vdl_plan_destroy(vdl_plan *p) {
   if (!p) return VDL_EINVAL;
   free_temps(p);
   for (auto &g : p->groups) if (g.fused) vdl_fused_destroy(g.fused);
+  for (auto &o : p->outputs) if (o.pinned) cudaFreeHost(o.pinned);
   for (auto *g : p->pgroups) { if (g->probe) vdl_probe_destroy(g->probe); delete g; }
   for (auto *g : p->egroups) { if (g->probe) vdl_probe_destroy(g->probe); delete g; }
   delete p->join;

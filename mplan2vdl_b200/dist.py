@@ -81,16 +81,17 @@ class ShardedPlan:
         dist.barrier(group=self.group)
         return True
 
-    def step(self) -> dict:
+    def step(self, copy: bool = True) -> dict:
+        """copy=False: the arrays are views of pinned host buffers owned by the library, valid until the next step."""
         if self.world == 1 or self.peer_mode:
-            return self.plan.run()                      # one launch per fused scan: its last thread block finalizes
-        out = self._step_all_gather()
+            return self.plan.run(copy)                  # one launch per fused scan: its last thread block finalizes
+        out = self._step_all_gather(copy)
         if self._want_peer:                             # the scans exist now: switch to the peer-memory combine
             self._want_peer = False
             self.peer_mode = self._setup_peers()
         return out
 
-    def _step_all_gather(self) -> dict:
+    def _step_all_gather(self, copy: bool = True) -> dict:
         self.plan.run_local()
         ptrs = []
         with torch.cuda.stream(self._stream):           # NCCL is ordered after the scan on the library's stream
@@ -102,7 +103,7 @@ class ShardedPlan:
                     self._gathered.append(None)
                 self._gathered[i] = g                   # keep alive until finish() has consumed it
                 ptrs.append(g.data_ptr())
-        return self.plan.finish(ptrs, self.world)
+        return self.plan.finish(ptrs, self.world, copy)
 
     def close(self):
         for p in self._opened:

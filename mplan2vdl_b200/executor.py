@@ -247,21 +247,24 @@ class Plan:
         self.ctx.check(self.L.vdl_plan_probe_kernel_ms(self.h, C.byref(ms)))
         return ms.value
 
-    def finish(self, gathered_ptrs=None, nranks: int = 1) -> dict:
+    def finish(self, gathered_ptrs=None, nranks: int = 1, copy: bool = True) -> dict:
         arr = None
         if gathered_ptrs is not None:
             arr = (C.c_void_p * len(gathered_ptrs))(*gathered_ptrs)
         self.ctx.check(self.L.vdl_plan_finish(self.h, arr, nranks))
-        return self.outputs()
+        return self.outputs(copy)
 
-    def run(self) -> dict:
+    def run(self, copy: bool = True) -> dict:
         self.ctx.check(self.L.vdl_plan_run(self.h))
-        return self.outputs()
+        return self.outputs(copy)
 
-    def outputs(self) -> dict:
+    def outputs(self, copy: bool = True) -> dict:
+        """{output name: int64 array}.  copy=False returns views of the library's pinned host buffers, valid until the
+        plan runs again or is closed."""
         out = {}
         for i in range(self.L.vdl_plan_num_outputs(self.h)):
             name, data, n = C.c_char_p(), C.POINTER(C.c_int64)(), C.c_int64()
             self.ctx.check(self.L.vdl_plan_output(self.h, i, C.byref(name), C.byref(data), C.byref(n)))
-            out[name.value.decode()] = np.ctypeslib.as_array(data, shape=(n.value,)).copy() if n.value else np.zeros(0, np.int64)
+            arr = np.ctypeslib.as_array(data, shape=(n.value,)) if n.value else np.zeros(0, np.int64)
+            out[name.value.decode()] = arr.copy() if copy and n.value else arr
         return out
