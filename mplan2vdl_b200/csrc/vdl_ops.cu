@@ -99,6 +99,56 @@ __global__ void __launch_bounds__(1024, 1) exclusive_scan_kernel(i64 *data, i64 
   if (tid == 0) *total = carry;
 }
 
+// Large inputs (radix histograms: 256 counters per 4096 rows; a billion-row FoldSelect: 244 K block counts): scan
+// 4096-element chunks in parallel, scan the chunk totals with the one-block kernel, add the chunk offsets back.
+#define SCAN_CHUNK 4096
+__global__ void __launch_bounds__(1024) scan_chunks_kernel(i64 *data, i64 n, i64 *chunk_sum) {
+  __shared__ i64 warp_sum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const i64 base = (i64)blockIdx.x * SCAN_CHUNK + tid * 4;
+  i64 v[4], t = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = base + k < n ? data[base + k] : 0; t += v[k]; }
+  i64 x = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { i64 y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) warp_sum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    i64 w = warp_sum[lane], q = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { i64 y = __shfl_up_sync(0xffffffffu, q, o); if (lane >= o) q += y; }
+    warp_sum[lane] = q - w;
+    if (lane == 31) chunk_sum[blockIdx.x] = q;
+  }
+  __syncthreads();
+  i64 run = warp_sum[warp] + x - t;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { if (base + k < n) data[base + k] = run; run += v[k]; }
+}
+__global__ void __launch_bounds__(1024) add_chunk_offsets_kernel(i64 *data, i64 n, const i64 *chunk_off) {
+  const i64 off = chunk_off[blockIdx.x], base = (i64)blockIdx.x * SCAN_CHUNK + threadIdx.x * 4;
+#pragma unroll
+  for (int k = 0; k < 4; k++) if (base + k < n) data[base + k] += off;
+}
+// elements of scratch a scan of n counters needs, counters included: [n counters][total][chunk sums][their total]
+static size_t scan_elems(i64 n) { return (size_t)n + 1 + 2 * (size_t)((n + SCAN_CHUNK - 1) / SCAN_CHUNK) + 64; }
+// exclusive scan of data[0..n) in place, total to data[n]; data must have scan_elems(n) elements
+static void device_exclusive_scan(vdl_ctx *ctx, i64 *data, i64 n) {
+  if (n <= 4 * SCAN_CHUNK) {
+    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(data, n, data + n);
+    ctx->launches++;
+    return;
+  }
+  const i64 nc = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  i64 *sums = data + n + 1;
+  scan_chunks_kernel<<<(unsigned)nc, 1024, 0, ctx->stream>>>(data, n, sums);
+  device_exclusive_scan(ctx, sums, nc);                        // recursion depth <= 2 for any realistic n
+  add_chunk_offsets_kernel<<<(unsigned)nc, 1024, 0, ctx->stream>>>(data, n, sums);
+  cudaMemcpyAsync(data + n, sums + nc, 8, cudaMemcpyDeviceToDevice, ctx->stream);
+  ctx->launches += 2;
+}
+
 #define SEL_TILE 4096   // rows per block of the flag-count / compaction kernels (16 steps of 256)
 
 // flag(i): FoldSelect -> pred[i] != 0 ; Fold head -> i == 0 || g[i] != g[i-1]
@@ -170,12 +220,12 @@ __global__ void __launch_bounds__(256) compact_kernel(Operand o, i64 n, const i6
 
 static int flag_scan(vdl_ctx *ctx, bool heads, const Operand &o, i64 n, i64 **block_off, i64 *total) {
   i64 nb = (n + SEL_TILE - 1) / SEL_TILE;
-  VDL_TRY(scratch_reserve(ctx, (size_t)(nb + 2) * 8));
+  VDL_TRY(scratch_reserve(ctx, scan_elems(nb) * 8));
   i64 *cnt = (i64 *)ctx->scratch;
   if (heads) flag_count_kernel<true><<<(unsigned)nb, 256, 0, ctx->stream>>>(o, n, cnt);
   else flag_count_kernel<false><<<(unsigned)nb, 256, 0, ctx->stream>>>(o, n, cnt);
-  exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(cnt, nb, cnt + nb);
-  ctx->launches += 2;
+  ctx->launches++;
+  device_exclusive_scan(ctx, cnt, nb);
   VDL_CUDA(ctx, cudaMemcpyAsync(total, cnt + nb, 8, cudaMemcpyDeviceToHost, ctx->stream));
   VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *block_off = cnt;
@@ -267,6 +317,13 @@ extern "C" int vdl_op_scatter(vdl_ctx *ctx, vdl_vec src, vdl_vec pos, int64_t ou
 // count needs (Q1: 6 bits = 1 pass; Q3's 38-bit composite key = 5 passes).
 #define RDX_TILE 4096
 
+__device__ __forceinline__ u64 bucket_of(i64 v, i64 pfrom, i64 pstep, i64 pcount) {
+  if (v <= pfrom) return 0;
+  u64 d = (u64)v - (u64)pfrom;
+  u64 b = pstep == 1 ? d : (d + (u64)pstep - 1) / (u64)pstep;     // every emitted Partition has unit-step pivots (Vlite.hs:1088-1091)
+  return b > (u64)pcount ? (u64)pcount : b;
+}
+
 __global__ void __launch_bounds__(256) bucket_kernel(Operand data, i64 n, i64 pfrom, i64 pstep, i64 pcount, u64 *__restrict__ key, i64 *__restrict__ idx) {
   i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -338,23 +395,71 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const u64 *__restric
   }
 }
 
+// One-pass variant for <= 256 buckets (every low-cardinality group-by: Q1's 32, Q5's 128): the same histogram / scan,
+// then the destination of row i is written straight to out[i] -- no key / index ping-pong, no inversion pass.
+__global__ void __launch_bounds__(256) bucket_hist_kernel(Operand data, i64 n, i64 pfrom, i64 pstep, i64 pcount, i64 nblocks, i64 *__restrict__ hist) {
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  i64 base = (i64)blockIdx.x * RDX_TILE;
+  for (int s = 0; s < RDX_TILE / 256; s++) {
+    i64 i = base + s * 256 + threadIdx.x;
+    if (i < n) atomicAdd(&h[(int)bucket_of(op_ld(data, i), pfrom, pstep, pcount)], 1);
+  }
+  __syncthreads();
+  hist[(i64)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+__global__ void __launch_bounds__(256) bucket_place_kernel(Operand data, i64 n, i64 pfrom, i64 pstep, i64 pcount, i64 nblocks,
+                                                           const i64 *__restrict__ offs, i64 *__restrict__ out) {
+  __shared__ int wcount[8][256];
+  __shared__ int wbase[8][256];
+  __shared__ int run[256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int w = 0; w < 8; w++) wcount[w][tid] = 0;
+  run[tid] = 0;
+  __syncthreads();
+  i64 base = (i64)blockIdx.x * RDX_TILE;
+  for (int s = 0; s < RDX_TILE / 256; s++) {
+    i64 i = base + s * 256 + tid;
+    bool valid = i < n;
+    int d = valid ? (int)bucket_of(op_ld(data, i), pfrom, pstep, pcount) : 256 + lane;
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    int rank_in_warp = __popc(peers & ((1u << lane) - 1));
+    if (valid && rank_in_warp == 0) wcount[warp][d] = __popc(peers);
+    __syncthreads();
+    {
+      int off = run[tid];
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        int c = wcount[w][tid];
+        wcount[w][tid] = 0;
+        wbase[w][tid] = off;
+        off += c;
+      }
+      run[tid] = off;
+    }
+    __syncthreads();
+    if (valid) out[i] = offs[(i64)d * nblocks + blockIdx.x] + wbase[warp][d] + rank_in_warp;
+  }
+}
+
 __global__ void __launch_bounds__(256) invert_perm_kernel(const i64 *__restrict__ order, i64 n, i64 *__restrict__ out) {
   i64 stride = (i64)gridDim.x * blockDim.x;
   for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) out[order[j]] = j;
 }
 
-__device__ __forceinline__ u64 bucket_of(i64 v, i64 pfrom, i64 pstep, i64 pcount) {
-  if (v <= pfrom) return 0;
-  u64 d = (u64)v - (u64)pfrom;
-  u64 b = (d + (u64)pstep - 1) / (u64)pstep;
-  return b > (u64)pcount ? (u64)pcount : b;
-}
 // rows already ordered by bucket (e.g. lineitem clustered on l_orderkey, storage.csv `sorted`)?  counts the descents
 __global__ void __launch_bounds__(256) descents_kernel(Operand data, i64 n, i64 pfrom, i64 pstep, i64 pcount, int *descents) {
-  i64 stride = (i64)gridDim.x * blockDim.x;
+  // 4 consecutive elements per thread (+ the next one): independent loads in flight, every element read ~1.25 times
+  const i64 stride = (i64)gridDim.x * blockDim.x * 4;
   int bad = 0;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += stride)
-    bad |= bucket_of(op_ld(data, i), pfrom, pstep, pcount) > bucket_of(op_ld(data, i + 1), pfrom, pstep, pcount);
+  for (i64 i0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += stride) {
+    u64 b[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) b[k] = i0 + k < n ? bucket_of(op_ld(data, i0 + k), pfrom, pstep, pcount) : ~0ull;
+#pragma unroll
+    for (int k = 0; k < 4; k++) bad |= b[k] > b[k + 1] && i0 + k + 1 < n;
+  }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAdd(descents, 1);
 }
 
@@ -372,7 +477,7 @@ extern "C" int vdl_op_partition(vdl_ctx *ctx, vdl_vec data, int64_t pfrom, int64
     VDL_TRY(scratch_reserve(ctx, 64));
     int *d_desc = (int *)ctx->scratch, h_desc = 1;
     VDL_CUDA(ctx, cudaMemsetAsync(d_desc, 0, sizeof(int), ctx->stream));
-    int g0 = (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 16));
+    int g0 = (int)std::max<i64>(1, std::min<i64>((n + 1023) / 1024, (i64)ctx->sm_count * 16));
     descents_kernel<<<g0, 256, 0, ctx->stream>>>(od, n, pfrom, pstep, pcount, d_desc);
     ctx->launches++;
     VDL_CUDA(ctx, cudaMemcpyAsync(&h_desc, d_desc, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -385,10 +490,20 @@ extern "C" int vdl_op_partition(vdl_ctx *ctx, vdl_vec data, int64_t pfrom, int64
   int bits = 0;
   while (bits < 63 && ((u64)pcount >> bits)) bits++;
   i64 nb = (n + RDX_TILE - 1) / RDX_TILE;
+  if (pcount < 256) {                       // buckets 0..pcount fit one digit
+    VDL_TRY(scratch_reserve(ctx, scan_elems(256 * nb) * 8));
+    i64 *h = (i64 *)ctx->scratch;
+    bucket_hist_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(od, n, pfrom, pstep, pcount, nb, h);
+    device_exclusive_scan(ctx, h, 256 * nb);
+    bucket_place_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(od, n, pfrom, pstep, pcount, nb, h, (i64 *)ctx->vecs[*out].ptr);
+    ctx->launches += 2;
+    VDL_CUDA(ctx, cudaGetLastError());
+    return VDL_OK;
+  }
   // temporaries: key/idx ping-pong + histogram
   vdl_vec tk[2], ti[2];
   for (int k = 0; k < 2; k++) { VDL_TRY(vec_new(ctx, VDL_I64, n, &tk[k])); VDL_TRY(vec_new(ctx, VDL_I64, n, &ti[k])); }
-  VDL_TRY(scratch_reserve(ctx, (size_t)(256 * nb + 2) * 8));
+  VDL_TRY(scratch_reserve(ctx, scan_elems(256 * nb) * 8));
   i64 *hist = (i64 *)ctx->scratch;
   u64 *key[2] = {(u64 *)ctx->vecs[tk[0]].ptr, (u64 *)ctx->vecs[tk[1]].ptr};
   i64 *idx[2] = {(i64 *)ctx->vecs[ti[0]].ptr, (i64 *)ctx->vecs[ti[1]].ptr};
@@ -398,9 +513,9 @@ extern "C" int vdl_op_partition(vdl_ctx *ctx, vdl_vec data, int64_t pfrom, int64
   int cur = 0;
   for (int shift = 0; shift < bits; shift += 8) {
     radix_hist_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(key[cur], n, shift, nb, hist);
-    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, 256 * nb, hist + 256 * nb);
+    device_exclusive_scan(ctx, hist, 256 * nb);
     radix_scatter_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(key[cur], idx[cur], n, shift, nb, hist, key[cur ^ 1], idx[cur ^ 1]);
-    ctx->launches += 3;
+    ctx->launches += 2;
     cur ^= 1;
   }
   invert_perm_kernel<<<grid, 256, 0, ctx->stream>>>(idx[cur], n, (i64 *)ctx->vecs[*out].ptr);
@@ -454,6 +569,11 @@ __global__ void __launch_bounds__(256) fold_runs_kernel(int op, Operand groups, 
     }
     i64 nr = __shfl_down_sync(0xffffffffu, rid, 1);
     bool last = lane == 31 || nr != rid;
+    // a run whose head AND end are inside this warp's 32 elements belongs to this lane alone: plain store
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const int head_lane = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));     // lane of this element's run head, -1 if in an earlier warp
+    const bool own = valid && last && lane < 31 && nr != rid && head_lane >= 0;
+    if (own) { out[rid] = v; continue; }
     if (valid && last) {
       if (op == VDL_FOLD_MIN) atomicMin((long long *)&out[rid], (long long)v);
       else if (op == VDL_FOLD_MAX) atomicMax((long long *)&out[rid], (long long)v);
