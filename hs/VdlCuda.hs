@@ -60,3 +60,17 @@ foreign import ccall safe "vdl_plan_finish" c_vdl_plan_finish :: Ptr VdlPlan -> 
 foreign import ccall safe "vdl_plan_num_outputs" c_vdl_plan_num_outputs :: Ptr VdlPlan -> IO CInt
 foreign import ccall safe "vdl_plan_output" c_vdl_plan_output :: Ptr VdlPlan -> CInt -> Ptr CString -> Ptr (Ptr Int64) -> Ptr Int64 -> IO CInt
 foreign import ccall safe "vdl_plan_destroy" c_vdl_plan_destroy :: Ptr VdlPlan -> IO CInt
+
+-- multi-GPU combine over peer memory (vdl_cuda.h "multi-GPU combine over peer memory"): after vdl_plan_set_peers,
+-- vdl_plan_run returns the GLOBAL result on every rank with one kernel launch per GPU and no collective library
+foreign import ccall safe "vdl_plan_exchange_bytes" c_vdl_plan_exchange_bytes :: Ptr VdlPlan -> CInt -> CInt -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_plan_set_peers" c_vdl_plan_set_peers :: Ptr VdlPlan -> CInt -> CInt -> CInt -> Ptr (Ptr ()) -> IO CInt
+foreign import ccall safe "vdl_ipc_alloc" c_vdl_ipc_alloc :: Ptr VdlCtx -> Int64 -> Ptr (Ptr ()) -> IO CInt
+foreign import ccall safe "vdl_ipc_export" c_vdl_ipc_export :: Ptr VdlCtx -> Ptr () -> CString -> IO CInt      -- 64-byte handle
+foreign import ccall safe "vdl_ipc_open" c_vdl_ipc_open :: Ptr VdlCtx -> CString -> Ptr (Ptr ()) -> IO CInt
+foreign import ccall safe "vdl_ipc_close" c_vdl_ipc_close :: Ptr VdlCtx -> Ptr () -> IO CInt
+foreign import ccall safe "vdl_ipc_free" c_vdl_ipc_free :: Ptr VdlCtx -> Ptr () -> IO CInt
+
+-- what the fusion passes did with a loaded program (Folds on the fused scan; FK-join Folds / vectors on the probe kernel)
+foreign import ccall safe "vdl_plan_stats" c_vdl_plan_stats :: Ptr VdlPlan -> Ptr CInt -> Ptr CInt -> Ptr CInt -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_plan_probe_stats" c_vdl_plan_probe_stats :: Ptr VdlPlan -> Ptr CInt -> Ptr CInt -> Ptr CInt -> IO CInt
