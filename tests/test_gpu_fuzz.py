@@ -1,0 +1,56 @@
+"""Randomised plans (tests/fuzz_plans.py): the program the translator restatement prints for a random query must give
+the same bits through the CPU oracle, the fused GPU paths (fused scan / FK-join probe, whichever the fusion passes
+pick) and the op-at-a-time GPU path."""
+import pytest
+
+import fuzz_plans
+from mplan2vdl_b200 import synth, tpch, vlite
+from util import assert_same, host_columns, run_gpu, run_oracle
+
+SF = 0.004
+
+
+def _run(catalog, rel, need_gpu=True, sf=SF):
+    text = vlite.translate(catalog, rel)
+    rows = {t: synth.table_rows(catalog, t, sf) for t in catalog.tables}
+    cols = host_columns(catalog, tpch.plan_columns(text), rows, sf=sf)
+    want = run_oracle(text, cols)
+    if not need_gpu:
+        return want, None
+    got, stats = run_gpu(text, cols, fuse=True)
+    assert_same(got, want)
+    got_u, stats_u = run_gpu(text, cols, fuse=False)
+    assert stats_u["fused_scans"] == 0 and stats_u["probe_folds"] == 0 and stats_u["probe_emits"] == 0
+    assert_same(got_u, want)
+    stats["loads"] = text.count(",Load,")
+    return want, stats
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(30))
+def test_random_single_table_plans(catalog, seed):
+    _, stats = _run(catalog, fuzz_plans.single_table(seed))
+    # every select -> map -> grouped fold over one table fuses into one scan (a bare COUNT(*) reads no column: per-op)
+    assert stats["fused_scans"] == 1 or stats["loads"] == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(30))
+def test_random_fk_join_plans(catalog, seed):
+    _, stats = _run(catalog, fuzz_plans.join_query(seed, catalog))
+    assert stats["probe_folds"] + stats["probe_emits"] >= 1      # the join chain runs on the probe kernel
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [100, 101, 102, 103, 104, 105])
+def test_random_plans_many_tiles(catalog, seed):
+    """~300 K lineitem rows: hundreds of probe tiles / scan tiles, look-back across tiles, several CTAs per scan."""
+    _run(catalog, fuzz_plans.single_table(seed), sf=0.05)
+    _run(catalog, fuzz_plans.join_query(seed, catalog), sf=0.05)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_plans_translate_and_run_in_the_oracle(catalog, seed):
+    for rel in (fuzz_plans.single_table(seed), fuzz_plans.join_query(seed, catalog)):
+        want, _ = _run(catalog, rel, need_gpu=False)
+        assert len(want) >= 1

@@ -137,3 +137,19 @@ def test_fk_join_plans_parity(catalog, q, sf):
     got, stats = run_gpu(text, cols)
     assert_same(got, want)
     assert len(next(iter(want.values()))) > 0
+
+
+def test_cli_prints_the_server_json_and_the_decoded_csv():
+    """`python -m mplan2vdl_b200` stands where the HTTP Voodoo server + resolve.py stood (eval_query.sh:18-26)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    plan = os.path.join(root, "plans", "q05.vdl")
+    out = subprocess.run([sys.executable, "-m", "mplan2vdl_b200", plan, "--sf", "0.01"], cwd=root, capture_output=True, text=True, check=True).stdout
+    doc = json.loads(out)
+    assert list(doc["results"]["tmp0"]) == [".n_name__nation__n_name"] and list(doc["results"]["tmp1"]) == [".revenue"]
+    csv = subprocess.run([sys.executable, "-m", "mplan2vdl_b200", "-", "--sf", "0.01", "--csv"], cwd=root, input=open(plan).read(),
+                         capture_output=True, text=True, check=True).stdout.splitlines()
+    assert csv[0] == "n_name,revenue" and len(csv) == 1 + len(doc["results"]["tmp1"][".revenue"])
