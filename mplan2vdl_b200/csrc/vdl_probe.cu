@@ -133,17 +133,19 @@ __device__ __forceinline__ void table_update(int op, i64 *p, i64 v) {
 struct StageRegs { const void *ptr[4]; i64 len[4]; int w4mask, shr, depth; i64 a, b, lo; u64 span; };
 
 // S.ptr[0] is the leaf's own column (the LAST load), S.ptr[D-1] the fact column (the first): all indexing static.
-template <int D>
+// The first hop is indexed by the fact row itself (in range: prepare checks the fact columns' lengths); PLAIN: the
+// term is the bare leaf (a = 0, b = 1), as in every predicate the lowering emits.
+template <int D, bool PLAIN>
 __device__ __forceinline__ bool chain_test(const StageRegs &S, i64 row, i64 row_base, bool &ok) {
   i64 v = row;
   if (D == 0) v = row_base + row;
 #pragma unroll
   for (int k = D - 1; k >= 0; k--) {
-    if ((u64)v >= (u64)S.len[k]) { ok = false; return false; }
+    if (k != D - 1 && (u64)v >= (u64)S.len[k]) { ok = false; return false; }
     v = ((S.w4mask >> k) & 1) ? (i64)__ldg((const int32_t *)S.ptr[k] + v) : __ldg((const i64 *)S.ptr[k] + v);
   }
   v >>= S.shr;
-  v = (i64)((u64)S.a + (u64)S.b * (u64)v);
+  if (!PLAIN) v = (i64)((u64)S.a + (u64)S.b * (u64)v);
   return (u64)v - (u64)S.lo <= S.span;
 }
 
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(P_THREADS, 8) probe_kernel(const __grid_consta
             l = L.parent; n = k + 1;
           }
         }
-        if (l < 0) { S.depth = n; S.shr = P.t.shr; S.a = P.t.a; S.b = P.t.b; S.lo = P.lo; S.span = P.span; }
+        if (l < 0) { S.depth = n; S.shr = P.t.shr; S.a = P.t.a; S.b = P.t.b; S.lo = P.lo; S.span = P.span; if (P.t.a == 0 && P.t.b == 1) S.depth += 8; }   // +8: plain
       }
       int n_out = 0;
       for (int j0 = 0; j0 < n_in; j0 += P_SUB * P_THREADS) {
@@ -205,21 +207,17 @@ __global__ void __launch_bounds__(P_THREADS, 8) probe_kernel(const __grid_consta
           const int j = j0 + k * P_THREADS + tid;
           r[k] = j < n_in ? (q == 0 ? j : (int)queue[cur][j]) : -1;
         }
-        if (S.depth == 1) {
-#pragma unroll
-          for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && chain_test<1>(S, base + r[k], d.row_base, ok);
-        } else if (S.depth == 2) {
-#pragma unroll
-          for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && chain_test<2>(S, base + r[k], d.row_base, ok);
-        } else if (S.depth == 3) {
-#pragma unroll
-          for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && chain_test<3>(S, base + r[k], d.row_base, ok);
-        } else if (S.depth == 4) {
-#pragma unroll
-          for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && chain_test<4>(S, base + r[k], d.row_base, ok);
-        } else if (S.depth == 0) {
-#pragma unroll
-          for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && chain_test<0>(S, base + r[k], d.row_base, ok);
+#define STAGE_CASE(DEPTH, PL)                                                                                                   \
+  _Pragma("unroll") for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && chain_test<DEPTH, PL>(S, base + r[k], d.row_base, ok)
+        if (S.depth == 8 + 2) { STAGE_CASE(2, true);
+        } else if (S.depth == 8 + 1) { STAGE_CASE(1, true);
+        } else if (S.depth == 8 + 3) { STAGE_CASE(3, true);
+        } else if (S.depth == 8 + 4) { STAGE_CASE(4, true);
+        } else if (S.depth == 1) { STAGE_CASE(1, false);
+        } else if (S.depth == 2) { STAGE_CASE(2, false);
+        } else if (S.depth == 3) { STAGE_CASE(3, false);
+        } else if (S.depth == 4) { STAGE_CASE(4, false);
+        } else if (S.depth == 0 || S.depth == 8) { STAGE_CASE(0, false);
         } else {      // generic: constants, column == column, deeper chains
 #pragma unroll 1
           for (int k = 0; k < P_SUB; k++) {
