@@ -256,6 +256,11 @@ typedef struct vdl_probe vdl_probe;
 int vdl_abi_sizeof_probe_desc(void);
 int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_probe **out);
 int vdl_probe_run(vdl_probe *p);                 /* asynchronous on the context stream */
+/* Sharded fact table, fold mode: run without finalizing, all-gather the partial tables ([nfolds + 2][domain] int64 each)
+ * with any transport, then merge + finalize (NULL, 1 = this rank alone). */
+int vdl_probe_run_ex(vdl_probe *p, int finalize);
+int vdl_probe_partials(vdl_probe *p, void **device_ptr, int64_t *n_int64);
+int vdl_probe_finalize(vdl_probe *p, const void *all_partials, int nranks);
 /* fold mode: host copy of fold `index` (0..nfolds-1) or post op (nfolds..); one vector entry per existing key */
 int vdl_probe_result_host(vdl_probe *p, int index, const int64_t **data, int64_t *len);
 /* emit mode: take ownership of the k-th emitted vector (synchronises for its length) */
@@ -277,6 +282,10 @@ int vdl_plan_probe_kernel_ms(vdl_plan *p, float *ms);   /* sum over the probe pa
 int vdl_plan_set_row_base(vdl_plan *p, int64_t row_base);
 int vdl_plan_run_local(vdl_plan *p);
 int vdl_plan_num_fused(vdl_plan *p);
+/* Partial aggregate tables of a sharded run, in the order vdl_plan_finish expects the gathered buffers: the fused scans,
+ * then the probe fold groups. */
+int vdl_plan_num_partials(vdl_plan *p);
+int vdl_plan_partials(vdl_plan *p, int i, void **device_ptr, int64_t *n_int64);
 /* Sharded execution without a collective library: exchange buffers of fused scan `fused_index` on every rank (see
  * vdl_fused_set_peers); afterwards vdl_plan_run() returns the GLOBAL result on every rank.  The size comes from
  * vdl_plan_exchange_bytes() once the plan has run at least once (vdl_plan_run_local). */

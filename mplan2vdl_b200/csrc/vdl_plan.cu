@@ -1062,7 +1062,7 @@ static int plan_run_local(vdl_plan *p, int self_finalize) {
   }
   for (auto *g : p->pgroups) {
     VDL_TRY(bind_probe(p, &g->b, &g->probe, &g->bound, &g->bound_rows, &g->bound_base));
-    VDL_TRY(vdl_probe_run(g->probe));
+    VDL_TRY(vdl_probe_run_ex(g->probe, self_finalize));
   }
   p->launches_last = ctx->launches - l0;
   p->local_done = true;
@@ -1095,18 +1095,33 @@ extern "C" int vdl_plan_set_peers(vdl_plan *p, int fused_index, int rank, int wo
   return VDL_OK;
 }
 
+extern "C" int vdl_plan_num_partials(vdl_plan *p) { return p ? (int)(p->groups.size() + p->pgroups.size()) : 0; }
+extern "C" int vdl_plan_partials(vdl_plan *p, int i, void **device_ptr, int64_t *n_int64) {
+  if (!p || i < 0 || i >= vdl_plan_num_partials(p)) return VDL_EINVAL;
+  if (i < (int)p->groups.size()) {
+    if (!p->groups[i].fused) return vdl_fail(p->ctx, VDL_EINVAL, "plan has not run yet");
+    return vdl_fused_partials(p->groups[i].fused, device_ptr, n_int64);
+  }
+  ProbeFoldGroup *g = p->pgroups[i - p->groups.size()];
+  if (!g->probe) return vdl_fail(p->ctx, VDL_EINVAL, "plan has not run yet");
+  return vdl_probe_partials(g->probe, device_ptr, n_int64);
+}
+
 extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int nranks) {
   if (!p) return VDL_EINVAL;
   vdl_ctx *ctx = p->ctx;
   if (!p->local_done) return vdl_fail(ctx, VDL_EINVAL, "vdl_plan_finish before vdl_plan_run_local");
   p->trace = getenv("VDL_TRACE") != nullptr;
   if (p->trace) p->trace_t0 = p->trace_last = now_ms();
-  if (nranks > 1 && (p->groups.empty() || !p->pgroups.empty() || !p->egroups.empty()))
-    return vdl_fail(ctx, VDL_EUNSUPPORTED, "only plans made of fused single-table scans can be row-sharded so far");
+  if (nranks > 1 && ((p->groups.empty() && p->pgroups.empty()) || !p->egroups.empty()))
+    return vdl_fail(ctx, VDL_EUNSUPPORTED, "only plans whose Folds all run on the fused scan / the probe kernel can be row-sharded so far");
   i64 l0 = ctx->launches;
-  if (!(p->self_finalized && nranks == 1 && !all_partials))
+  if (!(p->self_finalized && nranks == 1 && !all_partials)) {
     for (size_t gi = 0; gi < p->groups.size(); gi++)
       VDL_TRY(vdl_fused_finalize(p->groups[gi].fused, all_partials ? all_partials[gi] : nullptr, nranks));
+    for (size_t gi = 0; gi < p->pgroups.size(); gi++)
+      VDL_TRY(vdl_probe_finalize(p->pgroups[gi]->probe, all_partials ? all_partials[p->groups.size() + gi] : nullptr, nranks));
+  }
   bool ran_ops = false;
   for (auto &o : p->outputs) {
     int gi = p->group_of_node[o.node];

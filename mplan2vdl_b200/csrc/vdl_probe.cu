@@ -66,7 +66,9 @@ struct PFin {
   int32_t nfolds, npost;
   int32_t fold_op[VDL_MAX_AGGS];
   vdl_post_op post[VDL_MAX_POSTS];
-  const i64 *table;
+  const i64 *table;                 // nranks tables back to back (stride int64 each); one = this rank's own
+  i64 stride;
+  int32_t nranks, precomputed_choose;   // precomputed_choose: FoldChoose values already sit in the tables (multi-rank)
   i64 *out;                         // [(nfolds + npost)][domain] then [ngroups, errors]
   i64 *hmirror;
   const int *errflag;
@@ -322,6 +324,19 @@ __global__ void probe_init_kernel(const __grid_constant__ PDesc d) {
   }
 }
 
+// External combine (several ranks): every rank evaluates FoldChoose at ITS first row of each key and stores the value in
+// the fold's (otherwise unused) table row, so the tables alone carry everything the merge needs.
+__global__ void probe_choose_kernel(const __grid_constant__ PDesc d) {
+  for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < d.domain; k += (i64)gridDim.x * blockDim.x) {
+    if (d.table[(size_t)d.nfolds * d.domain + k] <= 0) continue;
+    const i64 first = d.table[(size_t)(d.nfolds + 1) * d.domain + k] - d.row_base;
+    bool ok = true;
+    for (int j = 0; j < d.nfolds; j++)
+      if (d.fold_op[j] == VDL_FOLD_CHOOSE) d.table[(size_t)j * d.domain + k] = prod_value(d, d.fold[j], first, ok);
+    if (!ok) atomicAdd(d.errflag, 1);
+  }
+}
+
 // One dense vector per fold in ascending key order (keys without rows dropped: G14), FoldChoose evaluated at the
 // key's first row, then the post ops; results mirrored into mapped host memory.
 __global__ void __launch_bounds__(256, 1) probe_finalize_kernel(const __grid_constant__ PDesc d, const __grid_constant__ PFin f) {
@@ -332,7 +347,9 @@ __global__ void __launch_bounds__(256, 1) probe_finalize_kernel(const __grid_con
   __syncthreads();
   for (i64 base = 0; base < f.domain; base += 256) {
     const i64 k = base + tid;
-    const i64 cnt = k < f.domain ? f.table[(size_t)f.nfolds * f.domain + k] : 0;
+    i64 cnt = 0;
+    if (k < f.domain)
+      for (int r = 0; r < f.nranks; r++) cnt += f.table[(size_t)r * f.stride + (size_t)f.nfolds * f.domain + k];
     const bool exists = cnt > 0;
     unsigned m = __ballot_sync(0xffffffffu, exists);
     if (lane == 0) warp_cnt[warp] = __popc(m);
@@ -341,14 +358,27 @@ __global__ void __launch_bounds__(256, 1) probe_finalize_kernel(const __grid_con
     for (int w = 0; w < 8; w++) { if (w < warp) before += warp_cnt[w]; total += warp_cnt[w]; }
     if (exists) {
       const i64 pos = running + before + __popc(m & ((1u << lane) - 1));
-      const i64 first = f.table[(size_t)(f.nfolds + 1) * f.domain + k] - d.row_base;
+      int best = 0;                 // rank that holds the key's first row
+      i64 firstg = INT64_MAX;
+      for (int r = 0; r < f.nranks; r++) {
+        const i64 fr = f.table[(size_t)r * f.stride + (size_t)(f.nfolds + 1) * f.domain + k];
+        if (fr < firstg) { firstg = fr; best = r; }
+      }
+      const i64 first = firstg - d.row_base;
       i64 ov[VDL_MAX_AGGS], pv[VDL_MAX_POSTS];
       bool ok = true;
       for (int j = 0; j < f.nfolds; j++) {
+        const int op = f.fold_op[j];
         i64 v;
-        if (f.fold_op[j] == VDL_FOLD_COUNT) v = cnt;
-        else if (f.fold_op[j] == VDL_FOLD_CHOOSE) v = prod_value(d, d.fold[j], first, ok);
-        else v = f.table[(size_t)j * f.domain + k];
+        if (op == VDL_FOLD_COUNT) v = cnt;
+        else if (op == VDL_FOLD_CHOOSE) v = f.precomputed_choose ? f.table[(size_t)best * f.stride + (size_t)j * f.domain + k] : prod_value(d, d.fold[j], first, ok);
+        else {
+          v = p_identity(op);
+          for (int r = 0; r < f.nranks; r++) {
+            const i64 x = f.table[(size_t)r * f.stride + (size_t)j * f.domain + k];
+            v = op == VDL_FOLD_MIN ? (x < v ? x : v) : (op == VDL_FOLD_MAX ? (x > v ? x : v) : (i64)((u64)v + (u64)x));
+          }
+        }
         ov[j] = v;
         f.out[(size_t)j * f.domain + pos] = v;
         if (f.hmirror) f.hmirror[(size_t)j * f.domain + pos] = v;
@@ -379,7 +409,7 @@ struct vdl_probe {
   vdl_ctx *ctx = nullptr;
   PDesc pd;
   PFin pf;
-  bool folding = true, ran = false, fetched = false;
+  bool folding = true, ran = false, fetched = false, finalized = false;
   vdl_vec table = 0;
   i64 *d_out = nullptr, *h_out = nullptr, *h_mapped = nullptr;
   i64 *d_total = nullptr;              // [0] survivors (emit mode)
@@ -486,7 +516,7 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
       return fail(vdl_fail(ctx, VDL_ENOMEM, "probe: result buffers"));
     p->pf.domain = d.domain; p->pf.nfolds = d.nfolds; p->pf.npost = desc->nposts;
     for (int j = 0; j < d.nfolds; j++) p->pf.fold_op[j] = d.fold_op[j];
-    p->pf.table = d.table; p->pf.out = p->d_out; p->pf.hmirror = p->h_mapped; p->pf.errflag = ctx->d_errflag;
+    p->pf.table = d.table; p->pf.nranks = 1; p->pf.stride = (i64)(d.nfolds + 2) * d.domain; p->pf.out = p->d_out; p->pf.hmirror = p->h_mapped; p->pf.errflag = ctx->d_errflag;
   } else {
     for (int e = 0; e < desc->nemits; e++)
       if (!prod(desc->emit[e], &d.emit[e])) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad emit %d", e));
@@ -503,7 +533,36 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
   return VDL_OK;
 }
 
-extern "C" int vdl_probe_run(vdl_probe *p) {
+extern "C" int vdl_probe_run(vdl_probe *p) { return vdl_probe_run_ex(p, 1); }
+
+extern "C" int vdl_probe_partials(vdl_probe *p, void **device_ptr, int64_t *n_int64) {
+  if (!p || !device_ptr || !n_int64 || !p->folding) return VDL_EINVAL;
+  *device_ptr = p->pd.table;
+  *n_int64 = (int64_t)(p->pd.nfolds + 2) * p->pd.domain;
+  return VDL_OK;
+}
+
+// Merge `nranks` partial tables laid out back to back (an all-gather result; NULL and 1: this rank's own) and finalize.
+extern "C" int vdl_probe_finalize(vdl_probe *p, const void *all_partials, int nranks) {
+  if (!p || !p->folding) return VDL_EINVAL;
+  vdl_ctx *ctx = p->ctx;
+  if (nranks < 1 || (nranks > 1 && !all_partials)) return vdl_fail(ctx, VDL_EINVAL, "probe finalize: nranks %d without gathered partials", nranks);
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  p->pf.table = all_partials ? (const i64 *)all_partials : p->pd.table;
+  p->pf.nranks = nranks;
+  p->pf.stride = (i64)(p->pd.nfolds + 2) * p->pd.domain;
+  p->pf.precomputed_choose = 1;
+  probe_finalize_kernel<<<1, 256, 0, ctx->stream>>>(p->pd, p->pf);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaGetLastError());
+  p->fetched = false;
+  p->finalized = true;
+  return VDL_OK;
+}
+
+// finalize != 0: single GPU, results on their way when this returns.  0 (fold mode): leave the complete partial
+// table (FoldChoose values included) for an external combine, then vdl_probe_finalize().
+extern "C" int vdl_probe_run_ex(vdl_probe *p, int finalize) {
   if (!p) return VDL_EINVAL;
   vdl_ctx *ctx = p->ctx;
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -532,8 +591,14 @@ extern "C" int vdl_probe_run(vdl_probe *p) {
     ctx->launches++;
   }
   VDL_CUDA(ctx, cudaEventRecord(p->ev1, ctx->stream));
-  if (p->folding) {
+  p->finalized = !p->folding || finalize != 0;
+  if (p->folding && finalize) {
+    p->pf.table = d.table; p->pf.nranks = 1; p->pf.stride = (i64)(d.nfolds + 2) * d.domain; p->pf.precomputed_choose = 0;
     probe_finalize_kernel<<<1, 256, 0, ctx->stream>>>(d, p->pf);
+    ctx->launches++;
+  } else if (p->folding) {
+    int cb = (int)std::min<i64>(ctx->sm_count, (d.domain + 255) / 256);
+    probe_choose_kernel<<<std::max(cb, 1), 256, 0, ctx->stream>>>(d);
     ctx->launches++;
   } else {
     VDL_CUDA(ctx, cudaMemcpyAsync(p->h_out, p->d_total, sizeof(i64), cudaMemcpyDeviceToHost, ctx->stream));
@@ -546,6 +611,7 @@ extern "C" int vdl_probe_run(vdl_probe *p) {
 static int probe_fetch(vdl_probe *p) {
   vdl_ctx *ctx = p->ctx;
   if (!p->ran) return vdl_fail(ctx, VDL_EINVAL, "probe has not run");
+  if (!p->finalized) return vdl_fail(ctx, VDL_EINVAL, "probe ran for an external combine: call vdl_probe_finalize first");
   if (p->fetched) return VDL_OK;
   VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (p->folding) {

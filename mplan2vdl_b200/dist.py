@@ -87,15 +87,15 @@ class ShardedPlan:
             return self.plan.run(copy)                  # one launch per fused scan: its last thread block finalizes
         out = self._step_all_gather(copy)
         if self._want_peer:                             # the scans exist now: switch to the peer-memory combine
-            self._want_peer = False
-            self.peer_mode = self._setup_peers()
+            self._want_peer = False                     # (probe fold groups combine through the all-gather path for now)
+            self.peer_mode = self.plan.num_partials == self.plan.num_fused and self._setup_peers()
         return out
 
     def _step_all_gather(self, copy: bool = True) -> dict:
         self.plan.run_local()
         ptrs = []
         with torch.cuda.stream(self._stream):           # NCCL is ordered after the scan on the library's stream
-            for i in range(self.plan.num_fused):
+            for i in range(self.plan.num_partials):
                 ptr, n = self.plan.partials(i)
                 local = torch.as_tensor(DeviceView(ptr, n), device=f"cuda:{self.ctx.device}")
                 g = gather_partial_tables(local, self.world, self.group)

@@ -221,12 +221,15 @@ class Plan:
     def num_fused(self) -> int:
         return self.L.vdl_plan_num_fused(self.h)
 
+    @property
+    def num_partials(self) -> int:
+        """Partial aggregate tables of a sharded run: the fused scans, then the probe fold groups."""
+        return self.L.vdl_plan_num_partials(self.h)
+
     def partials(self, i: int):
-        """(device pointer, number of int64) of fused scan i's partial table."""
-        f = C.c_void_p()
-        self.ctx.check(self.L.vdl_plan_fused(self.h, i, C.byref(f)))
+        """(device pointer, number of int64) of partial table i (finish() takes the gathered buffers in this order)."""
         p, n = C.c_void_p(), C.c_int64()
-        self.ctx.check(self.L.vdl_fused_partials(f, C.byref(p), C.byref(n)))
+        self.ctx.check(self.L.vdl_plan_partials(self.h, i, C.byref(p), C.byref(n)))
         return p.value, n.value
 
     def shape(self, i: int = 0) -> str:

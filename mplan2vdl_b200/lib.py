@@ -137,6 +137,11 @@ SYMBOLS = [
     ("vdl_probe_emit_take", _I, [_P, _I, C.POINTER(C.c_int32)]),
     ("vdl_probe_last_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
     ("vdl_probe_destroy", _I, [_P]),
+    ("vdl_plan_num_partials", _I, [_P]),
+    ("vdl_plan_partials", _I, [_P, _I, C.POINTER(_P), C.POINTER(_L)]),
+    ("vdl_probe_run_ex", _I, [_P, _I]),
+    ("vdl_probe_partials", _I, [_P, C.POINTER(_P), C.POINTER(_L)]),
+    ("vdl_probe_finalize", _I, [_P, _P, _I]),
     ("vdl_plan_probe_stats", _I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     ("vdl_plan_probe_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
     ("vdl_plan_set_row_base", _I, [_P, _L]),

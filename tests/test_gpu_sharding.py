@@ -117,3 +117,41 @@ def test_peer_memory_exchange_emulated_ranks(catalog, query, colnames, world):
         plans[r].close()
         ctxs[r].ipc_free(bufs[r])
         ctxs[r].close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fk_join_plan_sharded_through_probe_partials(catalog, world):
+    """Q5 (one probe fold group): lineitem row-range sharded, dimension tables replicated; the per-rank partial tables
+    (FoldChoose values included) are concatenated like an all-gather and merged by every rank's finalize."""
+    import torch
+    from mplan2vdl_b200 import synth
+    from mplan2vdl_b200.dist import DeviceView
+    from mplan2vdl_b200.executor import Context
+    sf, text = 0.01, plan_text("q05.vdl")
+    names = tpch.plan_columns(text)
+    rows = {t: synth.table_rows(catalog, t, sf) for t in catalog.tables}
+    cols = host_columns(catalog, names, rows, sf=sf)
+    want = run_oracle(text, cols)
+    assert len(want["revenue"]) > 0
+    ctxs, plans, tables = [], [], []
+    for rank in range(world):
+        start, n = tpch.shard_range(rows["lineitem"], rank, world)
+        ctx = Context(0)
+        for k, v in cols.items():
+            ctx.upload_column(k, v[start:start + n] if k.startswith("lineitem.") else v)
+        plan = ctx.plan(text)
+        plan.set_row_base(start)
+        plan.run_local()
+        assert plan.num_fused == 0 and plan.num_partials == 1
+        ptr, cnt = plan.partials(0)
+        ctx.synchronize()
+        tables.append(torch.as_tensor(DeviceView(ptr, cnt), device="cuda:0").clone())
+        ctxs.append(ctx)
+        plans.append(plan)
+    gathered = torch.cat(tables)
+    torch.cuda.synchronize()
+    for rank in range(world):
+        assert_same(plans[rank].finish([gathered.data_ptr()], world), want)
+    for p, c in zip(plans, ctxs):
+        p.close()
+        c.close()
