@@ -205,19 +205,6 @@ __device__ __forceinline__ StepRank step_rank(bool flag, int *wcnt /*[8]*/, int 
 
 // ---------------------------------------------------------------------------------- FoldSelect
 // Vlite.hs:721-730: idx = Fold FSel (pos_ p) p.  Dense model: global stable compaction of positions.
-__global__ void __launch_bounds__(256) compact_kernel(Operand o, i64 n, const i64 *__restrict__ block_off, i64 *__restrict__ out) {
-  __shared__ int wcnt[8];
-  i64 base = (i64)blockIdx.x * SEL_TILE;
-  i64 off = block_off[blockIdx.x];
-  int run = 0;
-  for (int s = 0; s < SEL_TILE / 256; s++) {
-    i64 i = base + s * 256 + threadIdx.x;
-    bool f = (i < n) && op_ld(o, i) != 0;
-    StepRank r = step_rank(f, wcnt, run);
-    if (f) out[off + r.rank] = i;
-  }
-}
-
 static int flag_scan(vdl_ctx *ctx, bool heads, const Operand &o, i64 n, i64 **block_off, i64 *total) {
   i64 nb = (n + SEL_TILE - 1) / SEL_TILE;
   VDL_TRY(scratch_reserve(ctx, scan_elems(nb) * 8));
@@ -232,6 +219,69 @@ static int flag_scan(vdl_ctx *ctx, bool heads, const Operand &o, i64 n, i64 **bl
   return VDL_OK;
 }
 
+// Single pass: a block takes 4096-element tiles in ticket order, reads its predicates ONCE (16 flags per thread kept
+// as a bit mask), gets the tile's output offset by a decoupled look-back over one 64-bit status word per tile
+// ((status << 62) | count; 1 = tile aggregate, 2 = inclusive prefix) and writes the positions in order.
+__global__ void __launch_bounds__(256) select_lookback_kernel(Operand o, i64 n, i64 ntiles, unsigned long long *state, unsigned int *ticket,
+                                                              i64 *__restrict__ out, i64 *total) {
+  __shared__ int wcnt[8];
+  __shared__ i64 s_off;
+  __shared__ unsigned int s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (;;) {
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const i64 tile = s_tile;
+    if (tile >= ntiles) break;
+    const i64 base = tile * SEL_TILE;
+    unsigned flags = 0;
+#pragma unroll
+    for (int s = 0; s < SEL_TILE / 256; s++) {
+      const i64 i = base + s * 256 + tid;
+      if (i < n && op_ld(o, i) != 0) flags |= 1u << s;
+    }
+    int c = __popc(flags);
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) c += __shfl_xor_sync(0xffffffffu, c, k);
+    if (lane == 0) wcnt[warp] = c;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long T = 0;
+      for (int w = 0; w < 8; w++) T += (unsigned long long)wcnt[w];
+      i64 excl = 0;
+      if (tile == 0) atomicExch(state, (2ull << 62) | T);
+      else {
+        atomicExch(state + tile, (1ull << 62) | T);
+        for (i64 j = tile - 1;; j--) {
+          unsigned long long st;
+          do { st = *((volatile unsigned long long *)(state + j)); } while ((st >> 62) == 0);
+          excl += (i64)(st & ((1ull << 62) - 1));
+          if ((st >> 62) == 2) break;
+        }
+        atomicExch(state + tile, (2ull << 62) | (unsigned long long)(excl + (i64)T));
+      }
+      s_off = excl;
+      if (tile == ntiles - 1) *total = excl + (i64)T;
+    }
+    __syncthreads();
+    i64 off = s_off;
+    // order inside the tile: step-major, then thread: rank by ballots per step
+#pragma unroll 1
+    for (int s = 0; s < SEL_TILE / 256; s++) {
+      const bool f = (flags >> s) & 1;
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      if (lane == 0) wcnt[warp] = __popc(m);
+      __syncthreads();
+      int before = 0, tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) { const int cw = wcnt[w]; if (w < warp) before += cw; tot += cw; }
+      if (f) out[off + before + __popc(m & ((1u << lane) - 1))] = base + s * 256 + tid;
+      off += tot;
+      __syncthreads();
+    }
+  }
+}
+
 extern "C" int vdl_op_fold_select(vdl_ctx *ctx, vdl_vec pred, vdl_vec *out) {
   if (!ctx || !out) return VDL_EINVAL;
   Vec *vp = vec_get(ctx, pred);
@@ -239,15 +289,27 @@ extern "C" int vdl_op_fold_select(vdl_ctx *ctx, vdl_vec pred, vdl_vec *out) {
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   i64 n = vp->len;
   Operand o = operand_of(*vp);
-  i64 total = 0, *off = nullptr;
-  if (n > 0) VDL_TRY(flag_scan(ctx, false, o, n, &off, &total));
-  VDL_TRY(vec_new(ctx, VDL_I64, total, out));
-  ctx->vecs[*out].domain = n;   // these positions index the predicate's row space (App. G2)
-  if (total > 0) {
-    compact_kernel<<<(unsigned)((n + SEL_TILE - 1) / SEL_TILE), 256, 0, ctx->stream>>>(o, n, off, (i64 *)ctx->vecs[*out].ptr);
-    ctx->launches++;
-    VDL_CUDA(ctx, cudaGetLastError());
+  if (n == 0) {
+    VDL_TRY(vec_new(ctx, VDL_I64, 0, out));
+    ctx->vecs[*out].domain = 0;
+    return VDL_OK;
   }
+  const i64 ntiles = (n + SEL_TILE - 1) / SEL_TILE;
+  VDL_TRY(scratch_reserve(ctx, (size_t)(ntiles + 4) * 8));
+  unsigned long long *state = (unsigned long long *)ctx->scratch;          // [ntiles] status words, then total, ticket
+  i64 *d_total = (i64 *)(state + ntiles);
+  unsigned int *ticket = (unsigned int *)(state + ntiles + 1);
+  VDL_CUDA(ctx, cudaMemsetAsync(state, 0, (size_t)(ntiles + 2) * 8, ctx->stream));
+  VDL_TRY(vec_new(ctx, VDL_I64, n, out));                                   // capacity n; the length is known after the pass
+  const int grid = (int)std::min<i64>(ntiles, (i64)ctx->sm_count * 8);
+  select_lookback_kernel<<<grid, 256, 0, ctx->stream>>>(o, n, ntiles, state, ticket, (i64 *)ctx->vecs[*out].ptr, d_total);
+  ctx->launches++;
+  i64 total = 0;
+  VDL_CUDA(ctx, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  Vec &v = ctx->vecs[*out];
+  v.len = total;
+  v.domain = n;   // these positions index the predicate's row space (App. G2)
   return VDL_OK;
 }
 
@@ -547,6 +609,28 @@ __global__ void __launch_bounds__(256) fold_runs_kernel(int op, Operand groups, 
   const int lane = threadIdx.x & 31;
   i64 base = (i64)blockIdx.x * SEL_TILE;
   i64 off = block_off[blockIdx.x];   // run heads before this block
+  if (block_off[blockIdx.x + 1] == off && op != VDL_FOLD_CHOOSE) {
+    // no run starts inside this tile: all of it continues run off-1 (long runs: a single-group fold, a sorted low-
+    // cardinality key) -> plain block reduction, ONE atomic per tile instead of one per warp and step
+    __shared__ i64 wred[8];
+    i64 v = fold_identity(op);
+    for (int s = 0; s < SEL_TILE / 256; s++) {
+      i64 i = base + s * 256 + threadIdx.x;
+      if (i < n) v = fold_combine(op, v, op == VDL_FOLD_COUNT ? 1 : op_ld(data, i));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fold_combine(op, v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) wred[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; w++) v = fold_combine(op, v, wred[w]);
+      i64 *dst = &out[off - 1];
+      if (op == VDL_FOLD_MIN) atomicMin((long long *)dst, (long long)v);
+      else if (op == VDL_FOLD_MAX) atomicMax((long long *)dst, (long long)v);
+      else atomicAdd((unsigned long long *)dst, (unsigned long long)v);
+    }
+    return;
+  }
   int run = 0;
   for (int s = 0; s < SEL_TILE / 256; s++) {
     i64 i = base + s * 256 + threadIdx.x;
