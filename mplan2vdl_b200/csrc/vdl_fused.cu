@@ -81,6 +81,7 @@ struct FinDesc {
 struct XDesc {
   int32_t rank, world;
   u64 epoch;                      // this step's number (1, 2, ...); parity double-buffers against a rank running ahead
+  u64 timeout_ns;                 // give up waiting for a peer after this long: error flag, never a hang
   i64 stride;                     // int64 per table
   i64 *peer[VDL_MAX_RANKS];       // base of every rank's buffer as seen from this GPU
 };
@@ -843,7 +844,7 @@ __device__ __forceinline__ const i64 *exchange_block(const XDesc &x, const i64 *
     const u64 *mine = (const u64 *)(x.peer[x.rank] + flags) + (size_t)par * x.world + tid;
     const u64 t0 = global_timer_ns();
     while (ld_acquire_sys(mine) < x.epoch) {
-      if (global_timer_ns() - t0 > 10000000000ull) { atomicAdd(errflag, 1 << 20); break; }   // a peer never arrived: fail, do not hang
+      if (global_timer_ns() - t0 > x.timeout_ns) { atomicAdd(errflag, 1 << 20); break; }   // a peer never arrived: fail, do not hang
       __nanosleep(64);
     }
   }
@@ -1433,6 +1434,8 @@ extern "C" int vdl_fused_set_peers(vdl_fused *f, int rank, int world, void *cons
   f->xd.rank = rank;
   f->xd.world = world;
   f->xd.stride = f->fd.part_stride;
+  f->xd.timeout_ns = 10000000000ull;                     // 10 s; VDL_PEER_TIMEOUT_MS overrides (tests)
+  if (const char *e = getenv("VDL_PEER_TIMEOUT_MS")) f->xd.timeout_ns = (u64)atoll(e) * 1000000ull;
   for (int r = 0; r < world; r++) {
     if (!peer_buffers[r]) return vdl_fail(f->ctx, VDL_EINVAL, "set_peers: buffer of rank %d is null", r);
     f->xd.peer[r] = (i64 *)peer_buffers[r];
@@ -1476,6 +1479,7 @@ static int fused_fetch(vdl_fused *f) {
   i64 ng = f->h_outbuf[n - 2], err = f->h_outbuf[n - 1];
   if (err) {
     cudaMemsetAsync(ctx->d_errflag, 0, sizeof(int), ctx->stream);
+    if (err >= (1 << 20)) return vdl_fail(ctx, VDL_ECUDA, "fused scan: a peer GPU never delivered its partial table (exchange timed out)");
     return vdl_fail(ctx, VDL_ERANGE, "fused scan: %lld rows produced a group key outside the key domain", (long long)err);
   }
   f->ngroups = ng;

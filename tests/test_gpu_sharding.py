@@ -155,3 +155,26 @@ def test_fk_join_plan_sharded_through_probe_partials(catalog, world):
     for p, c in zip(plans, ctxs):
         p.close()
         c.close()
+
+
+def test_peer_exchange_times_out_instead_of_hanging(catalog, monkeypatch):
+    """A rank whose peer never launches the step must come back with an error, not spin forever."""
+    from mplan2vdl_b200.executor import Context
+    from mplan2vdl_b200.lib import VdlError
+    monkeypatch.setenv("VDL_PEER_TIMEOUT_MS", "200")
+    rows, text = 20_000, plan_text("q06.vdl")
+    names = ["lineitem." + c for c in Q6_COLS]
+    ctx = Context(0)
+    for k, v in host_columns(catalog, names, {"lineitem": rows}).items():
+        ctx.upload_column(k, v)
+    plan = ctx.plan(text)
+    plan.run_local()
+    ctx.synchronize()
+    bufs = [ctx.ipc_alloc(plan.exchange_bytes(0, 2)) for _ in range(2)]      # "rank 1" exists only as a buffer
+    plan.set_peers(0, 0, 2, bufs)
+    with pytest.raises(VdlError, match="peer GPU never delivered"):
+        plan.run()
+    plan.close()
+    for b in bufs:
+        ctx.ipc_free(b)
+    ctx.close()
