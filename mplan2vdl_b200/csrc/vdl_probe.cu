@@ -20,7 +20,7 @@
 //   predicate lo <= term <= hi, or term == term; evaluated in chain order, first failure rejects the row
 // No validity vector, inverse index, position vector or gathered copy is ever materialised.
 //
-// Kernel shape: persistent thread blocks take 2048-row tiles in order from a ticket counter and evaluate the
+// Kernel shape: persistent thread blocks take 4096-row tiles in order from a ticket counter and evaluate the
 // predicates stage by stage, compacting the survivors in row order after each (see "staged evaluation" below; the
 // fact-column loads of a stage are coalesced, and the lineitem->orders index is clustered, so the first dimension
 // gather is nearly sequential too).  Fold mode accumulates into a shared-memory table per block (flushed with
@@ -33,7 +33,7 @@
 
 #include "vdl_internal.h"
 
-#define P_TILE 2048
+#define P_TILE 4096
 #define P_THREADS 128
 #define P_MAX_DEPTH 6
 #define P_SMEM_TABLE_BYTES (40 * 1024)
