@@ -30,6 +30,7 @@ QUERIES = {
     "q01": ("q01.vdl", 52),
     "q03": ("q03.vdl", None),
     "q05": ("q05.vdl", None),
+    "q12": ("q12.vdl", None),
 }
 
 

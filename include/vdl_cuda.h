@@ -226,14 +226,25 @@ int vdl_fused_last_kernel_ms(vdl_fused *f, float *ms);
  * the predicates of the whole join chain (handleGatherJoin / deduceMasks, Vlite.hs:1199-1280) and either
  * folds per group key or emits the surviving rows' expressions as dense vectors in row order.
  *   leaf       value(row) = column[ parent < 0 ? row : value of leaf `parent` (row) ]   (parent precedes the leaf)
- *   term       a + b * (leaf >> shr);  leaf -1: the constant a;  leaf -2: the global row id
- *   predicate  kind 0: lo <= t <= hi;  kind 1: t == u;  evaluated in order, the first failure rejects the row */
+ *   term       a + b * (leaf >> shr);  leaf -1: the constant a;  leaf -2: the global row id;
+ *              leaf -3-k: 1 if indicator predicate k holds at the row, else 0 (CASE WHEN ... THEN 1 ELSE 0)
+ *   predicate  kind 0: t in [lo, hi] or in one of the nmore further ranges [lo_more[i], hi_more[i]] (IN lists, <>);
+ *              kind 1: t cmp u, cmp = VDL_CMP_*;  evaluated in order, the first failure rejects the row */
 #define VDL_MAX_LEAVES 24
 #define VDL_MAX_PROBE_PREDS 12
 #define VDL_MAX_EMITS 8
+#define VDL_MAX_INDICATORS 4
+#define VDL_MAX_MORE_RANGES 3
+enum { VDL_CMP_EQ = 0, VDL_CMP_NE, VDL_CMP_GT, VDL_CMP_GE, VDL_CMP_LT, VDL_CMP_LE };
 typedef struct { vdl_vec column; int32_t parent; } vdl_leaf;
 typedef struct { int32_t leaf, shr; int64_t a, b; } vdl_term;
-typedef struct { int32_t kind, pad; vdl_term t, u; int64_t lo, hi; } vdl_probe_pred;
+typedef struct {
+  int32_t kind, cmp;
+  vdl_term t, u;
+  int64_t lo, hi;
+  int32_t nmore, pad;
+  int64_t lo_more[VDL_MAX_MORE_RANGES], hi_more[VDL_MAX_MORE_RANGES];
+} vdl_probe_pred;
 typedef struct { int32_t nfactors, pad; vdl_term factor[VDL_MAX_FACTORS]; } vdl_product;
 typedef struct { int32_t op, pad; vdl_product value; } vdl_probe_fold;       /* op: VDL_FOLD_* */
 typedef struct {
@@ -251,6 +262,8 @@ typedef struct {
   vdl_post_op post[VDL_MAX_POSTS];
   /* emit mode (nemits > 0): one dense int64 vector per expression, surviving rows in ascending row order */
   vdl_product emit[VDL_MAX_EMITS];
+  int32_t nindicators, pad2;
+  vdl_probe_pred indicator[VDL_MAX_INDICATORS];   /* predicates used as 0/1 values (their terms may not be indicators) */
 } vdl_probe_desc;
 typedef struct vdl_probe vdl_probe;
 int vdl_abi_sizeof_probe_desc(void);

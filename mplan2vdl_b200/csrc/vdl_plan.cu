@@ -641,7 +641,7 @@ bool try_probe_fold(vdl_plan *p, int ni) {
   } else {
     return false;
   }
-  if (space < 0 || j_is_base(J, space)) return false;  // single-table scans belong to the TMA-staged fused scan
+  if (space < 0) return false;   // (single-table Folds reach this point only when the TMA-staged fused scan could not express them)
   ProbeFoldGroup *g = nullptr;
   for (auto *q : p->pgroups) if (q->space == space && q->keynode == keynode) g = q;
   bool fresh = !g;
@@ -652,10 +652,8 @@ bool try_probe_fold(vdl_plan *p, int ni) {
     if (keynode >= 0) {
       const JSym K = janalyse(p, J, keynode);
       g->b.desc.nkeys = (int)K.fac.size();
-      for (size_t i = 0; i < K.fac.size(); i++) {
-        if (K.fac[i].leaf >= 0 && !pb_rooted(p, J, K.fac[i].leaf, J.spaces[space].table)) { delete g; return false; }
-        if (!pb_term(J, &g->b, K.fac[i], &g->b.desc.key[i])) { delete g; return false; }
-      }
+      for (size_t i = 0; i < K.fac.size(); i++)
+        if (!pb_term(p, J, &g->b, K.fac[i], J.spaces[space].table, &g->b.desc.key[i])) { delete g; return false; }
       g->b.desc.key_mask = K.mask;
       g->b.desc.domain = K.mask + 1;
     }
@@ -669,8 +667,7 @@ bool try_probe_fold(vdl_plan *p, int ni) {
     bool ones = value.fac.size() == 1 && value.fac[0].leaf == -1 && value.fac[0].a == 1;
     if (n.sub == VDL_FOLD_SUM && ones) spec.op = VDL_FOLD_COUNT;
     else {
-      for (auto &t : value.fac) if (t.leaf >= 0 && !pb_rooted(p, J, t.leaf, J.spaces[space].table)) ok = false;
-      ok = ok && pb_product(J, &g->b, value.fac, &spec.value);
+      ok = pb_product(p, J, &g->b, value.fac, J.spaces[space].table, &spec.value);
     }
   }
   int fi = -1;
@@ -712,7 +709,7 @@ void mark_emits(vdl_plan *p, int ni, std::vector<char> &seen) {
       if (fresh) { g = new EmitGroup(); g->space = z.space; if (!pb_init(p, J, z.space, &g->b)) { delete g; g = nullptr; } }
       if (g) {
         ProbeBuild saved = g->b;
-        if (pb_product(J, &g->b, z.fac, &g->b.desc.emit[g->b.desc.nemits])) {
+        if (pb_product(p, J, &g->b, z.fac, J.spaces[z.space].table, &g->b.desc.emit[g->b.desc.nemits])) {
           if (fresh) p->egroups.push_back(g);
           for (size_t i = 0; i < p->egroups.size(); i++) if (p->egroups[i] == g) p->egroup_of_node[ni] = (int)i;
           p->eslot_of_node[ni] = g->b.desc.nemits++;

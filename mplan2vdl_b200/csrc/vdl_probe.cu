@@ -40,7 +40,7 @@
 
 struct PLeaf { const void *ptr; i64 len; int32_t w4, parent; };
 struct PTerm { int32_t leaf, shr; i64 a, b; };             // leaf -1: constant a; -2: global row id
-struct PPred { int32_t kind, pad; PTerm t, u; i64 lo; u64 span; };
+struct PPred { int32_t kind, cmp; PTerm t, u; i64 lo; u64 span; int32_t nmore, pad; i64 lo_more[VDL_MAX_MORE_RANGES]; u64 span_more[VDL_MAX_MORE_RANGES]; };
 struct PProd { int32_t nfac, pad; PTerm f[VDL_MAX_FACTORS]; };
 
 struct PDesc {
@@ -53,6 +53,8 @@ struct PDesc {
   int32_t fold_op[VDL_MAX_AGGS];
   PProd fold[VDL_MAX_AGGS];
   PProd emit[VDL_MAX_EMITS];
+  int32_t nind, pad2;
+  PPred ind[VDL_MAX_INDICATORS];
   i64 *table;                       // fold mode: [nfolds + 2][domain]: fold accumulators, row count, first row
   i64 *emit_out[VDL_MAX_EMITS];     // emit mode: dense output vectors (capacity rows)
   unsigned long long *tile_state;   // emit mode look-back: (status << 62) | count; status 1 = tile aggregate, 2 = inclusive prefix
@@ -94,11 +96,37 @@ __device__ __forceinline__ i64 leaf_value(const PDesc &d, int l, i64 row, bool &
   }
   return idx;
 }
-__device__ __forceinline__ i64 term_value(const PDesc &d, const PTerm &t, i64 row, bool &ok) {
+__device__ __forceinline__ i64 plain_term_value(const PDesc &d, const PTerm &t, i64 row, bool &ok) {
   if (t.leaf == -1) return t.a;
   i64 v = t.leaf == -2 ? d.row_base + row : leaf_value(d, t.leaf, row, ok);
   if (t.shr) v >>= t.shr;
   return (i64)((u64)t.a + (u64)t.b * (u64)v);
+}
+// does predicate P hold at the row?  (its terms are plain: no indicators inside predicates)
+__device__ __forceinline__ bool pred_holds(const PDesc &d, const PPred &P, i64 row, bool &ok) {
+  const i64 t = plain_term_value(d, P.t, row, ok);
+  if (P.kind == 0) {
+    if ((u64)t - (u64)P.lo <= P.span) return true;
+    for (int k = 0; k < P.nmore; k++)
+      if ((u64)t - (u64)P.lo_more[k] <= P.span_more[k]) return true;
+    return false;
+  }
+  const i64 u = plain_term_value(d, P.u, row, ok);
+  switch (P.cmp) {
+    case VDL_CMP_EQ: return t == u;
+    case VDL_CMP_NE: return t != u;
+    case VDL_CMP_GT: return t > u;
+    case VDL_CMP_GE: return t >= u;
+    case VDL_CMP_LT: return t < u;
+    default: return t <= u;
+  }
+}
+__device__ __forceinline__ i64 term_value(const PDesc &d, const PTerm &t, i64 row, bool &ok) {
+  if (t.leaf <= -3) {                       // indicator of a predicate as a 0/1 value
+    const i64 v = pred_holds(d, d.ind[-3 - t.leaf], row, ok) ? 1 : 0;
+    return (i64)((u64)t.a + (u64)t.b * (u64)v);
+  }
+  return plain_term_value(d, t, row, ok);
 }
 __device__ __forceinline__ i64 prod_value(const PDesc &d, const PProd &p, i64 row, bool &ok) {
   i64 v = 1;
@@ -107,15 +135,7 @@ __device__ __forceinline__ i64 prod_value(const PDesc &d, const PProd &p, i64 ro
 }
 __device__ __forceinline__ bool row_passes(const PDesc &d, i64 row, bool &ok) {
   for (int q = 0; q < d.npreds; q++) {
-    const PPred &P = d.pred[q];
-    i64 t = term_value(d, P.t, row, ok);
-    if (!ok) return false;
-    if (P.kind == 0) {
-      if ((u64)t - (u64)P.lo > P.span) return false;
-    } else {
-      i64 u = term_value(d, P.u, row, ok);
-      if (!ok || t != u) return false;
-    }
+    if (!pred_holds(d, d.pred[q], row, ok) || !ok) return false;
   }
   return true;
 }
@@ -186,7 +206,7 @@ __global__ void __launch_bounds__(P_THREADS, 8) probe_kernel(const __grid_consta
       // the chain of this stage's term, if it has the fast form
       StageRegs S;
       S.depth = -1;
-      if (P.kind == 0 && P.t.leaf != -1) {
+      if (P.kind == 0 && P.nmore == 0 && P.t.leaf != -1) {
         int l = P.t.leaf, n = 0;
         S.w4mask = 0;
 #pragma unroll
@@ -220,16 +240,9 @@ __global__ void __launch_bounds__(P_THREADS, 8) probe_kernel(const __grid_consta
         } else if (S.depth == 3) { STAGE_CASE(3, false);
         } else if (S.depth == 4) { STAGE_CASE(4, false);
         } else if (S.depth == 0 || S.depth == 8) { STAGE_CASE(0, false);
-        } else {      // generic: constants, column == column, deeper chains
+        } else {      // generic: constants, column-vs-column comparisons, range sets, deeper chains
 #pragma unroll 1
-          for (int k = 0; k < P_SUB; k++) {
-            f[k] = false;
-            if (r[k] < 0) continue;
-            const i64 row = base + r[k];
-            i64 t = term_value(d, P.t, row, ok);
-            if (P.kind == 0) f[k] = (u64)t - (u64)P.lo <= P.span;
-            else f[k] = t == term_value(d, P.u, row, ok);
-          }
+          for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && pred_holds(d, P, base + r[k], ok);
         }
         // ordered append of the survivors of this round: (sub-round, warp, lane) order = queue order.  The P_SUB x 8
         // per-warp counts are scanned by every warp for itself with shuffles (lane = sub-round * 8 + warp).
@@ -422,7 +435,7 @@ struct vdl_probe {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
-static bool term_ok(const vdl_term &t, int nleaves) { return t.leaf >= -2 && t.leaf < nleaves && t.shr >= 0 && t.shr < 64; }
+static bool term_ok(const vdl_term &t, int nleaves, int nind = 0) { return t.leaf >= -2 - nind && t.leaf < nleaves && t.shr >= 0 && t.shr < 64; }
 static PTerm to_p(const vdl_term &t) { return PTerm{t.leaf, t.shr, t.a, t.b}; }
 
 extern "C" int vdl_abi_sizeof_probe_desc(void) { return (int)sizeof(vdl_probe_desc); }
@@ -457,26 +470,42 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
     if (depth > P_MAX_DEPTH) return fail(vdl_fail(ctx, VDL_EUNSUPPORTED, "probe: lookup chain deeper than %d", P_MAX_DEPTH));
     d.leaf[l] = PLeaf{v->ptr, v->len, v->dtype == VDL_I32, par};
   }
+  auto to_pred = [&](const vdl_probe_pred &s, PPred *o) -> bool {
+    if ((s.kind != 0 && s.kind != 1) || !term_ok(s.t, desc->nleaves) || (s.kind == 1 && (!term_ok(s.u, desc->nleaves) || s.cmp < VDL_CMP_EQ || s.cmp > VDL_CMP_LE)) ||
+        s.nmore < 0 || s.nmore > VDL_MAX_MORE_RANGES)
+      return false;
+    memset(o, 0, sizeof *o);
+    o->kind = s.kind; o->cmp = s.cmp; o->t = to_p(s.t); o->u = to_p(s.u);
+    if (s.kind == 0) {
+      // empty ranges are dropped; no range left: never true (0 in [1, 1])
+      i64 lo[1 + VDL_MAX_MORE_RANGES], hi[1 + VDL_MAX_MORE_RANGES];
+      int n = 0;
+      if (s.lo <= s.hi) { lo[n] = s.lo; hi[n++] = s.hi; }
+      for (int k = 0; k < s.nmore; k++) if (s.lo_more[k] <= s.hi_more[k]) { lo[n] = s.lo_more[k]; hi[n++] = s.hi_more[k]; }
+      if (n == 0) { o->t = PTerm{-1, 0, 0, 0}; o->lo = 1; o->span = 0; return true; }
+      o->lo = lo[0]; o->span = (u64)hi[0] - (u64)lo[0];
+      o->nmore = n - 1;
+      for (int k = 1; k < n; k++) { o->lo_more[k - 1] = lo[k]; o->span_more[k - 1] = (u64)hi[k] - (u64)lo[k]; }
+    }
+    return true;
+  };
   d.npreds = desc->npreds;
-  for (int q = 0; q < desc->npreds; q++) {
-    const vdl_probe_pred &s = desc->pred[q];
-    if (!term_ok(s.t, desc->nleaves) || (s.kind == 1 && !term_ok(s.u, desc->nleaves)) || (s.kind != 0 && s.kind != 1))
-      return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad predicate %d", q));
-    PPred &o = d.pred[q];
-    o.kind = s.kind; o.t = to_p(s.t); o.u = to_p(s.u);
-    if (s.kind == 0 && s.lo > s.hi) { o.lo = 1; o.span = 0; o.t = PTerm{-1, 0, 0, 0}; }    // never true: 0 in [1, 1]
-    else { o.lo = s.lo; o.span = (u64)s.hi - (u64)s.lo; }
-  }
+  for (int q = 0; q < desc->npreds; q++)
+    if (!to_pred(desc->pred[q], &d.pred[q])) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad predicate %d", q));
+  if (desc->nindicators < 0 || desc->nindicators > VDL_MAX_INDICATORS) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: %d indicators", desc->nindicators));
+  d.nind = desc->nindicators;
+  for (int q = 0; q < desc->nindicators; q++)
+    if (!to_pred(desc->indicator[q], &d.ind[q])) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad indicator %d", q));
   d.nkeys = desc->nkeys;
   for (int q = 0; q < desc->nkeys; q++) {
-    if (!term_ok(desc->key[q], desc->nleaves) || desc->key_shl[q] < 0 || desc->key_shl[q] > 63) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad key part %d", q));
+    if (!term_ok(desc->key[q], desc->nleaves, desc->nindicators) || desc->key_shl[q] < 0 || desc->key_shl[q] > 63) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad key part %d", q));
     d.key[q] = to_p(desc->key[q]);
     d.key_shl[q] = desc->key_shl[q];
   }
   auto prod = [&](const vdl_product &s, PProd *o) {
     if (s.nfactors < 0 || s.nfactors > VDL_MAX_FACTORS) return false;
     o->nfac = s.nfactors;
-    for (int t = 0; t < s.nfactors; t++) { if (!term_ok(s.factor[t], desc->nleaves)) return false; o->f[t] = to_p(s.factor[t]); }
+    for (int t = 0; t < s.nfactors; t++) { if (!term_ok(s.factor[t], desc->nleaves, desc->nindicators)) return false; o->f[t] = to_p(s.factor[t]); }
     return true;
   };
   p->folding = desc->nfolds > 0;

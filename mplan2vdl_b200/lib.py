@@ -54,7 +54,7 @@ class FusedDesc(C.Structure):
                 ("nposts", C.c_int32), ("post", PostOp * VDL_MAX_POSTS)]
 
 
-VDL_MAX_LEAVES, VDL_MAX_PROBE_PREDS, VDL_MAX_EMITS = 24, 12, 8
+VDL_MAX_LEAVES, VDL_MAX_PROBE_PREDS, VDL_MAX_EMITS, VDL_MAX_INDICATORS, VDL_MAX_MORE_RANGES = 24, 12, 8, 4, 3
 
 
 class Leaf(C.Structure):
@@ -66,7 +66,8 @@ class Term(C.Structure):
 
 
 class ProbePred(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("pad", C.c_int32), ("t", Term), ("u", Term), ("lo", C.c_int64), ("hi", C.c_int64)]
+    _fields_ = [("kind", C.c_int32), ("cmp", C.c_int32), ("t", Term), ("u", Term), ("lo", C.c_int64), ("hi", C.c_int64),
+                ("nmore", C.c_int32), ("pad", C.c_int32), ("lo_more", C.c_int64 * VDL_MAX_MORE_RANGES), ("hi_more", C.c_int64 * VDL_MAX_MORE_RANGES)]
 
 
 class Product(C.Structure):
@@ -82,7 +83,8 @@ class ProbeDesc(C.Structure):
                 ("leaf", Leaf * VDL_MAX_LEAVES), ("pred", ProbePred * VDL_MAX_PROBE_PREDS),
                 ("nkeys", C.c_int32), ("nfolds", C.c_int32), ("key", Term * VDL_MAX_KEYS), ("key_shl", C.c_int32 * VDL_MAX_KEYS),
                 ("key_mask", C.c_int64), ("domain", C.c_int64), ("fold", ProbeFold * VDL_MAX_AGGS),
-                ("nposts", C.c_int32), ("nemits", C.c_int32), ("post", PostOp * VDL_MAX_POSTS), ("emit", Product * VDL_MAX_EMITS)]
+                ("nposts", C.c_int32), ("nemits", C.c_int32), ("post", PostOp * VDL_MAX_POSTS), ("emit", Product * VDL_MAX_EMITS),
+                ("nindicators", C.c_int32), ("pad2", C.c_int32), ("indicator", ProbePred * VDL_MAX_INDICATORS)]
 
 
 # every symbol include/vdl_cuda.h declares: (name, restype, argtypes)

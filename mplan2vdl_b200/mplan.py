@@ -15,7 +15,7 @@ import datetime
 import re
 import sys
 
-from .vlite import Bin, Cast, GroupBy, Join, Lit, Project, Ref, Select, Table
+from .vlite import Bin, Cast, GroupBy, IfThenElse, In, Join, Lit, Project, Ref, Select, Table, Unary
 
 DATE = ("date",)
 
@@ -144,8 +144,13 @@ class Parser:
         if self.at("as"):
             self.take("as")
             alias = self.qname()
-        if self.peek()[1] in ("FILTER", "in", "notin", "!"):
-            raise NotImplementedError(f"mplan: {self.peek()[1]} expressions (Like / IN) are outside the executor's scope")
+        if self.at("in"):                                  # InExpr (Parser.y:207-209)
+            self.take("in"); self.take("(")
+            items = self.expr_list(")")
+            self.take(")")
+            return (("in", (e, alias), items), None)
+        if self.peek()[1] in ("FILTER", "notin", "!"):
+            raise NotImplementedError(f"mplan: {self.peek()[1]} expressions (Like / NOT IN) are outside the executor's scope")
         return (e, alias)
 
     def attrs(self):
@@ -263,9 +268,19 @@ class Front:
         if kind == "interval":                              # Mplan.hs:498-512
             a, m, b = self.sc(node[1][0]), self.sc(node[3][0]), self.sc(node[5][0])
             return Bin("LogAnd", Bin(INFIX[node[2]], a, m), Bin(INFIX[node[4]], m, b))
+        if kind == "in":                                    # Mplan.hs:514-522 (column IN literal list only)
+            (lnode, _), items = node[1], node[2]
+            if lnode[0] != "ref":
+                raise NotImplementedError("implement this case of IN operator (Mplan.hs:522)")
+            newctx = self._dtype_of_ref(lnode[1])
+            return In(Ref(lnode[1]), [self.sc(e, newctx) for e, _ in items])
         if kind == "call":
             fname, args = node[1], node[2]
             base = fname.split(".")[-1]
+            if base == "ifthenelse" and len(args) == 3:         # Mplan.hs:441-451
+                return IfThenElse(*(self.sc(a, ctx) for a, _ in args))
+            if len(args) == 1 and base in ("year", "sql_neg", "isnull"):      # Mplan.hs:106-112, 420-424
+                return Unary({"year": "Year", "sql_neg": "Neg", "isnull": "IsNull"}[base], self.sc(args[0][0], ctx))
             if len(args) == 2:
                 (x, _), (y, _) = args
                 # date +/- interval folded into a date literal (Mplan.hs:368-388)
@@ -283,7 +298,7 @@ class Front:
                 l = self.sc(x)
                 newctx = self._dtype_of_ref(l.name) if isinstance(l, Ref) else None
                 return Bin(BINFUN[base], l, self.sc(y, newctx))
-            raise NotImplementedError(f"mplan scalar function {fname}/{len(args)} (year, like, ifthenelse, identity ... are outside the executor's scope)")
+            raise NotImplementedError(f"mplan scalar function {fname}/{len(args)} (like, identity ... are outside the executor's scope)")
         raise NotImplementedError(f"mplan scalar {kind}")
 
     def conjunction(self, exprs):                           # Mplan.hs:549-559

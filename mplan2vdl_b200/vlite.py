@@ -194,6 +194,25 @@ class Cast:                 # only decimal->decimal casts change the representat
 
 
 @dataclass
+class In:                   # Mplan.hs:126
+    left: object
+    set: list
+
+
+@dataclass
+class IfThenElse:           # Mplan.hs:124
+    if_: object
+    then_: object
+    else_: object
+
+
+@dataclass
+class Unary:                # Mplan.hs:101-104, 122: op in Year | Neg | IsNull
+    op: str
+    arg: object
+
+
+@dataclass
 class Table:
     name: str
     columns: list           # [(column, alias or None)]  (JOINIDX columns: (fk index column, "%alias"), Mplan.hs:240-251)
@@ -291,6 +310,30 @@ class Lowering:
             return out.replace(dtype=("dec", e.point))
         if isinstance(e, Bin):
             return binop(e.op, self.sc(env, e.left), self.sc(env, e.right))
+        if isinstance(e, In):                              # 972-980: (s1 == x) || (s2 == x) || ...
+            x = self.sc(env, e.left)
+            eqs = [binop("Eq", self.sc(env, s), x) for s in e.set]
+            if not eqs:
+                raise ValueError("list is empty here")
+            out = eqs[0]
+            for q in eqs[1:]:
+                out = binop("LogOr", out, q)
+            return out
+        if isinstance(e, IfThenElse):
+            # 1001: ifthenelse(isnull(p), false, p) guards a predicate that is statically not null -> p
+            if isinstance(e.if_, Unary) and e.if_.op == "IsNull" and isinstance(e.then_, Lit) and e.then_.n == 0 and e.if_.arg == e.else_:
+                return self.sc(env, e.if_.arg)
+            cond, a, b = self.sc(env, e.if_), self.sc(env, e.then_), self.sc(env, e.else_)     # 1005-1009, `?.` 237-245
+            negcond = binop("Eq", cond, zeros_(cond))
+            poscond = binop("Sub", ones_(cond), negcond)
+            return binop("Add", binop("Mul", poscond, a), binop("Mul", negcond, b))
+        if isinstance(e, Unary):
+            x = self.sc(env, e.arg)
+            if e.op == "Year":                             # 988-994: ((days * 1000) + 1100) / 365243 (all operators infixl 9: G12)
+                return binop("Div", binop("Add", binop("Mul", x, const_(1000, x)), const_(1100, x)), const_(365243, x))
+            if e.op == "Neg":                              # 1016-1018
+                return binop("Sub", ones_(x), x)
+            raise NotImplementedError(f"unary {e.op}")
         raise NotImplementedError(e)
 
     # ---- relational operators: solve' (Vlite.hs:570-732) ----------------------------------------

@@ -94,3 +94,17 @@ def q5(c: dict) -> dict:
         rev = c["lineitem.l_extendedprice"][m] * (100 - c["lineitem.l_discount"][m])
     names = np.unique(name)
     return {"n_name__nation__n_name": names, "revenue": np.array([rev[name == n].sum(dtype=np.int64) for n in names], dtype=np.int64)}
+
+
+def q12(c: dict) -> dict:
+    """12.sql.mplan: per ship mode (MAIL = 40, SHIP = 160: dictionary.csv:86,89), lines received in 1994 that were
+    committed late, split by order priority 1-URGENT / 2-HIGH (40 / 104: dictionary.csv:78-79) vs the rest."""
+    L = lambda n: c["lineitem." + n]       # noqa: E731
+    sel = (L("l_shipdate") < L("l_commitdate")) & (L("l_commitdate") < L("l_receiptdate")) & (L("l_receiptdate") >= 728294) & \
+          (L("l_receiptdate") < 728659) & ((L("l_shipmode") == 40) | (L("l_shipmode") == 160))
+    prio = c["orders.o_orderpriority"][L("lineitem_orders")]
+    high = (prio == 40) | (prio == 104)
+    modes = np.unique(L("l_shipmode")[sel]).astype(np.int64)
+    return {"l_shipmode__lineitem__l_shipmode": modes,
+            "high_line_count": np.array([int((sel & high & (L("l_shipmode") == m)).sum()) for m in modes], dtype=np.int64),
+            "low_line_count": np.array([int((sel & ~high & (L("l_shipmode") == m)).sum()) for m in modes], dtype=np.int64)}

@@ -125,7 +125,7 @@ def test_q6_full_size_linearity(catalog):
     ctx.close()
 
 
-@pytest.mark.parametrize("q", ["q03.vdl", "q05.vdl"])
+@pytest.mark.parametrize("q", ["q03.vdl", "q05.vdl", "q12.vdl"])
 @pytest.mark.parametrize("sf", [0.002, 0.02])
 def test_fk_join_plans_parity(catalog, q, sf):
     """BASELINE config 3: the FK-join plans (Gather through join-index columns, Scatter-built validity / inverse
@@ -136,7 +136,10 @@ def test_fk_join_plans_parity(catalog, q, sf):
     want = run_oracle(text, cols)
     got, stats = run_gpu(text, cols)
     assert_same(got, want)
-    assert len(next(iter(want.values()))) > 0
+    assert stats["probe_folds"] + stats["probe_emits"] >= 1        # the join chain runs on the probe kernel
+    got_u, _ = run_gpu(text, cols, fuse=False)
+    assert_same(got_u, want)
+    assert len(next(iter(want.values()))) > 0 or q == "q12.vdl"   # (Q12 selects ~0.1 % of the rows: may be empty at SF 0.002)
 
 
 def test_cli_prints_the_server_json_and_the_decoded_csv():

@@ -27,7 +27,7 @@ def test_checked_in_join_plans_are_what_the_restatement_generates(catalog, q):
     assert vlite.translate(catalog, tpch_queries.QUERIES[q](catalog)) == plan_text(q + ".vdl")
 
 
-@pytest.mark.parametrize("q,ref", [("q03", sqlref.q3), ("q05", sqlref.q5)])
+@pytest.mark.parametrize("q,ref", [("q03", sqlref.q3), ("q05", sqlref.q5), ("q12", sqlref.q12)])
 @pytest.mark.parametrize("sf", [0.002, 0.01])
 def test_join_plans_oracle_matches_sql(catalog, q, ref, sf):
     text = plan_text(q + ".vdl")
