@@ -31,6 +31,7 @@ QUERIES = {
     "q03": ("q03.vdl", None),
     "q05": ("q05.vdl", None),
     "q12": ("q12.vdl", None),
+    "q19": ("q19.vdl", None),
 }
 
 

@@ -90,6 +90,10 @@ def infer_bounds(binop: str, l: Vexp, r: Vexp) -> tuple:      # Vlite.hs:417-467
         return (min(d), max(d))
     if binop == "Mod":
         return (0, u2 - 1)
+    if binop == "Min":
+        return (min(l1, l2), min(u1, u2))
+    if binop == "Max":
+        return (max(l1, l2), max(u1, u2))
     if binop == "BitAnd":
         return (0, min(max_for_width(l), max_for_width(r))) if l1 >= 0 and l2 >= 0 else (I64_MIN, I64_MAX)
     if binop == "BitOr":
@@ -323,10 +327,7 @@ class Lowering:
             # 1001: ifthenelse(isnull(p), false, p) guards a predicate that is statically not null -> p
             if isinstance(e.if_, Unary) and e.if_.op == "IsNull" and isinstance(e.then_, Lit) and e.then_.n == 0 and e.if_.arg == e.else_:
                 return self.sc(env, e.if_.arg)
-            cond, a, b = self.sc(env, e.if_), self.sc(env, e.then_), self.sc(env, e.else_)     # 1005-1009, `?.` 237-245
-            negcond = binop("Eq", cond, zeros_(cond))
-            poscond = binop("Sub", ones_(cond), negcond)
-            return binop("Add", binop("Mul", poscond, a), binop("Mul", negcond, b))
+            return select_arith(self.sc(env, e.if_), self.sc(env, e.then_), self.sc(env, e.else_))     # 1005-1009
         if isinstance(e, Unary):
             x = self.sc(env, e.arg)
             if e.op == "Year":                             # 988-994: ((days * 1000) + 1100) / 365243 (all operators infixl 9: G12)
@@ -523,9 +524,19 @@ def algebraic_identities(op, args, params):               # 1301-1331
     return None
 
 
-def lowering(op, args, params):                            # 1333-1340 (Neq only; Min/Max are not needed here)
+def select_arith(cond, a, b):                             # `?.` (Vlite.hs:237-245): make the condition boolean, then blend
+    negcond = binop("Eq", cond, zeros_(cond))
+    poscond = binop("Sub", ones_(cond), negcond)
+    return binop("Add", binop("Mul", poscond, a), binop("Mul", negcond, b))
+
+
+def lowering(op, args, params):                            # 1333-1340
     if op == "Binop" and params == ("Neq",):
         return binop("Sub", ones_(args[0]), binop("Eq", args[0], args[1]))
+    if op == "Binop" and params == ("Max",):
+        return select_arith(binop("Gt", args[0], args[1]), args[0], args[1])
+    if op == "Binop" and params == ("Min",):
+        return select_arith(binop("Lt", args[0], args[1]), args[0], args[1])
     return None
 
 

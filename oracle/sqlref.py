@@ -108,3 +108,29 @@ def q12(c: dict) -> dict:
     return {"l_shipmode__lineitem__l_shipmode": modes,
             "high_line_count": np.array([int((sel & high & (L("l_shipmode") == m)).sum()) for m in modes], dtype=np.int64),
             "low_line_count": np.array([int((sel & ~high & (L("l_shipmode") == m)).sum()) for m in modes], dtype=np.int64)}
+
+
+def q19(c: dict, dictionary: dict) -> dict:
+    """19.sql.mplan: discounted revenue of lineitems delivered in person by air whose part matches one of three
+    (brand, container set, quantity range, size range) combinations."""
+    D = dictionary
+    L = lambda n: c["lineitem." + n]                              # noqa: E731
+    P = lambda n: c["part." + n][L("lineitem_part")]              # noqa: E731
+
+    def inset(x, col, names):
+        m = np.zeros(len(x), bool)
+        for n in names:
+            m |= x == D[col][n]
+        return m
+    q, size, brand, cont = L("l_quantity"), P("p_size"), P("p_brand"), P("p_container")
+    base = (L("l_shipinstruct") == D["lineitem.l_shipinstruct"]["DELIVER IN PERSON"]) & inset(L("l_shipmode"), "lineitem.l_shipmode", ["AIR", "AIR REG"])
+    sm, med, lg = ["SM CASE", "SM BOX", "SM PACK", "SM PKG"], ["MED BAG", "MED BOX", "MED PKG", "MED PACK"], ["LG CASE", "LG BOX", "LG PACK", "LG PKG"]
+    pb = (size >= 1) & (size <= 15) & inset(brand, "part.p_brand", ["Brand#12", "Brand#23", "Brand#34"]) & inset(cont, "part.p_container", sm + med + lg)
+    c1 = (brand == D["part.p_brand"]["Brand#12"]) & inset(cont, "part.p_container", sm) & (q >= 100) & (q <= 1100) & (size >= 1) & (size <= 5)
+    c2 = (brand == D["part.p_brand"]["Brand#23"]) & inset(cont, "part.p_container", med) & (q >= 1000) & (q <= 2000) & (size >= 1) & (size <= 10)
+    c3 = (brand == D["part.p_brand"]["Brand#34"]) & inset(cont, "part.p_container", lg) & (q >= 2000) & (q <= 3000) & (size >= 1) & (size <= 15)
+    m = base & pb & (c1 | c2 | c3)
+    if not m.any():
+        return {"revenue": np.zeros(0, np.int64)}
+    with np.errstate(over="ignore"):
+        return {"revenue": np.array([(L("l_extendedprice")[m] * (100 - L("l_discount")[m])).sum(dtype=np.int64)], dtype=np.int64)}

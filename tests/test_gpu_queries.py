@@ -156,3 +156,16 @@ def test_cli_prints_the_server_json_and_the_decoded_csv():
     csv = subprocess.run([sys.executable, "-m", "mplan2vdl_b200", "-", "--sf", "0.01", "--csv"], cwd=root, input=open(plan).read(),
                          capture_output=True, text=True, check=True).stdout.splitlines()
     assert csv[0] == "n_name,revenue" and len(csv) == 1 + len(doc["results"]["tmp1"][".revenue"])
+
+
+def test_q19_parity(catalog):
+    """Q19: the OR of three conjunctions does not normalise to a conjunct, so the plan mixes the probe kernel (the
+    join below the OR) with op-at-a-time evaluation above it; fused, unfused and oracle agree."""
+    from util import q19_columns
+    text, cols = q19_columns(catalog, sf=0.02)
+    want = run_oracle(text, cols)
+    assert len(want["revenue"]) == 1
+    got, stats = run_gpu(text, cols)
+    assert_same(got, want)
+    got_u, _ = run_gpu(text, cols, fuse=False)
+    assert_same(got_u, want)

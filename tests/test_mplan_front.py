@@ -12,7 +12,7 @@ needs_reference = pytest.mark.skipif(not os.path.isdir(FIXTURES), reason="refere
 
 
 @needs_reference
-@pytest.mark.parametrize("n,plan", [("06", "q06.vdl"), ("03", "q03.vdl"), ("05", "q05.vdl"), ("12", "q12.vdl")])
+@pytest.mark.parametrize("n,plan", [("06", "q06.vdl"), ("03", "q03.vdl"), ("05", "q05.vdl"), ("12", "q12.vdl"), ("19", "q19.vdl")])
 def test_reference_fixture_translates_to_the_checked_in_program(catalog, n, plan):
     text = open(os.path.join(FIXTURES, f"{n}.sql.mplan")).read()
     assert mplan.translate_mplan(catalog, text) == plan_text(plan)      # q06.vdl is pinned by the reference README

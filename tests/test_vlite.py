@@ -47,3 +47,12 @@ def test_bounds_inference_and_key_packing(catalog):
     sp, od = low.load_as("orders", "orders.o_shippriority", None), low.load_as("orders", "orders.o_orderdate", None)
     assert vlite.get_bit_width(low.make_composite_key([ok, sp, od])) == 38
     assert tpch_queries.day(1994, 1, 1) == 728294 and tpch_queries.day(1995, 3, 15) == 728732 and tpch_queries.day(1998, 9, 2) == 729999
+
+
+def test_q19_oracle_matches_sql(catalog):
+    """Q19 from the reference fixture (IN lists, sql_min / sql_max, an OR of three conjunctions over a join)."""
+    from util import q19_columns
+    text, cols = q19_columns(catalog)
+    got = run_oracle(text, cols)
+    assert_same(got, sqlref.q19(cols, catalog.dictionary))
+    assert len(got["revenue"]) == 1

@@ -63,3 +63,25 @@ def run_gpu(plan, cols, fuse=True, ctx=None):
     finally:
         if own:
             ctx.close()
+
+
+def q19_columns(cat, sf=0.01, seed=19):
+    """Synthetic tables for Q19 with the string-coded columns redrawn from the codes the query mentions (plus a few
+    others), so that its very selective predicate keeps some rows (the uniform recipe over [min, max] almost never
+    hits 'DELIVER IN PERSON' x 'AIR' x three brands x twelve containers)."""
+    from mplan2vdl_b200 import tpch
+    text = plan_text("q19.vdl")
+    rows = {t: synth.table_rows(cat, t, sf) for t in cat.tables}
+    cols = host_columns(cat, tpch.plan_columns(text), rows, sf=sf)
+    rng = np.random.default_rng(seed)
+    D = cat.dictionary
+
+    def draw(col, names, extra, n):
+        codes = [D[col][x] for x in names] + extra
+        return np.array(codes, dtype=np.int64)[rng.integers(0, len(codes), n)]
+    n, npart = rows["lineitem"], rows["part"]
+    cols["lineitem.l_shipinstruct"] = draw("lineitem.l_shipinstruct", ["DELIVER IN PERSON"], [24, 32], n)
+    cols["lineitem.l_shipmode"] = draw("lineitem.l_shipmode", ["AIR", "MAIL"], [16], n)
+    cols["part.p_brand"] = draw("part.p_brand", ["Brand#12", "Brand#23", "Brand#34"], [16, 32], npart)
+    cols["part.p_container"] = draw("part.p_container", ["SM CASE", "SM BOX", "MED BAG", "MED PKG", "LG CASE", "LG PKG", "SM PKG", "LG BOX"], [8], npart)
+    return text, cols
