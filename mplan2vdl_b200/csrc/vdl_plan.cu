@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -607,6 +608,7 @@ struct ProbeFoldGroup {
   int space = -1, keynode = -1;
   ProbeBuild b;
   std::map<int, int> fold_of_node;
+  std::map<int, int> post_of_node;      // Binary output node -> post op (evaluated by the probe's finalize kernel)
   vdl_probe *probe = nullptr;
   std::vector<vdl_vec> bound;
   i64 bound_rows = -1, bound_base = -1;
@@ -697,7 +699,7 @@ void mark_emits(vdl_plan *p, int ni, std::vector<char> &seen) {
   JoinAnalysis &J = *p->join;
   const Node &n = p->nodes[ni];
   if (n.op == N_FOLD && (p->group_of_node[ni] >= 0 || p->pgroup_of_node[ni] >= 0)) return;
-  if (n.op == N_BINARY && p->group_of_node[ni] >= 0) return;
+  if (n.op == N_BINARY && (p->group_of_node[ni] >= 0 || p->pgroup_of_node[ni] >= 0)) return;
   const JSym &z = janalyse(p, J, ni);
   if ((n.op == N_GATHER || n.op == N_BINARY) && z.kind == Z_VALUE && z.space >= 0 && !j_is_base(J, z.space) && !j_is_const(z)) {
     bool rooted = true;
@@ -824,8 +826,76 @@ int fuse(vdl_plan *p) {
     p->join->done.assign(nn, 0);
     std::vector<int> uses(nn, 0);
     for (auto &n : p->nodes) for (int a : {n.a, n.b, n.c}) if (a >= 0) uses[a]++;
+    // Folds may be consumed by OUTPUT expressions made of elementwise ops over Folds and constants (AVG's Divide):
+    // those become post ops of the probe's finalize kernel.  A Fold with any other consumer is not fused.
+    std::vector<int> post_refs(nn, 0), bin_refs(nn, 0);
+    std::vector<char> in_out_expr(nn, 0);
+    {
+      std::vector<int> stack;
+      for (auto &o : p->outputs) if (p->nodes[o.node].op == N_BINARY) stack.push_back(o.node);
+      while (!stack.empty()) {
+        int ni = stack.back(); stack.pop_back();
+        if (in_out_expr[ni]) continue;
+        in_out_expr[ni] = 1;
+        const Node &n = p->nodes[ni];
+        for (int a : {n.a, n.b}) {
+          if (a < 0) continue;
+          const Node &c = p->nodes[a];
+          if (c.op == N_FOLD) post_refs[a]++;
+          else if (c.op == N_BINARY) { stack.push_back(a); bin_refs[a]++; }
+          else if (c.op == N_RANGEV && c.k1 == 0 && c.a >= 0 && p->nodes[c.a].op == N_FOLD) post_refs[c.a]++;   // a constant as long as a Fold result
+        }
+      }
+    }
+    for (size_t i = 0; i < nn; i++)        // an inner node of an output expression that something else consumes too: no post ops in this plan
+      if (in_out_expr[i] && uses[i] != bin_refs[i]) { std::fill(post_refs.begin(), post_refs.end(), 0); break; }
     for (size_t i = 0; i < nn; i++)
-      if (p->nodes[i].op == N_FOLD && p->group_of_node[i] < 0 && uses[i] == 0) try_probe_fold(p, (int)i);
+      if (p->nodes[i].op == N_FOLD && p->group_of_node[i] < 0 && uses[i] == post_refs[i]) try_probe_fold(p, (int)i);
+    // outputs over probe Folds -> post ops; if one cannot be expressed, the Folds it needs fall back to op-at-a-time
+    std::function<int(int, int *, i64 *)> ppost = [&](int ni, int *gi, i64 *val) -> int {
+      const Node &n = p->nodes[ni];
+      if (n.op == N_FOLD) {
+        int g = p->pgroup_of_node[ni];
+        if (g < 0 || (*gi >= 0 && *gi != g)) return -1;
+        *gi = g; *val = p->pgroups[g]->fold_of_node[ni];
+        return VDL_POST_FOLD;
+      }
+      if (n.op == N_RANGEV && n.k1 == 0) { i64 d; if (ppost(n.a, gi, &d) < 0) return -1; *val = n.k0; return VDL_POST_CONST; }
+      if (n.op == N_BINARY) {
+        vdl_post_op op; memset(&op, 0, sizeof op);
+        op.op = n.sub;
+        int ka = ppost(n.a, gi, &op.a); if (ka < 0) return -1;
+        int kb = ppost(n.b, gi, &op.b); if (kb < 0 || *gi < 0) return -1;
+        op.a_kind = ka; op.b_kind = kb;
+        ProbeFoldGroup &g = *p->pgroups[*gi];
+        auto it = g.post_of_node.find(ni);
+        if (it != g.post_of_node.end()) { *val = it->second; return VDL_POST_POST; }
+        if (g.b.desc.nposts == VDL_MAX_POSTS) return -1;
+        g.b.desc.post[g.b.desc.nposts] = op;
+        g.post_of_node[ni] = g.b.desc.nposts;
+        *val = g.b.desc.nposts++;
+        return VDL_POST_POST;
+      }
+      return -1;
+    };
+    bool unfuse = false;
+    for (auto &o : p->outputs) {
+      if (p->nodes[o.node].op != N_BINARY) continue;
+      int gi = -1; i64 v;
+      if (ppost(o.node, &gi, &v) == VDL_POST_POST) p->pgroup_of_node[o.node] = gi;
+      else unfuse = true;       // some consumer of a fused Fold is not a post op: be safe, un-fuse every probe fold group
+    }
+    if (unfuse) {
+      bool any_needed = false;
+      for (size_t i = 0; i < nn; i++) if (p->nodes[i].op == N_FOLD && p->pgroup_of_node[i] >= 0 && post_refs[i] > 0) any_needed = true;
+      if (any_needed) {
+        for (auto *g : p->pgroups) delete g;
+        p->pgroups.clear();
+        std::fill(p->pgroup_of_node.begin(), p->pgroup_of_node.end(), -1);
+        for (size_t i = 0; i < nn; i++)            // keep the Folds nobody consumes
+          if (p->nodes[i].op == N_FOLD && p->group_of_node[i] < 0 && uses[i] == 0) try_probe_fold(p, (int)i);
+      }
+    }
     std::vector<char> seen(nn, 0);
     for (auto &o : p->outputs) mark_emits(p, o.node, seen);
   }
@@ -1125,7 +1195,8 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
     if (p->pgroup_of_node[o.node] >= 0) {   // a Fold over a joined space: the probe's result buffer is already on its way
       ProbeFoldGroup &g = *p->pgroups[p->pgroup_of_node[o.node]];
       const int64_t *data; int64_t len;
-      VDL_TRY(vdl_probe_result_host(g.probe, g.fold_of_node[o.node], &data, &len));
+      const int idx = p->nodes[o.node].op == N_FOLD ? g.fold_of_node[o.node] : g.b.desc.nfolds + g.post_of_node[o.node];
+      VDL_TRY(vdl_probe_result_host(g.probe, idx, &data, &len));
       o.data = data; o.len = len;
       continue;
     }

@@ -169,3 +169,24 @@ def test_q19_parity(catalog):
     assert_same(got, want)
     got_u, _ = run_gpu(text, cols, fuse=False)
     assert_same(got_u, want)
+
+
+def test_avg_over_a_join_is_a_post_op_of_the_probe(catalog):
+    """AVG = Divide(FoldSum x, FoldSum 1) (Vlite.hs:1038-1041) over a joined space: both Folds run in the one probe pass
+    and the Divide inside its finalize kernel -- no emitted vectors, no op-at-a-time tail."""
+    from mplan2vdl_b200 import tpch_queries as Q, vlite
+    from mplan2vdl_b200.vlite import Bin, Cast, GroupBy, Join, Lit, Project, Ref, Select, Table
+    orders = Select(Table("orders", [("orders.o_orderdate", None), ("orders.%TID%", None)]),
+                    Q.between(Lit(Q.DATE, Q.day(1994, 1, 1)), Ref("orders.o_orderdate"), Lit(Q.DATE, Q.day(1996, 1, 1))))
+    lineitem = Table("lineitem", Q.li("l_quantity", "l_returnflag") + [("lineitem.lineitem_orders", "lineitem.%lineitem_orders")])
+    j = Join(lineitem, orders, [Bin("Eq", Ref("lineitem.%lineitem_orders"), Ref("orders.%TID%"))])
+    g = GroupBy(j, [("lineitem.l_returnflag", None)], [(("FChoose", Ref("lineitem.l_returnflag")), None),
+                                                        (("Avg", Cast(None, Ref("lineitem.l_quantity"))), "L1.L1"), (("Count",), "L2.L2")])
+    text = vlite.translate(catalog, Project(g, [(Ref("lineitem.l_returnflag"), None), (Ref("L1"), "L1.avg_qty"), (Ref("L2"), "L2.cnt")]))
+    rows = {t: synth.table_rows(catalog, t, 0.01) for t in catalog.tables}
+    cols = host_columns(catalog, tpch.plan_columns(text), rows, sf=0.01)
+    want = run_oracle(text, cols)
+    got, stats = run_gpu(text, cols)
+    assert_same(got, want)
+    assert stats["probe_folds"] == 1 and stats["probe_emits"] == 0 and stats["launches"] <= 4
+    assert len(want["avg_qty"]) == 3
