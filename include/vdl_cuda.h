@@ -287,6 +287,12 @@ int vdl_plan_load(vdl_ctx *ctx, const char *vdl_text, int flags, vdl_plan **out)
 /* Statements parsed, distinct nodes after structural CSE (App. G10), fused scans, kernel launches
  * of the last run. */
 int vdl_plan_stats(vdl_plan *p, int *statements, int *nodes, int *fused_scans, int64_t *launches);
+/* Sharded run of a plan whose probe passes EMIT vectors (high-cardinality group-bys: Q3): after vdl_plan_run_local every
+ * rank holds its shard's survivors; concatenate them over the ranks in rank order (= global row order; any transport) and
+ * substitute the result before vdl_plan_finish, which then evaluates the remaining ops on the global vectors. */
+int vdl_plan_num_emits(vdl_plan *p);
+int vdl_plan_emit(vdl_plan *p, int i, void **device_ptr, int64_t *len);              /* synchronises */
+int vdl_plan_emit_replace(vdl_plan *p, int i, void *device_ptr, int64_t len);        /* caller-owned device memory */
 /* FK-join plans: Folds run by the probe kernel, probe passes in emit mode, vectors those materialise. */
 int vdl_plan_probe_stats(vdl_plan *p, int *fold_groups, int *emit_groups, int *emitted_vectors);
 int vdl_plan_probe_kernel_ms(vdl_plan *p, float *ms);   /* sum over the probe passes of the last run; synchronises */

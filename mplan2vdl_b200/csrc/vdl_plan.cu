@@ -935,22 +935,25 @@ int bind_probe(vdl_plan *p, ProbeBuild *b, vdl_probe **probe, std::vector<vdl_ve
   return VDL_OK;
 }
 
+int run_emit_group(vdl_plan *p, EmitGroup &g) {
+  if (g.ran) return VDL_OK;
+  VDL_TRY(bind_probe(p, &g.b, &g.probe, &g.bound, &g.bound_rows, &g.bound_base));
+  VDL_TRY(vdl_probe_run(g.probe));
+  for (size_t k = 0; k < g.nodes.size(); k++) {
+    vdl_vec v;
+    VDL_TRY(vdl_probe_emit_take(g.probe, (int)k, &v));
+    p->val[g.nodes[k]] = v;
+    p->temps.push_back(v);
+  }
+  g.ran = true;
+  return VDL_OK;
+}
+
 int eval(vdl_plan *p, int ni, vdl_vec *out) {
   vdl_ctx *ctx = p->ctx;
   if (p->val[ni]) { *out = p->val[ni]; return VDL_OK; }
   if (p->egroup_of_node[ni] >= 0) {        // materialised by one probe pass together with its siblings of the same space
-    EmitGroup &g = *p->egroups[p->egroup_of_node[ni]];
-    if (!g.ran) {
-      VDL_TRY(bind_probe(p, &g.b, &g.probe, &g.bound, &g.bound_rows, &g.bound_base));
-      VDL_TRY(vdl_probe_run(g.probe));
-      for (size_t k = 0; k < g.nodes.size(); k++) {
-        vdl_vec v;
-        VDL_TRY(vdl_probe_emit_take(g.probe, (int)k, &v));
-        p->val[g.nodes[k]] = v;
-        p->temps.push_back(v);
-      }
-      g.ran = true;
-    }
+    VDL_TRY(run_emit_group(p, *p->egroups[p->egroup_of_node[ni]]));
     *out = p->val[ni];
     return VDL_OK;
   }
@@ -1131,6 +1134,8 @@ static int plan_run_local(vdl_plan *p, int self_finalize) {
     VDL_TRY(bind_probe(p, &g->b, &g->probe, &g->bound, &g->bound_rows, &g->bound_base));
     VDL_TRY(vdl_probe_run_ex(g->probe, self_finalize));
   }
+  if (!self_finalize)        // sharded run: the survivors' vectors are exchanged between ranks before the tail is evaluated
+    for (auto *g : p->egroups) VDL_TRY(run_emit_group(p, *g));
   p->launches_last = ctx->launches - l0;
   p->local_done = true;
   p->self_finalized = self_finalize != 0;
@@ -1162,6 +1167,44 @@ extern "C" int vdl_plan_set_peers(vdl_plan *p, int fused_index, int rank, int wo
   return VDL_OK;
 }
 
+// ---- vectors emitted by probe passes, for the exchange of survivors in a sharded run --------------------------------
+static bool emit_slot(vdl_plan *p, int i, EmitGroup **g, int *k) {
+  for (auto *q : p->egroups) {
+    if (i < (int)q->nodes.size()) { *g = q; *k = i; return true; }
+    i -= (int)q->nodes.size();
+  }
+  return false;
+}
+extern "C" int vdl_plan_num_emits(vdl_plan *p) {
+  int n = 0;
+  if (p) for (auto *g : p->egroups) n += (int)g->nodes.size();
+  return n;
+}
+extern "C" int vdl_plan_emit(vdl_plan *p, int i, void **device_ptr, int64_t *len) {
+  EmitGroup *g; int k;
+  if (!p || !device_ptr || !len || !emit_slot(p, i, &g, &k)) return VDL_EINVAL;
+  if (!g->ran) return vdl_fail(p->ctx, VDL_EINVAL, "emitted vectors exist after vdl_plan_run_local");
+  Vec *v = vec_get(p->ctx, p->val[g->nodes[k]]);
+  if (!v) return VDL_EINVAL;
+  *device_ptr = v->ptr;
+  *len = v->len;
+  return VDL_OK;
+}
+// Substitute emitted vector i by caller-owned device memory (the concatenation of all ranks' survivors, in rank order
+// = global row order); it must stay valid until vdl_plan_finish returns.
+extern "C" int vdl_plan_emit_replace(vdl_plan *p, int i, void *device_ptr, int64_t len) {
+  EmitGroup *g; int k;
+  if (!p || len < 0 || (len > 0 && !device_ptr) || !emit_slot(p, i, &g, &k)) return VDL_EINVAL;
+  if (!g->ran) return vdl_fail(p->ctx, VDL_EINVAL, "emitted vectors exist after vdl_plan_run_local");
+  vdl_vec h;
+  VDL_TRY(vec_new_range(p->ctx, 0, 0, 0, &h));
+  Vec &v = p->ctx->vecs[h];
+  v.is_range = false; v.ptr = device_ptr; v.dtype = VDL_I64; v.len = len; v.cap_rows = len; v.owned = false; v.domain = -1;
+  p->val[g->nodes[k]] = h;          // the local vector stays in temps and is released with them
+  p->temps.push_back(h);
+  return VDL_OK;
+}
+
 extern "C" int vdl_plan_num_partials(vdl_plan *p) { return p ? (int)(p->groups.size() + p->pgroups.size()) : 0; }
 extern "C" int vdl_plan_partials(vdl_plan *p, int i, void **device_ptr, int64_t *n_int64) {
   if (!p || i < 0 || i >= vdl_plan_num_partials(p)) return VDL_EINVAL;
@@ -1180,8 +1223,8 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
   if (!p->local_done) return vdl_fail(ctx, VDL_EINVAL, "vdl_plan_finish before vdl_plan_run_local");
   p->trace = getenv("VDL_TRACE") != nullptr;
   if (p->trace) p->trace_t0 = p->trace_last = now_ms();
-  if (nranks > 1 && ((p->groups.empty() && p->pgroups.empty()) || !p->egroups.empty()))
-    return vdl_fail(ctx, VDL_EUNSUPPORTED, "only plans whose Folds all run on the fused scan / the probe kernel can be row-sharded so far");
+  if (nranks > 1 && p->groups.empty() && p->pgroups.empty() && p->egroups.empty())
+    return vdl_fail(ctx, VDL_EUNSUPPORTED, "a plan without a fused scan or a probe pass cannot be row-sharded");
   i64 l0 = ctx->launches;
   if (!(p->self_finalized && nranks == 1 && !all_partials)) {
     for (size_t gi = 0; gi < p->groups.size(); gi++)

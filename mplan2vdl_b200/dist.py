@@ -26,6 +26,30 @@ class DeviceView:
         self.__cuda_array_interface__ = {"shape": (n_int64,), "typestr": "<i8", "data": (ptr, False), "version": 2}
 
 
+def gather_survivors(local: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """All-gather vectors of DIFFERENT lengths (each rank's surviving rows of an emitted vector) into their
+    concatenation in rank order: lengths first, then the vectors padded to the longest."""
+    import torch.distributed as dist
+    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    lens = torch.empty(world, dtype=torch.int64, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(lens, n, group=group)
+    else:
+        parts = list(lens.view(world, 1).unbind(0))
+        dist.all_gather(parts, n, group=group)
+    lens = lens.tolist()
+    width = max(max(lens), 1)
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[:local.numel()] = local
+    out = torch.empty(world * width, dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(out, padded, group=group)
+    else:
+        parts = list(out.view(world, width).unbind(0))
+        dist.all_gather(parts, padded, group=group)
+    return torch.cat([out[r * width:r * width + lens[r]] for r in range(world)]) if sum(lens) else out[:0]
+
+
 def gather_partial_tables(local: torch.Tensor, world: int, group=None) -> torch.Tensor:
     """All-gather one rank-local partial table (1-D int64 tensor, CPU/gloo or CUDA/nccl) into [world * n]."""
     import torch.distributed as dist
@@ -88,7 +112,7 @@ class ShardedPlan:
         out = self._step_all_gather(copy)
         if self._want_peer:                             # the scans exist now: switch to the peer-memory combine
             self._want_peer = False                     # (probe fold groups combine through the all-gather path for now)
-            self.peer_mode = self.plan.num_partials == self.plan.num_fused and self._setup_peers()
+            self.peer_mode = self.plan.num_partials == self.plan.num_fused and self.plan.num_emits == 0 and self._setup_peers()
         return out
 
     def _step_all_gather(self, copy: bool = True) -> dict:
@@ -103,6 +127,15 @@ class ShardedPlan:
                     self._gathered.append(None)
                 self._gathered[i] = g                   # keep alive until finish() has consumed it
                 ptrs.append(g.data_ptr())
+            self._survivors = []
+            for i in range(self.plan.num_emits):        # plans that emit vectors: every rank continues on ALL survivors
+                ptr, n = self.plan.emit(i)
+                local = torch.as_tensor(DeviceView(ptr, n), device=f"cuda:{self.ctx.device}") if n else \
+                    torch.empty(0, dtype=torch.int64, device=f"cuda:{self.ctx.device}")
+                g = gather_survivors(local, self.world, self.group)
+                self._survivors.append(g)
+                self.plan.emit_replace(i, g.data_ptr() if g.numel() else 0, g.numel())
+            self._stream.synchronize()                  # the gathered vectors are complete before the library reads them
         return self.plan.finish(ptrs, self.world, copy)
 
     def close(self):

@@ -222,6 +222,19 @@ class Plan:
         return self.L.vdl_plan_num_fused(self.h)
 
     @property
+    def num_emits(self) -> int:
+        """Vectors emitted by probe passes (sharded runs exchange them between run_local() and finish())."""
+        return self.L.vdl_plan_num_emits(self.h)
+
+    def emit(self, i: int):
+        p, n = C.c_void_p(), C.c_int64()
+        self.ctx.check(self.L.vdl_plan_emit(self.h, i, C.byref(p), C.byref(n)))
+        return p.value or 0, n.value
+
+    def emit_replace(self, i: int, ptr: int, n: int):
+        self.ctx.check(self.L.vdl_plan_emit_replace(self.h, i, C.c_void_p(ptr), n))
+
+    @property
     def num_partials(self) -> int:
         """Partial aggregate tables of a sharded run: the fused scans, then the probe fold groups."""
         return self.L.vdl_plan_num_partials(self.h)

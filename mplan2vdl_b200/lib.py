@@ -139,6 +139,9 @@ SYMBOLS = [
     ("vdl_probe_emit_take", _I, [_P, _I, C.POINTER(C.c_int32)]),
     ("vdl_probe_last_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
     ("vdl_probe_destroy", _I, [_P]),
+    ("vdl_plan_num_emits", _I, [_P]),
+    ("vdl_plan_emit", _I, [_P, _I, C.POINTER(_P), C.POINTER(_L)]),
+    ("vdl_plan_emit_replace", _I, [_P, _I, _P, _L]),
     ("vdl_plan_num_partials", _I, [_P]),
     ("vdl_plan_partials", _I, [_P, _I, C.POINTER(_P), C.POINTER(_L)]),
     ("vdl_probe_run_ex", _I, [_P, _I]),

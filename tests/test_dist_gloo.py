@@ -104,3 +104,34 @@ def test_two_rank_gloo_partials_merge_to_the_whole_table_answer():
     assert list(got) == list(whole)
     for k in whole:
         np.testing.assert_array_equal(np.asarray(got[k]), whole[k], err_msg=k)
+
+
+def survivors_worker(rank, world, port, q):
+    from mplan2vdl_b200.dist import gather_survivors
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = []
+    for lens in ([3, 5], [0, 4], [2, 0], [0, 0]):                      # uneven and empty shards
+        local = torch.arange(lens[rank], dtype=torch.int64) + 100 * rank
+        out.append(gather_survivors(local, world).tolist())
+    if rank == 1:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_survivor_exchange_concatenates_in_rank_order():
+    """The exchange a sharded emit plan (Q3) needs: vectors of different lengths, concatenated in rank order."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=survivors_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [[0, 1, 2, 100, 101, 102, 103, 104], [100, 101, 102, 103], [0, 1], []]

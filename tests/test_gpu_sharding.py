@@ -178,3 +178,54 @@ def test_peer_exchange_times_out_instead_of_hanging(catalog, monkeypatch):
     for b in bufs:
         ctx.ipc_free(b)
     ctx.close()
+
+
+@pytest.mark.parametrize("q", ["q03.vdl", "q19.vdl"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_emit_plans_sharded_by_exchanging_survivors(catalog, q, world):
+    """Plans whose probe passes EMIT vectors (Q3: high-cardinality group-by; Q19: an OR above the join): every rank
+    probes its lineitem shard, the survivors are concatenated in rank order (what dist.gather_survivors does with
+    all-gathers) and every rank evaluates the remaining ops on the global vectors."""
+    import torch
+    from mplan2vdl_b200 import synth
+    from mplan2vdl_b200.dist import DeviceView
+    from mplan2vdl_b200.executor import Context
+    from util import q19_columns
+    sf, text = 0.01, plan_text(q)
+    if q == "q19.vdl":
+        text, cols = q19_columns(catalog, sf=sf)
+    else:
+        rows_all = {t: synth.table_rows(catalog, t, sf) for t in catalog.tables}
+        cols = host_columns(catalog, tpch.plan_columns(text), rows_all, sf=sf)
+    nli = len(cols["lineitem.lineitem_l_orderkey_l_linenumber_pkey"])
+    want = run_oracle(text, cols)
+    assert len(next(iter(want.values()))) > 0
+    ctxs, plans = [], []
+    for rank in range(world):
+        start, n = tpch.shard_range(nli, rank, world)
+        ctx = Context(0)
+        for k, v in cols.items():
+            ctx.upload_column(k, v[start:start + n] if k.startswith("lineitem.") else v)
+        plan = ctx.plan(text)
+        plan.set_row_base(start)
+        plan.run_local()
+        ctxs.append(ctx)
+        plans.append(plan)
+    nem = plans[0].num_emits
+    assert nem >= 1 and plans[0].num_partials == 0
+    keep = []
+    for i in range(nem):
+        parts = []
+        for rank in range(world):
+            ptr, n = plans[rank].emit(i)
+            parts.append(torch.as_tensor(DeviceView(ptr, n), device="cuda:0").clone() if n else torch.empty(0, dtype=torch.int64, device="cuda:0"))
+        g = torch.cat(parts)
+        keep.append(g)
+        torch.cuda.synchronize()
+        for rank in range(world):
+            plans[rank].emit_replace(i, g.data_ptr() if g.numel() else 0, g.numel())
+    for rank in range(world):
+        assert_same(plans[rank].finish([], world), want)
+    for p, c in zip(plans, ctxs):
+        p.close()
+        c.close()
