@@ -74,3 +74,10 @@ foreign import ccall safe "vdl_ipc_free" c_vdl_ipc_free :: Ptr VdlCtx -> Ptr () 
 -- what the fusion passes did with a loaded program (Folds on the fused scan; FK-join Folds / vectors on the probe kernel)
 foreign import ccall safe "vdl_plan_stats" c_vdl_plan_stats :: Ptr VdlPlan -> Ptr CInt -> Ptr CInt -> Ptr CInt -> Ptr Int64 -> IO CInt
 foreign import ccall safe "vdl_plan_probe_stats" c_vdl_plan_probe_stats :: Ptr VdlPlan -> Ptr CInt -> Ptr CInt -> Ptr CInt -> IO CInt
+
+-- sharded runs of FK-join plans: partial tables of every fused scan / probe fold group, and the vectors probe passes emit
+foreign import ccall safe "vdl_plan_num_partials" c_vdl_plan_num_partials :: Ptr VdlPlan -> IO CInt
+foreign import ccall safe "vdl_plan_partials" c_vdl_plan_partials :: Ptr VdlPlan -> CInt -> Ptr (Ptr ()) -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_plan_num_emits" c_vdl_plan_num_emits :: Ptr VdlPlan -> IO CInt
+foreign import ccall safe "vdl_plan_emit" c_vdl_plan_emit :: Ptr VdlPlan -> CInt -> Ptr (Ptr ()) -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_plan_emit_replace" c_vdl_plan_emit_replace :: Ptr VdlPlan -> CInt -> Ptr () -> Int64 -> IO CInt
