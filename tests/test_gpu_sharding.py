@@ -119,20 +119,21 @@ def test_peer_memory_exchange_emulated_ranks(catalog, query, colnames, world):
         ctxs[r].close()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_fk_join_plan_sharded_through_probe_partials(catalog, world):
+@pytest.mark.parametrize("world,sf", [(2, 0.01), (3, 0.01), (4, 0.002)])      # (4, 0.002): the last rank's shard is empty
+def test_fk_join_plan_sharded_through_probe_partials(catalog, world, sf):
     """Q5 (one probe fold group): lineitem row-range sharded, dimension tables replicated; the per-rank partial tables
     (FoldChoose values included) are concatenated like an all-gather and merged by every rank's finalize."""
     import torch
     from mplan2vdl_b200 import synth
     from mplan2vdl_b200.dist import DeviceView
     from mplan2vdl_b200.executor import Context
-    sf, text = 0.01, plan_text("q05.vdl")
+    text = plan_text("q05.vdl")
     names = tpch.plan_columns(text)
     rows = {t: synth.table_rows(catalog, t, sf) for t in catalog.tables}
     cols = host_columns(catalog, names, rows, sf=sf)
     want = run_oracle(text, cols)
-    assert len(want["revenue"]) > 0
+    assert len(want["revenue"]) > 0 or sf < 0.01
+    assert sf >= 0.01 or tpch.shard_range(rows["lineitem"], world - 1, world)[1] == 0
     ctxs, plans, tables = [], [], []
     for rank in range(world):
         start, n = tpch.shard_range(rows["lineitem"], rank, world)
@@ -181,8 +182,8 @@ def test_peer_exchange_times_out_instead_of_hanging(catalog, monkeypatch):
 
 
 @pytest.mark.parametrize("q", ["q03.vdl", "q19.vdl"])
-@pytest.mark.parametrize("world", [2, 3])
-def test_emit_plans_sharded_by_exchanging_survivors(catalog, q, world):
+@pytest.mark.parametrize("world,sf", [(2, 0.01), (3, 0.01), (4, 0.002)])       # (4, 0.002): the last rank's shard is empty
+def test_emit_plans_sharded_by_exchanging_survivors(catalog, q, world, sf):
     """Plans whose probe passes EMIT vectors (Q3: high-cardinality group-by; Q19: an OR above the join): every rank
     probes its lineitem shard, the survivors are concatenated in rank order (what dist.gather_survivors does with
     all-gathers) and every rank evaluates the remaining ops on the global vectors."""
@@ -191,7 +192,7 @@ def test_emit_plans_sharded_by_exchanging_survivors(catalog, q, world):
     from mplan2vdl_b200.dist import DeviceView
     from mplan2vdl_b200.executor import Context
     from util import q19_columns
-    sf, text = 0.01, plan_text(q)
+    text = plan_text(q)
     if q == "q19.vdl":
         text, cols = q19_columns(catalog, sf=sf)
     else:
@@ -199,7 +200,7 @@ def test_emit_plans_sharded_by_exchanging_survivors(catalog, q, world):
         cols = host_columns(catalog, tpch.plan_columns(text), rows_all, sf=sf)
     nli = len(cols["lineitem.lineitem_l_orderkey_l_linenumber_pkey"])
     want = run_oracle(text, cols)
-    assert len(next(iter(want.values()))) > 0
+    assert len(next(iter(want.values()))) > 0 or sf < 0.01
     ctxs, plans = [], []
     for rank in range(world):
         start, n = tpch.shard_range(nli, rank, world)
