@@ -38,6 +38,7 @@ extern "C" int vdl_ctx_create(int device, vdl_ctx **out) {
   ctx->device = device;
   ctx->vecs.resize(1);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess || (e = cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaMalloc(&ctx->d_errflag, sizeof(int))) != cudaSuccess || (e = cudaMemset(ctx->d_errflag, 0, sizeof(int))) != cudaSuccess) {
     snprintf(g_noctx_err, sizeof g_noctx_err, "vdl_ctx_create: %s", cudaGetErrorString(e));
     delete ctx;
@@ -66,6 +67,8 @@ extern "C" int vdl_ctx_destroy(vdl_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->d_errflag) cudaFree(ctx->d_errflag);
+  if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return VDL_OK;

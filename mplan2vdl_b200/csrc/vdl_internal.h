@@ -33,6 +33,8 @@ struct Vec {
 struct vdl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // device->host copies of plan outputs, overlapped with the evaluation of the next output
+  cudaEvent_t copy_event = nullptr;
   int sm_count = 148;
   int smem_optin = 0;
   std::vector<Vec> vecs;    // handle = index, 0 unused

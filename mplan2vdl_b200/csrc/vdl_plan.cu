@@ -1232,7 +1232,7 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
     for (size_t gi = 0; gi < p->pgroups.size(); gi++)
       VDL_TRY(vdl_probe_finalize(p->pgroups[gi]->probe, all_partials ? all_partials[p->groups.size() + gi] : nullptr, nranks));
   }
-  bool ran_ops = false;
+  bool ran_ops = false, copies_pending = false;
   for (auto &o : p->outputs) {
     int gi = p->group_of_node[o.node];
     if (p->pgroup_of_node[o.node] >= 0) {   // a Fold over a joined space: the probe's result buffer is already on its way
@@ -1263,10 +1263,20 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
       if (cudaHostAlloc(&o.pinned, want * sizeof(i64), cudaHostAllocDefault) != cudaSuccess) { free_temps(p); return vdl_fail(ctx, VDL_ENOMEM, "output buffer of %lld values", (long long)len); }
       o.cap = want;
     }
-    rc = vdl_vec_download(ctx, v, o.pinned, len);
-    if (rc) { free_temps(p); return rc; }
+    Vec *vv = vec_get(ctx, v);
+    if (vv && !vv->is_range && vv->dtype == VDL_I64 && len > 0) {
+      // the copy runs on its own stream behind an event, so the next output's kernels overlap it; one wait at the end
+      VDL_CUDA(ctx, cudaEventRecord(ctx->copy_event, ctx->stream));
+      VDL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
+      VDL_CUDA(ctx, cudaMemcpyAsync(o.pinned, vv->ptr, (size_t)len * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      copies_pending = true;
+    } else {
+      rc = vdl_vec_download(ctx, v, o.pinned, len);
+      if (rc) { free_temps(p); return rc; }
+    }
     o.data = o.pinned; o.len = len;
   }
+  if (copies_pending) VDL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));     // before the temporaries are released
   int rc = ran_ops ? check_errflag(ctx, "plan") : VDL_OK;
   p->launches_last += ctx->launches - l0;
   free_temps(p);
