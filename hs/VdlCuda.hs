@@ -17,6 +17,7 @@ import Foreign.Ptr (Ptr)
 data VdlCtx
 data VdlPlan
 data VdlFused
+data VdlMapDesc   -- vdl_map_desc: marshalled with Foreign.Storable by the caller (layout in vdl_cuda.h)
 type VdlVec = Int32
 
 -- status codes (vdl_cuda.h)
@@ -46,6 +47,8 @@ foreign import ccall safe "vdl_vec_free" c_vdl_vec_free :: Ptr VdlCtx -> VdlVec 
 foreign import ccall safe "vdl_op_range" c_vdl_op_range :: Ptr VdlCtx -> Int64 -> Int64 -> Int64 -> Ptr VdlVec -> IO CInt
 foreign import ccall safe "vdl_op_binary" c_vdl_op_binary :: Ptr VdlCtx -> CInt -> VdlVec -> VdlVec -> Ptr VdlVec -> IO CInt
 foreign import ccall safe "vdl_op_fold_select" c_vdl_op_fold_select :: Ptr VdlCtx -> VdlVec -> Ptr VdlVec -> IO CInt
+foreign import ccall safe "vdl_op_map" c_vdl_op_map :: Ptr VdlCtx -> Ptr VdlMapDesc -> Ptr VdlVec -> Ptr VdlVec -> Ptr VdlVec -> IO CInt
+foreign import ccall unsafe "vdl_abi_sizeof_map_desc" c_vdl_abi_sizeof_map_desc :: IO CInt
 foreign import ccall safe "vdl_op_gather" c_vdl_op_gather :: Ptr VdlCtx -> VdlVec -> VdlVec -> Ptr VdlVec -> IO CInt
 foreign import ccall safe "vdl_op_scatter" c_vdl_op_scatter :: Ptr VdlCtx -> VdlVec -> VdlVec -> Int64 -> Ptr VdlVec -> IO CInt
 foreign import ccall safe "vdl_op_partition" c_vdl_op_partition :: Ptr VdlCtx -> VdlVec -> Int64 -> Int64 -> Int64 -> Ptr VdlVec -> IO CInt
@@ -73,6 +76,7 @@ foreign import ccall safe "vdl_ipc_free" c_vdl_ipc_free :: Ptr VdlCtx -> Ptr () 
 
 -- what the fusion passes did with a loaded program (Folds on the fused scan; FK-join Folds / vectors on the probe kernel)
 foreign import ccall safe "vdl_plan_stats" c_vdl_plan_stats :: Ptr VdlPlan -> Ptr CInt -> Ptr CInt -> Ptr CInt -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_plan_map_stats" c_vdl_plan_map_stats :: Ptr VdlPlan -> Ptr CInt -> Ptr CInt -> IO CInt
 foreign import ccall safe "vdl_plan_probe_stats" c_vdl_plan_probe_stats :: Ptr VdlPlan -> Ptr CInt -> Ptr CInt -> Ptr CInt -> IO CInt
 
 -- sharded runs of FK-join plans: partial tables of every fused scan / probe fold group, and the vectors probe passes emit

@@ -114,6 +114,31 @@ int vdl_vec_free(vdl_ctx *ctx, vdl_vec v);
 int vdl_op_range(vdl_ctx *ctx, int64_t from, int64_t step, int64_t len, vdl_vec *out);
 /* Elementwise binary op (Vdl.hs:436-439); a and b have equal length. */
 int vdl_op_binary(vdl_ctx *ctx, int op, vdl_vec a, vdl_vec b, vdl_vec *out);
+/* A tree of elementwise ops, Gathers and Ranges over vectors of ONE length in one launch: what the same chain of
+ * vdl_op_binary / vdl_op_gather / vdl_op_range calls computes, without materialising the intermediates (the plan
+ * executor groups the op-at-a-time remainder of a plan this way).  A register program is run per row i:
+ *   VDL_LOGICAL_AND..VDL_MODULO   reg[dst] = op(reg[a], reg[b])
+ *   VDL_MAP_LOAD                  reg[dst] = inputs[b][i]
+ *   VDL_MAP_RANGE                 reg[dst] = imm[a] + i * imm[b]
+ *   VDL_MAP_GATHER                reg[dst] = tables[b][reg[a]]   (out of range: 0 and the context's error flag, like vdl_op_gather)
+ * All inputs have the result's length (an input no instruction loads is only a length witness); tables have any
+ * length.  The result is the register written by the last instruction. */
+#define VDL_MAP_MAX_INPUTS 48
+#define VDL_MAP_MAX_TABLES 8
+#define VDL_MAP_MAX_INSTRS 160
+#define VDL_MAP_MAX_IMMS 32
+#define VDL_MAP_MAX_REGS 32
+#define VDL_MAP_GATHER 16
+#define VDL_MAP_LOAD 17
+#define VDL_MAP_RANGE 18
+typedef struct vdl_map_instr { int16_t op, dst, a, b; } vdl_map_instr;
+typedef struct vdl_map_desc {
+  int32_t ninputs, ntables, ninstrs, nimms;
+  vdl_map_instr instr[VDL_MAP_MAX_INSTRS];
+  int64_t imm[VDL_MAP_MAX_IMMS];
+} vdl_map_desc;
+int vdl_op_map(vdl_ctx *ctx, const vdl_map_desc *desc, const vdl_vec *inputs, const vdl_vec *tables, vdl_vec *out);
+int vdl_abi_sizeof_map_desc(void);
 /* FoldSelect with fold = pos_ pred (Vlite.hs:721-730): ascending positions of non-zero pred. */
 int vdl_op_fold_select(vdl_ctx *ctx, vdl_vec pred, vdl_vec *out);
 /* Gather (Vdl.hs:438): out[i] = src[pos[i]]. */
@@ -295,6 +320,8 @@ int vdl_plan_emit(vdl_plan *p, int i, void **device_ptr, int64_t *len);         
 int vdl_plan_emit_replace(vdl_plan *p, int i, void *device_ptr, int64_t len);        /* caller-owned device memory */
 /* FK-join plans: Folds run by the probe kernel, probe passes in emit mode, vectors those materialise. */
 int vdl_plan_probe_stats(vdl_plan *p, int *fold_groups, int *emit_groups, int *emitted_vectors);
+/* Map clusters of the op-at-a-time remainder: how many vdl_op_map launches stand for how many plan nodes. */
+int vdl_plan_map_stats(vdl_plan *p, int *clusters, int *nodes_covered);
 int vdl_plan_probe_kernel_ms(vdl_plan *p, float *ms);   /* sum over the probe passes of the last run; synchronises */
 /* Phase 1: everything up to and including the fused scans (local shard). */
 /* Global row id of this shard's row 0 (row-range sharding of the fact table; default 0). */

@@ -2,8 +2,10 @@
 // emitted graph runs op-at-a-time when the fusion pass does not apply, and for the per-op sweep.
 // Semantics: SURVEY.md section 2.3 / Appendix G (dense vectors, int64 wraparound).
 #include <stdio.h>
+#include <string.h>
 
 #include <algorithm>
+#include <memory>
 
 #include "vdl_internal.h"
 
@@ -56,6 +58,95 @@ extern "C" int vdl_op_binary(vdl_ctx *ctx, int op, vdl_vec a, vdl_vec b, vdl_vec
   i64 want = (n / 2 + 255) / 256;
   int blocks = (int)std::max<i64>(1, std::min<i64>(want, (i64)ctx->sm_count * 16));
   binary_table[op]<<<blocks, 256, 0, ctx->stream>>>(oa, ob, (i64 *)ctx->vecs[*out].ptr, n);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaGetLastError());
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- map (expression tree in one launch)
+// The op-at-a-time remainder of a plan is mostly long chains of elementwise ops over short vectors (Q19's OR of ANDs over
+// the join's survivors: ~150 launches of a few microseconds each).  One launch interprets the whole tree per row: the
+// program is the same for every thread (no divergence), the register file lives in local memory (L1), and each input is
+// read from HBM once instead of once per consumer.
+struct MapArgs {
+  Operand in[VDL_MAP_MAX_INPUTS];
+  Operand tab[VDL_MAP_MAX_TABLES];
+  i64 tab_len[VDL_MAP_MAX_TABLES];
+  vdl_map_desc d;
+};
+
+__global__ void __launch_bounds__(256) map_kernel(const __grid_constant__ MapArgs m, i64 *__restrict__ out, i64 n, int *errflag) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  const int nt = m.d.ninstrs;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    i64 r[VDL_MAP_MAX_REGS];
+    int last = 0;
+    for (int t = 0; t < nt; t++) {
+      const vdl_map_instr ins = m.d.instr[t];
+      i64 v;
+      if (ins.op == VDL_MAP_LOAD) {
+        v = op_ld(m.in[ins.b], i);
+      } else if (ins.op == VDL_MAP_RANGE) {
+        v = (i64)((u64)m.d.imm[ins.a] + (u64)i * (u64)m.d.imm[ins.b]);
+      } else if (ins.op == VDL_MAP_GATHER) {
+        const i64 a = r[ins.a];
+        if ((u64)a >= (u64)m.tab_len[ins.b]) { atomicAdd(errflag, 1); v = 0; }
+        else v = op_ld(m.tab[ins.b], a);
+      } else {
+        v = binop_apply(ins.op, r[ins.a], r[ins.b]);
+      }
+      r[ins.dst] = v;
+      last = ins.dst;
+    }
+    out[i] = r[last];
+  }
+}
+
+extern "C" int vdl_abi_sizeof_map_desc(void) { return (int)sizeof(vdl_map_desc); }
+
+extern "C" int vdl_op_map(vdl_ctx *ctx, const vdl_map_desc *d, const vdl_vec *inputs, const vdl_vec *tables, vdl_vec *out) {
+  if (!ctx || !d || !out || !inputs || (d->ntables > 0 && !tables)) return VDL_EINVAL;
+  if (d->ninputs < 1 || d->ninputs > VDL_MAP_MAX_INPUTS || d->ntables < 0 || d->ntables > VDL_MAP_MAX_TABLES || d->ninstrs < 1 ||
+      d->ninstrs > VDL_MAP_MAX_INSTRS || d->nimms < 0 || d->nimms > VDL_MAP_MAX_IMMS)
+    return vdl_fail(ctx, VDL_EINVAL, "map: %d inputs, %d tables, %d instructions, %d immediates out of range", d->ninputs, d->ntables, d->ninstrs, d->nimms);
+  MapArgs *mp = new MapArgs();          // ~3 KB: off the stack
+  std::unique_ptr<MapArgs> hold(mp);
+  MapArgs &m = *mp;
+  m.d = *d;
+  i64 n = -1;
+  for (int k = 0; k < d->ninputs; k++) {
+    Vec *v = vec_get(ctx, inputs[k]);
+    if (!v) return VDL_EINVAL;
+    if (n >= 0 && v->len != n) return vdl_fail(ctx, VDL_EINVAL, "elementwise op on lengths %lld vs %lld", (long long)n, (long long)v->len);
+    n = v->len;
+    m.in[k] = operand_of(*v);
+  }
+  for (int k = 0; k < d->ntables; k++) {
+    Vec *v = vec_get(ctx, tables[k]);
+    if (!v) return VDL_EINVAL;
+    m.tab[k] = operand_of(*v);
+    m.tab_len[k] = v->len;
+  }
+  i64 domain = -1;
+  unsigned written = 0;
+  auto reg_ok = [&](int r, bool read) { return r >= 0 && r < VDL_MAP_MAX_REGS && (!read || (written >> r & 1)); };
+  for (int t = 0; t < d->ninstrs; t++) {
+    const vdl_map_instr &ins = d->instr[t];
+    bool ok = reg_ok(ins.dst, false);
+    if (ins.op == VDL_MAP_LOAD) ok = ok && ins.b >= 0 && ins.b < d->ninputs;
+    else if (ins.op == VDL_MAP_RANGE) ok = ok && ins.a >= 0 && ins.a < d->nimms && ins.b >= 0 && ins.b < d->nimms;
+    else if (ins.op == VDL_MAP_GATHER) ok = ok && reg_ok(ins.a, true) && ins.b >= 0 && ins.b < d->ntables;
+    else ok = ok && ins.op >= 0 && ins.op <= VDL_MODULO && reg_ok(ins.a, true) && reg_ok(ins.b, true);
+    if (!ok) return vdl_fail(ctx, VDL_EINVAL, "map: instruction %d (op %d dst %d a %d b %d) is malformed or reads a register nothing wrote", t, ins.op, ins.dst, ins.a, ins.b);
+    written |= 1u << ins.dst;
+    if (t == d->ninstrs - 1 && ins.op == VDL_MAP_GATHER) domain = ctx->vecs[tables[ins.b]].domain;   // gathering positions keeps their index space
+  }
+  VDL_TRY(vec_new(ctx, VDL_I64, n, out));
+  ctx->vecs[*out].domain = domain;
+  if (n == 0) return VDL_OK;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  int blocks = (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 8));
+  map_kernel<<<blocks, 256, 0, ctx->stream>>>(m, (i64 *)ctx->vecs[*out].ptr, n, ctx->d_errflag);
   ctx->launches++;
   VDL_CUDA(ctx, cudaGetLastError());
   return VDL_OK;

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <functional>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -54,6 +55,14 @@ struct Sym {
   bool masked = false;
   int n0 = -1, n1 = -1;        // S_SELECTION: pred node; S_PARTITION: key node; S_SORTED: partition node, inner node
   i64 lo = 0, cnt = 0;         // S_PARTITION pivots RangeC(lo, cnt, 1)
+};
+
+// Elementwise / Gather / Range nodes of the op-at-a-time remainder that run as ONE vdl_op_map launch (build_clusters).
+struct MapCluster {
+  int root = -1;
+  std::vector<int> members;             // ascending node index = evaluation order; the root is last
+  std::vector<int> inputs, tables;      // leaf nodes: row-aligned inputs / Gather sources
+  vdl_map_desc desc;
 };
 
 struct FusedFold { int node; vdl_fold_spec spec; };
@@ -99,6 +108,8 @@ struct vdl_plan {
   std::vector<int> pgroup_of_node;      // Fold node -> probe fold group or -1
   std::vector<EmitGroup *> egroups;
   std::vector<int> egroup_of_node, eslot_of_node;   // node materialised by a probe in emit mode -> group, slot
+  std::vector<MapCluster> clusters;
+  std::vector<int> cluster_of_root;     // node -> index into clusters when it is the root of one, else -1
   i64 row_base = 0;
   // run state
   std::vector<vdl_vec> val;
@@ -778,6 +789,152 @@ int post_operand(vdl_plan *p, int ni, int *gi, i64 *val) {
   return -1;
 }
 
+// ---- map clusters ------------------------------------------------------------------------------------------------
+// What is left for op-at-a-time evaluation after the scans and probe passes is dominated by chains of elementwise ops
+// (Q19: the OR of three AND groups over the join's survivors, ~150 nodes).  A cluster is a root node plus every
+// Binary / Gather / RangeV descendant ALL of whose consumers are inside the cluster, so nothing outside ever needs an
+// interior value and the leaves cannot depend on members; it compiles to one register program (vdl_op_map).
+// `cons` counts consumer edges of the demand-driven evaluation only (nodes inside fused scans / probe passes are dead here).
+void live_walk(vdl_plan *p, int ni, std::vector<char> &live, std::vector<int> &cons) {
+  if (live[ni]) return;
+  live[ni] = 1;
+  if (p->egroup_of_node[ni] >= 0) return;
+  const Node &n = p->nodes[ni];
+  auto use = [&](int a) { cons[a]++; live_walk(p, a, live, cons); };
+  const bool fused = p->group_of_node[ni] >= 0 || p->pgroup_of_node[ni] >= 0;
+  switch (n.op) {
+    case N_RANGEV: use(n.a); break;
+    case N_BINARY: if (!fused) { use(n.a); use(n.b); } break;
+    case N_FSELECT: use(n.b); break;
+    case N_GATHER: use(n.a); use(n.b); break;
+    case N_SCATTER: use(n.a); use(n.c); break;
+    case N_PARTITION: use(n.a); break;
+    case N_FOLD: if (!fused) { use(n.a); use(n.b); } break;
+    default: break;
+  }
+}
+
+// Register program of a cluster; false when it exceeds vdl_op_map's limits.
+bool compile_cluster(vdl_plan *p, MapCluster *c) {
+  std::vector<int> mem = c->members;
+  std::sort(mem.begin(), mem.end());
+  std::set<int> in_cluster(mem.begin(), mem.end());
+  c->inputs.clear(); c->tables.clear();
+  memset(&c->desc, 0, sizeof c->desc);
+  vdl_map_desc &d = c->desc;
+  auto slot = [](std::vector<int> &v, int x) { for (size_t i = 0; i < v.size(); i++) if (v[i] == x) return (int)i; v.push_back(x); return (int)v.size() - 1; };
+  // values: members and loaded inputs; last use position (in member order) for register release
+  std::map<int, int> last_use;
+  for (size_t t = 0; t < mem.size(); t++) {
+    const Node &n = p->nodes[mem[t]];
+    if (n.op == N_BINARY) { last_use[n.a] = (int)t; last_use[n.b] = (int)t; }
+    else if (n.op == N_GATHER) last_use[n.b] = (int)t;
+  }
+  std::map<int, int> reg_of;
+  unsigned busy = 0;
+  auto alloc = [&]() { for (int r = 0; r < VDL_MAP_MAX_REGS; r++) if (!(busy >> r & 1)) { busy |= 1u << r; return r; } return -1; };
+  auto emit = [&](int op, int dst, int a, int b) {
+    if (d.ninstrs == VDL_MAP_MAX_INSTRS) return false;
+    d.instr[d.ninstrs++] = vdl_map_instr{(int16_t)op, (int16_t)dst, (int16_t)a, (int16_t)b};
+    return true;
+  };
+  auto imm = [&](i64 v) { for (int i = 0; i < d.nimms; i++) if (d.imm[i] == v) return i; if (d.nimms == VDL_MAP_MAX_IMMS) return -1; d.imm[d.nimms] = v; return d.nimms++; };
+  auto operand = [&](int node) -> int {       // register holding `node`'s value at this point (loads a leaf on first use)
+    auto it = reg_of.find(node);
+    if (it != reg_of.end()) return it->second;
+    if (in_cluster.count(node)) return -1;    // members are defined before use (ascending order); cannot happen
+    int r = alloc();
+    if (r < 0) return -1;
+    int k = slot(c->inputs, node);
+    if (k >= VDL_MAP_MAX_INPUTS || !emit(VDL_MAP_LOAD, r, 0, k)) return -1;
+    reg_of[node] = r;
+    return r;
+  };
+  for (size_t t = 0; t < mem.size(); t++) {
+    const int ni = mem[t];
+    const Node &n = p->nodes[ni];
+    int ra = -1, rb = -1, tab = -1;
+    if (n.op == N_BINARY) { ra = operand(n.a); rb = operand(n.b); if (ra < 0 || rb < 0) return false; }
+    else if (n.op == N_GATHER) { ra = operand(n.b); tab = slot(c->tables, n.a); if (ra < 0 || tab >= VDL_MAP_MAX_TABLES) return false; }
+    else if (n.op == N_RANGEV) { if (!in_cluster.count(n.a)) { if (slot(c->inputs, n.a) >= VDL_MAP_MAX_INPUTS) return false; } }   // length witness
+    // operands dying here free their registers before the destination is chosen (the kernel reads before it writes)
+    for (int o : {n.op == N_BINARY ? n.a : -1, n.op == N_BINARY || n.op == N_GATHER ? n.b : -1})
+      if (o >= 0 && last_use[o] == (int)t) { auto it = reg_of.find(o); if (it != reg_of.end()) { busy &= ~(1u << it->second); reg_of.erase(it); } }
+    int rd = alloc();
+    if (rd < 0) return false;
+    bool ok;
+    if (n.op == N_BINARY) ok = emit(n.sub, rd, ra, rb);
+    else if (n.op == N_GATHER) ok = emit(VDL_MAP_GATHER, rd, ra, tab);
+    else { int i0 = imm(n.k0), i1 = imm(n.k1); ok = i0 >= 0 && i1 >= 0 && emit(VDL_MAP_RANGE, rd, i0, i1); }
+    if (!ok) return false;
+    reg_of[ni] = rd;
+    if (!last_use.count(ni) && ni != c->root) { busy &= ~(1u << rd); reg_of.erase(ni); }    // only a length witness for a member RangeV
+  }
+  d.ninputs = (int)c->inputs.size();
+  d.ntables = (int)c->tables.size();
+  return d.ninputs >= 1 && mem.back() == c->root;
+}
+
+void build_clusters(vdl_plan *p) {
+  const int nn = (int)p->nodes.size();
+  p->cluster_of_root.assign(nn, -1);
+  if (getenv("VDL_NO_MAP")) return;
+  for (int i = 0; i < nn; i++) for (int a : {p->nodes[i].a, p->nodes[i].b, p->nodes[i].c}) if (a >= i) return;   // not in definition order: leave the plan alone
+  std::vector<char> live(nn, 0);
+  std::vector<int> cons(nn, 0);
+  for (auto &o : p->outputs) {
+    if (p->group_of_node[o.node] >= 0 || p->pgroup_of_node[o.node] >= 0) continue;
+    cons[o.node]++;
+    live_walk(p, o.node, live, cons);
+  }
+  auto eligible = [&](int ni) {
+    const Node &n = p->nodes[ni];
+    if (!live[ni] || p->egroup_of_node[ni] >= 0 || p->group_of_node[ni] >= 0 || p->pgroup_of_node[ni] >= 0) return false;
+    return n.op == N_BINARY || n.op == N_GATHER || n.op == N_RANGEV;
+  };
+  std::vector<int> member_of(nn, -1);
+  for (int ni = nn - 1; ni >= 0; ni--) {
+    if (member_of[ni] >= 0 || !eligible(ni) || p->nodes[ni].op == N_RANGEV) continue;
+    MapCluster c;
+    c.root = ni;
+    c.members.push_back(ni);
+    member_of[ni] = ni;
+    std::set<int> refused;
+    for (bool changed = true; changed;) {
+      changed = false;
+      for (size_t k = 0; k < c.members.size(); k++) {
+        const Node &m = p->nodes[c.members[k]];
+        for (int dnode : {m.op == N_BINARY ? m.a : -1, m.op == N_RANGEV ? m.a : m.b}) {     // row-aligned operands (a Gather's source is a table)
+          if (dnode < 0 || member_of[dnode] >= 0 || refused.count(dnode) || !eligible(dnode)) continue;
+          int inside = 0;
+          for (int q : c.members) {
+            const Node &mq = p->nodes[q];
+            if (mq.op == N_BINARY) inside += (mq.a == dnode) + (mq.b == dnode);
+            else if (mq.op == N_GATHER) inside += (mq.b == dnode);
+            else inside += (mq.a == dnode);
+          }
+          if (inside != cons[dnode]) continue;
+          MapCluster trial = c;
+          trial.members.push_back(dnode);
+          if (!compile_cluster(p, &trial)) { refused.insert(dnode); continue; }
+          c.members.push_back(dnode);
+          member_of[dnode] = ni;
+          changed = true;
+        }
+      }
+    }
+    int real = 0;
+    for (int q : c.members) if (p->nodes[q].op != N_RANGEV) real++;
+    if (real < 2 || !compile_cluster(p, &c)) {       // a lone op: the per-op kernel is as good
+      for (int q : c.members) member_of[q] = -1;
+      continue;
+    }
+    std::sort(c.members.begin(), c.members.end());
+    p->cluster_of_root[ni] = (int)p->clusters.size();
+    p->clusters.push_back(c);
+  }
+}
+
 int fuse(vdl_plan *p) {
   size_t nn = p->nodes.size();
   p->sym.assign(nn, Sym());
@@ -786,6 +943,7 @@ int fuse(vdl_plan *p) {
   p->pgroup_of_node.assign(nn, -1);
   p->egroup_of_node.assign(nn, -1);
   p->eslot_of_node.assign(nn, -1);
+  p->cluster_of_root.assign(nn, -1);
   if (!(p->flags & VDL_PLAN_FUSE)) return VDL_OK;
   for (size_t i = 0; i < nn; i++)
     if (p->nodes[i].op == N_FOLD) try_fuse_fold(p, (int)i);
@@ -899,6 +1057,7 @@ int fuse(vdl_plan *p) {
     std::vector<char> seen(nn, 0);
     for (auto &o : p->outputs) mark_emits(p, o.node, seen);
   }
+  build_clusters(p);
   return VDL_OK;
 }
 
@@ -960,6 +1119,13 @@ int eval(vdl_plan *p, int ni, vdl_vec *out) {
   const Node &n = p->nodes[ni];
   vdl_vec r = 0, a = 0, b = 0, c = 0;
   bool temp = true;
+  if (p->cluster_of_root[ni] >= 0) {        // this node and its private elementwise / Gather subtree: one launch
+    const MapCluster &mc = p->clusters[p->cluster_of_root[ni]];
+    std::vector<vdl_vec> in(mc.inputs.size()), tab(mc.tables.size());
+    for (size_t k = 0; k < in.size(); k++) VDL_TRY(eval(p, mc.inputs[k], &in[k]));
+    for (size_t k = 0; k < tab.size(); k++) VDL_TRY(eval(p, mc.tables[k], &tab[k]));
+    VDL_TRY(vdl_op_map(ctx, &mc.desc, in.data(), tab.data(), &r));
+  } else
   switch (n.op) {
     case N_LOAD: VDL_TRY(vdl_column_lookup(ctx, n.name.c_str(), &r)); temp = false; break;
     case N_RANGEV: {
@@ -1057,6 +1223,8 @@ extern "C" int vdl_plan_load(vdl_ctx *ctx, const char *vdl_text, int flags, vdl_
         fprintf(stderr, "\n");
       }
     }
+    for (auto &c : p->clusters)
+      fprintf(stderr, "[vdl plan]   map cluster: root %d, %zu nodes, %d inputs, %d tables, %d instructions\n", c.root, c.members.size(), c.desc.ninputs, c.desc.ntables, c.desc.ninstrs);
     for (auto *g : p->egroups) {
       fprintf(stderr, "[vdl plan]   probe emit: table %s, %d leaves, %d predicates, nodes", p->tables[p->join->spaces[g->space].table].c_str(), g->b.desc.nleaves, g->b.desc.npreds);
       for (int n : g->nodes) fprintf(stderr, " %d", n);
@@ -1083,6 +1251,15 @@ extern "C" int vdl_plan_probe_stats(vdl_plan *p, int *fold_groups, int *emit_gro
   int n = 0;
   for (auto *g : p->egroups) n += (int)g->nodes.size();
   if (emitted_vectors) *emitted_vectors = n;
+  return VDL_OK;
+}
+
+extern "C" int vdl_plan_map_stats(vdl_plan *p, int *clusters, int *nodes_covered) {
+  if (!p) return VDL_EINVAL;
+  if (clusters) *clusters = (int)p->clusters.size();
+  int n = 0;
+  for (auto &c : p->clusters) n += (int)c.members.size();
+  if (nodes_covered) *nodes_covered = n;
   return VDL_OK;
 }
 

@@ -119,6 +119,21 @@ class Context:
     def op_binary(self, op: str, a: int, b: int) -> int:
         return self._out(self.L.vdl_op_binary, _lib.BINARY_OPS.index(op), a, b)
 
+    def op_map(self, program, inputs, tables=(), imms=()) -> int:
+        """One launch for a register program over row-aligned `inputs` (vdl_op_map).  program: (op, dst, a, b) with op a
+        binary op name, "Load" (b = input), "Range" (a, b = indices into imms: from, step) or "Gather" (a = register
+        holding the position, b = table)."""
+        d = _lib.MapDesc()
+        d.ninputs, d.ntables, d.ninstrs, d.nimms = len(inputs), len(tables), len(program), len(imms)
+        special = {"Gather": _lib.VDL_MAP_GATHER, "Load": _lib.VDL_MAP_LOAD, "Range": _lib.VDL_MAP_RANGE}
+        for t, (op, dst, a, b) in enumerate(program):
+            d.instr[t] = _lib.MapInstr(special[op] if op in special else _lib.BINARY_OPS.index(op), dst, a, b)
+        for k, v in enumerate(imms):
+            d.imm[k] = v
+        ins = (C.c_int32 * max(1, len(inputs)))(*inputs)
+        tabs = (C.c_int32 * max(1, len(tables)))(*tables)
+        return self._out(self.L.vdl_op_map, C.byref(d), ins, tabs)
+
     def op_fold_select(self, pred: int) -> int:
         return self._out(self.L.vdl_op_fold_select, pred)
 
@@ -197,8 +212,11 @@ class Plan:
         self.ctx.check(self.L.vdl_plan_stats(self.h, C.byref(s), C.byref(n), C.byref(f), C.byref(l)))
         pf, pe, pv = C.c_int(), C.c_int(), C.c_int()
         self.ctx.check(self.L.vdl_plan_probe_stats(self.h, C.byref(pf), C.byref(pe), C.byref(pv)))
+        mc, mn = C.c_int(), C.c_int()
+        self.ctx.check(self.L.vdl_plan_map_stats(self.h, C.byref(mc), C.byref(mn)))
         return {"statements": s.value, "nodes": n.value, "fused_scans": f.value, "launches": l.value,
-                "probe_folds": pf.value, "probe_emits": pe.value, "emitted_vectors": pv.value}
+                "probe_folds": pf.value, "probe_emits": pe.value, "emitted_vectors": pv.value,
+                "map_clusters": mc.value, "map_nodes": mn.value}
 
     def set_row_base(self, row_base: int):
         self.ctx.check(self.L.vdl_plan_set_row_base(self.h, row_base))

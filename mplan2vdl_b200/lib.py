@@ -87,6 +87,19 @@ class ProbeDesc(C.Structure):
                 ("nindicators", C.c_int32), ("pad2", C.c_int32), ("indicator", ProbePred * VDL_MAX_INDICATORS)]
 
 
+VDL_MAP_MAX_INPUTS, VDL_MAP_MAX_TABLES, VDL_MAP_MAX_INSTRS, VDL_MAP_MAX_IMMS, VDL_MAP_MAX_REGS = 48, 8, 160, 32, 32
+VDL_MAP_GATHER, VDL_MAP_LOAD, VDL_MAP_RANGE = 16, 17, 18
+
+
+class MapInstr(C.Structure):
+    _fields_ = [("op", C.c_int16), ("dst", C.c_int16), ("a", C.c_int16), ("b", C.c_int16)]
+
+
+class MapDesc(C.Structure):
+    _fields_ = [("ninputs", C.c_int32), ("ntables", C.c_int32), ("ninstrs", C.c_int32), ("nimms", C.c_int32),
+                ("instr", MapInstr * VDL_MAP_MAX_INSTRS), ("imm", C.c_int64 * VDL_MAP_MAX_IMMS)]
+
+
 # every symbol include/vdl_cuda.h declares: (name, restype, argtypes)
 _P, _I, _L = C.c_void_p, C.c_int, C.c_int64
 SYMBOLS = [
@@ -113,6 +126,8 @@ SYMBOLS = [
     ("vdl_vec_free", _I, [_P, C.c_int32]),
     ("vdl_op_range", _I, [_P, _L, _L, _L, C.POINTER(C.c_int32)]),
     ("vdl_op_binary", _I, [_P, _I, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    ("vdl_op_map", _I, [_P, C.POINTER(MapDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    ("vdl_abi_sizeof_map_desc", _I, []),
     ("vdl_op_fold_select", _I, [_P, C.c_int32, C.POINTER(C.c_int32)]),
     ("vdl_op_gather", _I, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     ("vdl_op_scatter", _I, [_P, C.c_int32, C.c_int32, _L, C.POINTER(C.c_int32)]),
@@ -148,6 +163,7 @@ SYMBOLS = [
     ("vdl_probe_partials", _I, [_P, C.POINTER(_P), C.POINTER(_L)]),
     ("vdl_probe_finalize", _I, [_P, _P, _I]),
     ("vdl_plan_probe_stats", _I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    ("vdl_plan_map_stats", _I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     ("vdl_plan_probe_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
     ("vdl_plan_set_row_base", _I, [_P, _L]),
     ("vdl_plan_exchange_bytes", _I, [_P, _I, _I, C.POINTER(_L)]),
@@ -185,6 +201,8 @@ def load():
             fn.restype, fn.argtypes = res, args
         if L.vdl_abi_sizeof_probe_desc() != C.sizeof(ProbeDesc):
             raise RuntimeError("vdl_probe_desc layout mismatch between lib.py and libvdl_cuda.so")
+        if L.vdl_abi_sizeof_map_desc() != C.sizeof(MapDesc):
+            raise ImportError("vdl_map_desc layout mismatch between lib.py and libvdl_cuda.so")
         if L.vdl_abi_sizeof_fused_desc() != C.sizeof(FusedDesc):
             raise ImportError("vdl_fused_desc layout mismatch between lib.py and libvdl_cuda.so")
         _lib = L

@@ -102,3 +102,69 @@ def test_errors_are_reported_not_fatal():
     out = ctx.plan("1,Load,t.x\n2,Project,out,Id 1,val\n3,MaterializeCompact,Id 2\n").run()
     np.testing.assert_array_equal(out["out"], [0, 1, 2])
     ctx.close()
+
+
+def test_op_map_register_program():
+    """vdl_op_map directly: one launch for ((a + 7*i) * b > c) | t[a & 3], against numpy."""
+    from mplan2vdl_b200.executor import Context
+    from mplan2vdl_b200.lib import VdlError
+    rng = np.random.default_rng(5)
+    n = 100_003
+    a = rng.integers(-2**40, 2**40, n).astype(I64)
+    b = rng.integers(-2**20, 2**20, n).astype(np.int32)
+    c = rng.integers(-2**60, 2**60, n).astype(I64)
+    t = np.array([0, 8, 16, 32], I64)
+    ctx = Context(0)
+    try:
+        va, vb, vc, vt = (ctx.upload_column(f"t.{k}", v) for k, v in (("a", a), ("b", b), ("c", c), ("t", t)))
+        prog = [("Load", 0, 0, 0), ("Range", 1, 0, 1), ("Add", 1, 0, 1), ("Load", 2, 0, 1), ("Multiply", 1, 1, 2), ("Load", 2, 0, 2),
+                ("Greater", 1, 1, 2), ("Range", 2, 2, 0), ("BitwiseAnd", 0, 0, 2), ("Gather", 0, 0, 0), ("BitwiseOr", 3, 1, 0)]
+        out = ctx.download(ctx.op_map(prog, [va, vb, vc], [vt], imms=[0, 7, 3]))
+        i = np.arange(n, dtype=I64)
+        want = (((a + 7 * i) * b.astype(I64)) > c).astype(I64) | t[a & 3]
+        np.testing.assert_array_equal(out, want)
+        with pytest.raises(VdlError):          # register 5 is read before anything wrote it
+            ctx.op_map([("Load", 0, 0, 0), ("Add", 1, 0, 5)], [va])
+        with pytest.raises(VdlError):          # inputs of different lengths
+            ctx.op_map([("Load", 0, 0, 0), ("Load", 1, 0, 1), ("Add", 1, 0, 1)], [va, vt])
+        # a Gather instruction out of range: value 0 and the context's error flag, which the next plan run reports
+        out = ctx.download(ctx.op_map([("Load", 0, 0, 0), ("Gather", 1, 0, 0)], [vc], [vt]))
+        np.testing.assert_array_equal(out, np.where((c >= 0) & (c < 4), t[np.clip(c, 0, 3)], 0))
+        with pytest.raises(VdlError):
+            ctx.plan("1,Load,t.t\n2,Project,val,Id 1,t\n3,RangeV,val,0,Id 2,1\n4,Gather,Id 2,Id 3,val\n5,Project,o,Id 4,val\n6,MaterializeCompact,Id 5\n").run()
+    finally:
+        ctx.close()
+
+
+MAP_PLAN = (
+    "1,Load,t.a\n2,Project,val,Id 1,a\n3,Load,t.b\n4,Project,val,Id 3,b\n"
+    "5,RangeV,val,100,Id 2,0\n6,Greater,val,Id 2,val,Id 5,val\n"                    # a > 100
+    "7,RangeV,val,7,Id 6,0\n8,Equals,val,Id 4,val,Id 7,val\n"                        # b == 7 (constant as long as an interior node)
+    "9,LogicalOr,val,Id 6,val,Id 8,val\n"
+    "10,Multiply,val,Id 2,val,Id 4,val\n11,Add,val,Id 10,val,Id 10,val\n"            # shared interior node
+    "12,Multiply,val,Id 11,val,Id 9,val\n"
+    "13,Load,t.k\n14,Project,val,Id 13,k\n15,Load,t.d\n16,Project,val,Id 15,d\n17,Gather,Id 16,Id 14,val\n"
+    "18,Add,val,Id 12,val,Id 17,val\n"
+    "19,RangeV,val,0,Id 18,1\n20,FoldSelect,val,Id 19,val,Id 9,val\n21,Gather,Id 18,Id 20,val\n"   # node 9 also feeds a FoldSelect: materialised
+    "22,Project,out,Id 18,val\n23,MaterializeCompact,Id 22\n24,Project,sel,Id 21,val\n25,MaterializeCompact,Id 24\n")
+
+
+@pytest.mark.parametrize("n", [0, 1, 1000, 300_007])
+def test_map_clusters_in_plans(n):
+    """Chains of elementwise ops / gathers in the op-at-a-time remainder run as vdl_op_map launches (build_clusters);
+    nodes something outside the chain consumes are still materialised."""
+    rng = np.random.default_rng(n)
+    cols = dict(a=rng.integers(0, 200, n).astype(I64), b=rng.integers(0, 10, n).astype(I64), k=rng.integers(0, 50, n).astype(I64),
+                d=rng.integers(-2**50, 2**50, 50).astype(I64))
+    both(MAP_PLAN, **cols)
+    _, stats = run_gpu(MAP_PLAN, {"t." + k: v for k, v in cols.items()}, fuse=True)
+    assert stats["map_clusters"] >= 2 and stats["map_nodes"] >= 8, stats
+    _, stats0 = run_gpu(MAP_PLAN, {"t." + k: v for k, v in cols.items()}, fuse=False)
+    assert stats0["map_clusters"] == 0 and stats0["launches"] > stats["launches"]
+
+
+def test_map_cluster_gather_out_of_range():
+    from mplan2vdl_b200.lib import VdlError
+    cols = {"t.a": np.arange(10, dtype=I64), "t.b": np.arange(10, dtype=I64), "t.k": np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 50], I64), "t.d": np.arange(50, dtype=I64)}
+    with pytest.raises(VdlError):
+        run_gpu(MAP_PLAN, cols, fuse=True)
