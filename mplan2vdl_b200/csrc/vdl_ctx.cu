@@ -65,6 +65,7 @@ extern "C" int vdl_ctx_destroy(vdl_ctx *ctx) {
   for (auto &v : ctx->vecs)
     if (v.live && v.owned && v.ptr) cudaFreeAsync(v.ptr, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
+  vdl_jit_destroy(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->d_errflag) cudaFree(ctx->d_errflag);
   if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);

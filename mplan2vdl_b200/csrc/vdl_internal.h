@@ -44,6 +44,7 @@ struct vdl_ctx {
   int *d_errflag = nullptr; // device-side error counter (Gather/Scatter range checks)
   void *scratch = nullptr;  // reusable scratch for scans / histograms
   size_t scratch_bytes = 0;
+  void *jit = nullptr;      // vdl_jit.cu: specialised vdl_op_map kernels
 };
 
 int vdl_fail(vdl_ctx *ctx, int code, const char *fmt, ...);
@@ -73,6 +74,16 @@ struct Operand {
   i64 from, step;
 };
 Operand operand_of(const Vec &v);
+
+// vdl_op_map's kernel arguments (interpreter in vdl_ops.cu, run-time specialisation in vdl_jit.cu)
+struct MapArgs {
+  Operand in[VDL_MAP_MAX_INPUTS];
+  Operand tab[VDL_MAP_MAX_TABLES];
+  i64 tab_len[VDL_MAP_MAX_TABLES];
+  vdl_map_desc d;
+};
+int vdl_jit_map_launch(vdl_ctx *ctx, const MapArgs &m, i64 *out, i64 n, int blocks);   // 1 launched, 0 use the interpreter, <0 error
+void vdl_jit_destroy(vdl_ctx *ctx);
 
 u64 vdl_fused_epoch(vdl_fused *f);
 void vdl_fused_set_epoch(vdl_fused *f, u64 e);

@@ -68,13 +68,7 @@ extern "C" int vdl_op_binary(vdl_ctx *ctx, int op, vdl_vec a, vdl_vec b, vdl_vec
 // the join's survivors: ~150 launches of a few microseconds each).  One launch interprets the whole tree per row: the
 // program is the same for every thread (no divergence), the register file lives in local memory (L1), and each input is
 // read from HBM once instead of once per consumer.
-struct MapArgs {
-  Operand in[VDL_MAP_MAX_INPUTS];
-  Operand tab[VDL_MAP_MAX_TABLES];
-  i64 tab_len[VDL_MAP_MAX_TABLES];
-  vdl_map_desc d;
-};
-
+#define VDL_MAP_JIT_MIN_ROWS (1 << 16)
 __global__ void __launch_bounds__(256) map_kernel(const __grid_constant__ MapArgs m, i64 *__restrict__ out, i64 n, int *errflag) {
   const i64 stride = (i64)gridDim.x * blockDim.x;
   const int nt = m.d.ninstrs;
@@ -146,7 +140,10 @@ extern "C" int vdl_op_map(vdl_ctx *ctx, const vdl_map_desc *d, const vdl_vec *in
   if (n == 0) return VDL_OK;
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   int blocks = (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 8));
-  map_kernel<<<blocks, 256, 0, ctx->stream>>>(m, (i64 *)ctx->vecs[*out].ptr, n, ctx->d_errflag);
+  // long vectors: a kernel specialised to this program (vdl_jit.cu); short ones are launch-bound either way
+  int jitted = n >= VDL_MAP_JIT_MIN_ROWS ? vdl_jit_map_launch(ctx, m, (i64 *)ctx->vecs[*out].ptr, n, blocks) : 0;
+  if (jitted < 0) return VDL_ECUDA;
+  if (!jitted) map_kernel<<<blocks, 256, 0, ctx->stream>>>(m, (i64 *)ctx->vecs[*out].ptr, n, ctx->d_errflag);
   ctx->launches++;
   VDL_CUDA(ctx, cudaGetLastError());
   return VDL_OK;
