@@ -66,6 +66,7 @@ extern "C" int vdl_ctx_destroy(vdl_ctx *ctx) {
     if (v.live && v.owned && v.ptr) cudaFreeAsync(v.ptr, ctx->stream);
   cudaStreamSynchronize(ctx->stream);
   vdl_jit_destroy(ctx);
+  if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->d_errflag) cudaFree(ctx->d_errflag);
   if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
@@ -163,10 +164,26 @@ int scratch_reserve(vdl_ctx *ctx, size_t bytes) {
   return VDL_OK;
 }
 
+__global__ void scalar_mail_kernel(const unsigned char *src, unsigned char *dst, int bytes) {
+  for (int i = 0; i < bytes; i++) dst[i] = src[i];
+}
+
+int read_scalar(vdl_ctx *ctx, const void *device_src, void *host_dst, int bytes) {
+  if (bytes < 0 || bytes > 64) return vdl_fail(ctx, VDL_EINVAL, "read_scalar: %d bytes", bytes);
+  if (!ctx->h_mail) {
+    VDL_CUDA(ctx, cudaHostAlloc(&ctx->h_mail, 64, cudaHostAllocMapped));
+    VDL_CUDA(ctx, cudaHostGetDevicePointer(&ctx->d_mail, ctx->h_mail, 0));
+  }
+  scalar_mail_kernel<<<1, 1, 0, ctx->stream>>>((const unsigned char *)device_src, (unsigned char *)ctx->d_mail, bytes);
+  VDL_CUDA(ctx, cudaGetLastError());
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(host_dst, ctx->h_mail, (size_t)bytes);
+  return VDL_OK;
+}
+
 int check_errflag(vdl_ctx *ctx, const char *what) {
   int flag = 0;
-  VDL_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_errflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  VDL_TRY(read_scalar(ctx, ctx->d_errflag, &flag, sizeof(int)));
   if (flag) {
     cudaMemsetAsync(ctx->d_errflag, 0, sizeof(int), ctx->stream);
     return vdl_fail(ctx, VDL_ERANGE, "%s: %d positions out of range", what, flag);
@@ -335,8 +352,7 @@ extern "C" int vdl_column_analyze(vdl_ctx *ctx, vdl_vec col, int64_t *vmin, int6
       else minmax_kernel<i64><<<blocks, 256, 0, ctx->stream>>>((const i64 *)v->ptr, v->len, (i64 *)ctx->scratch);
       ctx->launches++;
     }
-    VDL_CUDA(ctx, cudaMemcpyAsync(res, ctx->scratch, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VDL_TRY(read_scalar(ctx, ctx->scratch, res, 16));
     v->vmin = res[0];
     v->vmax = res[1];
     v->has_stats = true;

@@ -44,6 +44,7 @@ struct vdl_ctx {
   int *d_errflag = nullptr; // device-side error counter (Gather/Scatter range checks)
   void *scratch = nullptr;  // reusable scratch for scans / histograms
   size_t scratch_bytes = 0;
+  void *h_mail = nullptr, *d_mail = nullptr;   // 64 B of mapped pinned memory: scalars the host waits for (read_scalar)
   void *jit = nullptr;      // vdl_jit.cu: specialised vdl_op_map kernels
 };
 
@@ -66,6 +67,10 @@ int vec_new_range(vdl_ctx *ctx, i64 from, i64 step, i64 len, vdl_vec *out);
 Vec *vec_get(vdl_ctx *ctx, vdl_vec v);                                    // nullptr + error if invalid
 int scratch_reserve(vdl_ctx *ctx, size_t bytes);
 int check_errflag(vdl_ctx *ctx, const char *what);                        // synchronises
+// Host copy of a device scalar (<= 64 bytes) once the stream has reached this point.  A one-thread kernel stores it to
+// mapped host memory, so the read never queues on the copy engine behind a bulk device->host copy of another stream
+// (plan outputs); synchronises the context's stream.
+int read_scalar(vdl_ctx *ctx, const void *device_src, void *host_dst, int bytes);
 
 // Operand as the per-op kernels see it.
 struct Operand {

@@ -301,8 +301,7 @@ static int flag_scan(vdl_ctx *ctx, bool heads, const Operand &o, i64 n, i64 **bl
   else flag_count_kernel<false><<<(unsigned)nb, 256, 0, ctx->stream>>>(o, n, cnt);
   ctx->launches++;
   device_exclusive_scan(ctx, cnt, nb);
-  VDL_CUDA(ctx, cudaMemcpyAsync(total, cnt + nb, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  VDL_TRY(read_scalar(ctx, cnt + nb, total, 8));
   *block_off = cnt;
   return VDL_OK;
 }
@@ -393,8 +392,7 @@ extern "C" int vdl_op_fold_select(vdl_ctx *ctx, vdl_vec pred, vdl_vec *out) {
   select_lookback_kernel<<<grid, 256, 0, ctx->stream>>>(o, n, ntiles, state, ticket, (i64 *)ctx->vecs[*out].ptr, d_total);
   ctx->launches++;
   i64 total = 0;
-  VDL_CUDA(ctx, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  VDL_TRY(read_scalar(ctx, d_total, &total, 8));
   Vec &v = ctx->vecs[*out];
   v.len = total;
   v.domain = n;   // these positions index the predicate's row space (App. G2)
@@ -630,8 +628,7 @@ extern "C" int vdl_op_partition(vdl_ctx *ctx, vdl_vec data, int64_t pfrom, int64
     int g0 = (int)std::max<i64>(1, std::min<i64>((n + 1023) / 1024, (i64)ctx->sm_count * 16));
     descents_kernel<<<g0, 256, 0, ctx->stream>>>(od, n, pfrom, pstep, pcount, d_desc);
     ctx->launches++;
-    VDL_CUDA(ctx, cudaMemcpyAsync(&h_desc, d_desc, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VDL_TRY(read_scalar(ctx, d_desc, &h_desc, sizeof(int)));
     if (h_desc == 0) return vec_new_range(ctx, 0, 1, n, out);      // (its domain is n: positions 0..n-1)
   }
   VDL_TRY(vec_new(ctx, VDL_I64, n, out));
