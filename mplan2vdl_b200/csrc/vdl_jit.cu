@@ -178,7 +178,7 @@ cudaKernel_t compile(vdl_ctx *ctx, JitCache *jc, const std::string &src) {
 // Launches the specialised kernel for `m` on the context's stream.  Returns 1 when it did, 0 when the caller should run
 // the interpreter (NVRTC missing, compilation failed, VDL_NO_JIT), negative on a launch error.
 int vdl_jit_map_launch(vdl_ctx *ctx, const MapArgs &m, i64 *out, i64 n, int blocks) {
-  static const bool off = getenv("VDL_NO_JIT") != nullptr;
+  const bool off = getenv("VDL_NO_JIT") != nullptr;
   if (off || !nvrtc_load()) return 0;
   if (!ctx->jit) ctx->jit = new JitCache();
   JitCache *jc = (JitCache *)ctx->jit;

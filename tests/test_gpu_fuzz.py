@@ -55,3 +55,26 @@ def test_random_plans_translate_and_run_in_the_oracle(catalog, seed):
     for rel in (fuzz_plans.single_table(seed), fuzz_plans.join_query(seed, catalog)):
         want, _ = _run(catalog, rel, need_gpu=False)
         assert len(want) >= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(0, 40, 2))
+@pytest.mark.parametrize("jit", [True, False])
+def test_random_plans_through_map_clusters(catalog, seed, jit, monkeypatch):
+    """The same random plans with the probe pass switched off (VDL_NO_PROBE): predicates, CASE arithmetic and FK fetches
+    stay in the op-at-a-time remainder, which build_clusters (vdl_plan.cu) turns into vdl_op_map register programs --
+    interpreted (VDL_NO_JIT) or compiled at run time for the vectors of >= 65536 rows."""
+    monkeypatch.setenv("VDL_NO_PROBE", "1")
+    if not jit:
+        monkeypatch.setenv("VDL_NO_JIT", "1")
+    sf = 0.02                       # ~120 K lineitem rows: long enough for the specialised kernels
+    nodes = 0
+    for rel in (fuzz_plans.single_table(seed), fuzz_plans.join_query(seed, catalog)):
+        text = vlite.translate(catalog, rel)
+        rows = {t: synth.table_rows(catalog, t, sf) for t in catalog.tables}
+        cols = host_columns(catalog, tpch.plan_columns(text), rows, sf=sf)
+        got, stats = run_gpu(text, cols, fuse=True)
+        assert stats["probe_folds"] == 0 and stats["probe_emits"] == 0
+        assert_same(got, run_oracle(text, cols))
+        nodes += stats["map_nodes"]
+    assert nodes >= 2
