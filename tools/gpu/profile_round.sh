@@ -1,8 +1,10 @@
 # Round profile capture: for each workload, (1) plain run must exit 0, (2) launch list with gpu__time_duration,
 # (3) one ncu --set full capture of the dominant kernel.  Outputs under gpurun_out/ with prefix $1.
 pre=${1:-r01b}
+only=${2:-.}          # regex over the workload tags
 run() {  # tag kernel-regex skip bench-args...
   tag=$1; kre=$2; skip=$3; shift 3
+  echo "$tag" | grep -Eq "$only" || return 0
   python bench.py "$@" --no-e2e --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/${pre}_$tag.plain.json 2> gpurun_out/${pre}_$tag.plain.err || { echo "$tag: plain run failed"; tail -3 gpurun_out/${pre}_$tag.plain.err; return; }
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${pre}_launches_$tag.csv \
     python bench.py "$@" --no-e2e --no-cpu-baseline --steps 3 --warmup 3 > /dev/null 2>&1
@@ -15,3 +17,5 @@ run q01_sf10 fused_scan_fold 4 --query q01 --sf 10
 run q01_sf100 fused_scan_fold 4 --query q01 --sf 100
 run q05_sf10 probe_kernel 4 --query q05 --sf 10
 run q03_sf10 probe_kernel 4 --query q03 --sf 10
+run q12_sf10 probe_kernel 4 --query q12 --sf 10
+run q19_sf10 probe_kernel 4 --query q19 --sf 10
