@@ -181,7 +181,9 @@ __device__ __forceinline__ bool chain_test(const StageRegs &S, i64 row, i64 row_
 __global__ void __launch_bounds__(P_THREADS, 8) probe_kernel(const __grid_constant__ PDesc d) {
   extern __shared__ __align__(16) unsigned char psm[];
   __shared__ uint16_t queue[2][P_TILE];
-  __shared__ int wcnt[P_SUB][P_THREADS / 32];
+  __shared__ int s_cnt[3];                        // survivors appended by stage q: s_cnt[(q + 1) % 3]
+  __shared__ unsigned int s_bits[P_TILE / 32];    // emit mode: the tile's survivors as a bitmap, to put them back in row order
+  __shared__ int wsum[P_THREADS / 32];
   __shared__ i64 s_off;
   __shared__ unsigned int s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(P_THREADS, 8) probe_kernel(const __grid_consta
   i64 *tab = (folding && d.smem_table) ? stab : d.table;
 
   for (;;) {
-    if (tid == 0) s_tile = atomicAdd(d.ticket, 1u);
+    if (tid == 0) { s_tile = atomicAdd(d.ticket, 1u); s_cnt[1] = 0; }
     __syncthreads();
     const i64 tile = s_tile;
     if (tile >= d.ntiles) break;
@@ -258,30 +260,27 @@ __global__ void __launch_bounds__(P_THREADS, 8) probe_kernel(const __grid_consta
 #pragma unroll 1
           for (int k = 0; k < P_SUB; k++) f[k] = r[k] >= 0 && pred_holds(d, P, base + r[k], ok);
         }
-        // ordered append of the survivors of this round: (sub-round, warp, lane) order = queue order.  The P_SUB x 8
-        // per-warp counts are scanned by every warp for itself with shuffles (lane = sub-round * 8 + warp).
+        // append this round's survivors to the next stage's queue.  Queue order is irrelevant to a stage (and to a
+        // fold); emit mode restores row order once, at the end.  One shared atomic per warp and round, no barrier.
         unsigned m[P_SUB];
+        int wtotal = 0;
 #pragma unroll
-        for (int k = 0; k < P_SUB; k++) {
-          m[k] = __ballot_sync(0xffffffffu, f[k]);
-          if (lane == 0) wcnt[k][warp] = __popc(m[k]);
+        for (int k = 0; k < P_SUB; k++) { m[k] = __ballot_sync(0xffffffffu, f[k]); wtotal += __popc(m[k]); }
+        if (wtotal) {
+          int at = 0;
+          if (lane == 0) at = atomicAdd(&s_cnt[(q + 1) % 3], wtotal);
+          at = __shfl_sync(0xffffffffu, at, 0);
+#pragma unroll
+          for (int k = 0; k < P_SUB; k++) {
+            if (f[k]) queue[cur ^ 1][at + __popc(m[k] & ((1u << lane) - 1))] = (uint16_t)r[k];
+            at += __popc(m[k]);
+          }
         }
-        __syncthreads();
-        static_assert(P_SUB * (P_THREADS / 32) == 32, "one counter per lane");
-        const int c = (&wcnt[0][0])[lane];
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int excl = incl - c, total = __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-        for (int k = 0; k < P_SUB; k++) {
-          const int mine = n_out + __shfl_sync(0xffffffffu, excl, k * (P_THREADS / 32) + warp);
-          if (f[k]) queue[cur ^ 1][mine + __popc(m[k] & ((1u << lane) - 1))] = (uint16_t)r[k];
-        }
-        n_out += total;
-        __syncthreads();
       }
-      n_in = n_out;
+      // the counter two stages ahead is idle: every thread read it (as its n_in) before the previous stage's barrier
+      if (tid == 0) s_cnt[(q + 2) % 3] = 0;
+      __syncthreads();
+      n_in = s_cnt[(q + 1) % 3];
       cur ^= 1;
     }
     const bool implicit = d.npreds == 0;            // no predicate at all: every row of the tile survives
@@ -302,6 +301,26 @@ __global__ void __launch_bounds__(P_THREADS, 8) probe_kernel(const __grid_consta
         atomicMin((long long *)(tab + (size_t)(d.nfolds + 1) * d.domain + key), (long long)(d.row_base + row));
       }
     } else {
+      if (!implicit) {
+        // survivors back into row order: bitmap of the tile, one 32-row word per thread, block scan of the word counts
+        static_assert(P_TILE / 32 == P_THREADS, "one bitmap word per thread");
+        s_bits[tid] = 0;
+        __syncthreads();
+        for (int j = tid; j < n_in; j += P_THREADS) { const unsigned rr = queue[cur][j]; atomicOr(&s_bits[rr >> 5], 1u << (rr & 31)); }
+        __syncthreads();
+        unsigned w = s_bits[tid];
+        const int c = __popc(w);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int at = incl - c;
+        for (int ww = 0; ww < warp; ww++) at += wsum[ww];
+        while (w) { const int b = __ffs(w) - 1; w &= w - 1; queue[cur ^ 1][at++] = (uint16_t)(tid * 32 + b); }
+        cur ^= 1;
+        __syncthreads();
+      }
       // tile offset by decoupled look-back over the tiles before this one
       if (tid == 0) {
         const unsigned long long T = (unsigned long long)n_in;
