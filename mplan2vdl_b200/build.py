@@ -28,7 +28,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("VDL_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + sources()
     env = dict(os.environ)
     env["PATH"] = "/usr/bin:" + env.get("PATH", "")      # host compiler: the distro gcc
     subprocess.check_call(cmd, env=env)

@@ -33,8 +33,13 @@
 
 #include "vdl_internal.h"
 
-#define P_TILE 4096
+#ifndef P_THREADS
 #define P_THREADS 128
+#endif
+#define P_TILE (P_THREADS * 32)   // one bitmap word per thread (emit mode)
+#ifndef P_BLOCKS
+#define P_BLOCKS 12   // resident blocks per SM: 40 registers per thread, 12 x 17.9 KB of shared memory (measured: 8 blocks x 64 regs +15 %, 10 x 48 +3 %, 16 = 12 by shared memory)
+#endif
 #define P_MAX_DEPTH 6
 #define P_SMEM_TABLE_BYTES (40 * 1024)
 
@@ -176,9 +181,11 @@ __device__ __forceinline__ bool chain_test(const StageRegs &S, i64 row, i64 row_
   return (u64)v - (u64)S.lo <= S.span;
 }
 
-#define P_SUB 8      // rows per thread and round of a stage
+#ifndef P_SUB
+#define P_SUB 4      // rows per thread and round of a stage (8 was best while every round ended in two barriers)
+#endif
 
-__global__ void __launch_bounds__(P_THREADS, 8) probe_kernel(const __grid_constant__ PDesc d) {
+__global__ void __launch_bounds__(P_THREADS, P_BLOCKS) probe_kernel(const __grid_constant__ PDesc d) {
   extern __shared__ __align__(16) unsigned char psm[];
   __shared__ uint16_t queue[2][P_TILE];
   __shared__ int s_cnt[3];                        // survivors appended by stage q: s_cnt[(q + 1) % 3]
@@ -236,7 +243,6 @@ __global__ void __launch_bounds__(P_THREADS, 8) probe_kernel(const __grid_consta
         }
         if (l < 0) { S.depth = n; S.shr = P.t.shr; S.a = P.t.a; S.b = P.t.b; S.lo = P.lo; S.span = P.span; if (P.t.a == 0 && P.t.b == 1) S.depth += 8; }   // +8: plain
       }
-      int n_out = 0;
       for (int j0 = 0; j0 < n_in; j0 += P_SUB * P_THREADS) {
         bool f[P_SUB];
         int r[P_SUB];
@@ -603,7 +609,7 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
   }
   cudaEventCreate(&p->ev0);
   cudaEventCreate(&p->ev1);
-  int per_sm = 8;
+  int per_sm = P_BLOCKS;
   p->grid = (int)std::max<i64>(1, std::min<i64>((i64)ctx->sm_count * per_sm, d.ntiles));
   if (p->smem > 48 * 1024) cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
   *out = p;
