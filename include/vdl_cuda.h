@@ -291,6 +291,10 @@ typedef struct {
   vdl_probe_pred indicator[VDL_MAX_INDICATORS];   /* predicates used as 0/1 values (their terms may not be indicators) */
 } vdl_probe_desc;
 typedef struct vdl_probe vdl_probe;
+/* Peer-memory combine for a probe in fold mode (same protocol and buffer layout as vdl_fused_set_peers; the table has
+ * (nfolds + 2) * domain int64): after vdl_probe_set_peers, vdl_probe_run_ex(p, 2) leaves the GLOBAL result on every rank. */
+int vdl_probe_exchange_bytes(vdl_probe *p, int world, int64_t *bytes);
+int vdl_probe_set_peers(vdl_probe *p, int rank, int world, void *const *peer_buffers);
 int vdl_abi_sizeof_probe_desc(void);
 int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_probe **out);
 int vdl_probe_run(vdl_probe *p);                 /* asynchronous on the context stream */
@@ -332,11 +336,12 @@ int vdl_plan_num_fused(vdl_plan *p);
  * then the probe fold groups. */
 int vdl_plan_num_partials(vdl_plan *p);
 int vdl_plan_partials(vdl_plan *p, int i, void **device_ptr, int64_t *n_int64);
-/* Sharded execution without a collective library: exchange buffers of fused scan `fused_index` on every rank (see
- * vdl_fused_set_peers); afterwards vdl_plan_run() returns the GLOBAL result on every rank.  The size comes from
+/* Sharded execution without a collective library: exchange buffers of partial table `index` (numbered like
+ * vdl_plan_partials: fused scans, then probe fold groups) on every rank (see vdl_fused_set_peers / vdl_probe_set_peers);
+ * once every partial table has its peers, vdl_plan_run() returns the GLOBAL result on every rank.  The size comes from
  * vdl_plan_exchange_bytes() once the plan has run at least once (vdl_plan_run_local). */
-int vdl_plan_exchange_bytes(vdl_plan *p, int fused_index, int world, int64_t *bytes);
-int vdl_plan_set_peers(vdl_plan *p, int fused_index, int rank, int world, void *const *peer_buffers);
+int vdl_plan_exchange_bytes(vdl_plan *p, int index, int world, int64_t *bytes);
+int vdl_plan_set_peers(vdl_plan *p, int index, int rank, int world, void *const *peer_buffers);
 int vdl_plan_fused(vdl_plan *p, int i, vdl_fused **out);
 /* Phase 2: finalize the fused scans (optionally from all-gathered partials, one buffer per fused scan,
  * NULL entries / nranks 1 for single GPU), run the remaining ops, copy outputs to the host. */

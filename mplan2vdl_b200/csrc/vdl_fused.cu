@@ -75,17 +75,6 @@ struct FinDesc {
   i64 *reset_table;              // this rank's partial table, re-initialised for the next launch after the merge, or null
 };
 
-// Peer-memory exchange of the partial tables (one buffer per rank, addressable by all ranks):
-//   data  [2 (epoch parity)][world][stride] int64   rank r's table of the step lands in slot [parity][r] of EVERY buffer
-//   flags [2][world] uint64                         epoch of the last step whose table rank r has fully stored
-struct XDesc {
-  int32_t rank, world;
-  u64 epoch;                      // this step's number (1, 2, ...); parity double-buffers against a rank running ahead
-  u64 timeout_ns;                 // give up waiting for a peer after this long: error flag, never a hang
-  i64 stride;                     // int64 per table
-  i64 *peer[VDL_MAX_RANKS];       // base of every rank's buffer as seen from this GPU
-};
-
 // ------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -122,17 +111,6 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
-}
-__device__ __forceinline__ void st_release_sys(u64 *p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) {
-  u64 v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ u64 global_timer_ns() {
-  u64 t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
 }
 template <int NC>
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }

@@ -90,10 +90,36 @@ struct MapArgs {
 int vdl_jit_map_launch(vdl_ctx *ctx, const MapArgs &m, i64 *out, i64 n, int blocks);   // 1 launched, 0 use the interpreter, <0 error
 void vdl_jit_destroy(vdl_ctx *ctx);
 
+// Peer-memory exchange of the partial tables (one buffer per rank, addressable by all ranks):
+//   data  [2 (epoch parity)][world][stride] int64   rank r's table of the step lands in slot [parity][r] of EVERY buffer
+//   flags [2][world] uint64                         epoch of the last step whose table rank r has fully stored
+struct XDesc {
+  int32_t rank, world;
+  u64 epoch;                      // this step's number (1, 2, ...); parity double-buffers against a rank running ahead
+  u64 timeout_ns;                 // give up waiting for a peer after this long: error flag, never a hang
+  i64 stride;                     // int64 per table
+  i64 *peer[VDL_MAX_RANKS];       // base of every rank's buffer as seen from this GPU
+};
+
+
+u64 vdl_probe_epoch(vdl_probe *p);
+void vdl_probe_set_epoch(vdl_probe *p, u64 e);
 u64 vdl_fused_epoch(vdl_fused *f);
 void vdl_fused_set_epoch(vdl_fused *f, u64 e);
 
 #ifdef __CUDACC__
+// system-scope release / acquire and a wall clock for the peer-memory exchange (vdl_fused.cu, vdl_probe.cu)
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) {
+  u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ u64 global_timer_ns() {
+  u64 t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // Elementwise op semantics (Vdl.hs:136-157, 209-231).  Comparisons / logicals give 0/1; BitShift: +k arithmetic right,
 // -k left (Vlite.hs:205-208); Divide truncates, x/0 := 0, INT64_MIN/-1 wraps; Modulo is the C remainder, x%0 := 0.
 __device__ __forceinline__ i64 binop_apply(int op, i64 a, i64 b) {

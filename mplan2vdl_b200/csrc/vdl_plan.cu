@@ -623,6 +623,9 @@ struct ProbeFoldGroup {
   vdl_probe *probe = nullptr;
   std::vector<vdl_vec> bound;
   i64 bound_rows = -1, bound_base = -1;
+  // peer-memory combine (vdl_plan_set_peers): re-applied whenever the probe is re-prepared
+  int peer_rank = -1, peer_world = 0;
+  std::vector<void *> peers;
 };
 struct EmitGroup {
   int space = -1;
@@ -1308,8 +1311,14 @@ static int plan_run_local(vdl_plan *p, int self_finalize) {
     VDL_TRY(vdl_fused_launch_ex(g.fused, self_finalize && g.peer_world > 0 ? 2 : self_finalize));
   }
   for (auto *g : p->pgroups) {
+    vdl_probe *before = g->probe;
+    const u64 epoch = before ? vdl_probe_epoch(before) : 0;       // (read before a re-prepare destroys the probe)
     VDL_TRY(bind_probe(p, &g->b, &g->probe, &g->bound, &g->bound_rows, &g->bound_base));
-    VDL_TRY(vdl_probe_run_ex(g->probe, self_finalize));
+    if (g->probe != before && g->peer_world > 0) {
+      VDL_TRY(vdl_probe_set_peers(g->probe, g->peer_rank, g->peer_world, g->peers.data()));
+      vdl_probe_set_epoch(g->probe, epoch);
+    }
+    VDL_TRY(vdl_probe_run_ex(g->probe, self_finalize && g->peer_world > 0 ? 2 : self_finalize));
   }
   if (!self_finalize)        // sharded run: the survivors' vectors are exchanged between ranks before the tail is evaluated
     for (auto *g : p->egroups) VDL_TRY(run_emit_group(p, *g));
@@ -1328,19 +1337,32 @@ extern "C" int vdl_plan_fused(vdl_plan *p, int i, vdl_fused **out) {
   return *out ? VDL_OK : vdl_fail(p->ctx, VDL_EINVAL, "plan has not run yet");
 }
 
-extern "C" int vdl_plan_exchange_bytes(vdl_plan *p, int fused_index, int world, int64_t *bytes) {
-  if (!p || fused_index < 0 || fused_index >= (int)p->groups.size()) return VDL_EINVAL;
-  if (!p->groups[fused_index].fused) return vdl_fail(p->ctx, VDL_EINVAL, "plan has not run yet");
-  return vdl_fused_exchange_bytes(p->groups[fused_index].fused, world, bytes);
+// `index` runs over the plan's partial tables in the order of vdl_plan_partials: fused scans first, then probe fold groups
+extern "C" int vdl_plan_exchange_bytes(vdl_plan *p, int index, int world, int64_t *bytes) {
+  if (!p || index < 0 || index >= (int)(p->groups.size() + p->pgroups.size())) return VDL_EINVAL;
+  if (index < (int)p->groups.size()) {
+    if (!p->groups[index].fused) return vdl_fail(p->ctx, VDL_EINVAL, "plan has not run yet");
+    return vdl_fused_exchange_bytes(p->groups[index].fused, world, bytes);
+  }
+  ProbeFoldGroup &g = *p->pgroups[index - p->groups.size()];
+  if (!g.probe) return vdl_fail(p->ctx, VDL_EINVAL, "plan has not run yet");
+  return vdl_probe_exchange_bytes(g.probe, world, bytes);
 }
 
-extern "C" int vdl_plan_set_peers(vdl_plan *p, int fused_index, int rank, int world, void *const *peer_buffers) {
-  if (!p || fused_index < 0 || fused_index >= (int)p->groups.size() || !peer_buffers || world < 1 || world > VDL_MAX_RANKS) return VDL_EINVAL;
-  FusedGroup &g = p->groups[fused_index];
+extern "C" int vdl_plan_set_peers(vdl_plan *p, int index, int rank, int world, void *const *peer_buffers) {
+  if (!p || index < 0 || index >= (int)(p->groups.size() + p->pgroups.size()) || !peer_buffers || world < 1 || world > VDL_MAX_RANKS) return VDL_EINVAL;
+  if (index < (int)p->groups.size()) {
+    FusedGroup &g = p->groups[index];
+    g.peer_rank = rank; g.peer_world = world;
+    g.peers.assign(peer_buffers, peer_buffers + world);
+    g.epoch = 0;
+    if (g.fused) VDL_TRY(vdl_fused_set_peers(g.fused, rank, world, g.peers.data()));
+    return VDL_OK;
+  }
+  ProbeFoldGroup &g = *p->pgroups[index - p->groups.size()];
   g.peer_rank = rank; g.peer_world = world;
   g.peers.assign(peer_buffers, peer_buffers + world);
-  g.epoch = 0;
-  if (g.fused) VDL_TRY(vdl_fused_set_peers(g.fused, rank, world, g.peers.data()));
+  if (g.probe) VDL_TRY(vdl_probe_set_peers(g.probe, rank, world, g.peers.data()));
   return VDL_OK;
 }
 

@@ -457,10 +457,36 @@ __global__ void __launch_bounds__(256, 1) probe_finalize_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------ host side
+// Multi-GPU combine over peer memory, as in the fused scan (XDesc, vdl_internal.h): one block stores this rank's partial
+// table (FoldChoose values included) into slot [parity][rank] of EVERY rank's exchange buffer over NVLink, publishes the
+// step's epoch and waits for the other ranks' flags; the finalize kernel that follows merges the `world` tables that
+// arrived in this rank's own buffer.  A peer that never arrives: error flag after the timeout, never a hang.
+__global__ void __launch_bounds__(256, 1) probe_exchange_kernel(const __grid_constant__ XDesc x, const i64 *table, int *errflag) {
+  const int tid = threadIdx.x;
+  const int par = (int)(x.epoch & 1);
+  const size_t slot = ((size_t)par * x.world + x.rank) * x.stride, flags = (size_t)2 * x.world * x.stride;
+  for (int p = 0; p < x.world; p++) {
+    i64 *dst = x.peer[p] + slot;
+    for (i64 i = tid; i < x.stride; i += 256) dst[i] = __ldcg(&table[i]);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < x.world) {
+    st_release_sys((u64 *)(x.peer[tid] + flags) + (size_t)par * x.world + x.rank, x.epoch);
+    const u64 *mine = (const u64 *)(x.peer[x.rank] + flags) + (size_t)par * x.world + tid;
+    const u64 t0 = global_timer_ns();
+    while (ld_acquire_sys(mine) < x.epoch) {
+      if (global_timer_ns() - t0 > x.timeout_ns) { atomicAdd(errflag, 1 << 20); break; }
+      __nanosleep(64);
+    }
+  }
+}
+
 struct vdl_probe {
   vdl_ctx *ctx = nullptr;
   PDesc pd;
   PFin pf;
+  XDesc xd;                            // world 0: no peer exchange configured
   bool folding = true, ran = false, fetched = false, finalized = false;
   vdl_vec table = 0;
   i64 *d_out = nullptr, *h_out = nullptr, *h_mapped = nullptr;
@@ -490,6 +516,7 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
   if (desc->rows < 0) return vdl_fail(ctx, VDL_EINVAL, "probe: negative row count");
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   vdl_probe *p = new vdl_probe();
+  memset(&p->xd, 0, sizeof p->xd);
   p->ctx = ctx;
   PDesc &d = p->pd;
   memset(&d, 0, sizeof d);
@@ -618,6 +645,32 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
 
 extern "C" int vdl_probe_run(vdl_probe *p) { return vdl_probe_run_ex(p, 1); }
 
+extern "C" int vdl_probe_exchange_bytes(vdl_probe *p, int world, int64_t *bytes) {
+  if (!p || !bytes || !p->folding || world < 1 || world > VDL_MAX_RANKS) return VDL_EINVAL;
+  const int64_t stride = (int64_t)(p->pd.nfolds + 2) * p->pd.domain;
+  *bytes = ((int64_t)2 * world * stride + 2 * world) * (int64_t)sizeof(i64);
+  return VDL_OK;
+}
+
+extern "C" int vdl_probe_set_peers(vdl_probe *p, int rank, int world, void *const *peer_buffers) {
+  if (!p || !p->folding || !peer_buffers || world < 1 || world > VDL_MAX_RANKS || rank < 0 || rank >= world) return VDL_EINVAL;
+  memset(&p->xd, 0, sizeof p->xd);
+  p->xd.rank = rank;
+  p->xd.world = world;
+  p->xd.stride = (i64)(p->pd.nfolds + 2) * p->pd.domain;
+  p->xd.timeout_ns = 10000000000ull;                     // 10 s; VDL_PEER_TIMEOUT_MS overrides (tests)
+  if (const char *e = getenv("VDL_PEER_TIMEOUT_MS")) p->xd.timeout_ns = (u64)atoll(e) * 1000000ull;
+  for (int r = 0; r < world; r++) {
+    if (!peer_buffers[r]) return vdl_fail(p->ctx, VDL_EINVAL, "set_peers: buffer of rank %d is null", r);
+    p->xd.peer[r] = (i64 *)peer_buffers[r];
+  }
+  return VDL_OK;
+}
+
+// step counter of the peer exchange; the plan carries it over when a probe is re-prepared on the same buffers
+u64 vdl_probe_epoch(vdl_probe *p) { return p->xd.epoch; }
+void vdl_probe_set_epoch(vdl_probe *p, u64 e) { p->xd.epoch = e; }
+
 extern "C" int vdl_probe_partials(vdl_probe *p, void **device_ptr, int64_t *n_int64) {
   if (!p || !device_ptr || !n_int64 || !p->folding) return VDL_EINVAL;
   *device_ptr = p->pd.table;
@@ -675,7 +728,17 @@ extern "C" int vdl_probe_run_ex(vdl_probe *p, int finalize) {
   }
   VDL_CUDA(ctx, cudaEventRecord(p->ev1, ctx->stream));
   p->finalized = !p->folding || finalize != 0;
-  if (p->folding && finalize) {
+  if (p->folding && finalize == 2) {       // peer-memory combine: every rank ends with the global result, no host round trip
+    if (p->xd.world < 1) return vdl_fail(ctx, VDL_EINVAL, "probe: peer exchange requested before vdl_probe_set_peers");
+    p->xd.epoch++;
+    int cb = (int)std::min<i64>(ctx->sm_count, (d.domain + 255) / 256);
+    probe_choose_kernel<<<std::max(cb, 1), 256, 0, ctx->stream>>>(d);
+    probe_exchange_kernel<<<1, 256, 0, ctx->stream>>>(p->xd, d.table, ctx->d_errflag);
+    p->pf.table = p->xd.peer[p->xd.rank] + (size_t)(p->xd.epoch & 1) * p->xd.world * p->xd.stride;
+    p->pf.nranks = p->xd.world; p->pf.stride = p->xd.stride; p->pf.precomputed_choose = 1;
+    probe_finalize_kernel<<<1, 256, 0, ctx->stream>>>(d, p->pf);
+    ctx->launches += 3;
+  } else if (p->folding && finalize) {
     p->pf.table = d.table; p->pf.nranks = 1; p->pf.stride = (i64)(d.nfolds + 2) * d.domain; p->pf.precomputed_choose = 0;
     probe_finalize_kernel<<<1, 256, 0, ctx->stream>>>(d, p->pf);
     ctx->launches++;
@@ -702,6 +765,7 @@ static int probe_fetch(vdl_probe *p) {
     i64 err = p->h_out[tail + 1];
     if (err) {
       cudaMemsetAsync(ctx->d_errflag, 0, sizeof(int), ctx->stream);
+      if (err >= (1 << 20)) return vdl_fail(ctx, VDL_ECUDA, "probe: a peer GPU never delivered its partial table (exchange timed out)");
       return vdl_fail(ctx, VDL_ERANGE, "probe: %lld rows had a lookup index or group key out of range", (long long)err);
     }
     p->ngroups = p->h_out[tail];

@@ -80,7 +80,7 @@ class ShardedPlan:
         import torch.distributed as dist
         ok, ptr_lists = 1, []
         try:
-            for i in range(self.plan.num_fused):
+            for i in range(self.plan.num_partials):       # fused scans, then probe fold groups
                 mine = self.ctx.ipc_alloc(self.plan.exchange_bytes(i, self.world))
                 self._mine.append(mine)
                 handles = [None] * self.world
@@ -111,8 +111,8 @@ class ShardedPlan:
             return self.plan.run(copy)                  # one launch per fused scan: its last thread block finalizes
         out = self._step_all_gather(copy)
         if self._want_peer:                             # the scans exist now: switch to the peer-memory combine
-            self._want_peer = False                     # (probe fold groups combine through the all-gather path for now)
-            self.peer_mode = self.plan.num_partials == self.plan.num_fused and self.plan.num_emits == 0 and self._setup_peers()
+            self._want_peer = False                     # (plans that emit survivors keep the all-gather path)
+            self.peer_mode = self.plan.num_partials > 0 and self.plan.num_emits == 0 and self._setup_peers()
         return out
 
     def _step_all_gather(self, copy: bool = True) -> dict:

@@ -147,6 +147,8 @@ SYMBOLS = [
     ("vdl_fused_last_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
     ("vdl_plan_load", _I, [_P, C.c_char_p, _I, C.POINTER(_P)]),
     ("vdl_plan_stats", _I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
+    ("vdl_probe_exchange_bytes", _I, [_P, _I, C.POINTER(_L)]),
+    ("vdl_probe_set_peers", _I, [_P, _I, _I, C.POINTER(_P)]),
     ("vdl_abi_sizeof_probe_desc", _I, []),
     ("vdl_probe_prepare", _I, [_P, C.POINTER(ProbeDesc), C.POINTER(_P)]),
     ("vdl_probe_run", _I, [_P]),

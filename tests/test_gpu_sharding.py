@@ -181,6 +181,80 @@ def test_peer_exchange_times_out_instead_of_hanging(catalog, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("q", ["q05.vdl", "q12.vdl"])
+@pytest.mark.parametrize("world,sf", [(2, 0.01), (4, 0.01), (4, 0.002)])       # (4, 0.002): the last rank's shard is empty
+def test_probe_fold_plans_combine_over_peer_memory(catalog, q, world, sf):
+    """FK-join plans whose Folds run on the probe kernel: each rank's partial table crosses to every rank's exchange
+    buffer inside a kernel (probe_exchange_kernel), the finalize merges them -- vdl_plan_run returns the global result on
+    every rank, no collective, no host round trip.  Emulated ranks (one context + host thread each), three steps."""
+    import threading
+    from mplan2vdl_b200 import synth
+    from mplan2vdl_b200.executor import Context
+    text = plan_text(q)
+    rows = {t: synth.table_rows(catalog, t, sf) for t in catalog.tables}
+    cols = host_columns(catalog, tpch.plan_columns(text), rows, sf=sf)
+    want = run_oracle(text, cols)
+    ctxs, plans = [], []
+    for rank in range(world):
+        start, n = tpch.shard_range(rows["lineitem"], rank, world)
+        ctx = Context(0)
+        for k, v in cols.items():
+            ctx.upload_column(k, v[start:start + n] if k.startswith("lineitem.") else v)
+        plan = ctx.plan(text)
+        plan.set_row_base(start)
+        plan.run_local()
+        ctx.synchronize()
+        assert plan.num_fused == 0 and plan.num_partials == 1 and plan.num_emits == 0
+        ctxs.append(ctx)
+        plans.append(plan)
+    bufs = [ctxs[r].ipc_alloc(plans[r].exchange_bytes(0, world)) for r in range(world)]
+    for r in range(world):
+        plans[r].set_peers(0, r, world, bufs)
+    for step in range(3):
+        results, errors = [None] * world, []
+
+        def work(r):
+            try:
+                results[r] = plans[r].run()
+            except Exception as e:          # pragma: no cover
+                errors.append(e)
+        threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(60)
+        assert not errors, errors
+        for r in range(world):
+            assert_same(results[r], want)
+    for r in range(world):
+        plans[r].close()
+        ctxs[r].ipc_free(bufs[r])
+        ctxs[r].close()
+
+
+def test_probe_peer_exchange_times_out_instead_of_hanging(catalog, monkeypatch):
+    from mplan2vdl_b200 import synth
+    from mplan2vdl_b200.executor import Context
+    from mplan2vdl_b200.lib import VdlError
+    monkeypatch.setenv("VDL_PEER_TIMEOUT_MS", "200")
+    text = plan_text("q12.vdl")
+    rows = {t: synth.table_rows(catalog, t, 0.002) for t in catalog.tables}
+    ctx = Context(0)
+    for k, v in host_columns(catalog, tpch.plan_columns(text), rows, sf=0.002).items():
+        ctx.upload_column(k, v)
+    plan = ctx.plan(text)
+    plan.run_local()
+    ctx.synchronize()
+    bufs = [ctx.ipc_alloc(plan.exchange_bytes(0, 2)) for _ in range(2)]      # "rank 1" exists only as a buffer
+    plan.set_peers(0, 0, 2, bufs)
+    with pytest.raises(VdlError, match="peer GPU never delivered"):
+        plan.run()
+    plan.close()
+    for b in bufs:
+        ctx.ipc_free(b)
+    ctx.close()
+
+
 @pytest.mark.parametrize("q", ["q03.vdl", "q19.vdl"])
 @pytest.mark.parametrize("world,sf", [(2, 0.01), (3, 0.01), (4, 0.002)])       # (4, 0.002): the last rank's shard is empty
 def test_emit_plans_sharded_by_exchanging_survivors(catalog, q, world, sf):
