@@ -367,8 +367,9 @@ def main():
             "metric": f"tpch_{args.query}_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic", "config": workload_config(args),
-            "combine": "none (single GPU)" if world == 1 else ("peer-memory exchange fused into the scan kernel's last thread block (NVLink stores + epoch flags), no collective"
-                                                                 if sharded.peer_mode else "NCCL all-gather of the partial tables + finalize kernel"),
+            "combine": "none (single GPU)" if world == 1 else (("peer-memory exchange fused into the scan kernel's last thread block (NVLink stores + epoch flags), no collective"
+                                                                  if plan.num_fused else "peer-memory exchange kernel after the probe pass (NVLink stores + epoch flags) + finalize, no collective")
+                                                                 if sharded.peer_mode else "NCCL all-gather of the partial tables / survivors + finalize"),
             "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "wall_ms_per_step": wall_ms / args.steps, "result": {k: [int(x) for x in v[:8]] for k, v in result.items()},
