@@ -313,8 +313,12 @@ def main():
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f).get(f"{args.query}_sf{args.sf:g}")
-            if tr:
+            if tr and world == 1:
                 roofline["traffic"] = tr
+                # a selective plan (probe kernel) never touches most columns of the rows it rejects: the DRAM bytes
+                # ncu counted are then the honest numerator, the all-columns algorithmic figure an upper bound
+                roofline["dram_gbs_by_traffic"] = tr / (statistics.mean(kernel_ms) / 1e3) / 1e9
+                roofline["frac_by_traffic"] = roofline["dram_gbs_by_traffic"] / peak
     except Exception:
         pass
 
