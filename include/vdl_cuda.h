@@ -139,6 +139,10 @@ typedef struct vdl_map_desc {
 } vdl_map_desc;
 int vdl_op_map(vdl_ctx *ctx, const vdl_map_desc *desc, const vdl_vec *inputs, const vdl_vec *tables, vdl_vec *out);
 int vdl_abi_sizeof_map_desc(void);
+/* Host-only check of the run-time specialisation of vdl_op_map (no GPU needed): generates the CUDA C of a program that
+ * uses every instruction, compiles it with NVRTC for sm_100a.  VDL_OK, VDL_ENOTFOUND (no NVRTC here: the interpreting
+ * kernel is used) or VDL_ECUDA with NVRTC's log. */
+int vdl_jit_selftest(char *log, int log_capacity);
 /* FoldSelect with fold = pos_ pred (Vlite.hs:721-730): ascending positions of non-zero pred. */
 int vdl_op_fold_select(vdl_ctx *ctx, vdl_vec pred, vdl_vec *out);
 /* Gather (Vdl.hs:438): out[i] = src[pos[i]]. */

@@ -202,6 +202,45 @@ int vdl_jit_map_launch(vdl_ctx *ctx, const MapArgs &m, i64 *out, i64 n, int bloc
   return 1;
 }
 
+// Host-only self-test (no GPU needed): print a program that uses every instruction kind and storage kind as CUDA C and
+// compile it with NVRTC for sm_100a.  0 = compiled; VDL_ENOTFOUND = NVRTC not present on this machine; VDL_ECUDA =
+// NVRTC rejected the source (the log is copied to `log`).
+extern "C" int vdl_jit_selftest(char *log, int log_capacity) {
+  if (log && log_capacity > 0) log[0] = 0;
+  MapArgs m;
+  memset(&m, 0, sizeof m);
+  vdl_map_desc &d = m.d;
+  d.ninputs = 3; d.ntables = 2; d.nimms = 2;
+  d.imm[0] = -5; d.imm[1] = 3;
+  m.in[0].kind = 0; m.in[1].kind = 1; m.in[2].kind = 2;
+  m.tab[0].kind = 0; m.tab[1].kind = 1;
+  int t = 0;
+  for (int k = 0; k < 3; k++) d.instr[t++] = vdl_map_instr{VDL_MAP_LOAD, (int16_t)k, 0, (int16_t)k};
+  d.instr[t++] = vdl_map_instr{VDL_MAP_RANGE, 3, 0, 1};
+  for (int op = VDL_LOGICAL_AND; op <= VDL_MODULO; op++) d.instr[t++] = vdl_map_instr{(int16_t)op, (int16_t)(4 + op % 2), (int16_t)(op % 4), (int16_t)((op + 1) % 4)};
+  d.instr[t++] = vdl_map_instr{VDL_MAP_GATHER, 6, 4, 0};
+  d.instr[t++] = vdl_map_instr{VDL_MAP_GATHER, 7, 5, 1};
+  d.instr[t++] = vdl_map_instr{VDL_ADD, 6, 6, 7};
+  d.ninstrs = t;
+  if (!nvrtc_load()) return VDL_ENOTFOUND;
+  Nvrtc &N = g_nvrtc;
+  const std::string src = generate(m);
+  void *prog = nullptr;
+  if (N.create(&prog, src.c_str(), "vdl_map_jit.cu", 0, nullptr, nullptr) != 0) return VDL_ECUDA;
+  const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+  const int rc = N.compile(prog, 3, opts);
+  size_t ls = 0, cs = 0;
+  N.log_size(prog, &ls);
+  if (log && log_capacity > 1 && ls > 1) {
+    std::string l(ls + 1, '\0');
+    N.log(prog, &l[0]);
+    snprintf(log, (size_t)log_capacity, "%s", l.c_str());
+  }
+  if (rc == 0) N.cubin_size(prog, &cs);
+  N.destroy(&prog);
+  return rc == 0 && cs > 0 ? VDL_OK : VDL_ECUDA;
+}
+
 void vdl_jit_destroy(vdl_ctx *ctx) {
   if (!ctx->jit) return;
   JitCache *jc = (JitCache *)ctx->jit;

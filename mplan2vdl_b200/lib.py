@@ -128,6 +128,7 @@ SYMBOLS = [
     ("vdl_op_binary", _I, [_P, _I, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     ("vdl_op_map", _I, [_P, C.POINTER(MapDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("vdl_abi_sizeof_map_desc", _I, []),
+    ("vdl_jit_selftest", _I, [C.c_char_p, _I]),
     ("vdl_op_fold_select", _I, [_P, C.c_int32, C.POINTER(C.c_int32)]),
     ("vdl_op_gather", _I, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     ("vdl_op_scatter", _I, [_P, C.c_int32, C.c_int32, _L, C.POINTER(C.c_int32)]),

@@ -48,3 +48,17 @@ def test_product_never_imports_the_oracle():
             src = open(os.path.join(dirpath, f)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
             assert not re.search(r"#include[^\n]*oracle|libvdl_oracle", src), f
+
+
+def test_map_specialisation_compiles_without_a_gpu():
+    """vdl_jit.cu prints a register program as CUDA C and compiles it with NVRTC for sm_100a -- host-only work, so the
+    generator is checked here (every instruction kind, every storage kind); running the kernel is a GPU test."""
+    import ctypes
+    from mplan2vdl_b200 import lib
+    L = lib.load()
+    log = ctypes.create_string_buffer(8192)
+    rc = L.vdl_jit_selftest(log, len(log))
+    if rc == 3:                       # VDL_ENOTFOUND: no libnvrtc on this machine, the interpreting kernel is used
+        import pytest
+        pytest.skip("NVRTC not installed")
+    assert rc == 0, log.value.decode(errors="replace")
