@@ -1452,7 +1452,7 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
     ran_ops = true;
     vdl_vec v;
     int rc = eval(p, o.node, &v);
-    if (rc) { free_temps(p); return rc; }
+    if (rc) { if (copies_pending) cudaStreamSynchronize(ctx->copy_stream); free_temps(p); return rc; }
     i64 len;
     VDL_TRY(vdl_vec_len(ctx, v, &len));
     if ((size_t)len > o.cap) {              // pinned, so the copy is one DMA at PCIe rate
@@ -1471,7 +1471,7 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
       copies_pending = true;
     } else {
       rc = vdl_vec_download(ctx, v, o.pinned, len);
-      if (rc) { free_temps(p); return rc; }
+      if (rc) { if (copies_pending) cudaStreamSynchronize(ctx->copy_stream); free_temps(p); return rc; }
     }
     o.data = o.pinned; o.len = len;
   }
