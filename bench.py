@@ -115,19 +115,19 @@ def cpu_oracle_rate(cat, query: str, sf: float, target_seconds: float = 12.0, ma
     """Time the CPU oracle (kind "port": the reference ships no executor) on a bounded sample of the same workload:
     the first `rows` lineitem rows of the same synthetic table.  Returns (rows/s, sample rows, threads, seconds list)."""
     from mplan2vdl_b200 import synth, tpch
-    from oracle.oracle import Oracle, gen_column, max_threads
+    from oracle.oracle import Oracle, gen_column
     text = tpch.plan_text(QUERIES[query][0])
     names = tpch.plan_columns(text)
     seed = synth.seed_for(sf)
-    threads = max_threads()
+    threads = host_threads()        # set explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
 
     def run(rows, reps):
         orc = Oracle()
         for n in names:
-            orc.bind(n, gen_column(synth.column_spec(cat, n, sf), rows, 0, seed))
+            orc.bind(n, gen_column(synth.column_spec(cat, n, sf), rows, 0, seed, threads))
         secs = []
         for _ in range(reps):
-            orc.run(text)
+            orc.run(text, threads)
             secs.append(orc.seconds)
         return secs
 
