@@ -190,3 +190,14 @@ def test_avg_over_a_join_is_a_post_op_of_the_probe(catalog):
     assert_same(got, want)
     assert stats["probe_folds"] == 1 and stats["probe_emits"] == 0 and stats["launches"] <= 4
     assert len(want["avg_qty"]) == 3
+
+
+@pytest.mark.parametrize("q", ["q01", "q03", "q05", "q06", "q12", "q19"])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_cuda_path_reproduces_the_committed_answers(catalog, q, fuse):
+    """libvdl_cuda (fused paths, and op-at-a-time) against tests/golden/tpch_sf0.01_answers.json: known answers that do
+    not depend on the CPU oracle being run next to it."""
+    from util import golden_case
+    text, cols, want = golden_case(catalog, q)
+    got, _ = run_gpu(text, cols, fuse=fuse)
+    assert_same(got, want)

@@ -39,3 +39,11 @@ def test_q1_oracle_matches_sql(catalog, rows):
 def test_q1_threads_do_not_change_results(catalog):
     cols = host_columns(catalog, ["lineitem." + c for c in Q1_COLS], {"lineitem": 50_000})
     assert_same(run_oracle(plan_text("q01.vdl"), cols, threads=1), run_oracle(plan_text("q01.vdl"), cols, threads=8))
+
+
+@pytest.mark.parametrize("q", ["q01", "q03", "q05", "q06", "q12", "q19"])
+def test_oracle_reproduces_the_committed_answers(catalog, q):
+    """The plan interpreter against tests/golden/tpch_sf0.01_answers.json (the SQL-level evaluation, committed)."""
+    from util import golden_case
+    text, cols, want = golden_case(catalog, q)
+    assert_same(run_oracle(text, cols), want)

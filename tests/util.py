@@ -85,3 +85,21 @@ def q19_columns(cat, sf=0.01, seed=19):
     cols["part.p_brand"] = draw("part.p_brand", ["Brand#12", "Brand#23", "Brand#34"], [16, 32], npart)
     cols["part.p_container"] = draw("part.p_container", ["SM CASE", "SM BOX", "MED BAG", "MED PKG", "LG CASE", "LG PKG", "SM PKG", "LG BOX"], [8], npart)
     return text, cols
+
+
+def golden_case(cat, q):
+    """(plan text, host columns, committed answer) of query `q` at SF 0.01: tests/golden/tpch_sf0.01_answers.json, written
+    by tools/make_golden_results.py from the SQL-level numpy evaluation (oracle/sqlref.py)."""
+    import json
+    from mplan2vdl_b200 import tpch
+    with open(os.path.join(ROOT, "tests", "golden", "tpch_sf0.01_answers.json")) as f:
+        g = json.load(f)
+    sf = g["sf"]
+    assert g["seed"] == synth.seed_for(sf)
+    if q == "q19":
+        text, cols = q19_columns(cat, sf=sf)
+    else:
+        text = plan_text(q + ".vdl")
+        rows = {t: synth.table_rows(cat, t, sf) for t in cat.tables}
+        cols = host_columns(cat, tpch.plan_columns(text), rows, sf=sf)
+    return text, cols, {k: np.asarray(v, dtype=np.int64) for k, v in g["answers"][q].items()}
