@@ -11,13 +11,15 @@ module VdlCuda where
 import Data.Int (Int32, Int64)
 import Data.Word (Word64)
 import Foreign.C.String (CString)
-import Foreign.C.Types (CInt (..))
+import Foreign.C.Types (CFloat (..), CInt (..))
 import Foreign.Ptr (Ptr)
 
 data VdlCtx
 data VdlPlan
 data VdlFused
 data VdlProbe
+data VdlFusedDesc  -- vdl_fused_desc / vdl_probe_desc: marshalled with Foreign.Storable by the caller (layouts in vdl_cuda.h)
+data VdlProbeDesc
 data VdlMapDesc   -- vdl_map_desc: marshalled with Foreign.Storable by the caller (layout in vdl_cuda.h)
 type VdlVec = Int32
 
@@ -89,3 +91,43 @@ foreign import ccall safe "vdl_plan_partials" c_vdl_plan_partials :: Ptr VdlPlan
 foreign import ccall safe "vdl_plan_num_emits" c_vdl_plan_num_emits :: Ptr VdlPlan -> IO CInt
 foreign import ccall safe "vdl_plan_emit" c_vdl_plan_emit :: Ptr VdlPlan -> CInt -> Ptr (Ptr ()) -> Ptr Int64 -> IO CInt
 foreign import ccall safe "vdl_plan_emit_replace" c_vdl_plan_emit_replace :: Ptr VdlPlan -> CInt -> Ptr () -> Int64 -> IO CInt
+
+-- fused scan / FK-join probe / remaining context, column and plan entry points (tools/gen_hs_imports.py keeps this list
+-- in step with include/vdl_cuda.h; tests/test_abi.py checks that every declaration has an import)
+foreign import ccall safe "vdl_abi_sizeof_fused_desc" c_vdl_abi_sizeof_fused_desc :: IO CInt
+foreign import ccall safe "vdl_ctx_stream" c_vdl_ctx_stream :: Ptr VdlCtx -> IO (Ptr ())
+foreign import ccall safe "vdl_ctx_synchronize" c_vdl_ctx_synchronize :: Ptr VdlCtx -> IO CInt
+foreign import ccall safe "vdl_ctx_launch_count" c_vdl_ctx_launch_count :: Ptr VdlCtx -> IO Int64
+foreign import ccall safe "vdl_column_bind" c_vdl_column_bind :: Ptr VdlCtx -> CString -> CInt -> Int64 -> Int64 -> Ptr () -> Ptr VdlVec -> IO CInt
+foreign import ccall safe "vdl_column_download" c_vdl_column_download :: Ptr VdlCtx -> VdlVec -> Ptr () -> Int64 -> IO CInt
+foreign import ccall safe "vdl_column_analyze" c_vdl_column_analyze :: Ptr VdlCtx -> VdlVec -> Ptr Int64 -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_column_drop" c_vdl_column_drop :: Ptr VdlCtx -> CString -> IO CInt
+foreign import ccall safe "vdl_vec_dtype" c_vdl_vec_dtype :: Ptr VdlCtx -> VdlVec -> Ptr CInt -> IO CInt
+foreign import ccall safe "vdl_vec_device_ptr" c_vdl_vec_device_ptr :: Ptr VdlCtx -> VdlVec -> IO (Ptr ())
+foreign import ccall safe "vdl_fused_prepare" c_vdl_fused_prepare :: Ptr VdlCtx -> Ptr VdlFusedDesc -> Ptr (Ptr VdlFused) -> IO CInt
+foreign import ccall safe "vdl_fused_launch" c_vdl_fused_launch :: Ptr VdlFused -> IO CInt
+foreign import ccall safe "vdl_fused_launch_ex" c_vdl_fused_launch_ex :: Ptr VdlFused -> CInt -> IO CInt
+foreign import ccall safe "vdl_fused_partials" c_vdl_fused_partials :: Ptr VdlFused -> Ptr (Ptr ()) -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_fused_finalize" c_vdl_fused_finalize :: Ptr VdlFused -> Ptr () -> CInt -> IO CInt
+foreign import ccall safe "vdl_fused_num_groups" c_vdl_fused_num_groups :: Ptr VdlFused -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_fused_result" c_vdl_fused_result :: Ptr VdlFused -> CInt -> Ptr VdlVec -> IO CInt
+foreign import ccall safe "vdl_fused_result_host" c_vdl_fused_result_host :: Ptr VdlFused -> CInt -> Ptr (Ptr Int64) -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_fused_post_host" c_vdl_fused_post_host :: Ptr VdlFused -> CInt -> Ptr (Ptr Int64) -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_fused_shape_name" c_vdl_fused_shape_name :: Ptr VdlFused -> IO CString
+foreign import ccall safe "vdl_fused_destroy" c_vdl_fused_destroy :: Ptr VdlFused -> IO CInt
+foreign import ccall safe "vdl_fused_exchange_bytes" c_vdl_fused_exchange_bytes :: Ptr VdlFused -> CInt -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_fused_set_peers" c_vdl_fused_set_peers :: Ptr VdlFused -> CInt -> CInt -> Ptr (Ptr ()) -> IO CInt
+foreign import ccall safe "vdl_fused_last_kernel_ms" c_vdl_fused_last_kernel_ms :: Ptr VdlFused -> Ptr CFloat -> IO CInt
+foreign import ccall safe "vdl_abi_sizeof_probe_desc" c_vdl_abi_sizeof_probe_desc :: IO CInt
+foreign import ccall safe "vdl_probe_prepare" c_vdl_probe_prepare :: Ptr VdlCtx -> Ptr VdlProbeDesc -> Ptr (Ptr VdlProbe) -> IO CInt
+foreign import ccall safe "vdl_probe_run" c_vdl_probe_run :: Ptr VdlProbe -> IO CInt
+foreign import ccall safe "vdl_probe_run_ex" c_vdl_probe_run_ex :: Ptr VdlProbe -> CInt -> IO CInt
+foreign import ccall safe "vdl_probe_partials" c_vdl_probe_partials :: Ptr VdlProbe -> Ptr (Ptr ()) -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_probe_finalize" c_vdl_probe_finalize :: Ptr VdlProbe -> Ptr () -> CInt -> IO CInt
+foreign import ccall safe "vdl_probe_result_host" c_vdl_probe_result_host :: Ptr VdlProbe -> CInt -> Ptr (Ptr Int64) -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_probe_emit_take" c_vdl_probe_emit_take :: Ptr VdlProbe -> CInt -> Ptr VdlVec -> IO CInt
+foreign import ccall safe "vdl_probe_last_kernel_ms" c_vdl_probe_last_kernel_ms :: Ptr VdlProbe -> Ptr CFloat -> IO CInt
+foreign import ccall safe "vdl_probe_destroy" c_vdl_probe_destroy :: Ptr VdlProbe -> IO CInt
+foreign import ccall safe "vdl_plan_probe_kernel_ms" c_vdl_plan_probe_kernel_ms :: Ptr VdlPlan -> Ptr CFloat -> IO CInt
+foreign import ccall safe "vdl_plan_num_fused" c_vdl_plan_num_fused :: Ptr VdlPlan -> IO CInt
+foreign import ccall safe "vdl_plan_fused" c_vdl_plan_fused :: Ptr VdlPlan -> CInt -> Ptr (Ptr VdlFused) -> IO CInt

@@ -62,3 +62,16 @@ def test_map_specialisation_compiles_without_a_gpu():
         import pytest
         pytest.skip("NVRTC not installed")
     assert rc == 0, log.value.decode(errors="replace")
+
+
+def test_haskell_binding_imports_every_entry_point():
+    """hs/VdlCuda.hs (source only: no GHC in this image) must carry a `foreign import` for every function the header
+    declares -- INTEGRATION.md section 2 promises the reference-side binding is complete."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "vdl_cuda.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(vdl_[a-z0-9_]+)\s*\(", h))
+    imported = set(re.findall(r'foreign import ccall \w+ "(vdl_[a-z0-9_]+)"', open(os.path.join(root, "hs", "VdlCuda.hs")).read()))
+    assert declared - imported == set(), sorted(declared - imported)
+    assert imported - declared == set(), sorted(imported - declared)
