@@ -694,6 +694,12 @@ bool try_probe_fold(vdl_plan *p, int ni) {
       else { fi = g->b.desc.nfolds; g->b.desc.fold[g->b.desc.nfolds++] = spec; }
     }
   }
+  if (ok) {     // the pass walks the fact table's rows: it needs at least one column of it (a bare COUNT(*), or a selection
+                // that folded to "never", reads none -- those stay op-at-a-time)
+    bool fact_leaf = false;
+    for (int l = 0; l < g->b.desc.nleaves; l++) if (g->b.desc.leaf[l].parent < 0) fact_leaf = true;
+    ok = fact_leaf;
+  }
   if (!ok) {
     g->b = saved;
     if (fresh) delete g;
@@ -725,7 +731,10 @@ void mark_emits(vdl_plan *p, int ni, std::vector<char> &seen) {
       if (fresh) { g = new EmitGroup(); g->space = z.space; if (!pb_init(p, J, z.space, &g->b)) { delete g; g = nullptr; } }
       if (g) {
         ProbeBuild saved = g->b;
-        if (pb_product(p, J, &g->b, z.fac, J.spaces[z.space].table, &g->b.desc.emit[g->b.desc.nemits])) {
+        bool fact_leaf = false;
+        if (pb_product(p, J, &g->b, z.fac, J.spaces[z.space].table, &g->b.desc.emit[g->b.desc.nemits]))
+          for (int l = 0; l < g->b.desc.nleaves; l++) if (g->b.desc.leaf[l].parent < 0) fact_leaf = true;
+        if (fact_leaf) {         // (a pass needs a column of the fact table to walk: see try_probe_fold)
           if (fresh) p->egroups.push_back(g);
           for (size_t i = 0; i < p->egroups.size(); i++) if (p->egroups[i] == g) p->egroup_of_node[ni] = (int)i;
           p->eslot_of_node[ni] = g->b.desc.nemits++;

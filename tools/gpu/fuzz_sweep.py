@@ -38,6 +38,8 @@ for seed in range(first, last):
                     np.testing.assert_array_equal(got[k], want[k], err_msg=k)
             except Exception as e:
                 bad += 1
-                print(f"MISMATCH {kind} seed {seed} {mode}: {type(e).__name__} {str(e)[:300]}".replace("\n", " "), flush=True)
+                print(f"MISMATCH {kind} seed {seed} {mode}: {type(e).__name__} {str(e)[:600]}".replace("\n", " "), flush=True)
+                ctx.close()                      # the failed run left its columns registered: start clean
+                ctx = Context(0)
 os.environ.pop("VDL_NO_PROBE", None)
 print(f"{n} runs, {bad} failures")
