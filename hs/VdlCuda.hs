@@ -24,8 +24,8 @@ data VdlMapDesc   -- vdl_map_desc: marshalled with Foreign.Storable by the calle
 type VdlVec = Int32
 
 -- status codes (vdl_cuda.h)
-vdlOk, vdlEInval, vdlECuda, vdlENotFound, vdlEUnsupported, vdlERange, vdlENoMem :: CInt
-vdlOk = 0; vdlEInval = 1; vdlECuda = 2; vdlENotFound = 3; vdlEUnsupported = 4; vdlERange = 5; vdlENoMem = 6
+vdlOk, vdlEInval, vdlECuda, vdlENotFound, vdlEUnsupported, vdlERange, vdlENoMem, vdlEStale :: CInt
+vdlOk = 0; vdlEInval = 1; vdlECuda = 2; vdlENotFound = 3; vdlEUnsupported = 4; vdlERange = 5; vdlENoMem = 6; vdlEStale = 7
 
 -- storage types: Types.hs sizeOf SInt32 = 4, SInt64 / SDecimal = 8
 vdlI32, vdlI64 :: CInt
@@ -38,6 +38,8 @@ foreign import ccall safe "vdl_last_error" c_vdl_last_error :: Ptr VdlCtx -> IO 
 
 -- columns: what `Load n` (Vlite.hs Vx) binds
 foreign import ccall safe "vdl_column_alloc" c_vdl_column_alloc :: Ptr VdlCtx -> CString -> CInt -> Int64 -> Ptr VdlVec -> IO CInt
+foreign import ccall safe "vdl_column_touch" c_vdl_column_touch :: Ptr VdlCtx -> VdlVec -> IO CInt
+foreign import ccall safe "vdl_vec_generation" c_vdl_vec_generation :: Ptr VdlCtx -> VdlVec -> Ptr Word64 -> IO CInt
 foreign import ccall safe "vdl_column_upload" c_vdl_column_upload :: Ptr VdlCtx -> VdlVec -> Ptr () -> Int64 -> IO CInt
 foreign import ccall safe "vdl_column_fill_synthetic" c_vdl_column_fill_synthetic
   :: Ptr VdlCtx -> VdlVec -> Word64 -> Word64 -> CInt -> Int64 -> Int64 -> Int64 -> Int64 -> Int64 -> IO CInt

@@ -42,7 +42,8 @@ enum {
   VDL_ENOTFOUND = 3,   /* Load of a column that is not registered */
   VDL_EUNSUPPORTED = 4,/* op outside the supported vocabulary (Like, CrossProduct*, Semisort) */
   VDL_ERANGE = 5,      /* Gather/Scatter position out of range */
-  VDL_ENOMEM = 6
+  VDL_ENOMEM = 6,
+  VDL_ESTALE = 7       /* a prepared scan / probe was launched after one of its columns was rewritten or dropped */
 };
 
 /* storage types (reference Types.hs:66-89: SInt32 4 B; SInt64/SDecimal 8 B) */
@@ -81,11 +82,19 @@ int64_t vdl_ctx_launch_count(vdl_ctx *ctx);
 /* Allocate a named column of `rows` values of `dtype` in HBM (padded for 16-byte bulk copies). */
 int vdl_column_alloc(vdl_ctx *ctx, const char *name, int dtype, int64_t rows, vdl_vec *out);
 /* Register caller-owned device memory (e.g. a torch tensor) as a named column; the memory must
- * stay valid AND UNCHANGED while registered (the library caches column statistics; drop and re-bind after
- * writing to it) and be 16-byte aligned.  capacity_rows >= rows is how many rows
- * may be read past the logical end (bulk copies round the tail up to 16 bytes). */
+ * stay valid while registered and be 16-byte aligned; after writing to it call vdl_column_touch (the library
+ * caches column statistics and bakes proofs derived from them into prepared scans).  capacity_rows >= rows is
+ * how many rows may be read past the logical end (bulk copies round the tail up to 16 bytes). */
 int vdl_column_bind(vdl_ctx *ctx, const char *name, int dtype, int64_t rows, int64_t capacity_rows,
                     void *device_ptr, vdl_vec *out);
+/* The caller wrote to the column's memory behind the library's back: renew its write generation (below). */
+int vdl_column_touch(vdl_ctx *ctx, vdl_vec col);
+/* Write generation of a vector: unique within the context, renewed by creation, vdl_column_upload,
+ * vdl_column_fill_synthetic and vdl_column_touch.  Prepared scans / probes record (handle, generation) of their
+ * columns -- the role bounds.csv plays for the reference's inferBounds (Vlite.hs:417-467) is played by statistics of
+ * the data itself, so the proofs must follow the data: a plan re-analyses and re-prepares when a pair changed, and a
+ * direct vdl_fused_launch / vdl_probe_run on a stale object fails with VDL_ESTALE instead of computing with old proofs. */
+int vdl_vec_generation(vdl_ctx *ctx, vdl_vec v, uint64_t *generation);
 /* Host -> device copy of a whole column (pageable or pinned host memory). */
 int vdl_column_upload(vdl_ctx *ctx, vdl_vec col, const void *host, int64_t rows);
 /* Device -> host copy of a whole column in its stored type (the inverse of vdl_column_upload). */

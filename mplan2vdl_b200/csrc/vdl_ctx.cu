@@ -116,8 +116,20 @@ int vec_new(vdl_ctx *ctx, int dtype, i64 len, vdl_vec *out) {
   v.cap_rows = bytes / dtype;
   v.owned = true;
   v.live = true;
+  v.gen = ++ctx->gen_counter;
   *out = h;
   return VDL_OK;
+}
+
+void vec_written(vdl_ctx *ctx, Vec *v) {
+  v->gen = ++ctx->gen_counter;
+  v->has_stats = false;
+}
+
+bool vec_identity(vdl_ctx *ctx, vdl_vec h, u64 *gen) {
+  if (!ctx || h <= 0 || (size_t)h >= ctx->vecs.size() || !ctx->vecs[h].live) return false;
+  *gen = ctx->vecs[h].gen;
+  return true;
 }
 
 int vec_new_range(vdl_ctx *ctx, i64 from, i64 step, i64 len, vdl_vec *out) {
@@ -130,6 +142,7 @@ int vec_new_range(vdl_ctx *ctx, i64 from, i64 step, i64 len, vdl_vec *out) {
   v.from = from;
   v.step = step;
   v.len = len;
+  v.gen = ++ctx->gen_counter;
   if (from == 0 && step == 1) v.domain = len;
   *out = h;
   return VDL_OK;
@@ -241,9 +254,28 @@ extern "C" int vdl_column_bind(vdl_ctx *ctx, const char *name, int dtype, int64_
   v.len = rows;
   v.cap_rows = capacity_rows;
   v.live = true;
+  v.gen = ++ctx->gen_counter;
   v.name = name;
   ctx->columns[name] = h;
   *out = h;
+  return VDL_OK;
+}
+
+// The caller wrote to the memory of a column (caller-owned memory registered with vdl_column_bind, or the pointer of
+// vdl_vec_device_ptr): cached statistics are dropped and every prepared scan / probe over it re-proves its
+// assumptions before its next launch.
+extern "C" int vdl_column_touch(vdl_ctx *ctx, vdl_vec col) {
+  Vec *v = vec_get(ctx, col);
+  if (!v) return VDL_EINVAL;
+  if (v->is_range) return vdl_fail(ctx, VDL_EINVAL, "cannot touch a range vector");
+  vec_written(ctx, v);
+  return VDL_OK;
+}
+
+extern "C" int vdl_vec_generation(vdl_ctx *ctx, vdl_vec h, uint64_t *gen) {
+  Vec *v = vec_get(ctx, h);
+  if (!v || !gen) return VDL_EINVAL;
+  *gen = v->gen;
   return VDL_OK;
 }
 
@@ -266,7 +298,7 @@ extern "C" int vdl_column_upload(vdl_ctx *ctx, vdl_vec col, const void *host, in
   if (!v || !host) return VDL_EINVAL;
   if (v->is_range || rows != v->len) return vdl_fail(ctx, VDL_EINVAL, "upload of %lld rows into a vector of %lld", (long long)rows, (long long)v->len);
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
-  v->has_stats = false;
+  vec_written(ctx, v);
   VDL_CUDA(ctx, cudaMemcpyAsync(v->ptr, host, (size_t)(rows * v->dtype), cudaMemcpyHostToDevice, ctx->stream));
   VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return VDL_OK;
@@ -399,7 +431,7 @@ extern "C" int vdl_column_fill_synthetic(vdl_ctx *ctx, vdl_vec col, uint64_t see
   if (v->is_range) return vdl_fail(ctx, VDL_EINVAL, "cannot fill a range vector");
   if (kind < 0 || kind > 2 || (kind == VDL_SYNTH_FKDENSE && p1 <= 0) || (kind == VDL_SYNTH_UNIFORM && p0 <= 0))
     return vdl_fail(ctx, VDL_EINVAL, "bad synthetic spec kind=%d p0=%lld p1=%lld", kind, (long long)p0, (long long)p1);
-  v->has_stats = false;
+  vec_written(ctx, v);
   if (v->len == 0) return VDL_OK;
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   u64 base = host_splitmix64(seed ^ (stream * 0x9E3779B97F4A7C15ULL));

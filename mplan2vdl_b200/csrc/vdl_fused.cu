@@ -947,7 +947,19 @@ struct vdl_fused {
   const char *shape = "generic";
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  // identity of the columns at prepare time (the proofs above hold for exactly this data)
+  int ncols = 0;
+  vdl_vec col_handle[VDL_MAX_COLS] = {0};
+  u64 col_gen[VDL_MAX_COLS] = {0};
 };
+
+bool vdl_fused_current(vdl_fused *f) {
+  for (int c = 0; c < f->ncols; c++) {
+    u64 g;
+    if (!vec_identity(f->ctx, f->col_handle[c], &g) || g != f->col_gen[c]) return false;
+  }
+  return true;
+}
 
 #include "vdl_shapes.cuh"
 
@@ -1047,7 +1059,10 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     k.col[c] = v->ptr;
     k.width[c] = v->dtype;
     rowbytes += v->dtype;
+    f->col_handle[c] = desc->column[c];
+    f->col_gen[c] = v->gen;
   }
+  f->ncols = desc->ncolumns;
   for (int i = 0; i < desc->npreds; i++) {
     const vdl_range_pred &p = desc->pred[i];
     if (p.column < 0 || p.column >= desc->ncolumns || p.shr < 0 || p.shr > 63) { delete f; return vdl_fail(ctx, VDL_EINVAL, "fused scan: bad predicate %d", i); }
@@ -1352,6 +1367,8 @@ extern "C" int vdl_fused_launch_ex(vdl_fused *f, int self_finalize) {
   if (!f) return VDL_EINVAL;
   vdl_ctx *ctx = f->ctx;
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!vdl_fused_current(f))
+    return vdl_fail(ctx, VDL_ESTALE, "fused scan: a column was rewritten or dropped after vdl_fused_prepare (its statistics proofs no longer hold): prepare again");
   f->finalized = false;
   f->ngroups = -1;
   if (!f->table_clean) {

@@ -27,6 +27,10 @@ struct Vec {
   i64 domain = -1;          // length of the vector these values index into; -1 unknown (App. G2)
   bool has_stats = false;   // vmin/vmax computed on the device by vdl_column_analyze (invalidated by writes)
   i64 vmin = 0, vmax = 0;
+  // Write generation: unique within the context (taken from vdl_ctx::gen_counter) and renewed by every write the
+  // library can see (creation, upload, synthetic fill, vdl_column_touch).  A prepared scan / probe records
+  // (handle, generation) of its columns: a different pair means other data, another allocation or a recycled handle.
+  u64 gen = 0;
   std::string name;
 };
 
@@ -46,6 +50,7 @@ struct vdl_ctx {
   size_t scratch_bytes = 0;
   void *h_mail = nullptr, *d_mail = nullptr;   // 64 B of mapped pinned memory: scalars the host waits for (read_scalar)
   void *jit = nullptr;      // vdl_jit.cu: specialised vdl_op_map kernels
+  u64 gen_counter = 0;      // source of Vec::gen
 };
 
 int vdl_fail(vdl_ctx *ctx, int code, const char *fmt, ...);
@@ -65,6 +70,9 @@ int vdl_cuda_fail(vdl_ctx *ctx, cudaError_t e, const char *what);
 int vec_new(vdl_ctx *ctx, int dtype, i64 len, vdl_vec *out);              // allocates HBM
 int vec_new_range(vdl_ctx *ctx, i64 from, i64 step, i64 len, vdl_vec *out);
 Vec *vec_get(vdl_ctx *ctx, vdl_vec v);                                    // nullptr + error if invalid
+void vec_written(vdl_ctx *ctx, Vec *v);                                   // new generation, statistics dropped
+// (handle, generation) of a live stored vector, or false
+bool vec_identity(vdl_ctx *ctx, vdl_vec v, u64 *gen);
 int scratch_reserve(vdl_ctx *ctx, size_t bytes);
 int check_errflag(vdl_ctx *ctx, const char *what);                        // synchronises
 // Host copy of a device scalar (<= 64 bytes) once the stream has reached this point.  A one-thread kernel stores it to
@@ -102,6 +110,10 @@ struct XDesc {
 };
 
 
+// Do the columns a prepared scan / probe was built from still hold what they held at prepare time?  (The statistics
+// proofs -- int32 narrowing, 32-bit accumulators, the static shape -- and the device pointers are baked in.)
+bool vdl_fused_current(vdl_fused *f);
+bool vdl_probe_current(vdl_probe *p);
 u64 vdl_probe_epoch(vdl_probe *p);
 void vdl_probe_set_epoch(vdl_probe *p, u64 e);
 u64 vdl_fused_epoch(vdl_fused *f);

@@ -1095,7 +1095,7 @@ int bind_probe(vdl_plan *p, ProbeBuild *b, vdl_probe **probe, std::vector<vdl_ve
     }
   }
   if (rows < 0) return vdl_fail(ctx, VDL_EUNSUPPORTED, "probe: no fact column among the leaves");
-  if (!*probe || h != *bound || rows != *bound_rows || p->row_base != *bound_base) {
+  if (!*probe || !vdl_probe_current(*probe) || h != *bound || rows != *bound_rows || p->row_base != *bound_base) {
     if (*probe) { vdl_probe_destroy(*probe); *probe = nullptr; }
     b->desc.rows = rows;
     b->desc.row_base = p->row_base;
@@ -1305,7 +1305,9 @@ static int plan_run_local(vdl_plan *p, int self_finalize) {
         return vdl_fail(ctx, VDL_EINVAL, "columns of table %s differ in length (%lld vs %lld)", p->tables[g.table].c_str(), (long long)len, (long long)rows);
       rows = len;
     }
-    if (!g.fused || h != g.bound || rows != g.bound_rows || p->row_base != g.bound_base) {
+    // (re)prepare when the binding changed OR a bound column was written since (new write generation): the scan's
+    // int32-narrowing / 32-bit-accumulator / static-shape proofs come from statistics of the data it was prepared on
+    if (!g.fused || !vdl_fused_current(g.fused) || h != g.bound || rows != g.bound_rows || p->row_base != g.bound_base) {
       if (g.fused) { g.epoch = vdl_fused_epoch(g.fused); vdl_fused_destroy(g.fused); g.fused = nullptr; }
       g.desc.rows = rows;
       g.desc.row_base = p->row_base;

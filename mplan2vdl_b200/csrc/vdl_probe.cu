@@ -498,7 +498,19 @@ struct vdl_probe {
   int grid = 1;
   size_t smem = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // identity of the leaf columns at prepare time (device pointers and lengths are baked into the descriptor)
+  int nleaves = 0;
+  vdl_vec leaf_handle[VDL_MAX_LEAVES] = {0};
+  u64 leaf_gen[VDL_MAX_LEAVES] = {0};
 };
+
+bool vdl_probe_current(vdl_probe *p) {
+  for (int l = 0; l < p->nleaves; l++) {
+    u64 g;
+    if (!vec_identity(p->ctx, p->leaf_handle[l], &g) || g != p->leaf_gen[l]) return false;
+  }
+  return true;
+}
 
 static bool term_ok(const vdl_term &t, int nleaves, int nind = 0) { return t.leaf >= -2 - nind && t.leaf < nleaves && t.shr >= 0 && t.shr < 64; }
 static PTerm to_p(const vdl_term &t) { return PTerm{t.leaf, t.shr, t.a, t.b}; }
@@ -535,6 +547,9 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
     for (int q = par; q >= 0; q = desc->leaf[q].parent) depth++;
     if (depth > P_MAX_DEPTH) return fail(vdl_fail(ctx, VDL_EUNSUPPORTED, "probe: lookup chain deeper than %d", P_MAX_DEPTH));
     d.leaf[l] = PLeaf{v->ptr, v->len, v->dtype == VDL_I32, par};
+    p->leaf_handle[l] = desc->leaf[l].column;
+    p->leaf_gen[l] = v->gen;
+    p->nleaves = l + 1;
   }
   auto to_pred = [&](const vdl_probe_pred &s, PPred *o) -> bool {
     if ((s.kind != 0 && s.kind != 1) || !term_ok(s.t, desc->nleaves) || (s.kind == 1 && (!term_ok(s.u, desc->nleaves) || s.cmp < VDL_CMP_EQ || s.cmp > VDL_CMP_LE)) ||
@@ -702,6 +717,8 @@ extern "C" int vdl_probe_run_ex(vdl_probe *p, int finalize) {
   if (!p) return VDL_EINVAL;
   vdl_ctx *ctx = p->ctx;
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!vdl_probe_current(p))
+    return vdl_fail(ctx, VDL_ESTALE, "probe: a column was rewritten or dropped after vdl_probe_prepare: prepare again");
   PDesc &d = p->pd;
   p->fetched = false;
   p->ngroups = p->nselected = -1;

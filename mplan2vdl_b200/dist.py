@@ -73,19 +73,33 @@ class ShardedPlan:
         self._gathered = []
         self._want_peer = world > 1 and (peer if peer is not None else not os.environ.get("VDL_NO_PEER"))
         self.peer_mode = False
+        self.peer_fallback = None          # why the peer-memory combine is not in use (None: it is, or was never wanted)
         self._mine, self._opened = [], []
 
     def _setup_peers(self) -> bool:
-        """Allocate / exchange / map the exchange buffers (after the scans exist, i.e. after one step).  Collective."""
+        """Allocate / exchange / map the exchange buffers (after the scans exist, i.e. after one step).  Collective:
+        EVERY rank takes part in every all_gather_object and in the final MIN all_reduce whatever failed locally (a
+        rank that left the sequence early would leave the others in a mismatched collective: a hang), the ranks agree
+        once on success, and on failure everything opened or allocated so far is released again."""
         import torch.distributed as dist
-        ok, ptr_lists = 1, []
-        try:
-            for i in range(self.plan.num_partials):       # fused scans, then probe fold groups
-                mine = self.ctx.ipc_alloc(self.plan.exchange_bytes(i, self.world))
-                self._mine.append(mine)
-                handles = [None] * self.world
-                dist.all_gather_object(handles, self.ctx.ipc_export(mine), group=self.group)
-                ptrs = []
+        ok, ptr_lists, why = 1, [], ""
+        for i in range(self.plan.num_partials):       # fused scans, then probe fold groups
+            mine, blob = None, None
+            if ok:
+                try:
+                    mine = self.ctx.ipc_alloc(self.plan.exchange_bytes(i, self.world))
+                    self._mine.append(mine)
+                    blob = self.ctx.ipc_export(mine)
+                except Exception as e:
+                    ok, why = 0, f"partial table {i}: {e}"
+            handles = [None] * self.world
+            dist.all_gather_object(handles, blob, group=self.group)       # None = "this rank could not export"
+            if ok and any(h is None for h in handles):
+                ok, why = 0, f"partial table {i}: a peer could not export its buffer"
+            if not ok:
+                continue
+            ptrs = []
+            try:
                 for r, h in enumerate(handles):
                     if r == self.rank:
                         ptrs.append(mine)
@@ -93,12 +107,14 @@ class ShardedPlan:
                         ptrs.append(self.ctx.ipc_open(h))
                         self._opened.append(ptrs[-1])
                 ptr_lists.append(ptrs)
-        except Exception as e:                      # no peer mapping on this box: every rank falls back together
-            print(f"[vdl] rank {self.rank}: peer-memory exchange unavailable ({e}); using the all-gather path", flush=True)
-            ok = 0
-        flag = torch.tensor([ok], device=f"cuda:{self.ctx.device}")
+            except Exception as e:
+                ok, why = 0, f"partial table {i}: {e}"
+        flag = torch.tensor([ok], device=f"cuda:{self.ctx.device}" if torch.cuda.is_available() else "cpu")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 0:
+            self.peer_fallback = why or "a peer rank could not map the exchange buffers"
+            print(f"[vdl] rank {self.rank}: peer-memory exchange unavailable ({self.peer_fallback}); using the all-gather path", flush=True)
+            self.close()                                 # unmap / free what this rank did manage to set up
             return False
         for i, ptrs in enumerate(ptr_lists):
             self.plan.set_peers(i, self.rank, self.world, ptrs)

@@ -63,6 +63,21 @@ class Context:
         """Host->device copy into an existing column (host memory may be pinned: then the copy is a straight DMA)."""
         self.check(self.L.vdl_column_upload(self.h, v, host_ptr, rows))
 
+    def touch(self, v: int):
+        """Tell the library that the column's memory was written behind its back (bound tensors, device_ptr())."""
+        self.check(self.L.vdl_column_touch(self.h, v))
+
+    def generation(self, v: int) -> int:
+        g = C.c_uint64()
+        self.check(self.L.vdl_vec_generation(self.h, v, C.byref(g)))
+        return g.value
+
+    def analyze(self, v: int):
+        """Exact (min, max) of a column, computed on the device and cached until the column is written again."""
+        lo, hi = C.c_int64(), C.c_int64()
+        self.check(self.L.vdl_column_analyze(self.h, v, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def download_into(self, v: int, host_ptr: int, rows: int):
         """Device->host copy of a column in its stored type."""
         self.check(self.L.vdl_column_download(self.h, v, host_ptr, rows))

@@ -113,6 +113,8 @@ SYMBOLS = [
     ("vdl_ctx_launch_count", _L, [_P]),
     ("vdl_column_alloc", _I, [_P, C.c_char_p, _I, _L, C.POINTER(C.c_int32)]),
     ("vdl_column_bind", _I, [_P, C.c_char_p, _I, _L, _L, _P, C.POINTER(C.c_int32)]),
+    ("vdl_column_touch", _I, [_P, C.c_int32]),
+    ("vdl_vec_generation", _I, [_P, C.c_int32, C.POINTER(C.c_uint64)]),
     ("vdl_column_upload", _I, [_P, C.c_int32, _P, _L]),
     ("vdl_column_download", _I, [_P, C.c_int32, _P, _L]),
     ("vdl_column_fill_synthetic", _I, [_P, C.c_int32, C.c_uint64, C.c_uint64, _I, _L, _L, _L, _L, _L]),

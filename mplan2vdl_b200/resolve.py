@@ -31,33 +31,36 @@ def to_server_json(outputs: dict, timings_us: dict | None = None) -> str:
 
 
 def resolve(doc: dict | str, cat: Catalog) -> list:
-    """[(column name, values)] with dictionary codes replaced by strings -- resolve.py:52-94, same rules:
-    the key's leading '.' is dropped (the reference keeps it in undecoded names; it never reaches decoded ones),
-    names without a ``__table__column`` origin or without a dictionary pass through, unknown codes stay numeric."""
+    """[(column name, values)] with dictionary codes replaced by strings -- resolve.py:52-94, same rules and the same
+    bytes: the key's leading '.' STAYS in every header (resolve.py:64,76: ``outputname = names[0]`` of
+    ``".alias__table__column".split('__')``), names without exactly a ``__table__column`` origin or without a dictionary
+    pass through whole, unknown codes stay numeric.  Pinned against the reference's own decoder by
+    tests/golden/resolve_*.{json,csv} (tools/make_golden_resolve.py)."""
     if isinstance(doc, str):
         doc = json.loads(doc)
     cols = []
     for res in doc.get("results", {}).values():
         (k, vals), = res.items()
         vals = vals or []
-        names = k.lstrip(".").split("__")
+        names = k.split("__")
         if len(names) != 3:
-            cols.append((k.lstrip("."), list(vals)))
+            cols.append((k, list(vals)))
             continue
         alias, table, column = names
         decoder = {code: s for s, code in cat.dictionary.get(f"{table}.{column}", {}).items()}
         if not decoder:
-            cols.append((k.lstrip("."), list(vals)))
+            cols.append((k, list(vals)))
             continue
         cols.append((alias, [decoder.get(v, v) for v in vals]))
     return cols
 
 
 def to_csv(cols: list) -> str:
-    """resolve.py:97-107: header row, then the rows, short columns padded with '-'."""
+    """resolve.py:97-107: header row, then the rows, short columns padded with '-'; csv.writer's default dialect
+    (``\r\n`` line ends), as the reference."""
     n = max((len(v) for _, v in cols), default=0)
     buf = io.StringIO()
-    w = csv.writer(buf, lineterminator="\n")
+    w = csv.writer(buf)
     w.writerow([name for name, _ in cols])
     for i in range(n):
         w.writerow([v[i] if i < len(v) else "-" for _, v in cols])

@@ -135,3 +135,90 @@ def test_two_rank_gloo_survivor_exchange_concatenates_in_rank_order():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got == [[0, 1, 2, 100, 101, 102, 103, 104], [100, 101, 102, 103], [0, 1], []]
+
+
+class _FakeCtx:
+    """Stands for executor.Context in the peer-setup test: buffers are integers, `fail` picks what breaks on which rank."""
+    device = 0
+
+    def __init__(self, rank, fail):
+        self.rank, self.fail, self.freed, self.closed, self.n = rank, fail, [], [], 0
+
+    def ipc_alloc(self, nbytes):
+        self.n += 1
+        if self.fail == ("alloc", self.rank, self.n):
+            raise RuntimeError("out of memory")
+        return 1000 * (self.rank + 1) + self.n
+
+    def ipc_export(self, ptr):
+        return b"h%d" % ptr
+
+    def ipc_open(self, handle):
+        if self.fail[0] == "open" and self.fail[1] == self.rank and handle.endswith(b"%d" % self.fail[2]):
+            raise RuntimeError("peer access denied")
+        return int(handle[1:]) + 500000
+
+    def ipc_close(self, ptr):
+        self.closed.append(ptr)
+
+    def ipc_free(self, ptr):
+        self.freed.append(ptr)
+
+
+class _FakePlan:
+    num_partials, num_emits = 3, 0
+
+    def __init__(self):
+        self.peers = {}
+
+    def set_row_base(self, b):
+        pass
+
+    def exchange_bytes(self, i, world):
+        return 4096
+
+    def set_peers(self, i, rank, world, ptrs):
+        self.peers[i] = list(ptrs)
+
+
+def peer_setup_worker(rank, world, port, q):
+    from mplan2vdl_b200.dist import ShardedPlan
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = []
+    # nothing fails; rank 1 cannot open rank 0's SECOND buffer; rank 0 cannot allocate its second buffer
+    for fail in (("none", -1, 0), ("open", 1, 2), ("alloc", 0, 2)):
+        ctx, plan = _FakeCtx(rank, fail), _FakePlan()
+        sp = ShardedPlan.__new__(ShardedPlan)
+        sp.ctx, sp.plan, sp.rank, sp.world, sp.group = ctx, plan, rank, world, None
+        sp._mine, sp._opened, sp.peer_fallback = [], [], None
+        ok = sp._setup_peers()
+        res.append((ok, len(plan.peers), sorted(ctx.freed), sorted(ctx.closed), sp.peer_fallback))
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_setup_stays_collective_when_one_rank_fails():
+    """an ipc_open / ipc_alloc failure on one rank must not leave the other rank in a mismatched collective
+    (hang); both fall back together and release what they had mapped."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=peer_setup_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        ok0, npeers0, freed0, closed0, why0 = got[rank][0]
+        assert ok0 and npeers0 == 3 and not freed0 and not closed0 and why0 is None
+        for case in (1, 2):
+            ok, npeers, freed, closed, why = got[rank][case]
+            assert not ok and npeers == 0 and why
+            assert len(freed) >= 1                      # its own buffers were freed again
+    assert len(got[0][1][3]) >= 1                       # rank 0 had opened rank 1's first buffer: closed again

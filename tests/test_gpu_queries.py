@@ -155,7 +155,7 @@ def test_cli_prints_the_server_json_and_the_decoded_csv():
     assert list(doc["results"]["tmp0"]) == [".n_name__nation__n_name"] and list(doc["results"]["tmp1"]) == [".revenue"]
     csv = subprocess.run([sys.executable, "-m", "mplan2vdl_b200", "-", "--sf", "0.01", "--csv"], cwd=root, input=open(plan).read(),
                          capture_output=True, text=True, check=True).stdout.splitlines()
-    assert csv[0] == "n_name,revenue" and len(csv) == 1 + len(doc["results"]["tmp1"][".revenue"])
+    assert csv[0] == ".n_name,.revenue" and len(csv) == 1 + len(doc["results"]["tmp1"][".revenue"])
 
 
 def test_q19_parity(catalog):
