@@ -114,6 +114,7 @@ def host_threads() -> int:
 def cpu_oracle_rate(cat, query: str, sf: float, target_seconds: float = 12.0, max_rows: int = 59_986_052, steps: int = 1):
     """Time the CPU oracle (kind "port": the reference ships no executor) on a bounded sample of the same workload:
     the first `rows` lineitem rows of the same synthetic table.  Returns (rows/s, sample rows, threads, seconds list)."""
+    max_rows = min(max_rows, CPU_ARM_MAX_ROWS)
     from mplan2vdl_b200 import synth, tpch
     from oracle.oracle import Oracle, gen_column
     text = tpch.plan_text(QUERIES[query][0])
@@ -168,6 +169,23 @@ def run_reference(args):
 
 
 L2_BYTES = 126e6
+CPU_ARM_MAX_ROWS = 59_986_052
+
+
+def check_parity(cat, query: str, sf: float, result: dict, chunk_rows: int = 40_000_000) -> dict:
+    """"parity check ... in the same run".  The CPU oracle over ALL rows of the workload, the fact
+    table generated and consumed `chunk_rows` at a time (oracle/chunked.py), compared bit for bit with what the GPU returned."""
+    import numpy as np
+    from mplan2vdl_b200 import tpch
+    from oracle import chunked
+    t0 = time.perf_counter()
+    text = tpch.plan_text(QUERIES[query][0])
+    want, co = chunked.run_chunked(text, cat, sf, chunk_rows=chunk_rows, threads=host_threads())
+    bad = [k for k in want if k not in result or not np.array_equal(np.asarray(result[k], dtype=np.int64), want[k])]
+    bad += [k for k in result if k not in want]
+    return {"status": "exact" if not bad else "MISMATCH", "against": "CPU oracle (oracle/vdl_oracle.c) over the whole table, chunked",
+            "rows_checked": co.rows, "outputs_checked": len(want), "values_checked": int(sum(len(v) for v in want.values())),
+            "mismatched_outputs": bad, "oracle_seconds": round(co.seconds, 2), "seconds": round(time.perf_counter() - t0, 2)}
 
 
 def workload_config(args):
@@ -185,6 +203,9 @@ def workload_config(args):
             "l2": ("inputs far exceed the 126 MB L2; no flush needed between steps" if total_bytes / max(args.gpus, 1) >= 4 * L2_BYTES else
                    "inputs per GPU are within 4x the 126 MB L2: between timed steps a 256 MB buffer is written, then a second 256 MB "
                    "buffer is read so that the flush's dirty lines are written back (both outside the per-step events)"),
+            "cpu_arm": f"cpu_baseline / --impl reference time the op-at-a-time CPU oracle on a PREFIX of the same table (at most the first "
+                       f"{min(CPU_ARM_MAX_ROWS, rows_total)} of {rows_total} lineitem rows per step) and report rows/s of that prefix: a scan "
+                       "extrapolates linearly, but it is a sample, not the whole table",
             "parallelism": f"lineitem row-range sharded over {args.gpus} GPU(s), dimension tables replicated"}
 
 
@@ -199,6 +220,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the whole-table CPU-oracle check of the result")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -370,6 +392,10 @@ def main():
                "sample": f"first {srows} lineitem rows of the same synthetic table; op-at-a-time CPU oracle (OpenMP), "
                          f"{len(secs)} runs, median {statistics.median(secs):.2f} s, total {sum(secs):.1f} s"}
 
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = check_parity(cat, args.query, args.sf, result)
+
     if rank == 0:
         line = {
             "metric": f"tpch_{args.query}_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
@@ -381,7 +407,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "wall_ms_per_step": wall_ms / args.steps, "result": {k: [int(x) for x in v[:8]] for k, v in result.items()},
-            "plan": plan.stats(),
+            "plan": plan.stats(), "parity": parity,
         }
         print(json.dumps(line), flush=True)
     plan.close()
@@ -389,6 +415,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity and parity["status"] != "exact":
+        raise SystemExit(f"bench.py: PARITY MISMATCH against the CPU oracle in outputs {parity['mismatched_outputs']}")
 
 
 if __name__ == "__main__":
