@@ -206,6 +206,9 @@ def workload_config(args):
             "cpu_arm": f"cpu_baseline / --impl reference time the op-at-a-time CPU oracle on a PREFIX of the same table (at most the first "
                        f"{min(CPU_ARM_MAX_ROWS, rows_total)} of {rows_total} lineitem rows per step) and report rows/s of that prefix: a scan "
                        "extrapolates linearly, but it is a sample, not the whole table",
+            "e2e_storage": "e2e = host columns in the executor's narrow storage format (int32 wherever a column's exact min/max fit, e.g. Q6: "
+                           "16 instead of 28 bytes per lineitem row on the wire and in HBM); the same measurement with every column in the "
+                           "reference's widths (Types.hs:129-140) is reported as e2e_reference_storage; value / roofline use the reference widths",
             "parallelism": f"lineitem row-range sharded over {args.gpus} GPU(s), dimension tables replicated"}
 
 
@@ -348,42 +351,75 @@ def main():
     except Exception:
         pass
 
-    # end to end through the public API with HOST buffers: H2D of every column + run + D2H of the result, per step
-    e2e = None
+    # end to end through the public API with HOST buffers: H2D of every column + column analysis + (re)prepare + run + D2H of
+    # the result, per step.  Two host storage formats, both timed:
+    #   reference  every column in the reference's storage model (Types.hs:129-140: decimals / oids / string codes 8 bytes)
+    #   narrow     the executor's own format (SURVEY.md App. G11 "narrower storage as a separately reported variant"):
+    #              a column whose exact min / max (vdl_column_analyze at load time) fit int32 is kept as int32, on the host
+    #              and in HBM -- lossless, the kernels sign-extend; fewer bytes cross PCIe and HBM
+    # "e2e" (the headline) is the narrow format with its own byte counts; "e2e_reference_storage" is printed next to it.
+    e2e = e2e_ref = None
     if not args.no_e2e:
         handles = [ctx.lookup(n) for n in names]
         widths = [synth.column_spec(cat, n, args.sf).width for n in names]
         nrows = [info["rows"][n.split(".")[0]] for n in names]
+
+        def measure(handles, host, label):
+            h2d = sum(b.numel() * b.element_size() for b in host)
+
+            def e2e_step():
+                for h, b, nr in zip(handles, host, nrows):
+                    ctx.upload_into(h, b.data_ptr(), nr)     # new write generation: the plan re-analyses and re-prepares
+                return step()
+
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                r2 = e2e_step()
+            barrier()
+            e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+            if world > 1:
+                t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_s = float(t[0])
+            for k in result:
+                assert np.array_equal(r2[k], result[k]), f"e2e ({label}) result differs from the device-resident result"
+            d2h = sum(8 * len(v) for v in result.values())
+            return {"value": rows_total / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps, "timing": "host wall clock, barrier + synchronize both sides; "
+                    "every step uploads all columns from pinned host memory, re-analyses them (min/max), re-prepares the scan and runs the plan",
+                    "h2d_gbs": h2d / e2e_s / 1e9, "storage": label,
+                    "bytes_per_lineitem_row_on_the_wire": round(sum(b.element_size() for b, n in zip(host, names) if n.startswith("lineitem.")), 1)}
+
+        # exact statistics decide the narrow format (outside the timed region: the storage format is chosen at load time)
+        narrow_w = []
+        for h, w in zip(handles, widths):
+            lo, hi = ctx.analyze(h)
+            narrow_w.append(4 if (w == 4 or (lo >= -2**31 and hi < 2**31)) else 8)
         host = []
         for h, w, nr in zip(handles, widths, nrows):
-            buf = torch.empty(nr * w, dtype=torch.uint8, pin_memory=True)
+            buf = torch.empty(nr, dtype=torch.int32 if w == 4 else torch.int64, pin_memory=True)
             ctx.download_into(h, buf.data_ptr(), nr)
             host.append(buf)
-        h2d = sum(b.numel() for b in host)
-
-        def e2e_step():
-            for h, b, nr in zip(handles, host, nrows):
-                ctx.upload_into(h, b.data_ptr(), nr)
-            return step()
-
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            r2 = e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t[0])
-        for k in result:
-            assert np.array_equal(r2[k], result[k]), "e2e result differs from the device-resident result"
-        d2h = sum(8 * len(v) for v in result.values())
-        e2e = {"value": rows_total / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps, "timing": "host wall clock, barrier + synchronize both sides",
-               "h2d_gbs": h2d / e2e_s / 1e9}
+        e2e_ref = measure(handles, host, "reference (Types.hs widths)")
+        host_n = []
+        for n, b, w in zip(names, host, narrow_w):
+            if b.element_size() == w:
+                host_n.append(b)
+            else:
+                nb = torch.empty(b.numel(), dtype=torch.int32, pin_memory=True)
+                nb.copy_(b)                                  # lossless by the statistics above
+                host_n.append(nb)
         del host
+        handles_n = []
+        for n, b, nr in zip(names, host_n, nrows):          # same names, narrower columns: the plan re-binds by name
+            ctx.drop_column(n)
+            handles_n.append(ctx.alloc_column(n, b.element_size(), nr))
+        e2e = measure(handles_n, host_n, "narrow (int32 where the column statistics allow)")
+        e2e["kernel_ms"] = plan.kernel_ms(0) if plan.num_fused else plan.probe_kernel_ms()
+        e2e["kernel"] = plan.shape(0) if plan.num_fused else "probe"
+        del host_n
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -405,7 +441,7 @@ def main():
                                                                   if plan.num_fused else "peer-memory exchange kernel after the probe pass (NVLink stores + epoch flags) + finalize, no collective")
                                                                  if sharded.peer_mode else "NCCL all-gather of the partial tables / survivors + finalize"),
             "roofline": roofline,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_reference_storage": e2e_ref, "gpu_launches": launches, "clocks": clocks,
             "wall_ms_per_step": wall_ms / args.steps, "result": {k: [int(x) for x in v[:8]] for k, v in result.items()},
             "plan": plan.stats(), "parity": parity,
         }

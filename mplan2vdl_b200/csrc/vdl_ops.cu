@@ -52,7 +52,12 @@ extern "C" int vdl_op_binary(vdl_ctx *ctx, int op, vdl_vec a, vdl_vec b, vdl_vec
   if (va->len != vb->len) return vdl_fail(ctx, VDL_EINVAL, "elementwise op on lengths %lld vs %lld", (long long)va->len, (long long)vb->len);
   i64 n = va->len;
   Operand oa = operand_of(*va), ob = operand_of(*vb);
+  // positions `p % k` with a constant k > 0 -- the scatter size hint of addScatterSizeHint (Vlite.hs:1117-1120) -- index
+  // a space of k slots (App. G2 / G9)
+  i64 dom = -1;
+  if (op == VDL_MODULO && vb->is_range && vb->step == 0 && vb->from > 0) dom = vb->from;
   VDL_TRY(vec_new(ctx, VDL_I64, n, out));
+  ctx->vecs[*out].domain = dom;
   if (n == 0) return VDL_OK;
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   i64 want = (n / 2 + 255) / 256;
@@ -122,6 +127,8 @@ extern "C" int vdl_op_map(vdl_ctx *ctx, const vdl_map_desc *d, const vdl_vec *in
     m.tab_len[k] = v->len;
   }
   i64 domain = -1;
+  i64 regconst[VDL_MAP_MAX_REGS];      // constant value of a register, when isconst
+  bool isconst[VDL_MAP_MAX_REGS] = {false};
   unsigned written = 0;
   auto reg_ok = [&](int r, bool read) { return r >= 0 && r < VDL_MAP_MAX_REGS && (!read || (written >> r & 1)); };
   for (int t = 0; t < d->ninstrs; t++) {
@@ -133,7 +140,15 @@ extern "C" int vdl_op_map(vdl_ctx *ctx, const vdl_map_desc *d, const vdl_vec *in
     else ok = ok && ins.op >= 0 && ins.op <= VDL_MODULO && reg_ok(ins.a, true) && reg_ok(ins.b, true);
     if (!ok) return vdl_fail(ctx, VDL_EINVAL, "map: instruction %d (op %d dst %d a %d b %d) is malformed or reads a register nothing wrote", t, ins.op, ins.dst, ins.a, ins.b);
     written |= 1u << ins.dst;
-    if (t == d->ninstrs - 1 && ins.op == VDL_MAP_GATHER) domain = ctx->vecs[tables[ins.b]].domain;   // gathering positions keeps their index space
+    // index space of the result (App. G2): gathering positions keeps their space; `p % k` is the scatter size hint
+    i64 dm = -1, cv = 0;
+    bool ic = false;
+    if (ins.op == VDL_MAP_GATHER) dm = ctx->vecs[tables[ins.b]].domain;
+    else if (ins.op == VDL_MAP_LOAD) dm = ctx->vecs[inputs[ins.b]].domain;
+    else if (ins.op == VDL_MAP_RANGE) { ic = d->imm[ins.b] == 0; cv = d->imm[ins.a]; }
+    else if (ins.op == VDL_MODULO && isconst[ins.b] && regconst[ins.b] > 0) dm = regconst[ins.b];
+    regconst[ins.dst] = cv; isconst[ins.dst] = ic;
+    if (t == d->ninstrs - 1) domain = dm;
   }
   VDL_TRY(vec_new(ctx, VDL_I64, n, out));
   ctx->vecs[*out].domain = domain;

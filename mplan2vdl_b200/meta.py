@@ -42,6 +42,7 @@ class Column:
     mtype: str = ""      # Monet type name from storage.csv ("" if the column is only in bounds.csv)
     width: int = 8       # bytes in this executor's storage model
     is_sorted: bool = False
+    scale: int = 0       # DECIMAL(p, s) of the schema: the column's display type DDecimal{point = s} (Types.hs:143-153)
 
     @property
     def qualified(self) -> str:
@@ -90,7 +91,7 @@ class Catalog:
                 "rows": t.rows, "pkey": t.pkey, "pkey_name": t.pkey_name,
                 "fkeys": [vars(f) for f in t.fkeys],
                 "columns": {c.name: {"min": c.vmin, "max": c.vmax, "count": c.count, "tz": c.trailing_zeros,
-                                     "mtype": c.mtype, "width": c.width, "sorted": c.is_sorted}
+                                     "mtype": c.mtype, "width": c.width, "sorted": c.is_sorted, "scale": c.scale}
                             for c in t.columns.values()},
             }
         return out
@@ -103,7 +104,7 @@ class Catalog:
             tab.fkeys = [ForeignKey(**f) for f in t["fkeys"]]
             for cn, c in t["columns"].items():
                 tab.columns[cn] = Column(tn, cn, c["min"], c["max"], c["count"], c["tz"], c["mtype"], c["width"],
-                                         c.get("sorted", False))
+                                         c.get("sorted", False), c.get("scale", 0))
             cat.tables[tn] = tab
         return cat
 
@@ -150,6 +151,7 @@ def read_dictionary(path: str) -> dict:
 
 _RE_TABLE = re.compile(r'CREATE TABLE\s+"(\w+)"\."(\w+)"\s*\(', re.I)
 _RE_PKEY = re.compile(r'CONSTRAINT\s+"(\w+)"\s+PRIMARY KEY\s*\(([^)]*)\)', re.I)
+_RE_COLDEF = re.compile(r'^\s*"(\w+)"\s+([A-Za-z]+)\s*(?:\(\s*(\d+)\s*(?:,\s*(\d+)\s*)?\))?')
 _RE_FKEY = re.compile(r'CONSTRAINT\s+"(\w+)"\s+FOREIGN KEY\s*\(([^)]*)\)\s+REFERENCES\s+"(\w+)"\."(\w+)"\s*\(([^)]*)\)', re.I)
 
 
@@ -158,7 +160,7 @@ def _names(s: str) -> list:
 
 
 def read_schema(path: str) -> dict:
-    """``msqldump -D`` DDL -> {table: (pkey_name, pkey_cols, [ForeignKey])} (SchemaParser.y:62-141)."""
+    """``msqldump -D`` DDL -> {table: (pkey_name, pkey_cols, [ForeignKey], {column: decimal scale})} (SchemaParser.y:62-141)."""
     out = {}
     cur = None
     with open(path) as f:
@@ -166,7 +168,7 @@ def read_schema(path: str) -> dict:
             m = _RE_TABLE.search(line)
             if m:
                 cur = m.group(2)
-                out[cur] = ["", [], []]
+                out[cur] = ["", [], [], {}]
                 continue
             if cur is None:
                 continue
@@ -177,6 +179,10 @@ def read_schema(path: str) -> dict:
             m = _RE_PKEY.search(line)
             if m:
                 out[cur][0], out[cur][1] = m.group(1), _names(m.group(2))
+                continue
+            m = _RE_COLDEF.match(line)
+            if m and m.group(2).lower() == "decimal" and m.group(4) is not None:
+                out[cur][3][m.group(1)] = int(m.group(4))          # column type specs (getTspecs, Config.hs:187-188)
     return out
 
 
@@ -194,9 +200,12 @@ def load_metadata(directory: str) -> Catalog:
             col.width = _WIDTH[col.mtype]
         tab.columns[col.name] = col
         tab.rows = max(tab.rows, col.count)
-    for t, (pk_name, pk_cols, fks) in read_schema(os.path.join(directory, "schema.msqldump")).items():
+    for t, (pk_name, pk_cols, fks, scales) in read_schema(os.path.join(directory, "schema.msqldump")).items():
         if t in cat.tables:
             cat.tables[t].pkey_name, cat.tables[t].pkey, cat.tables[t].fkeys = pk_name, pk_cols, fks
+            for c, sc in scales.items():
+                if c in cat.tables[t].columns:
+                    cat.tables[t].columns[c].scale = sc
     dpath = os.path.join(directory, "dictionary.csv")
     if os.path.exists(dpath):
         cat.dictionary = read_dictionary(dpath)

@@ -15,7 +15,7 @@ import datetime
 import re
 import sys
 
-from .vlite import Bin, Cast, GroupBy, IfThenElse, In, Join, Lit, Project, Ref, Select, Table, Unary
+from .vlite import Bin, Cast, GroupBy, Identity, IfThenElse, In, Join, Lit, Project, Ref, Select, Table, Unary
 
 DATE = ("date",)
 
@@ -279,6 +279,8 @@ class Front:
             base = fname.split(".")[-1]
             if base == "ifthenelse" and len(args) == 3:         # Mplan.hs:441-451
                 return IfThenElse(*(self.sc(a, ctx) for a, _ in args))
+            if len(args) == 1 and base == "identity":          # Mplan.hs:392-396: a row id, whatever the argument
+                return Identity()
             if len(args) == 1 and base in ("year", "sql_neg", "isnull"):      # Mplan.hs:106-112, 420-424
                 return Unary({"year": "Year", "sql_neg": "Neg", "isnull": "IsNull"}[base], self.sc(args[0][0], ctx))
             if len(args) == 2:
@@ -358,10 +360,9 @@ class Front:
         if relop == "select":
             return Select(self.solve(children[0]), self.conjunction(lists[0]))
         if relop in ("join", "semijoin", "antijoin", "left outer join"):
-            if relop != "join":
-                raise NotImplementedError(f"{relop} (outside the executor's scope)")
+            variant = {"join": "Plain", "semijoin": "LeftSemi", "antijoin": "LeftAnti", "left outer join": "LeftOuter"}[relop]   # classify_join (Mplan.hs:334-356)
             l, r = children
-            return Join(self.solve(l), self.solve(r), [self.sc(e) for e, _ in lists[0]])
+            return Join(self.solve(l), self.solve(r), [self.sc(e) for e, _ in lists[0]], variant)
         raise NotImplementedError(f"relational operator {relop!r} (Mplan.hs:332)")
 
 

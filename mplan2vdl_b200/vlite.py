@@ -104,6 +104,18 @@ def infer_bounds(binop: str, l: Vexp, r: Vexp) -> tuple:      # Vlite.hs:417-467
     raise NotImplementedError(binop)
 
 
+def binop_dtype(binop: str, lt: tuple, rt: tuple) -> tuple:    # display type of a Binop (Vlite.hs:393-412)
+    if binop == "Mul" and lt[0] == "dec" and rt[0] == "dec":
+        return ("dec", lt[1] + rt[1])
+    if binop == "Div" and lt[0] == "dec" and rt[0] == "dec":
+        if lt[1] - rt[1] < 0:
+            raise NotImplementedError("need to implement conversion for this division (Vlite.hs:399)")
+        return ("dec", lt[1] - rt[1])
+    if binop in ("Gt", "Lt", "Leq", "Geq", "Eq", "Neq") and lt == rt:
+        return ("dec", 0)
+    return lt
+
+
 def complete(op: str, args: tuple, params: tuple = ()) -> Vexp:
     """complete (Vlite.hs:247-257): inferMetadata 269-414, inferLineage 469-493, inferUniqueness 495-517."""
     name, lineage, quant = None, None, "Any"
@@ -138,7 +150,7 @@ def complete(op: str, args: tuple, params: tuple = ()) -> Vexp:
             dl, du = data.bounds
             if foldop == "FSum":
                 ext = [dl, dl * data.count, du, du * data.count]
-                info = dict(bounds=(min(ext), max(ext)), count=cb, tz=data.tz, dtype=("dec", data.dtype[1] if data.dtype[0] == "dec" else 0))
+                info = dict(bounds=(min(ext), max(ext)), count=cb, tz=data.tz, dtype=("dec", data.dtype[1] if data.dtype[0] == "dec" else 0))   # 346-349
             else:
                 info = dict(bounds=(dl, du), count=cb, tz=data.tz, dtype=data.dtype)
                 if data.lineage:
@@ -154,7 +166,7 @@ def complete(op: str, args: tuple, params: tuple = ()) -> Vexp:
         (binop,) = params
         l, r = args
         tz = l.tz - r.bounds[1] if binop == "BitShift" else 0
-        info = dict(bounds=infer_bounds(binop, l, r), count=min(l.count, r.count), tz=tz, dtype=l.dtype)
+        info = dict(bounds=infer_bounds(binop, l, r), count=min(l.count, r.count), tz=tz, dtype=binop_dtype(binop, l.dtype, r.dtype))
     else:
         raise NotImplementedError(op)
     return Vexp(op=op, args=args, params=params, lineage=lineage, quant=quant, name=name, **info)
@@ -217,6 +229,11 @@ class Unary:                # Mplan.hs:101-104, 122: op in Year | Neg | IsNull
 
 
 @dataclass
+class Identity:             # Mplan.hs:119 `Identity {e}`: "returns a rowid"
+    pass
+
+
+@dataclass
 class Table:
     name: str
     columns: list           # [(column, alias or None)]  (JOINIDX columns: (fk index column, "%alias"), Mplan.hs:240-251)
@@ -274,17 +291,29 @@ class Lowering:
 
     def __init__(self, catalog):
         self.cat = catalog
-        self.fk = {}            # (fact column, dim column) -> (join order, fk index column, dim table)  (Config.hs:200-218)
+        # makeFKEntries (Config.hs:200-218): every foreign key is known by its column pairs ("implicit": l_orderkey =
+        # o_orderkey; composite keys need all their pairs) and by its index column against the dimension's row ids
+        # ("explicit": lineitem.lineitem_orders = orders.%TID%), in both argument orders
+        self.fk = {}            # (left lineage column, right lineage column) -> (join order, fk id)
+        self.fkcols = {}        # fk id -> (sorted (fact column, dim column) pairs that complete it, fk index column)
+        self._masks = {}
         for t in catalog.tables.values():
             for f in t.fkeys:
                 idx, tid = f"{t.name}.{f.name}", f"{f.ref_table}.%TID%"
-                self.fk[(idx, tid)] = ("FactDim", idx, f.ref_table)
-                self.fk[(tid, idx)] = ("DimFact", idx, f.ref_table)
+                self.fkcols[("explicit", idx)] = ([(idx, tid)], idx)
+                self.fk[(idx, tid)] = ("FactDim", ("explicit", idx))
+                self.fk[(tid, idx)] = ("DimFact", ("explicit", idx))
+                pairs = sorted((f"{t.name}.{lc}", f"{f.ref_table}.{rc}") for lc, rc in zip(f.columns, f.ref_columns))
+                self.fkcols[("implicit", idx)] = (pairs, idx)
+                for lc, rc in pairs:
+                    self.fk.setdefault((lc, rc), ("FactDim", ("implicit", idx)))
+                    self.fk.setdefault((rc, lc), ("DimFact", ("implicit", idx)))
 
     # ---- leaves ---------------------------------------------------------------------------
     def _load(self, qualified: str) -> Vexp:
         c = self.cat.column(qualified)
-        dt = ("str", qualified) if c.mtype in ("char", "varchar") else (("date",) if c.mtype == "date" else ("dec", 0))
+        # display type (getDTypeOfMType, Types.hs:143-153): DECIMAL(p, s) columns carry their scale
+        dt = ("str", qualified) if c.mtype in ("char", "varchar") else (("date",) if c.mtype == "date" else ("dec", c.scale if c.mtype == "decimal" else 0))
         return Vexp(op="Load", params=(qualified,), bounds=(c.vmin, c.vmax), count=c.count, tz=c.trailing_zeros, dtype=dt)
 
     def ref_vector(self, table: str) -> Vexp:             # getRefVector, VdlFormat (Vlite.hs:734-741)
@@ -305,6 +334,8 @@ class Lowering:
             return env.lookup(e.name)
         if isinstance(e, Lit):                              # typedconst_ n vref dt (982-983)
             return const_(e.n, env.list[0]).replace(dtype=e.dtype)
+        if isinstance(e, Identity):                         # 985-986: pos_ of the first vector in scope
+            return pos_(env.list[0])
         if isinstance(e, Cast):
             v = self.sc(env, e.arg)
             if e.point is None or v.dtype[0] != "dec" or v.dtype[1] == e.point:
@@ -421,25 +452,40 @@ class Lowering:
             acc.insert(0, v.replace(name=out))
         return acc
 
-    # ---- FK join (Vlite.hs:682-719, 764-903, 1199-1282) ------------------------------------------
+    # ---- joins (Vlite.hs:682-719, 764-903, 1199-1282) ------------------------------------------------
     def join(self, rel: Join) -> list:
         left, right = self.solve(rel.left), self.solve(rel.right)
-        specs, extras = [], []
-        for c in rel.conds:
-            spec = self._classify(c, left, right)
-            (specs if spec else extras).append(spec or c)
-        if len(specs) != 1:
-            raise NotImplementedError("join that is not a single complete FK (Vlite.hs:719)")
-        if extras:                                         # 714-718: Select over the Join with the FK condition only
-            if len(extras) != 1 or rel.variant != "Plain":
-                raise NotImplementedError("extra join conditions")
+        specs, extras = self.separate_fk_joinable(rel.conds, left, right)
+        if len(specs) == 1 and not extras:                 # 686-690
+            order = specs[0][0]
+            if order == "FactDim":
+                return self.handle_gather_join(left, right, rel.variant, specs[0])
+            return self.handle_gather_join(right, left, rel.variant, specs[0])
+        if not specs and len(extras) == 1 and isinstance(extras[0], Bin):
+            # 691-713: one side is a single value (one column, count 1): broadcast it and select the other side's rows.
+            # (The join variant is not looked at: Plain, LeftSemi and LeftAnti all take this path in the reference.)
+            cond = extras[0]
+            for mine, other, mine_is_left in ((left, right, True), (right, left, False)):
+                try:
+                    key_mine = self.sc(mine, cond.left if mine_is_left else cond.right)
+                    key_other = self.sc(other, cond.right if mine_is_left else cond.left)
+                except KeyError:
+                    continue
+                if key_mine.count == 1 and len(mine.list) == 1:
+                    broadcast = gather(key_mine, zeros_(key_other))
+                    boolean = binop(cond.op, broadcast, key_other) if mine_is_left else binop(cond.op, key_other, broadcast)
+                    gathermask = fold("FSel", pos_(boolean), boolean)
+                    return [gather(c, gathermask) for c in other.list]
+        if len(specs) == 1 and len(extras) == 1:           # 714-718: Select over the Join with the FK condition only
+            if rel.variant != "Plain":
+                raise NotImplementedError("can only do this rewrite for plain joins (Vlite.hs:718)")
             fkconds = [c for c in rel.conds if c is not extras[0]]
             return self.solve_list(Select(Join(rel.left, rel.right, fkconds, rel.variant), extras[0]))
-        order, factmask, dimmask, joinidx, factquant = specs[0]
-        fact, dim = (left, right) if order == "FactDim" else (right, left)
-        if rel.variant != "Plain":
-            raise NotImplementedError(rel.variant)
-        # deduceMasks (1248-1280)
+        raise NotImplementedError("not handling this join case right now (Vlite.hs:719): a join that is not a single complete FK")
+
+    def handle_gather_join(self, fact: Env, dim: Env, variant: str, spec) -> list:
+        """handleGatherJoin (Vlite.hs:1199-1232) over deduceMasks (1248-1280), VdlFormat."""
+        order, factmask, dimmask, joinidx, factquant = spec
         if dimmask.quant != "Unique":
             raise ValueError("the dimension column is not known to be unique (Vlite.hs:1280)")
         fact_dim_idx = self._load(joinidx)
@@ -447,14 +493,59 @@ class Lowering:
         valid = scattered_to(ones_(dimmask), dimmask)
         inv = scattered_to(pos_(dimmask), dimmask)
         selectboolean, gathermask = gather(valid, fprime_dim_idx), gather(inv, fprime_dim_idx)
-        # handleGatherJoin (1199-1209)
         selectmask = fold("FSel", pos_(selectboolean), selectboolean).replace(comment="selectmask")
         gathered = [gather(c, selectmask) for c in [gathermask] + fact.list]
         clean_gathermask, cleaned_fact = gathered[0], gathered[1:]
-        return cleaned_fact + [gather(c, clean_gathermask) for c in dim.list]
+        if variant == "Plain":
+            return cleaned_fact + [gather(c, clean_gathermask) for c in dim.list]
+        if variant == "LeftSemi":                          # 1212-1222: semantics of the LEFT side
+            if order == "FactDim":
+                return cleaned_fact
+            # dim semijoin fact: mark the dim' rows some fact' row points at.  The scatter positions are the UNCLEANED gather
+            # mask (a fact' row whose dim row is not selected reads slot 0 of the inverse index, i.e. marks dim' row 0: the
+            # reference's graph, kept literally) with the size hint `% vmax` of addScatterSizeHint (1117-1120)
+            scattermask = gathermask.replace(comment="dim semijoin fact scattermask")
+            if scattermask.bounds[0] < 0:
+                raise ValueError("scatter size hint needs non-negative positions (Vlite.hs:1119)")
+            hinted = binop("Mod", scattermask, const_(scattermask.bounds[1], scattermask).replace(comment="scatter size hint for voodoo backend"))
+            qualified = scattered_to(ones_(scattermask), hinted)
+            dimsel = fold("FSel", pos_(qualified), qualified)
+            return [gather(c, dimsel) for c in dim.list]
+        if variant == "LeftAnti":                          # 1226-1232
+            if order != "FactDim":
+                raise NotImplementedError("TODO implement anti for dimension table (Vlite.hs:1232)")
+            # G13: the reference subtracts the POSITIONS vector (selectmask) from ones, not the boolean; kept literally
+            antiboolean = binop("Sub", ones_(selectmask), selectmask)
+            antigather = fold("FSel", pos_(antiboolean), antiboolean)
+            return [gather(c, antigather) for c in fact.list]
+        raise NotImplementedError(f"{variant} join (Vlite.hs:1223-1225)")
+
+    def separate_fk_joinable(self, conds, left: Env, right: Env):
+        """separateFKJoinable / classifyExpr / processPartials (Vlite.hs:764-903): equality conditions between columns whose
+        lineages form (part of) a foreign key accumulate per (fact mask, dim mask, key); a key whose column pairs are all
+        present becomes a join spec, everything else is returned as a plain condition.  (Self joins over a primary key,
+        PartialSelfJoinSpec, are not restated: they stay conditions.)"""
+        partial, extras = {}, []
+        for c in conds:
+            hit = self._classify(c, left, right)
+            if hit is None:
+                extras.append(c)
+                continue
+            key, pair, quant = hit
+            acc = partial.setdefault(key, [[], "Any", []])
+            acc[0].append(pair)
+            acc[1] = "Unique" if "Unique" in (acc[1], quant) else "Any"
+            acc[2].append(c)
+        specs = []
+        for (fm, dm, order, fkid), (pairs, quant, origs) in partial.items():
+            need, joinidx = self.fkcols[fkid]
+            if sorted(pairs) == need:
+                specs.append((order, self._masks[fm].replace(comment="factmask"), self._masks[dm].replace(comment="dimmmask"), joinidx, quant))
+            else:
+                extras = origs + extras
+        return specs, extras
 
     def _classify(self, cond, left: Env, right: Env):
-        """classifyExpr / processPartials (Vlite.hs:856-903) for single-column FK references."""
         if not (isinstance(cond, Bin) and cond.op == "Eq" and isinstance(cond.left, Ref) and isinstance(cond.right, Ref)):
             return None
 
@@ -472,10 +563,11 @@ class Lowering:
         hit = self.fk.get((lv.lineage[0], rv.lineage[0]))
         if not hit:
             return None
-        order, joinidx, _dim = hit
-        if order == "FactDim":
-            return (order, lv.lineage[1].replace(comment="factmask"), rv.lineage[1].replace(comment="dimmmask"), joinidx, lv.quant)
-        return (order, rv.lineage[1].replace(comment="factmask"), lv.lineage[1].replace(comment="dimmmask"), joinidx, rv.quant)
+        order, fkid = hit
+        fv, dv = (lv, rv) if order == "FactDim" else (rv, lv)
+        self._masks[fv.lineage[1].sid] = fv.lineage[1]
+        self._masks[dv.lineage[1].sid] = dv.lineage[1]
+        return (fv.lineage[1].sid, dv.lineage[1].sid, order, fkid), (fv.lineage[0], dv.lineage[0]), fv.quant
 
 
 # ------------------------------------------------------------------------------------------ cleanup passes

@@ -32,7 +32,8 @@
  *   FoldSelect,val,Id fold,val,Id p   ascending positions i with p[i]!=0 (fold must be pos_) Vlite.hs:721-730
  *   Gather,Id src,Id pos,val          out[i]=src[pos[i]]                                     Vlite.hs:86-87
  *   Scatter,Id src,Id fold,val,Id pos out[pos[i]]=src[i], unwritten=0, length = index-space
- *                                     of pos (G2: see domain_of), positions assumed unique    Vlite.hs:1057-1059,1268-1275
+ *                                     of pos (G2: see domain_of); positions unique, or        Vlite.hs:1057-1059,1268-1275
+ *                                     duplicates that carry the same value (semijoin marks)   Vlite.hs:1214-1222
  *   Partition,val,Id data,val,Id piv  destination positions of the STABLE sort of rows by
  *                                     bucket(data) = #pivots < data[i]  (G3)                  Vlite.hs:1082-1098,1057-1060
  *   Fold{Sum,Min,Max,Choose,Count}    one output per run of equal consecutive `groups`
@@ -262,6 +263,10 @@ static int op_binary(orc_env *e, int op, const vec *a, const vec *b, vec *out) {
   else if (ka == K_RANGE && a->step == 0 && kb == K_COL32) { i64 x = a->from; const int32_t *y = b->d32; LOOP(x, (i64)y[i]) }
   else { LOOP(vget(a, i), vget(b, i)) }
 #undef LOOP
+  /* positions `p % k`, k a positive constant: the scatter size hint (addScatterSizeHint, Vlite.hs:1117-1120; G9) --
+     they index a space of k slots (G2), whatever p indexed (an empty dim' still receives the slot-0 writes of the
+     partnerless fact rows, Vlite.hs:1214-1218) */
+  if (op == OP_MOD && b->kind == K_RANGE && b->step == 0 && b->from > 0) out->domain = b->from;
   return 0;
 }
 
