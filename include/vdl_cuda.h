@@ -40,14 +40,15 @@ enum {
   VDL_EINVAL = 1,      /* bad argument / malformed plan text */
   VDL_ECUDA = 2,       /* CUDA runtime error (message has the cudaError string) */
   VDL_ENOTFOUND = 3,   /* Load of a column that is not registered */
-  VDL_EUNSUPPORTED = 4,/* op outside the supported vocabulary (Like, CrossProduct*, Semisort) */
+  VDL_EUNSUPPORTED = 4,/* op outside the supported vocabulary (CrossProduct*, Semisort) */
   VDL_ERANGE = 5,      /* Gather/Scatter position out of range */
   VDL_ENOMEM = 6,
   VDL_ESTALE = 7       /* a prepared scan / probe was launched after one of its columns was rewritten or dropped */
 };
 
-/* storage types (reference Types.hs:66-89: SInt32 4 B; SInt64/SDecimal 8 B) */
-enum { VDL_I32 = 4, VDL_I64 = 8 };
+/* storage types (reference Types.hs:66-89: SInt32 4 B; SInt64/SDecimal 8 B); VDL_U8: the bytes of a string heap,
+ * `Load,<table>.<col>.heap` (Vdl.hs:244-247) -- such a vector can only be the dictionary argument of vdl_op_like */
+enum { VDL_U8 = 1, VDL_I32 = 4, VDL_I64 = 8 };
 
 /* binary elementwise ops, in the order of `Voodop` (Vdl.hs:110-123) */
 enum {
@@ -152,6 +153,11 @@ int vdl_abi_sizeof_map_desc(void);
  * uses every instruction, compiles it with NVRTC for sm_100a.  VDL_OK, VDL_ENOTFOUND (no NVRTC here: the interpreting
  * kernel is used) or VDL_ECUDA with NVRTC's log. */
 int vdl_jit_selftest(char *log, int log_capacity);
+/* Like (Vlite.hs:1010-1014 -> Vdl.hs:244-247, 444-447): out[i] = 1 if the NUL-terminated string at byte offset data[i] of
+ * the string heap matches the SQL LIKE pattern (`%` any run of bytes, `_` any one byte, no escape character,
+ * case-sensitive), else 0.  An offset outside the heap raises the context's range error (VDL_ERANGE at the next check). */
+#define VDL_LIKE_MAX_PATTERN 128
+int vdl_op_like(vdl_ctx *ctx, vdl_vec data, vdl_vec heap, const char *pattern, vdl_vec *out);
 /* FoldSelect with fold = pos_ pred (Vlite.hs:721-730): ascending positions of non-zero pred. */
 int vdl_op_fold_select(vdl_ctx *ctx, vdl_vec pred, vdl_vec *out);
 /* Gather (Vdl.hs:438): out[i] = src[pos[i]]. */

@@ -101,7 +101,7 @@ static i64 padded_bytes(int dtype, i64 rows) {
 }
 
 int vec_new(vdl_ctx *ctx, int dtype, i64 len, vdl_vec *out) {
-  if (dtype != VDL_I32 && dtype != VDL_I64) return vdl_fail(ctx, VDL_EINVAL, "dtype must be VDL_I32 or VDL_I64, got %d", dtype);
+  if (dtype != VDL_I32 && dtype != VDL_I64 && dtype != VDL_U8) return vdl_fail(ctx, VDL_EINVAL, "dtype must be VDL_I32, VDL_I64 or VDL_U8 (string heap), got %d", dtype);
   if (len < 0) return vdl_fail(ctx, VDL_EINVAL, "negative length %lld", (long long)len);
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   void *p = nullptr;
@@ -148,12 +148,22 @@ int vec_new_range(vdl_ctx *ctx, i64 from, i64 step, i64 len, vdl_vec *out) {
   return VDL_OK;
 }
 
-Vec *vec_get(vdl_ctx *ctx, vdl_vec h) {
+Vec *vec_get_any(vdl_ctx *ctx, vdl_vec h) {
   if (!ctx || h <= 0 || (size_t)h >= ctx->vecs.size() || !ctx->vecs[h].live) {
     vdl_fail(ctx, VDL_EINVAL, "invalid vector handle %d", (int)h);
     return nullptr;
   }
   return &ctx->vecs[h];
+}
+
+// numeric vectors only: a string heap (VDL_U8) is nothing but the dictionary argument of vdl_op_like
+Vec *vec_get(vdl_ctx *ctx, vdl_vec h) {
+  Vec *v = vec_get_any(ctx, h);
+  if (v && v->dtype == VDL_U8) {
+    vdl_fail(ctx, VDL_EINVAL, "vector %d (%s) is a string heap: it can only be the dictionary of a Like", (int)h, v->name.c_str());
+    return nullptr;
+  }
+  return v;
 }
 
 Operand operand_of(const Vec &v) {
@@ -205,23 +215,23 @@ int check_errflag(vdl_ctx *ctx, const char *what) {
 }
 
 extern "C" int vdl_vec_len(vdl_ctx *ctx, vdl_vec h, int64_t *len) {
-  Vec *v = vec_get(ctx, h);
+  Vec *v = vec_get_any(ctx, h);
   if (!v || !len) return VDL_EINVAL;
   *len = v->len;
   return VDL_OK;
 }
 extern "C" int vdl_vec_dtype(vdl_ctx *ctx, vdl_vec h, int *dtype) {
-  Vec *v = vec_get(ctx, h);
+  Vec *v = vec_get_any(ctx, h);
   if (!v || !dtype) return VDL_EINVAL;
   *dtype = v->dtype;
   return VDL_OK;
 }
 extern "C" void *vdl_vec_device_ptr(vdl_ctx *ctx, vdl_vec h) {
-  Vec *v = vec_get(ctx, h);
+  Vec *v = vec_get_any(ctx, h);
   return v ? v->ptr : nullptr;
 }
 extern "C" int vdl_vec_free(vdl_ctx *ctx, vdl_vec h) {
-  Vec *v = vec_get(ctx, h);
+  Vec *v = vec_get_any(ctx, h);
   if (!v) return VDL_EINVAL;
   if (!v->name.empty()) ctx->columns.erase(v->name);
   if (v->owned && v->ptr) VDL_CUDA(ctx, cudaFreeAsync(v->ptr, ctx->stream));   // ordered after the stream's pending readers
@@ -242,7 +252,7 @@ extern "C" int vdl_column_alloc(vdl_ctx *ctx, const char *name, int dtype, int64
 extern "C" int vdl_column_bind(vdl_ctx *ctx, const char *name, int dtype, int64_t rows, int64_t capacity_rows,
                                void *device_ptr, vdl_vec *out) {
   if (!ctx || !name || !out) return VDL_EINVAL;
-  if (dtype != VDL_I32 && dtype != VDL_I64) return vdl_fail(ctx, VDL_EINVAL, "dtype must be VDL_I32 or VDL_I64");
+  if (dtype != VDL_I32 && dtype != VDL_I64 && dtype != VDL_U8) return vdl_fail(ctx, VDL_EINVAL, "dtype must be VDL_I32, VDL_I64 or VDL_U8");
   if (((uintptr_t)device_ptr & 15) != 0) return vdl_fail(ctx, VDL_EINVAL, "column %s: device pointer must be 16-byte aligned", name);
   if (rows < 0 || capacity_rows < rows) return vdl_fail(ctx, VDL_EINVAL, "column %s: capacity %lld < rows %lld", name, (long long)capacity_rows, (long long)rows);
   if (ctx->columns.count(name)) return vdl_fail(ctx, VDL_EINVAL, "column %s already registered", name);
@@ -265,7 +275,7 @@ extern "C" int vdl_column_bind(vdl_ctx *ctx, const char *name, int dtype, int64_
 // vdl_vec_device_ptr): cached statistics are dropped and every prepared scan / probe over it re-proves its
 // assumptions before its next launch.
 extern "C" int vdl_column_touch(vdl_ctx *ctx, vdl_vec col) {
-  Vec *v = vec_get(ctx, col);
+  Vec *v = vec_get_any(ctx, col);
   if (!v) return VDL_EINVAL;
   if (v->is_range) return vdl_fail(ctx, VDL_EINVAL, "cannot touch a range vector");
   vec_written(ctx, v);
@@ -273,7 +283,7 @@ extern "C" int vdl_column_touch(vdl_ctx *ctx, vdl_vec col) {
 }
 
 extern "C" int vdl_vec_generation(vdl_ctx *ctx, vdl_vec h, uint64_t *gen) {
-  Vec *v = vec_get(ctx, h);
+  Vec *v = vec_get_any(ctx, h);
   if (!v || !gen) return VDL_EINVAL;
   *gen = v->gen;
   return VDL_OK;
@@ -294,7 +304,7 @@ extern "C" int vdl_column_drop(vdl_ctx *ctx, const char *name) {
 }
 
 extern "C" int vdl_column_upload(vdl_ctx *ctx, vdl_vec col, const void *host, int64_t rows) {
-  Vec *v = vec_get(ctx, col);
+  Vec *v = vec_get_any(ctx, col);
   if (!v || !host) return VDL_EINVAL;
   if (v->is_range || rows != v->len) return vdl_fail(ctx, VDL_EINVAL, "upload of %lld rows into a vector of %lld", (long long)rows, (long long)v->len);
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -305,7 +315,7 @@ extern "C" int vdl_column_upload(vdl_ctx *ctx, vdl_vec col, const void *host, in
 }
 
 extern "C" int vdl_column_download(vdl_ctx *ctx, vdl_vec col, void *host, int64_t rows) {
-  Vec *v = vec_get(ctx, col);
+  Vec *v = vec_get_any(ctx, col);
   if (!v || !host) return VDL_EINVAL;
   if (v->is_range || rows != v->len) return vdl_fail(ctx, VDL_EINVAL, "download of %lld rows from a vector of %lld", (long long)rows, (long long)v->len);
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));

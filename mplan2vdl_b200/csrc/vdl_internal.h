@@ -69,7 +69,8 @@ int vdl_cuda_fail(vdl_ctx *ctx, cudaError_t e, const char *what);
 // vector table
 int vec_new(vdl_ctx *ctx, int dtype, i64 len, vdl_vec *out);              // allocates HBM
 int vec_new_range(vdl_ctx *ctx, i64 from, i64 step, i64 len, vdl_vec *out);
-Vec *vec_get(vdl_ctx *ctx, vdl_vec v);                                    // nullptr + error if invalid
+Vec *vec_get(vdl_ctx *ctx, vdl_vec v);                                    // nullptr + error if invalid or a string heap
+Vec *vec_get_any(vdl_ctx *ctx, vdl_vec v);                                // string heaps (VDL_U8) too
 void vec_written(vdl_ctx *ctx, Vec *v);                                   // new generation, statistics dropped
 // (handle, generation) of a live stored vector, or false
 bool vec_identity(vdl_ctx *ctx, vdl_vec v, u64 *gen);

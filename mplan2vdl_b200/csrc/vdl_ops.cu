@@ -68,6 +68,58 @@ extern "C" int vdl_op_binary(vdl_ctx *ctx, int op, vdl_vec a, vdl_vec b, vdl_vec
   return VDL_OK;
 }
 
+// ---------------------------------------------------------------------------------- Like over a string heap
+// Vlite.hs:1010-1014 -> Vdl.hs:244-247: the data vector holds byte offsets into the column's string heap.  One thread per
+// row reads its (NUL-terminated) string and runs the glob match with one backtrack point (the last `%`): sequential byte
+// reads of a string that is 8-byte aligned and a few tens of bytes long, so a row costs its 8-byte offset plus one or two
+// 32-byte sectors of the heap (L2-resident for dictionary-like columns such as p_type).  Bound: HBM / L2 bandwidth.
+struct LikeArgs { char pat[VDL_LIKE_MAX_PATTERN]; };
+__global__ void __launch_bounds__(256) like_kernel(Operand data, const unsigned char *__restrict__ heap, i64 heap_len, const __grid_constant__ LikeArgs a,
+                                                   i64 *__restrict__ out, i64 n, int *errflag) {
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    const i64 off = op_ld(data, i);
+    if ((u64)off >= (u64)heap_len) { atomicAdd(errflag, 1); out[i] = 0; continue; }
+    const unsigned char *s = heap + off, *end = heap + heap_len, *star_s = nullptr;
+    int p = 0, star_p = -1;
+    bool ok = true;
+    while (s < end && *s) {
+      const char c = a.pat[p];
+      if (c == '%') { star_p = ++p; star_s = s; }
+      else if (c && (c == '_' || (unsigned char)c == *s)) { p++; s++; }
+      else if (star_p >= 0) { p = star_p; s = ++star_s; }
+      else { ok = false; break; }
+    }
+    if (ok) {
+      while (a.pat[p] == '%') p++;
+      ok = a.pat[p] == 0;
+    }
+    out[i] = ok ? 1 : 0;
+  }
+}
+
+extern "C" int vdl_op_like(vdl_ctx *ctx, vdl_vec data, vdl_vec heap, const char *pattern, vdl_vec *out) {
+  if (!ctx || !out || !pattern) return VDL_EINVAL;
+  Vec *vd = vec_get(ctx, data), *vh = vec_get_any(ctx, heap);
+  if (!vd || !vh) return VDL_EINVAL;
+  if (vh->dtype != VDL_U8) return vdl_fail(ctx, VDL_EINVAL, "Like: the dictionary must be a string heap (a VDL_U8 vector; Load,<table>.<col>.heap)");
+  if (strlen(pattern) >= VDL_LIKE_MAX_PATTERN) return vdl_fail(ctx, VDL_EUNSUPPORTED, "Like: pattern longer than %d bytes", VDL_LIKE_MAX_PATTERN - 1);
+  const i64 n = vd->len;
+  const Operand od = operand_of(*vd);
+  const unsigned char *hp = (const unsigned char *)vh->ptr;
+  const i64 hl = vh->len;
+  VDL_TRY(vec_new(ctx, VDL_I64, n, out));
+  if (n == 0) return VDL_OK;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  LikeArgs a;
+  memset(&a, 0, sizeof a);
+  strcpy(a.pat, pattern);
+  int blocks = (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 16));
+  like_kernel<<<blocks, 256, 0, ctx->stream>>>(od, hp, hl, a, (i64 *)ctx->vecs[*out].ptr, n, ctx->d_errflag);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaGetLastError());
+  return VDL_OK;
+}
+
 // ---------------------------------------------------------------------------------- map (expression tree in one launch)
 // The op-at-a-time remainder of a plan is mostly long chains of elementwise ops over short vectors (Q19's OR of ANDs over
 // the join's survivors: ~150 launches of a few microseconds each).  One launch interprets the whole tree per row: the

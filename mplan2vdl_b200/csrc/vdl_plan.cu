@@ -27,13 +27,13 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 
 namespace {
 
-enum NodeOp { N_LOAD, N_RANGEV, N_RANGEC, N_BINARY, N_FSELECT, N_GATHER, N_SCATTER, N_PARTITION, N_FOLD };
+enum NodeOp { N_LOAD, N_RANGEV, N_RANGEC, N_BINARY, N_FSELECT, N_GATHER, N_SCATTER, N_PARTITION, N_FOLD, N_LIKE };
 
 struct Node {
   int op = 0, sub = 0;         // sub: binary op / fold op
   int a = -1, b = -1, c = -1;  // argument node indices
   i64 k0 = 0, k1 = 0, k2 = 0;  // RangeV: from, step; RangeC: from, count, step
-  std::string name;            // Load: "table.column"
+  std::string name;            // Load: "table.column"; Like: the pattern
 };
 
 // data points at the result's host copy: the fused scan's / probe's mapped result buffer, or this output's own pinned buffer
@@ -215,7 +215,12 @@ int parse_plan(vdl_plan *p, const char *text) {
     } else if (op == "Scatter") {
       if (f.size() != 7 || f[4] != "val" || f[6] != "val" || !arg(f[2], &n.a) || !arg(f[3], &n.b) || !arg(f[5], &n.c)) return bad();
       n.op = N_SCATTER;
-    } else if (op == "Like" || op == "CrossProductOuter" || op == "CrossProductInner" || op == "Semisort") {
+    } else if (op == "Like") {              // id,Like,val,Id data,val,Id heap,val,pattern (Vdl.hs:444-447); the pattern may contain commas
+      if (f.size() < 8 || f[2] != "val" || f[4] != "val" || f[6] != "val" || !arg(f[3], &n.a) || !arg(f[5], &n.b)) return bad();
+      n.op = N_LIKE;
+      n.name = f[7];
+      for (size_t k = 8; k < f.size(); k++) n.name += "," + f[k];
+    } else if (op == "CrossProductOuter" || op == "CrossProductInner" || op == "Semisort") {
       return vdl_fail(ctx, VDL_EUNSUPPORTED, "plan line %d: op %s is outside the supported vocabulary", lineno, op.c_str());
     } else {
       if (f.size() != 7 || f[2] != "val" || f[4] != "val" || f[6] != "val" || !arg(f[3], &n.a) || !arg(f[5], &n.b)) return bad();
@@ -750,6 +755,7 @@ void mark_emits(vdl_plan *p, int ni, std::vector<char> &seen) {
     case N_RANGEV: mark_emits(p, n.a, seen); break;
     case N_BINARY: case N_GATHER: case N_FOLD: mark_emits(p, n.a, seen); mark_emits(p, n.b, seen); break;
     case N_FSELECT: mark_emits(p, n.b, seen); break;
+    case N_LIKE: mark_emits(p, n.a, seen); break;
     case N_SCATTER: mark_emits(p, n.a, seen); mark_emits(p, n.c, seen); break;
     case N_PARTITION: mark_emits(p, n.a, seen); break;
     default: break;
@@ -818,6 +824,7 @@ void live_walk(vdl_plan *p, int ni, std::vector<char> &live, std::vector<int> &c
     case N_RANGEV: use(n.a); break;
     case N_BINARY: if (!fused) { use(n.a); use(n.b); } break;
     case N_FSELECT: use(n.b); break;
+    case N_LIKE: use(n.a); use(n.b); break;
     case N_GATHER: use(n.a); use(n.b); break;
     case N_SCATTER: use(n.a); use(n.c); break;
     case N_PARTITION: use(n.a); break;
@@ -1157,16 +1164,34 @@ int eval(vdl_plan *p, int ni, vdl_vec *out) {
       break;
     }
     case N_GATHER: VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.b, &b)); VDL_TRY(vdl_op_gather(ctx, a, b, &r)); break;
+    case N_LIKE: VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.b, &b)); VDL_TRY(vdl_op_like(ctx, a, b, n.name.c_str(), &r)); break;
     case N_SCATTER: {
       VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.c, &c));
       Vec *pv = vec_get(ctx, c), *sv = vec_get(ctx, a);
       if (!pv || !sv) return VDL_EINVAL;
-      if (pv->domain < 0) return vdl_fail(ctx, VDL_EUNSUPPORTED, "Scatter: output length unknown (positions carry no index space; App. G2)");
-      if (pv->is_range && pv->from == 0 && pv->step == 1 && pv->len == pv->domain && sv->len == pv->len && !sv->is_range && sv->dtype == VDL_I64) {
+      i64 out_len = pv->domain;
+      if (out_len < 0 && p->join) {
+        // positions materialised by a probe pass carry no index space of their own; when the join analysis knows them to
+        // be row ids of a table (the dimension selection of deduceMasks, Vlite.hs:1268-1275), the output has that table's
+        // length -- the reference's `dimref` (Vlite.hs:782; App. G2)
+        const JSym &pt = janalyse(p, *p->join, n.c);
+        if (j_is_rowid(pt) && pt.space >= 0) {
+          const std::string prefix = p->tables[p->join->spaces[pt.space].table] + ".";
+          for (const Node &ld : p->nodes)
+            if (ld.op == N_LOAD && ld.name.compare(0, prefix.size(), prefix) == 0 && !(ld.name.size() > 5 && ld.name.compare(ld.name.size() - 5, 5, ".heap") == 0)) {
+              vdl_vec h; VDL_TRY(vdl_column_lookup(ctx, ld.name.c_str(), &h));
+              VDL_TRY(vdl_vec_len(ctx, h, &out_len));
+              break;
+            }
+          pv = vec_get(ctx, c); sv = vec_get(ctx, a);
+        }
+      }
+      if (out_len < 0) return vdl_fail(ctx, VDL_EUNSUPPORTED, "Scatter: output length unknown (positions carry no index space; App. G2)");
+      if (pv->is_range && pv->from == 0 && pv->step == 1 && pv->len == out_len && sv->len == pv->len && !sv->is_range && sv->dtype == VDL_I64) {
         r = a; temp = false;       // scattering by the identity permutation (Partition of keys already in order): the source itself
         break;
       }
-      VDL_TRY(vdl_op_scatter(ctx, a, c, pv->domain, &r));
+      VDL_TRY(vdl_op_scatter(ctx, a, c, out_len, &r));
       break;
     }
     case N_PARTITION: {
@@ -1198,7 +1223,7 @@ int eval(vdl_plan *p, int ni, vdl_vec *out) {
     double t1 = now_ms();
     i64 len = 0;
     vdl_vec_len(ctx, r, &len);
-    static const char *OPN[] = {"Load", "RangeV", "RangeC", "Binary", "FoldSelect", "Gather", "Scatter", "Partition", "Fold"};
+    static const char *OPN[] = {"Load", "RangeV", "RangeC", "Binary", "FoldSelect", "Gather", "Scatter", "Partition", "Fold", "Like"};
     fprintf(stderr, "[vdl trace] node %3d %-10s sub %2d len %10lld  %8.3f ms (cumulative since plan start %8.3f)\n", ni, OPN[n.op], n.sub, (long long)len,
             t1 - p->trace_last, t1 - p->trace_t0);
     p->trace_last = now_ms();

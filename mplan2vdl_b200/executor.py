@@ -51,9 +51,9 @@ class Context:
         return v.value
 
     def upload_column(self, name: str, arr: np.ndarray) -> int:
-        """Allocate + host->device copy of an int32/int64 numpy column."""
-        if arr.dtype not in (np.int32, np.int64):
-            raise TypeError(f"{name}: columns are int32 or int64, got {arr.dtype}")
+        """Allocate + host->device copy of an int32/int64 numpy column (uint8: the bytes of a string heap, `<col>.heap`)."""
+        if arr.dtype not in (np.int32, np.int64, np.uint8):
+            raise TypeError(f"{name}: columns are int32 or int64 (uint8 for a string heap), got {arr.dtype}")
         arr = np.ascontiguousarray(arr)
         v = self.alloc_column(name, arr.dtype.itemsize, arr.shape[0])
         self.check(self.L.vdl_column_upload(self.h, v, arr.ctypes.data, arr.shape[0]))
@@ -148,6 +148,9 @@ class Context:
         ins = (C.c_int32 * max(1, len(inputs)))(*inputs)
         tabs = (C.c_int32 * max(1, len(tables)))(*tables)
         return self._out(self.L.vdl_op_map, C.byref(d), ins, tabs)
+
+    def op_like(self, data: int, heap: int, pattern: str) -> int:
+        return self._out(self.L.vdl_op_like, data, heap, pattern.encode())
 
     def op_fold_select(self, pred: int) -> int:
         return self._out(self.L.vdl_op_fold_select, pred)

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libvdl_cuda.so")
 
-VDL_I32, VDL_I64 = 4, 8
+VDL_U8, VDL_I32, VDL_I64 = 1, 4, 8
 VDL_PLAN_FUSE = 1
 BINARY_OPS = ["LogicalAnd", "LogicalOr", "BitwiseAnd", "BitwiseOr", "BitShift", "Equals", "Add", "Subtract",
               "Greater", "Multiply", "Divide", "Modulo"]
@@ -131,6 +131,7 @@ SYMBOLS = [
     ("vdl_op_map", _I, [_P, C.POINTER(MapDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("vdl_abi_sizeof_map_desc", _I, []),
     ("vdl_jit_selftest", _I, [C.c_char_p, _I]),
+    ("vdl_op_like", _I, [_P, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_int32)]),
     ("vdl_op_fold_select", _I, [_P, C.c_int32, C.POINTER(C.c_int32)]),
     ("vdl_op_gather", _I, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     ("vdl_op_scatter", _I, [_P, C.c_int32, C.c_int32, _L, C.POINTER(C.c_int32)]),

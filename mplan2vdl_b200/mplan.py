@@ -15,7 +15,7 @@ import datetime
 import re
 import sys
 
-from .vlite import Bin, Cast, GroupBy, Identity, IfThenElse, In, Join, Lit, Project, Ref, Select, Table, Unary
+from .vlite import Bin, Cast, GroupBy, Identity, IfThenElse, In, Join, Like, Lit, Project, Ref, Select, Table, Unary
 
 DATE = ("date",)
 
@@ -149,8 +149,20 @@ class Parser:
             items = self.expr_list(")")
             self.take(")")
             return (("in", (e, alias), items), None)
-        if self.peek()[1] in ("FILTER", "notin", "!"):
-            raise NotImplementedError(f"mplan: {self.peek()[1]} expressions (Like / NOT IN) are outside the executor's scope")
+        if self.peek()[1] in ("FILTER", "!") and self.peek()[0] == "word":       # FilterExpr (Parser.y:202-206)
+            negated = self.at("!")
+            if negated:
+                self.take("!")
+            self.take("FILTER")
+            oper = self.take(kind="word")[1]
+            self.take("(")
+            pattern = self.expr()
+            self.take(",")
+            escape = self.basic()
+            self.take(")")
+            return (("filter", oper, negated, (e, alias), pattern, escape), None)
+        if self.at("notin"):                               # Parser.y:212; rejected by Mplan.hs:522
+            raise NotImplementedError("implement this case of IN operator (Mplan.hs:522): notin")
         return (e, alias)
 
     def attrs(self):
@@ -274,11 +286,24 @@ class Front:
                 raise NotImplementedError("implement this case of IN operator (Mplan.hs:522)")
             newctx = self._dtype_of_ref(lnode[1])
             return In(Ref(lnode[1]), [self.sc(e, newctx) for e, _ in items])
+        if kind == "filter":                                # Mplan.hs:524-545: x [!] FILTER like (char[char(n) "pattern"], char "")
+            _, oper, negated, (arg, _a), (pat, palias), escape = node
+            ok = (oper == "like" and palias is None and pat[0] == "cast" and pat[1] == ("char", []) and pat[2][0][0] == "lit" and
+                  pat[2][0][1][0] == "char" and len(pat[2][0][1][1]) == 1 and escape[0] == "lit" and escape[1] == ("char", []) and escape[2] == "")
+            if not ok:
+                raise NotImplementedError(f"mplan filter operator {oper} (Mplan.hs:547)")
+            like = Like(self.sc(arg, ctx), pat[2][0][2])
+            return Unary("Neg", like) if negated else like
         if kind == "call":
             fname, args = node[1], node[2]
             base = fname.split(".")[-1]
             if base == "ifthenelse" and len(args) == 3:         # Mplan.hs:441-451
                 return IfThenElse(*(self.sc(a, ctx) for a, _ in args))
+            if base == "like" and len(args) == 2:              # Mplan.hs:398-417: sys.like(x, char[char(n) "pattern"])
+                pat = args[1][0]
+                if not (pat[0] == "cast" and pat[1] == ("char", []) and pat[2][0][0] == "lit" and pat[2][0][1][0] == "char" and len(pat[2][0][1][1]) == 1):
+                    raise NotImplementedError("implement this 'like' case (Mplan.hs:419)")
+                return Like(self.sc(args[0][0], ctx), pat[2][0][2])
             if len(args) == 1 and base == "identity":          # Mplan.hs:392-396: a row id, whatever the argument
                 return Identity()
             if len(args) == 1 and base in ("year", "sql_neg", "isnull"):      # Mplan.hs:106-112, 420-424

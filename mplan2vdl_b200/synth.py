@@ -116,3 +116,87 @@ def column_spec(cat: Catalog, qualified: str, sf: float) -> ColumnSpec:
     tz = col.trailing_zeros if col.vmax > col.vmin else 0
     nvals = ((col.vmax - col.vmin) >> tz) + 1
     return ColumnSpec(qualified, col.width, UNIFORM, col.vmin, 1 << tz, nvals, 0, stream)
+
+
+# ------------------------------------------------------------------------------------------ string heaps
+# `Like` reads the strings of a char / varchar column from its heap, `Load,<table>.<col>.heap` (Vdl.hs:244-247): a byte
+# vector in which every string is NUL-terminated; the column itself holds byte offsets into it (MonetDB's layout; the
+# offsets of bounds.csv are multiples of 8, trailing_zeros = 3).  The synthetic heap of a column is a POOL of distinct
+# strings built from the TPC-H word lists (dbgen's grammar, reduced), laid out from the column's minimum offset on, each
+# padded to the next multiple of 8; a row draws a pool entry with the same counter-based hash as the UNIFORM kind, so
+# shards and the host agree.  Returns numpy arrays; the heap is small (<= a few MB), the offsets are per row.
+_SYLL1 = ["STANDARD", "SMALL", "MEDIUM", "LARGE", "ECONOMY", "PROMO"]
+_SYLL2 = ["ANODIZED", "BURNISHED", "PLATED", "POLISHED", "BRUSHED"]
+_SYLL3 = ["TIN", "NICKEL", "BRASS", "STEEL", "COPPER"]
+_COLORS = ("almond antique aquamarine azure beige bisque black blanched blue blush brown burlywood burnished chartreuse chiffon "
+           "chocolate coral cornflower cornsilk cream cyan dark deep dim dodger drab firebrick floral forest frosted gainsboro "
+           "ghost goldenrod green grey honeydew hot indian ivory khaki lace lavender lawn lemon light lime linen magenta maroon "
+           "medium metallic midnight mint misty moccasin navajo navy olive orange orchid pale papaya peach peru pink plum powder "
+           "puff purple red rose rosy royal saddle salmon sandy seashell sienna sky slate smoke snow spring steel tan thistle "
+           "tomato turquoise violet wheat white yellow").split()
+_FILLER = ("furiously carefully quickly slyly blithely final ironic regular express bold pending even silent unusual special "
+           "Customer Complaints Recommends requests deposits packages accounts foxes ideas theodolites pinto beans instructions "
+           "dependencies excuses platelets asymptotes courts dolphins multipliers sauternes warthogs frets dinos attainments "
+           "somas Tiresias patterns forges braids hockey players frays warhorses dugouts notornis epitaphs pearls tithes "
+           "waters orbits gifts sheaves depths sentiments decoys realms pains grouches escapades").split()
+
+
+def _sm64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+def string_pool(qualified: str) -> list:
+    """The distinct strings of a column's synthetic heap, in heap order."""
+    col = qualified.split(".", 1)[1]
+    if col == "p_type":
+        return [f"{a} {b} {c}" for a in _SYLL1 for b in _SYLL2 for c in _SYLL3]
+    h0 = _fnv1a(qualified + ".heap")
+    words, n, k = (_COLORS, 16384, 5) if col == "p_name" else (_FILLER, 4096, 9)
+    out = []
+    for i in range(n):
+        h = _sm64(h0 + i)
+        ws = []
+        for j in range(k):
+            h = _sm64(h + j)
+            ws.append(words[h % len(words)])
+        out.append(" ".join(ws))
+    return out
+
+
+def is_heap(qualified: str) -> bool:
+    return qualified.endswith(".heap")
+
+
+def string_heap(cat: Catalog, qualified: str):
+    """(heap bytes as numpy uint8, offsets of the pool entries as numpy int64) of column `qualified` (no `.heap` suffix)."""
+    import numpy as np
+    c = cat.column(qualified)
+    start = max(16, (c.vmin + 7) // 8 * 8) if c.vmin > -(1 << 62) else 16
+    pool = string_pool(qualified)
+    offs, parts, at = [], [bytes(start)], start
+    for s in pool:
+        b = s.encode() + b"\0"
+        b += bytes(-len(b) % 8)
+        offs.append(at)
+        parts.append(b)
+        at += len(b)
+    return np.frombuffer(b"".join(parts), dtype=np.uint8).copy(), np.asarray(offs, dtype=np.int64)
+
+
+def string_offsets(cat: Catalog, qualified: str, rows: int, row_offset: int, seed: int):
+    """Offsets column of `rows` rows from global row `row_offset`: pool entry mulhi64(splitmix64(base + row), |pool|)."""
+    import numpy as np
+    _heap, offs = string_heap(cat, qualified)
+    base = _sm64((seed ^ (_fnv1a(qualified) * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        x = (np.arange(rows, dtype=np.uint64) + np.uint64(row_offset) + np.uint64(base)) + np.uint64(0x9E3779B97F4A7C15)
+        z = x
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    idx = ((z >> np.uint64(32)) * np.uint64(len(offs)) >> np.uint64(32)).astype(np.int64)      # mulhi on the high word: uniform enough
+    return offs[idx]

@@ -39,14 +39,23 @@ def load_synthetic(ctx, cat: Catalog, columns, sf: float, rank: int = 0, world: 
     """Generate the named columns in place on ctx's GPU.  Returns {"row_base": int, "rows": {table: rows on this GPU}}."""
     seed = synth.seed_for(sf)
     rows_here, row_base = {}, 0
+    heaps = {q[:-len(".heap")] for q in columns if synth.is_heap(q)}     # string columns whose heap a Like reads
     for q in columns:
         table = q.split(".")[0]
+        if synth.is_heap(q):                               # the bytes of the heap: host-built (small), uploaded once
+            heap, _ = synth.string_heap(cat, q[:-len(".heap")])
+            ctx.upload_column(q, heap)
+            continue
         total = (rows_override or {}).get(table, synth.table_rows(cat, table, sf))
         if table == FACT_TABLE:
             start, n = shard_range(total, rank, world)
             row_base = start
         else:
             start, n = 0, total
+        if q in heaps:                                     # ... and its offsets column: pool entries drawn per global row
+            ctx.upload_column(q, synth.string_offsets(cat, q, n, start, seed))
+            rows_here[table] = n
+            continue
         spec = synth.column_spec(cat, q, sf)
         if table in (rows_override or {}) and spec.kind == synth.FKDENSE:
             spec = synth.ColumnSpec(spec.name, spec.width, spec.kind, spec.vmin, spec.stride, spec.p0, total, spec.stream)

@@ -159,6 +159,8 @@ def complete(op: str, args: tuple, params: tuple = ()) -> Vexp:
         pivots, pdata = args
         info = dict(bounds=(0, pivots.count - 1), count=pdata.count, tz=0, dtype=("dec", 0))
         quant = "Unique"
+    elif op == "Like":                                     # 296-297
+        info = dict(bounds=(0, 1), count=args[0].count, tz=0, dtype=("dec", 0))
     elif op == "VShuffle":
         a = args[0]
         info = dict(bounds=a.bounds, count=a.count, tz=a.tz, dtype=a.dtype)
@@ -231,6 +233,12 @@ class Unary:                # Mplan.hs:101-104, 122: op in Year | Neg | IsNull
 @dataclass
 class Identity:             # Mplan.hs:119 `Identity {e}`: "returns a rowid"
     pass
+
+
+@dataclass
+class Like:                 # Mplan.hs:127
+    arg: object
+    pattern: str
 
 
 @dataclass
@@ -311,7 +319,11 @@ class Lowering:
 
     # ---- leaves ---------------------------------------------------------------------------
     def _load(self, qualified: str) -> Vexp:
-        c = self.cat.column(qualified)
+        t, cn = qualified.split(".", 1)
+        if cn.startswith("%") and cn[1:] in self.cat.tables[t].columns:      # constraints are known under `%name` too (Config.hs:144-146)
+            c = self.cat.tables[t].columns[cn[1:]]
+        else:
+            c = self.cat.column(qualified)
         # display type (getDTypeOfMType, Types.hs:143-153): DECIMAL(p, s) columns carry their scale
         dt = ("str", qualified) if c.mtype in ("char", "varchar") else (("date",) if c.mtype == "date" else ("dec", c.scale if c.mtype == "decimal" else 0))
         return Vexp(op="Load", params=(qualified,), bounds=(c.vmin, c.vmax), count=c.count, tz=c.trailing_zeros, dtype=dt)
@@ -336,6 +348,11 @@ class Lowering:
             return const_(e.n, env.list[0]).replace(dtype=e.dtype)
         if isinstance(e, Identity):                         # 985-986: pos_ of the first vector in scope
             return pos_(env.list[0])
+        if isinstance(e, Like):                             # 1010-1014: the string heap is found through the column's lineage
+            data = self.sc(env, e.arg)
+            if not data.lineage:
+                raise ValueError("cannot apply like expressions without knowing lineage (Vlite.hs:1014)")
+            return complete("Like", (data,), (e.pattern, data.lineage[0]))
         if isinstance(e, Cast):
             v = self.sc(env, e.arg)
             if e.point is None or v.dtype[0] != "dec" or v.dtype[1] == e.point:
@@ -647,6 +664,7 @@ class Emitter:
     def __init__(self):
         self.lines = []
         self.ids = {}
+        self.memo = {}
 
     def _emit(self, key, fields) -> int:
         if key in self.ids:
@@ -663,6 +681,14 @@ class Emitter:
         return self._emit(("RangeV", rmin, ref, rstep), ["RangeV", "val", str(rmin), f"Id {ref}", str(rstep)])
 
     def node(self, v: Vexp) -> int:
+        """Memoised on the structural id (voodooFromVexpMemo, Vdl.hs:171-180): a shared sub-DAG is walked once, and the
+        numbering is unchanged because `_emit` already returns the first id of a repeated statement."""
+        hit = self.memo.get(v.sid)
+        if hit is None:
+            hit = self.memo[v.sid] = self._node(v)
+        return hit
+
+    def _node(self, v: Vexp) -> int:
         if v.op == "Load":                                 # makeload (161-168): Load + Project(val <- column)
             name = v.params[0]
             ld = self._emit(("Load", name), ["Load", name])
@@ -710,6 +736,13 @@ class Emitter:
         if v.op == "VShuffle":
             a = self.node(v.args[0])
             return self._emit(("Shuffle", a), ["Shuffle", f"Id {a}"])
+        if v.op == "Like":                                 # 244-247: the dictionary is the column's string heap, `<table>.<col>.heap`
+            d = self.node(v.args[0])
+            pattern, col = v.params
+            heap = f"{col}.heap"
+            ld = self._emit(("Load", heap), ["Load", heap])
+            hp = self._emit(("ProjectIn", ld), ["Project", "val", f"Id {ld}", heap.split(".", 1)[1]])
+            return self._emit(("Like", d, hp, pattern), ["Like", "val", f"Id {d}", "val", f"Id {hp}", "val", pattern])
         raise NotImplementedError(v.op)
 
     def output(self, v: Vexp):

@@ -71,8 +71,8 @@ class Oracle:
             self._env = None
 
     def bind(self, name: str, arr: np.ndarray):
-        if arr.dtype not in (np.int32, np.int64):
-            raise TypeError(f"{name}: columns are int32 or int64 (Types.hs:84-87), got {arr.dtype}")
+        if arr.dtype not in (np.int32, np.int64) and not (arr.dtype == np.uint8 and name.endswith(".heap")):
+            raise TypeError(f"{name}: columns are int32 or int64 (Types.hs:84-87) -- or uint8 for a string heap --, got {arr.dtype}")
         arr = np.ascontiguousarray(arr)
         self._keep[name] = arr
         if lib().orc_bind_column(self._env, name.encode(), arr.ctypes.data, arr.dtype.itemsize, arr.shape[0]):

@@ -41,7 +41,10 @@
  *                                     empty input -> empty output (G14)                      Vlite.hs:1048-1070; Vdl.hs:255-264
  *   Shuffle,Id n                      identity (order-destroying hint)                        Vdl.hs:449-450
  *   MaterializeCompact,Id n           query output; name = the Project's <out>               Vdl.hs:278-292,452-453
- *   Like / CrossProduct* / Semisort   rejected (out of scope: SURVEY.md section 8 f3)
+ *   Like,val,Id d,val,Id heap,val,pat out[i] = 1 if the NUL-terminated string at byte offset d[i] of the column's string
+ *                                     heap (`Load,<table>.<col>.heap`, a byte vector) matches the SQL LIKE pattern
+ *                                     (% any run, _ any one byte, no escape, case-sensitive), else 0          Vdl.hs:244-247,444-447
+ *   CrossProduct* / Semisort          rejected (out of scope: SURVEY.md section 8 f3)
  *
  * Threads: OpenMP, row-range split per op, deterministic combine.
  */
@@ -58,12 +61,13 @@ typedef int64_t i64;
 typedef uint64_t u64;
 
 /* ------------------------------------------------------------------ vectors */
-enum { K_DENSE = 0, K_COL32 = 1, K_RANGE = 2, K_COL64 = 3 };
+enum { K_DENSE = 0, K_COL32 = 1, K_RANGE = 2, K_COL64 = 3, K_BYTES = 4 };
 typedef struct {
   int kind;
   i64 n;
   i64 *d;            /* K_DENSE (owned) or K_COL64 (borrowed) */
   const int32_t *d32;/* K_COL32 (borrowed) */
+  const unsigned char *d8; /* K_BYTES (borrowed): a string heap, only Like reads it */
   i64 from, step;    /* K_RANGE */
   i64 domain;        /* length of the vector these values index into; -1 unknown */
   int valid;
@@ -82,7 +86,7 @@ enum {
   OP_LOAD, OP_PROJECT, OP_RANGEV, OP_RANGEC,
   OP_LAND, OP_LOR, OP_BAND, OP_BOR, OP_SHIFT, OP_EQ, OP_ADD, OP_SUB, OP_GT, OP_MUL, OP_DIV, OP_MOD,
   OP_FCHOOSE, OP_FSELECT, OP_FMAX, OP_FSUM, OP_FMIN, OP_FCOUNT,
-  OP_GATHER, OP_SCATTER, OP_PARTITION, OP_SHUFFLE, OP_MATERIALIZE, OP_UNSUPPORTED
+  OP_GATHER, OP_SCATTER, OP_PARTITION, OP_SHUFFLE, OP_MATERIALIZE, OP_LIKE, OP_UNSUPPORTED
 };
 static const struct { const char *name; int op; } OPNAMES[] = {
   {"Load", OP_LOAD}, {"Project", OP_PROJECT}, {"RangeV", OP_RANGEV}, {"RangeC", OP_RANGEC},
@@ -93,14 +97,14 @@ static const struct { const char *name; int op; } OPNAMES[] = {
   {"FoldSum", OP_FSUM}, {"FoldMin", OP_FMIN}, {"FoldCount", OP_FCOUNT},
   {"Gather", OP_GATHER}, {"Scatter", OP_SCATTER}, {"Partition", OP_PARTITION},
   {"Shuffle", OP_SHUFFLE}, {"MaterializeCompact", OP_MATERIALIZE},
-  {"Like", OP_UNSUPPORTED}, {"CrossProductOuter", OP_UNSUPPORTED},
+  {"Like", OP_LIKE}, {"CrossProductOuter", OP_UNSUPPORTED},
   {"CrossProductInner", OP_UNSUPPORTED}, {"Semisort", OP_UNSUPPORTED}, {NULL, 0}};
 
 typedef struct {
   int id, op;
   int a, b, c;        /* argument node ids (0 = none) */
   i64 k0, k1, k2;     /* RangeV: from, step; RangeC: from, count, step */
-  char name[160];     /* Load: column; Project: out name */
+  char name[160];     /* Load: column; Project: out name; Like: pattern */
   int lastuse;        /* index of last statement that reads this node */
 } stmt;
 
@@ -137,7 +141,7 @@ const i64 *orc_output_data(orc_env *e, int i) { return e->outs[i].d; }
 
 /* Columns are borrowed, not copied.  width = 4 (int/date, Types.hs:84-87,129-140) or 8. */
 int orc_bind_column(orc_env *e, const char *name, const void *data, int width, i64 rows) {
-  if (width != 4 && width != 8) return fail(e, "column %s: width %d not 4/8", name, width);
+  if (width != 4 && width != 8 && width != 1) return fail(e, "column %s: width %d not 4/8 (or 1 for a string heap)", name, width);
   for (int i = 0; i < e->ncols; i++)
     if (!strcmp(e->cols[i].name, name)) {
       e->cols[i].data = data; e->cols[i].width = width; e->cols[i].rows = rows; return 0;
@@ -203,6 +207,13 @@ static int parse_plan(orc_env *e, const char *text, stmt **out_stmts, int *out_n
       case OP_SCATTER: /* id,Scatter,src,fold,val,pos,val (Vdl.hs:441-442) */
         NEED(7); VAL(4); VAL(6); bad = parse_ref(f[2], &s->a) | parse_ref(f[3], &s->b) | parse_ref(f[5], &s->c); break;
       case OP_SHUFFLE: case OP_MATERIALIZE: NEED(3); bad = parse_ref(f[2], &s->a); break;
+      case OP_LIKE: { /* id,Like,val,Id data,val,Id heap,val,pattern (Vdl.hs:444-447); a pattern may contain commas */
+        if (nf < 8) { bad = 1; goto done; }
+        VAL(2); VAL(4); VAL(6); bad = parse_ref(f[3], &s->a) | parse_ref(f[5], &s->b);
+        size_t w = 0; s->name[0] = 0;
+        for (int k = 7; k < nf; k++) w += (size_t)snprintf(s->name + w, sizeof s->name - w, "%s%s", k > 7 ? "," : "", f[k]);
+        break;
+      }
       case OP_UNSUPPORTED: free(st); return fail(e, "line %d: op %s is out of scope for the oracle", lineno, f[1]);
       default: /* binary ops and folds: Op,val,Id a,val,Id b,val */
         NEED(7); VAL(2); VAL(4); VAL(6); bad = parse_ref(f[3], &s->a) | parse_ref(f[5], &s->b); break;
@@ -434,6 +445,34 @@ static int op_fold(orc_env *e, int op, const vec *groups, const vec *data, vec *
   return 0;
 }
 
+/* Like: Vlite.hs:1010-1014 -> Vdl.hs:244-247.  SQL LIKE without escape: `%` matches any run of bytes (also none), `_`
+ * exactly one byte, everything else itself.  Greedy match with one backtrack point (the last `%`). */
+static int like_match(const unsigned char *s, const unsigned char *end, const char *p) {
+  const unsigned char *star_s = NULL; const char *star_p = NULL;
+  while (s < end && *s) {
+    if (*p == '%') { star_p = ++p; star_s = s; }
+    else if (*p && (*p == '_' || (unsigned char)*p == *s)) { p++; s++; }
+    else if (star_p) { p = star_p; s = ++star_s; }
+    else return 0;
+  }
+  while (*p == '%') p++;
+  return *p == 0;
+}
+static int op_like(orc_env *e, const vec *data, const vec *heap, const char *pattern, vec *out) {
+  if (heap->kind != K_BYTES) return fail(e, "Like: the dictionary must be a string heap (Load,<table>.<col>.heap)");
+  if (data->kind == K_BYTES) return fail(e, "Like: the data must be a vector of heap offsets");
+  i64 n = data->n, hl = heap->n, bad = 0;
+  *out = new_dense(n);
+  i64 *o = out->d;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+  for (i64 i = 0; i < n; i++) {
+    i64 off = vget(data, i);
+    if (off < 0 || off >= hl) { bad++; o[i] = 0; } else o[i] = like_match(heap->d8 + off, heap->d8 + hl, pattern);
+  }
+  if (bad) { vfree(out); return fail(e, "Like: %lld offsets outside the heap [0,%lld)", (long long)bad, (long long)hl); }
+  return 0;
+}
+
 /* ------------------------------------------------------------------ interpreter */
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
@@ -460,13 +499,18 @@ int orc_run(orc_env *e, const char *plan_text, int nthreads) {
     stmt *s = &st[i];
     vec *A = s->a ? &val[s->a] : NULL, *B = s->b ? &val[s->b] : NULL, *C = s->c ? &val[s->c] : NULL;
     vec r; memset(&r, 0, sizeof r); r.domain = -1;
+    if (s->op != OP_LIKE && s->op != OP_PROJECT && s->op != OP_LOAD &&
+        ((A && A->kind == K_BYTES) || (B && B->kind == K_BYTES) || (C && C->kind == K_BYTES))) {
+      rc = fail(e, "statement %d: a string heap can only be the dictionary of a Like", s->id); break;
+    }
     switch (s->op) {
       case OP_LOAD: {
         colbind *cb = NULL;
         for (int k = 0; k < e->ncols; k++) if (!strcmp(e->cols[k].name, s->name)) cb = &e->cols[k];
         if (!cb) { rc = fail(e, "Load: column %s is not bound", s->name); break; }
         r.valid = 1; r.n = cb->rows;
-        if (cb->width == 4) { r.kind = K_COL32; r.d32 = (const int32_t *)cb->data; }
+        if (cb->width == 1) { r.kind = K_BYTES; r.d8 = (const unsigned char *)cb->data; }
+        else if (cb->width == 4) { r.kind = K_COL32; r.d32 = (const int32_t *)cb->data; }
         else { r.kind = K_COL64; r.d = (i64 *)cb->data; }
         break;
       }
@@ -480,6 +524,7 @@ int orc_run(orc_env *e, const char *plan_text, int nthreads) {
       case OP_GATHER: rc = op_gather(e, A, B, &r); break;
       case OP_SCATTER: rc = op_scatter(e, A, C, &r); break;
       case OP_PARTITION: rc = op_partition(e, A, B, &r); break;
+      case OP_LIKE: rc = op_like(e, A, B, s->name, &r); break;
       case OP_FCHOOSE: case OP_FMAX: case OP_FSUM: case OP_FMIN: case OP_FCOUNT: rc = op_fold(e, s->op, A, B, &r); break;
       case OP_MATERIALIZE: {
         output *o = &e->outs[e->nouts++];

@@ -11,7 +11,7 @@ major (the packed key of makeCompositeKey, Vlite.hs:1123-1170, is monotone in th
 empty input; COUNT / AVG are FoldSum of 1 and integer Divide (Vlite.hs:1038-1046); arithmetic is int64."""
 import numpy as np
 
-from mplan2vdl_b200.vlite import Bin, Cast, GroupBy, Identity, IfThenElse, In, Join, Lit, Project, Ref, Select, Table, Unary
+from mplan2vdl_b200.vlite import Bin, Cast, GroupBy, Identity, IfThenElse, In, Join, Like, Lit, Project, Ref, Select, Table, Unary
 
 I64 = np.int64
 
@@ -53,6 +53,27 @@ def expr(f: Frame, e):
         return np.full(n, e.n, I64)
     if isinstance(e, Identity):
         return np.arange(n, dtype=I64)
+    if isinstance(e, Like):                                                  # SQL LIKE as a regular expression over the decoded strings
+        import re
+        arg = e.arg
+        while isinstance(arg, Cast):
+            arg = arg.arg
+        heap = HEAPS[f.origin_of(arg.name)]
+        rx = re.compile("".join(".*" if c == "%" else ("." if c == "_" else re.escape(c)) for c in e.pattern), re.S)
+        raw = heap.tobytes()
+        memo = {}
+        out = np.zeros(n, I64)
+        for i, off in enumerate(expr(f, arg)):
+            off = int(off)
+            if off not in memo:
+                memo[off] = 1 if rx.fullmatch(raw[off:raw.index(b"\0", off)].decode()) else 0
+            out[i] = memo[off]
+        return out
+    if isinstance(e, Unary) and e.op == "Year":                              # the query's meaning: the calendar year (not the emitted approximation)
+        import datetime
+        days = expr(f, e.arg)
+        u, inv = np.unique(days, return_inverse=True)
+        return np.array([datetime.date.fromordinal(int(d) - 365).year for d in u], dtype=I64)[inv]
     if isinstance(e, Unary) and e.op == "Neg":                               # `!`: 1 - x (Vlite.hs:1016-1018)
         return (1 - expr(f, e.arg)).astype(I64)
     if isinstance(e, Cast):
@@ -79,10 +100,12 @@ def expr(f: Frame, e):
     with np.errstate(over="ignore"):
         return {"Add": lambda: a + b, "Sub": lambda: a - b, "Mul": lambda: a * b,
                 "Lt": lambda: a < b, "Leq": lambda: a <= b, "Gt": lambda: a > b, "Geq": lambda: a >= b,
-                "Eq": lambda: a == b, "Neq": lambda: a != b,
+                "Eq": lambda: a == b, "Neq": lambda: a != b, "Div": lambda: tdiv(a, b),
+                "Min": lambda: np.minimum(a, b), "Max": lambda: np.maximum(a, b),
                 "LogAnd": lambda: (a != 0) & (b != 0), "LogOr": lambda: (a != 0) | (b != 0)}[e.op]().astype(I64)
 
 
+HEAPS = {}       # base column -> its string heap (uint8), filled by evaluate() from the data's `<col>.heap` entries
 POINTS = {}      # base column -> decimal point, filled by evaluate() from the catalogue when decimal casts matter
 
 
@@ -97,6 +120,8 @@ def point_of(f: Frame, e):
             return None
     if isinstance(e, Cast):
         return e.point if e.point is not None else point_of(f, e.arg)
+    if isinstance(e, IfThenElse):              # cond * then + !cond * else (Vlite.hs:237-245): the scale of `then`
+        return point_of(f, e.then_) or 0
     if isinstance(e, Bin):
         a, b = point_of(f, e.left), point_of(f, e.right)
         if e.op == "Mul":
@@ -273,6 +298,12 @@ def _rel(data: dict, r) -> Frame:
             out = Frame(None, np.zeros(0, I64), [(outname(agg, alias), np.zeros(0, I64)) for agg, alias in r.outputaggs], origin)
             out.points = points
             return out
+        # input keys may be aliased (ps_suppkey as L5.L5): the alias is in scope for the aggregates (Vlite.hs:626-634)
+        extra = [(a, f.get(k)) for k, a in r.inputkeys if a is not None]
+        if extra:
+            f2 = Frame(f.base, f.rows, f.cols + extra, dict(f.origin, **{a: f.origin_of(k) for k, a in r.inputkeys if a is not None}))
+            f2.points = f.points
+            f = f2
         keys = [f.get(k) for k, _ in r.inputkeys]
         if keys:
             order = np.lexsort(keys[::-1])                             # first key major, stable
@@ -347,6 +378,8 @@ def set_catalog(cat):
 
 def evaluate(data: dict, query) -> list:
     """The query's output columns, in order."""
+    HEAPS.clear()
+    HEAPS.update({k[:-5]: v for k, v in data.items() if k.endswith(".heap")})
     return [a for _, a in rel(data, query).cols]
 
 

@@ -189,3 +189,33 @@ def test_map_binary_semantics_match_per_op_kernels(n):
             np.testing.assert_array_equal(got, want, err_msg=op)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("pat", ["PROMO%", "%BRASS", "%green%", "%Customer%Complaints%", "%", "", "_", "__", "a,b", "%r%r%", "forest gree_", "%N"])
+def test_like_kat_and_pool(pat, catalog):
+    """vdl_op_like against the oracle: the hand-written strings of tests/test_oracle_ops.py, then a million rows drawn from the
+    synthetic p_type / p_name heaps."""
+    from mplan2vdl_b200 import synth
+    offs, heap = K.like_columns(K.STRINGS)
+    both(K.LIKE.format(pat=pat), **{"s": offs, "s.heap": heap})
+    for col in ("part.p_type", "part.p_name"):
+        h, _ = synth.string_heap(catalog, col)
+        o = synth.string_offsets(catalog, col, 1_000_003, 17, 99)
+        both(K.LIKE.format(pat=pat), **{"s": o, "s.heap": h})
+
+
+def test_like_rejects_a_bad_offset_and_a_heap_is_only_a_dictionary():
+    from mplan2vdl_b200.executor import Context
+    from mplan2vdl_b200.lib import VdlError
+    offs, heap = K.like_columns(K.STRINGS)
+    ctx = Context(0)
+    h = ctx.upload_column("t.s.heap", heap)
+    d = ctx.upload_column("t.s", np.array([0, len(heap) + 5], dtype=I64))
+    with pytest.raises(VdlError):
+        ctx.op_binary("Add", h, h)                 # a byte vector is not a numeric operand
+    out = ctx.op_like(d, h, "%")
+    with pytest.raises(VdlError):                  # offset past the heap: range error at the plan's check
+        p = ctx.plan(K.LIKE.format(pat="%"))
+        p.run()
+    ctx.free(out)
+    ctx.close()

@@ -157,3 +157,51 @@ def test_unsupported_ops_are_rejected_loudly():
 def test_metadata_suffix_is_ignored():
     plan = binop_plan("Add").replace("\n", " ;; Metadata {databounds = (0,1)}\n")
     np.testing.assert_array_equal(run(plan, a=A, b=B)["out"], (A + B))
+
+
+LIKE = ("1,Load,t.s\n2,Project,val,Id 1,s\n3,Load,t.s.heap\n4,Project,val,Id 3,s.heap\n"
+        "5,Like,val,Id 2,val,Id 4,val,{pat}\n6,Project,out,Id 5,val\n7,MaterializeCompact,Id 6\n")
+STRINGS = ["PROMO BRUSHED TIN", "ECONOMY ANODIZED BRASS", "", "forest green", "Customer slyly Complaints", "a,b", "%_"]
+
+
+def like_columns(strings):
+    heap, offs = bytearray(8), []
+    for s in strings:
+        offs.append(len(heap))
+        b = s.encode() + b"\0"
+        heap += b + bytes(-len(b) % 8)
+    return np.array(offs, dtype=I64), np.frombuffer(bytes(heap), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("pat,expect", [
+    ("PROMO%", [1, 0, 0, 0, 0, 0, 0]), ("%BRASS", [0, 1, 0, 0, 0, 0, 0]), ("%green%", [0, 0, 0, 1, 0, 0, 0]),
+    ("%Customer%Complaints%", [0, 0, 0, 0, 1, 0, 0]), ("%", [1, 1, 1, 1, 1, 1, 1]), ("", [0, 0, 1, 0, 0, 0, 0]),
+    ("_", [0, 0, 0, 0, 0, 0, 0]), ("__", [0, 0, 0, 0, 0, 0, 1]), ("a,b", [0, 0, 0, 0, 0, 1, 0]), ("%r%r%", [0, 0, 0, 1, 0, 0, 0]), ("%R%S%", [1, 1, 0, 0, 0, 0, 0]),
+    ("forest gree_", [0, 0, 0, 1, 0, 0, 0]), ("%TIN%TIN", [0, 0, 0, 0, 0, 0, 0]), ("%N", [1, 0, 0, 0, 0, 0, 0]),
+])
+def test_like_over_a_string_heap(pat, expect):
+    """Vdl.hs:244-247, 444-447: data = byte offsets into the column's heap; SQL LIKE, no escape, case-sensitive.  (In SQL
+    `%` and `_` in the DATA are ordinary characters: "%_" matches "__" but not "_".)"""
+    offs, heap = like_columns(STRINGS)
+    o = Oracle()
+    o.bind("t.s", offs)
+    o.bind("t.s.heap", heap)
+    np.testing.assert_array_equal(o.run(LIKE.format(pat=pat))["out"], expect)
+
+
+def test_like_offset_outside_the_heap_is_an_error():
+    offs, heap = like_columns(STRINGS)
+    o = Oracle()
+    o.bind("t.s", np.array([0, len(heap)], dtype=I64))
+    o.bind("t.s.heap", heap)
+    with pytest.raises(OracleError, match="outside the heap"):
+        o.run(LIKE.format(pat="%"))
+
+
+def test_a_heap_is_only_a_like_dictionary():
+    offs, heap = like_columns(STRINGS)
+    o = Oracle()
+    o.bind("t.s", offs)
+    o.bind("t.s.heap", heap)
+    with pytest.raises(OracleError, match="string heap"):
+        o.run("1,Load,t.s.heap\n2,Project,val,Id 1,s.heap\n3,MaterializeCompact,Id 2\n")

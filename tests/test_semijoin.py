@@ -1,5 +1,6 @@
-"""Semijoins, the dim-side semijoin's Scatter with size hint, and joins against a single value (SURVEY.md section 8 f3;
-Vlite.hs:691-713, 1212-1222, 1117-1120): the reference's fixtures 04 / 11 / 15.sql.mplan translated by the restated
+"""Semijoins, the dim-side semijoin's Scatter with size hint, antijoins, joins against a single value and Like over string
+heaps (Vlite.hs:691-713, 1010-1014, 1212-1232, 1117-1120): the reference's fixtures 04 / 09 / 11 /
+14 / 15 / 16.sql.mplan translated by the restated
 front end, interpreted by the CPU oracle, against the direct numpy evaluation of the relational IR (tests/ir_eval.py:
 value joins, no Voodoo ops).  The GPU tests run the same programs through libvdl_cuda."""
 import os
@@ -29,7 +30,7 @@ def columns_for(catalog, text, rel, sf=SF, tweak=True):
 
 
 @needs_reference
-@pytest.mark.parametrize("n", ["01", "03", "04", "05", "06", "11", "12", "15"])
+@pytest.mark.parametrize("n", ["01", "03", "04", "05", "06", "09", "11", "12", "14", "15", "16"])
 def test_fixture_program_agrees_with_the_direct_evaluation_of_its_ir(catalog, n):
     ir_eval.set_catalog(catalog)
     rel = mplan.relexpr_from_mplan(catalog, open(os.path.join(FIXTURES, f"{n}.sql.mplan")).read())
@@ -40,7 +41,7 @@ def test_fixture_program_agrees_with_the_direct_evaluation_of_its_ir(catalog, n)
     assert len(got) == len(want)
     for k, (g, w) in enumerate(zip(got, want)):
         np.testing.assert_array_equal(g, w, err_msg=f"output {k}")
-    if n in ("04", "11", "15"):
+    if n in ("04", "09", "11", "14", "15", "16"):
         assert len(got[0]) > 0
 
 
@@ -101,7 +102,7 @@ def test_semijoin_with_no_fact_row_selected(catalog):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("q", ["q04", "q11", "q15"])
+@pytest.mark.parametrize("q", ["q04", "q11", "q15", "q09", "q14", "q16", "q20"])
 @pytest.mark.parametrize("sf", [0.01, 0.1])
 def test_gpu_runs_the_semijoin_programs(catalog, q, sf):
     from util import run_gpu
@@ -111,8 +112,9 @@ def test_gpu_runs_the_semijoin_programs(catalog, q, sf):
     if "nation.n_name" in cols:
         cols["nation.n_name"] = cols["nation.n_name"].copy()
         cols["nation.n_name"][[3, 7, 11]] = catalog.dictionary["nation.n_name"]["GERMANY"]
+        cols["nation.n_name"][[2, 5, 13, 17]] = catalog.dictionary["nation.n_name"]["CANADA"]
     want = run_oracle(text, cols)
-    assert len(next(iter(want.values()))) > 0
+    assert len(next(iter(want.values()))) > 0 or q == "q20"     # (Q20's composite-FK chain is rarely satisfied by the uniform recipe)
     got, stats = run_gpu(text, cols)
     assert_same(got, want)
     got_u, _ = run_gpu(text, cols, fuse=False)

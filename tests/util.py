@@ -24,10 +24,15 @@ def host_columns(cat, qualified_names, rows_by_table, sf=1, seed=None, row_offse
     """{qualified: ndarray} generated on the host; rows_by_table overrides the SF cardinalities."""
     seed = synth.seed_for(sf) if seed is None else seed
     out = {}
+    heaps = {q[:-len(".heap")] for q in qualified_names if synth.is_heap(q)}
     for q in qualified_names:
-        spec = synth.column_spec(cat, q, sf)
         t = q.split(".")[0]
-        out[q] = gen_column(spec, rows_by_table[t], row_offset, seed)
+        if synth.is_heap(q):                     # string heap of a Like (uint8 bytes) ...
+            out[q] = synth.string_heap(cat, q[:-len(".heap")])[0]
+        elif q in heaps:                         # ... and the offsets into it
+            out[q] = synth.string_offsets(cat, q, rows_by_table[t], row_offset, seed)
+        else:
+            out[q] = gen_column(synth.column_spec(cat, q, sf), rows_by_table[t], row_offset, seed)
     return out
 
 
