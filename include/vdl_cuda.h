@@ -26,7 +26,9 @@
 #ifndef VDL_CUDA_H
 #define VDL_CUDA_H
 
+#ifndef __CUDACC_RTC__     /* (the library compiles some kernels at run time with NVRTC, which has no system headers) */
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -242,7 +244,11 @@ int vdl_fused_result(vdl_fused *f, int fold_index, vdl_vec *out);
 int vdl_fused_result_host(vdl_fused *f, int fold_index, const int64_t **data, int64_t *len);
 /* The same for post op `post_index` of the descriptor. */
 int vdl_fused_post_host(vdl_fused *f, int post_index, const int64_t **data, int64_t *len);
-/* Which instantiation of the scan kernel the descriptor was matched to: "generic" or the name of a static shape. */
+/* Host-only check of the run-time specialisation of the fused scan (no GPU needed): prints the shape-traits class of a
+ * grouped descriptor and compiles the scan kernel over it with NVRTC for sm_100a.  Return codes as vdl_jit_selftest. */
+int vdl_scan_jit_selftest(char *log, int log_capacity);
+/* Which instantiation of the scan kernel runs: "jit:<hash>" (the shape of this descriptor, compiled at run time), the name of
+ * a precompiled static shape, or "generic". */
 const char *vdl_fused_shape_name(vdl_fused *f);
 int vdl_fused_destroy(vdl_fused *f);
 /* ---- multi-GPU combine over peer memory (NVLink / NVSwitch), no collective library on the data path -------------

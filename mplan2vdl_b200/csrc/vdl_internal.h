@@ -8,10 +8,7 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/vdl_cuda.h"
-
-typedef int64_t i64;
-typedef uint64_t u64;
+#include "vdl_device.cuh"      // vdl_cuda.h, i64 / u64, XDesc, the device helpers shared with the run-time compiled kernels
 
 // A device vector.  Columns are vectors with a name.  Ranges (RangeV/RangeC) are kept virtual:
 // no HBM traffic until a consumer needs the values.
@@ -98,18 +95,9 @@ struct MapArgs {
 };
 int vdl_jit_map_launch(vdl_ctx *ctx, const MapArgs &m, i64 *out, i64 n, int blocks);   // 1 launched, 0 use the interpreter, <0 error
 void vdl_jit_destroy(vdl_ctx *ctx);
-
-// Peer-memory exchange of the partial tables (one buffer per rank, addressable by all ranks):
-//   data  [2 (epoch parity)][world][stride] int64   rank r's table of the step lands in slot [parity][r] of EVERY buffer
-//   flags [2][world] uint64                         epoch of the last step whose table rank r has fully stored
-struct XDesc {
-  int32_t rank, world;
-  u64 epoch;                      // this step's number (1, 2, ...); parity double-buffers against a rank running ahead
-  u64 timeout_ns;                 // give up waiting for a peer after this long: error flag, never a hang
-  i64 stride;                     // int64 per table
-  i64 *peer[VDL_MAX_RANKS];       // base of every rank's buffer as seen from this GPU
-};
-
+// NVRTC compile + load of one kernel, cached per context under `key` (vdl_jit.cu); ctx == nullptr: compile only
+cudaKernel_t vdl_jit_kernel(vdl_ctx *ctx, const std::string &key, const std::string &src, const char *kernel_name, int nheaders,
+                            const char *const *headers, const char *const *header_names, bool *ok, std::string *log);
 
 // Do the columns a prepared scan / probe was built from still hold what they held at prepare time?  (The statistics
 // proofs -- int32 narrowing, 32-bit accumulators, the static shape -- and the device pointers are baked in.)
@@ -120,43 +108,3 @@ void vdl_probe_set_epoch(vdl_probe *p, u64 e);
 u64 vdl_fused_epoch(vdl_fused *f);
 void vdl_fused_set_epoch(vdl_fused *f, u64 e);
 
-#ifdef __CUDACC__
-// system-scope release / acquire and a wall clock for the peer-memory exchange (vdl_fused.cu, vdl_probe.cu)
-__device__ __forceinline__ void st_release_sys(u64 *p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) {
-  u64 v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ u64 global_timer_ns() {
-  u64 t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Elementwise op semantics (Vdl.hs:136-157, 209-231).  Comparisons / logicals give 0/1; BitShift: +k arithmetic right,
-// -k left (Vlite.hs:205-208); Divide truncates, x/0 := 0, INT64_MIN/-1 wraps; Modulo is the C remainder, x%0 := 0.
-__device__ __forceinline__ i64 binop_apply(int op, i64 a, i64 b) {
-  switch (op) {
-    case VDL_LOGICAL_AND: return (a != 0) && (b != 0);
-    case VDL_LOGICAL_OR: return (a != 0) || (b != 0);
-    case VDL_BITWISE_AND: return a & b;
-    case VDL_BITWISE_OR: return a | b;
-    case VDL_BITSHIFT:
-      if (b >= 0) return b >= 64 ? (a < 0 ? -1 : 0) : (a >> b);
-      return b <= -64 ? 0 : (i64)((u64)a << (-b));
-    case VDL_EQUALS: return a == b;
-    case VDL_ADD: return (i64)((u64)a + (u64)b);
-    case VDL_SUBTRACT: return (i64)((u64)a - (u64)b);
-    case VDL_GREATER: return a > b;
-    case VDL_MULTIPLY: return (i64)((u64)a * (u64)b);
-    case VDL_DIVIDE:
-      if (b == 0) return 0;
-      if (b == -1) return (i64)(0 - (u64)a);
-      return a / b;
-    case VDL_MODULO:
-      if (b == 0 || b == -1) return 0;
-      return a % b;
-  }
-  return 0;
-}
-#endif

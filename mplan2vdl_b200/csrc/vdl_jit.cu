@@ -139,18 +139,21 @@ std::string generate(const MapArgs &m) {
   return s;
 }
 
-cudaKernel_t compile(vdl_ctx *ctx, JitCache *jc, const std::string &src) {
+cudaKernel_t compile(vdl_ctx *ctx, JitCache *jc, const std::string &src, const char *kernel_name = "vdl_map_jit", int nheaders = 0,
+                     const char *const *headers = nullptr, const char *const *header_names = nullptr, std::string *log_out = nullptr) {
   Nvrtc &N = g_nvrtc;
   void *prog = nullptr;
-  if (N.create(&prog, src.c_str(), "vdl_map_jit.cu", 0, nullptr, nullptr) != 0) return nullptr;
-  const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
-  int rc = N.compile(prog, 3, opts);
+  if (N.create(&prog, src.c_str(), "vdl_jit.cu", nheaders, headers, header_names) != 0) return nullptr;
+  // -default-device: the public header's (unannotated) function declarations are only declarations here
+  const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
+  int rc = N.compile(prog, 4, opts);
   if (rc != 0) {
     size_t ls = 0;
     N.log_size(prog, &ls);
     std::string log(ls + 1, '\0');
     if (ls) N.log(prog, &log[0]);
-    fprintf(stderr, "[vdl jit] NVRTC failed (%d); the interpreter runs instead.\n%s\n", rc, log.c_str());
+    if (log_out) *log_out = log;
+    fprintf(stderr, "[vdl jit] NVRTC failed (%d) for %s; the precompiled kernel runs instead.\n%s\n", rc, kernel_name, log.c_str());
     if (getenv("VDL_DEBUG_JIT")) fprintf(stderr, "%s\n", src.c_str());
     N.destroy(&prog);
     return nullptr;
@@ -163,7 +166,7 @@ cudaKernel_t compile(vdl_ctx *ctx, JitCache *jc, const std::string &src) {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t k = nullptr;
   if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
-      cudaLibraryGetKernel(&k, lib, "vdl_map_jit") != cudaSuccess) {
+      cudaLibraryGetKernel(&k, lib, kernel_name) != cudaSuccess) {
     fprintf(stderr, "[vdl jit] loading the compiled kernel failed (%s); the interpreter runs instead.\n", cudaGetErrorString(cudaGetLastError()));
     if (lib) cudaLibraryUnload(lib);
     return nullptr;
@@ -200,6 +203,35 @@ int vdl_jit_map_launch(vdl_ctx *ctx, const MapArgs &m, i64 *out, i64 n, int bloc
   cudaError_t e = cudaLaunchKernel((const void *)it->second, dim3(blocks), dim3(256), args, 0, ctx->stream);
   if (e != cudaSuccess) { vdl_cuda_fail(ctx, e, "launch of a specialised map kernel"); return -1; }
   return 1;
+}
+
+// Compile `src` (which may #include the in-memory `headers`) for sm_100a and return the kernel `kernel_name`, cached per
+// context under `key`.  nullptr: NVRTC is missing or rejected the source (also cached: no retry).  With `ctx == nullptr`
+// only the compilation is attempted (host-only check: the cubin is not loaded); *ok tells whether it succeeded.
+cudaKernel_t vdl_jit_kernel(vdl_ctx *ctx, const std::string &key, const std::string &src, const char *kernel_name, int nheaders,
+                            const char *const *headers, const char *const *header_names, bool *ok, std::string *log) {
+  if (ok) *ok = false;
+  if (!nvrtc_load()) { if (log) *log = "NVRTC is not installed"; return nullptr; }
+  if (!ctx) {
+    Nvrtc &N = g_nvrtc;
+    void *prog = nullptr;
+    if (N.create(&prog, src.c_str(), "vdl_jit.cu", nheaders, headers, header_names) != 0) return nullptr;
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
+    const int rc = N.compile(prog, 4, opts);
+    size_t ls = 0, cs = 0;
+    N.log_size(prog, &ls);
+    if (log && ls > 1) { log->assign(ls + 1, '\0'); N.log(prog, &(*log)[0]); }
+    if (rc == 0) N.cubin_size(prog, &cs);
+    N.destroy(&prog);
+    if (ok) *ok = rc == 0 && cs > 0;
+    return nullptr;
+  }
+  if (!ctx->jit) ctx->jit = new JitCache();
+  JitCache *jc = (JitCache *)ctx->jit;
+  auto it = jc->kernels.find(key);
+  if (it == jc->kernels.end()) it = jc->kernels.emplace(key, compile(ctx, jc, src, kernel_name, nheaders, headers, header_names, log)).first;
+  if (ok) *ok = it->second != nullptr;
+  return it->second;
 }
 
 // Host-only self-test (no GPU needed): print a program that uses every instruction kind and storage kind as CUDA C and

@@ -75,3 +75,16 @@ def test_haskell_binding_imports_every_entry_point():
     imported = set(re.findall(r'foreign import ccall \w+ "(vdl_[a-z0-9_]+)"', open(os.path.join(root, "hs", "VdlCuda.hs")).read()))
     assert declared - imported == set(), sorted(declared - imported)
     assert imported - declared == set(), sorted(imported - declared)
+
+
+def test_scan_specialisation_compiles_without_a_gpu():
+    """The fused scan's run-time shape: the traits class printed from a descriptor + fused_scan_fold_body, compiled by
+    NVRTC for sm_100a from the embedded headers (register-slot and shared-memory-table instantiations)."""
+    import ctypes
+    from mplan2vdl_b200 import lib
+    L = lib.load()
+    log = ctypes.create_string_buffer(1 << 16)
+    rc = L.vdl_scan_jit_selftest(log, len(log))
+    if rc == 3:
+        pytest.skip("NVRTC not installed")
+    assert rc == 0, log.value.decode(errors="replace")

@@ -35,7 +35,7 @@ def test_sf10_against_the_oracle(catalog, q):
     assert_same(got, want)
     assert stats["fused_scans"] + stats["probe_folds"] + stats["probe_emits"] >= 1
     if q == "q01":
-        assert stats["shape"] == "sel1_key2_sum5" and len(want["count_order"]) == 6
+        assert stats["shape"].startswith("jit:") and len(want["count_order"]) == 6     # the run-time compiled shape of this descriptor
 
 
 def test_q6_sf100_against_the_oracle(catalog):
@@ -63,7 +63,7 @@ def test_q1_sf100_two_shards_against_the_oracle(catalog):
         plan = ctx.plan(text)
         plan.set_row_base(info["row_base"])
         plan.run_local()
-        assert plan.shape(0) == "sel1_key2_sum5"
+        assert plan.shape(0).startswith("jit:")
         ptr, cnt = plan.partials(0)
         ctx.synchronize()
         tables.append(torch.as_tensor(DeviceView(ptr, cnt), device="cuda:0").clone())

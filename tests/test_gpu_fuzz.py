@@ -78,3 +78,44 @@ def test_random_plans_through_map_clusters(catalog, seed, jit, monkeypatch):
         assert_same(got, run_oracle(text, cols))
         nodes += stats["map_nodes"]
     assert nodes >= 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(0, 40, 3))
+def test_random_single_table_plans_through_the_runtime_compiled_scan(catalog, seed, monkeypatch):
+    """The fused scan specialised at run time (NVRTC) to the shape of each random descriptor -- forced for these small
+    tables with VDL_SCAN_JIT_MIN_ROWS=0 -- against the oracle, and against the generic kernel on the same data."""
+    monkeypatch.setenv("VDL_SCAN_JIT_MIN_ROWS", "0")
+    rel = fuzz_plans.single_table(seed)
+    text = vlite.translate(catalog, rel)
+    sf = 0.05
+    rows = {t: synth.table_rows(catalog, t, sf) for t in catalog.tables}
+    cols = host_columns(catalog, tpch.plan_columns(text), rows, sf=sf)
+    want = run_oracle(text, cols)
+    got, stats = run_gpu(text, cols)
+    assert_same(got, want)
+    if stats["fused_scans"]:
+        assert stats["shape"].startswith("jit:"), stats["shape"]
+        monkeypatch.setenv("VDL_GENERIC_ONLY", "1")
+        got_g, stats_g = run_gpu(text, cols)
+        assert stats_g["shape"] == "generic"
+        assert_same(got_g, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("query,colnames", [("q06.vdl", ["l_quantity", "l_extendedprice", "l_discount", "l_shipdate"]),
+                                            ("q01.vdl", ["l_quantity", "l_extendedprice", "l_discount", "l_shipdate", "l_tax", "l_returnflag", "l_linestatus"])])
+@pytest.mark.parametrize("narrow", [False, True])
+def test_runtime_compiled_scan_on_tpch_shapes(catalog, query, colnames, narrow, monkeypatch):
+    """Q6 / Q1 through the run-time compiled shape, with the reference's column widths and with the narrow storage format
+    (every column that fits as int32): the same bits as the oracle either way."""
+    import numpy as np
+    from util import plan_text
+    monkeypatch.setenv("VDL_SCAN_JIT_MIN_ROWS", "0")
+    cols = host_columns(catalog, ["lineitem." + c for c in colnames], {"lineitem": 700_001})
+    if narrow:
+        cols = {k: (v.astype(np.int32) if v.min() >= -2**31 and v.max() < 2**31 else v) for k, v in cols.items()}
+    want = run_oracle(plan_text(query), cols)
+    got, stats = run_gpu(plan_text(query), cols)
+    assert stats["shape"].startswith("jit:")
+    assert_same(got, want)
