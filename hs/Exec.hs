@@ -15,6 +15,7 @@
 --     (Scatter: App. G2).
 module Exec (runProgramText, evalVexp) where
 
+import qualified Data.ByteString.Char8 as C
 import qualified Data.HashMap.Strict as Map
 import Control.Monad.State
 import Foreign
@@ -81,8 +82,12 @@ evalVexp ctx vexp@V.Vexp { V.vx, V.info = ColInfo { count } } = do
       s <- evalVexp ctx shsource; p <- evalVexp ctx shpos; out (c_vdl_op_gather ctx s p)
     go V.Shuffle { V.shop = V.Scatter, V.shsource, V.shpos } = do
       s <- evalVexp ctx shsource; p <- evalVexp ctx shpos
-      -- explicit output length (App. G2): the metadata count of the scatter node (Vlite.hs:316-320) + 1
-      out (c_vdl_op_scatter ctx s p (fromInteger count + 1))
+      -- explicit output length (App. G2): the index space of the positions, which the library tracks (FoldSelect / pos_ /
+      -- Partition positions index their input's rows -- for a join scatter that is the dimension's row count, the
+      -- reference's `dimref`, Vlite.hs:782 --, `p % k` indexes k slots).  The node's metadata count (Vlite.hs:316-320) is
+      -- off by one and data-independent, so it is not used.
+      n <- liftIO $ alloca $ \q -> c_vdl_vec_index_space ctx p q >>= check ctx >> peek q
+      if n < 0 then error "Exec: Scatter positions without a known index space" else out (c_vdl_op_scatter ctx s p n)
     go V.Fold { V.foldop = V.FSel, V.fdata } = do { d <- evalVexp ctx fdata; out (c_vdl_op_fold_select ctx d) }
     go V.Fold { V.foldop, V.fgroups, V.fdata } = do
       g <- evalVexp ctx fgroups; d <- evalVexp ctx fdata
@@ -91,5 +96,9 @@ evalVexp ctx vexp@V.Vexp { V.vx, V.info = ColInfo { count } } = do
     go V.Partition { V.pdata, V.pivots = V.Vexp { V.vx = V.RangeC { V.rmin, V.rstep, V.rcount } } } = do
       d <- evalVexp ctx pdata
       out (c_vdl_op_partition ctx d (fromInteger rmin) (fromInteger rstep) (fromInteger rcount))
+    go V.Like { V.ldata, V.lpattern, V.lcol } = do           -- the dictionary is the column's string heap (Vdl.hs:244-247)
+      d <- evalVexp ctx ldata
+      h <- out $ \p -> withCString (show lcol ++ ".heap") $ \s -> c_vdl_column_lookup ctx s p
+      out (\p -> C.useAsCString lpattern $ \pat -> c_vdl_op_like ctx d h pat p)
     go V.VShuffle { V.varg } = evalVexp ctx varg
     go other = error ("Exec: op outside the supported vocabulary: " ++ show other)

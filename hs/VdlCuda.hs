@@ -18,6 +18,8 @@ data VdlCtx
 data VdlPlan
 data VdlFused
 data VdlProbe
+data VdlComm      -- vdl_comm: one context per GPU of the box, peer access enabled (single-process multi-GPU)
+data VdlCommPlan  -- vdl_comm_plan: one loaded program per rank, exchange buffers wired
 data VdlFusedDesc  -- vdl_fused_desc / vdl_probe_desc: marshalled with Foreign.Storable by the caller (layouts in vdl_cuda.h)
 data VdlProbeDesc
 data VdlMapDesc   -- vdl_map_desc: marshalled with Foreign.Storable by the caller (layout in vdl_cuda.h)
@@ -44,6 +46,7 @@ foreign import ccall safe "vdl_column_upload" c_vdl_column_upload :: Ptr VdlCtx 
 foreign import ccall safe "vdl_column_fill_synthetic" c_vdl_column_fill_synthetic
   :: Ptr VdlCtx -> VdlVec -> Word64 -> Word64 -> CInt -> Int64 -> Int64 -> Int64 -> Int64 -> Int64 -> IO CInt
 foreign import ccall safe "vdl_column_lookup" c_vdl_column_lookup :: Ptr VdlCtx -> CString -> Ptr VdlVec -> IO CInt
+foreign import ccall safe "vdl_vec_index_space" c_vdl_vec_index_space :: Ptr VdlCtx -> VdlVec -> Ptr Int64 -> IO CInt
 foreign import ccall safe "vdl_vec_len" c_vdl_vec_len :: Ptr VdlCtx -> VdlVec -> Ptr Int64 -> IO CInt
 foreign import ccall safe "vdl_vec_download" c_vdl_vec_download :: Ptr VdlCtx -> VdlVec -> Ptr Int64 -> Int64 -> IO CInt
 foreign import ccall safe "vdl_vec_free" c_vdl_vec_free :: Ptr VdlCtx -> VdlVec -> IO CInt
@@ -135,3 +138,15 @@ foreign import ccall safe "vdl_probe_destroy" c_vdl_probe_destroy :: Ptr VdlProb
 foreign import ccall safe "vdl_plan_probe_kernel_ms" c_vdl_plan_probe_kernel_ms :: Ptr VdlPlan -> Ptr CFloat -> IO CInt
 foreign import ccall safe "vdl_plan_num_fused" c_vdl_plan_num_fused :: Ptr VdlPlan -> IO CInt
 foreign import ccall safe "vdl_plan_fused" c_vdl_plan_fused :: Ptr VdlPlan -> CInt -> Ptr (Ptr VdlFused) -> IO CInt
+
+-- several GPUs driven from this one process (SURVEY.md section 8 b/e): the partial tables are exchanged inside the scan kernels
+foreign import ccall safe "vdl_plan_launch" c_vdl_plan_launch :: Ptr VdlPlan -> IO CInt
+foreign import ccall safe "vdl_comm_init_all" c_vdl_comm_init_all :: CInt -> Ptr CInt -> Ptr (Ptr VdlComm) -> IO CInt
+foreign import ccall safe "vdl_comm_size" c_vdl_comm_size :: Ptr VdlComm -> IO CInt
+foreign import ccall safe "vdl_comm_ctx" c_vdl_comm_ctx :: Ptr VdlComm -> CInt -> IO (Ptr VdlCtx)
+foreign import ccall safe "vdl_comm_last_error" c_vdl_comm_last_error :: Ptr VdlComm -> IO CString
+foreign import ccall safe "vdl_comm_destroy" c_vdl_comm_destroy :: Ptr VdlComm -> IO CInt
+foreign import ccall safe "vdl_comm_plan_load" c_vdl_comm_plan_load :: Ptr VdlComm -> CString -> CInt -> Ptr Int64 -> Ptr (Ptr VdlCommPlan) -> IO CInt
+foreign import ccall safe "vdl_comm_plan_rank" c_vdl_comm_plan_rank :: Ptr VdlCommPlan -> CInt -> IO (Ptr VdlPlan)
+foreign import ccall safe "vdl_comm_plan_run" c_vdl_comm_plan_run :: Ptr VdlCommPlan -> IO CInt
+foreign import ccall safe "vdl_comm_plan_destroy" c_vdl_comm_plan_destroy :: Ptr VdlCommPlan -> IO CInt

@@ -116,6 +116,11 @@ int vdl_column_drop(vdl_ctx *ctx, const char *name);
 /* ---- vectors ----------------------------------------------------------------------- */
 int vdl_vec_len(vdl_ctx *ctx, vdl_vec v, int64_t *len);
 int vdl_vec_dtype(vdl_ctx *ctx, vdl_vec v, int *dtype);
+/* The length of the vector the values of `v` index into, when the library knows it (App. G2): positions from FoldSelect /
+ * pos_ / Partition index their input's row space, a Gather or a Scatter keeps the space of its source's values, `p % k`
+ * (the scatter size hint, Vlite.hs:1117-1120) indexes k slots; -1 when unknown.  This is the explicit output length a
+ * caller passes to vdl_op_scatter (the reference's metadata `count = posmax`, Vlite.hs:316-320, is not usable for that). */
+int vdl_vec_index_space(vdl_ctx *ctx, vdl_vec v, int64_t *len);
 void *vdl_vec_device_ptr(vdl_ctx *ctx, vdl_vec v);
 /* Device -> host copy of v as int64 (int32 columns are sign-extended); `capacity` in elements. */
 int vdl_vec_download(vdl_ctx *ctx, vdl_vec v, int64_t *host, int64_t capacity);
@@ -373,10 +378,34 @@ int vdl_plan_fused(vdl_plan *p, int i, vdl_fused **out);
 int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int nranks);
 /* vdl_plan_run_local + vdl_plan_finish for one GPU. */
 int vdl_plan_run(vdl_plan *p);
+/* The launches of vdl_plan_run without the wait (asynchronous on the context's stream); vdl_plan_finish(p, NULL, 1) then
+ * awaits the results.  With peers set, issue every rank's vdl_plan_launch before awaiting any rank. */
+int vdl_plan_launch(vdl_plan *p);
 int vdl_plan_num_outputs(vdl_plan *p);
 /* Output i in MaterializeCompact order: name (the Project's <out>, Vdl.hs:278-292), host int64 data. */
 int vdl_plan_output(vdl_plan *p, int i, const char **name, const int64_t **data, int64_t *len);
 int vdl_plan_destroy(vdl_plan *p);
+
+/* ---- several GPUs of one box driven from ONE process (SURVEY.md section 8 b, e) ----------------------------------------
+ * A communicator owns one context per rank (devices[r], or device r when NULL; the same device may appear twice: ranks
+ * emulated on one GPU), with peer access enabled between the devices.  The caller registers rank r's row-range shard of the
+ * fact table -- and the replicated dimension tables -- with vdl_comm_ctx(c, r) under the usual column names, loads the
+ * program once for all ranks and runs it: one scan-kernel launch per GPU, whose last thread block exchanges the partial
+ * aggregate tables with the peers over NVLink and finalizes (no collective library on the data path); every rank's plan
+ * then holds the GLOBAL result (vdl_comm_plan_rank + vdl_plan_output).  What mplan2vdl_b200/dist.py does for
+ * one-process-per-GPU launches (torchrun, CUDA IPC handles); this is the form a single Haskell host binds. */
+typedef struct vdl_comm vdl_comm;
+typedef struct vdl_comm_plan vdl_comm_plan;
+int vdl_comm_init_all(int nranks, const int *devices, vdl_comm **out);
+int vdl_comm_size(vdl_comm *c);
+vdl_ctx *vdl_comm_ctx(vdl_comm *c, int rank);
+const char *vdl_comm_last_error(vdl_comm *c);
+int vdl_comm_destroy(vdl_comm *c);
+/* row_base[r]: global row id of rank r's first fact row (NULL: 0 everywhere). */
+int vdl_comm_plan_load(vdl_comm *c, const char *vdl_text, int flags, const int64_t *row_base, vdl_comm_plan **out);
+vdl_plan *vdl_comm_plan_rank(vdl_comm_plan *p, int rank);
+int vdl_comm_plan_run(vdl_comm_plan *p);
+int vdl_comm_plan_destroy(vdl_comm_plan *p);
 
 #ifdef __cplusplus
 }

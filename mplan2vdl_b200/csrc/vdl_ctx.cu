@@ -226,6 +226,12 @@ extern "C" int vdl_vec_dtype(vdl_ctx *ctx, vdl_vec h, int *dtype) {
   *dtype = v->dtype;
   return VDL_OK;
 }
+extern "C" int vdl_vec_index_space(vdl_ctx *ctx, vdl_vec h, int64_t *len) {
+  Vec *v = vec_get_any(ctx, h);
+  if (!v || !len) return VDL_EINVAL;
+  *len = v->domain;
+  return VDL_OK;
+}
 extern "C" void *vdl_vec_device_ptr(vdl_ctx *ctx, vdl_vec h) {
   Vec *v = vec_get_any(ctx, h);
   return v ? v->ptr : nullptr;

@@ -1365,6 +1365,9 @@ static int plan_run_local(vdl_plan *p, int self_finalize) {
 }
 
 extern "C" int vdl_plan_run_local(vdl_plan *p) { return plan_run_local(p, 0); }
+// The launches of vdl_plan_run without the wait: asynchronous on the context's stream; vdl_plan_finish(p, NULL, 1) awaits
+// the results.  With peers set (vdl_plan_set_peers) every rank's launches must be issued before any rank is awaited.
+extern "C" int vdl_plan_launch(vdl_plan *p) { return plan_run_local(p, 1); }
 
 extern "C" int vdl_plan_num_fused(vdl_plan *p) { return p ? (int)p->groups.size() : 0; }
 extern "C" int vdl_plan_fused(vdl_plan *p, int i, vdl_fused **out) {

@@ -123,6 +123,7 @@ SYMBOLS = [
     ("vdl_column_drop", _I, [_P, C.c_char_p]),
     ("vdl_vec_len", _I, [_P, C.c_int32, C.POINTER(_L)]),
     ("vdl_vec_dtype", _I, [_P, C.c_int32, C.POINTER(_I)]),
+    ("vdl_vec_index_space", _I, [_P, C.c_int32, C.POINTER(_L)]),
     ("vdl_vec_device_ptr", _P, [_P, C.c_int32]),
     ("vdl_vec_download", _I, [_P, C.c_int32, _P, _L]),
     ("vdl_vec_free", _I, [_P, C.c_int32]),
@@ -187,6 +188,16 @@ SYMBOLS = [
     ("vdl_plan_fused", _I, [_P, _I, C.POINTER(_P)]),
     ("vdl_plan_finish", _I, [_P, C.POINTER(_P), _I]),
     ("vdl_plan_run", _I, [_P]),
+    ("vdl_plan_launch", _I, [_P]),
+    ("vdl_comm_init_all", _I, [_I, C.POINTER(_I), C.POINTER(_P)]),
+    ("vdl_comm_size", _I, [_P]),
+    ("vdl_comm_ctx", _P, [_P, _I]),
+    ("vdl_comm_last_error", C.c_char_p, [_P]),
+    ("vdl_comm_destroy", _I, [_P]),
+    ("vdl_comm_plan_load", _I, [_P, C.c_char_p, _I, C.POINTER(_L), C.POINTER(_P)]),
+    ("vdl_comm_plan_rank", _P, [_P, _I]),
+    ("vdl_comm_plan_run", _I, [_P]),
+    ("vdl_comm_plan_destroy", _I, [_P]),
     ("vdl_plan_num_outputs", _I, [_P]),
     ("vdl_plan_output", _I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(_L)), C.POINTER(_L)]),
     ("vdl_plan_destroy", _I, [_P]),

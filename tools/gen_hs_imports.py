@@ -11,7 +11,7 @@ hs = open(os.path.join(ROOT, "hs", "VdlCuda.hs")).read()
 have = set(re.findall(r'foreign import ccall \w+ "(vdl_[a-z0-9_]+)"', hs))
 
 OPAQUE = {"vdl_ctx": "VdlCtx", "vdl_plan": "VdlPlan", "vdl_fused": "VdlFused", "vdl_probe": "VdlProbe", "vdl_fused_desc": "VdlFusedDesc",
-          "vdl_probe_desc": "VdlProbeDesc", "vdl_map_desc": "VdlMapDesc", "vdl_fold_spec": "VdlFoldSpec"}
+          "vdl_probe_desc": "VdlProbeDesc", "vdl_map_desc": "VdlMapDesc", "vdl_fold_spec": "VdlFoldSpec", "vdl_comm_plan": "VdlCommPlan", "vdl_comm": "VdlComm"}
 BASE = {"int": "CInt", "int32_t": "Int32", "int64_t": "Int64", "uint64_t": "Word64", "float": "CFloat", "vdl_vec": "VdlVec", "void": "()", "char": "CChar"}
 
 
