@@ -58,6 +58,7 @@ foreign import ccall safe "vdl_op_like" c_vdl_op_like :: Ptr VdlCtx -> VdlVec ->
 foreign import ccall safe "vdl_op_fold_select" c_vdl_op_fold_select :: Ptr VdlCtx -> VdlVec -> Ptr VdlVec -> IO CInt
 foreign import ccall safe "vdl_op_map" c_vdl_op_map :: Ptr VdlCtx -> Ptr VdlMapDesc -> Ptr VdlVec -> Ptr VdlVec -> Ptr VdlVec -> IO CInt
 foreign import ccall safe "vdl_jit_selftest" c_vdl_jit_selftest :: CString -> CInt -> IO CInt
+foreign import ccall safe "vdl_probe_jit_selftest" c_vdl_probe_jit_selftest :: CString -> CInt -> IO CInt
 foreign import ccall safe "vdl_scan_jit_selftest" c_vdl_scan_jit_selftest :: CString -> CInt -> IO CInt
 foreign import ccall unsafe "vdl_abi_sizeof_map_desc" c_vdl_abi_sizeof_map_desc :: IO CInt
 foreign import ccall safe "vdl_op_gather" c_vdl_op_gather :: Ptr VdlCtx -> VdlVec -> VdlVec -> Ptr VdlVec -> IO CInt

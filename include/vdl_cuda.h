@@ -252,6 +252,8 @@ int vdl_fused_post_host(vdl_fused *f, int post_index, const int64_t **data, int6
 /* Host-only check of the run-time specialisation of the fused scan (no GPU needed): prints the shape-traits class of a
  * grouped descriptor and compiles the scan kernel over it with NVRTC for sm_100a.  Return codes as vdl_jit_selftest. */
 int vdl_scan_jit_selftest(char *log, int log_capacity);
+/* The same for the FK-join probe: a descriptor printed as CUDA C (one straight-line function per predicate stage). */
+int vdl_probe_jit_selftest(char *log, int log_capacity);
 /* Which instantiation of the scan kernel runs: "jit:<hash>" (the shape of this descriptor, compiled at run time), the name of
  * a precompiled static shape, or "generic". */
 const char *vdl_fused_shape_name(vdl_fused *f);

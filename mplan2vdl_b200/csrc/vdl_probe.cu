@@ -33,60 +33,7 @@
 
 #include "vdl_internal.h"
 
-#ifndef P_THREADS
-#define P_THREADS 128
-#endif
-#define P_TILE (P_THREADS * 32)   // one bitmap word per thread (emit mode)
-#ifndef P_BLOCKS
-#define P_BLOCKS 12   // resident blocks per SM: 40 registers per thread, 12 x 17.9 KB of shared memory (measured: 8 blocks x 64 regs +15 %, 10 x 48 +3 %, 16 = 12 by shared memory)
-#endif
-#define P_MAX_DEPTH 6
-#define P_SMEM_TABLE_BYTES (40 * 1024)
-
-struct PLeaf { const void *ptr; i64 len; int32_t w4, parent; };
-struct PTerm { int32_t leaf, shr; i64 a, b; };             // leaf -1: constant a; -2: global row id
-struct PPred { int32_t kind, cmp; PTerm t, u; i64 lo; u64 span; int32_t nmore, pad; i64 lo_more[VDL_MAX_MORE_RANGES]; u64 span_more[VDL_MAX_MORE_RANGES]; };
-struct PProd { int32_t nfac, pad; PTerm f[VDL_MAX_FACTORS]; };
-
-struct PDesc {
-  i64 rows, row_base, key_mask, domain, ntiles;
-  int32_t nleaves, npreds, nkeys, nfolds, nemits, smem_table, pad0, pad1;
-  PLeaf leaf[VDL_MAX_LEAVES];
-  PPred pred[VDL_MAX_PROBE_PREDS];
-  PTerm key[VDL_MAX_KEYS];
-  int32_t key_shl[VDL_MAX_KEYS];
-  int32_t fold_op[VDL_MAX_AGGS];
-  PProd fold[VDL_MAX_AGGS];
-  PProd emit[VDL_MAX_EMITS];
-  int32_t nind, pad2;
-  PPred ind[VDL_MAX_INDICATORS];
-  // fact-table columns the predicate stages read for (nearly) every row: the tile's share of them (or that of the tile
-  // `pf_dist` tickets ahead) is pulled into L2 at the start, so the later stages' dependent loads pay L2, not DRAM, latency
-  int32_t npf, pf_dist;
-  const unsigned char *pf_ptr[VDL_MAX_LEAVES];
-  int32_t pf_shift[VDL_MAX_LEAVES];  // log2 bytes per value
-  i64 *table;                       // fold mode: [nfolds + 2][domain]: fold accumulators, row count, first row
-  i64 *emit_out[VDL_MAX_EMITS];     // emit mode: dense output vectors (capacity rows)
-  unsigned long long *tile_state;   // emit mode look-back: (status << 62) | count; status 1 = tile aggregate, 2 = inclusive prefix
-  unsigned int *ticket;
-  i64 *total;                       // emit mode: number of surviving rows
-  int *errflag;
-};
-
-struct PFin {
-  i64 domain;
-  int32_t nfolds, npost;
-  int32_t fold_op[VDL_MAX_AGGS];
-  vdl_post_op post[VDL_MAX_POSTS];
-  const i64 *table;                 // nranks tables back to back (stride int64 each); one = this rank's own
-  i64 stride;
-  int32_t nranks, precomputed_choose;   // precomputed_choose: FoldChoose values already sit in the tables (multi-rank)
-  i64 *out;                         // [(nfolds + npost)][domain] then [ngroups, errors]
-  i64 *hmirror;
-  const int *errflag;
-};
-
-__device__ __forceinline__ i64 p_identity(int op) { return op == VDL_FOLD_MIN ? INT64_MAX : (op == VDL_FOLD_MAX ? INT64_MIN : 0); }
+#include "vdl_probe_kernel.cuh"
 
 // value of leaf l at fact row `row` (local to the shard): walk the parent chain, then load top-down
 __device__ __forceinline__ i64 leaf_value(const PDesc &d, int l, i64 row, bool &ok) {
@@ -148,11 +95,6 @@ __device__ __forceinline__ bool row_passes(const PDesc &d, i64 row, bool &ok) {
     if (!pred_holds(d, d.pred[q], row, ok) || !ok) return false;
   }
   return true;
-}
-__device__ __forceinline__ void table_update(int op, i64 *p, i64 v) {
-  if (op == VDL_FOLD_MIN) atomicMin((long long *)p, (long long)v);
-  else if (op == VDL_FOLD_MAX) atomicMax((long long *)p, (long long)v);
-  else atomicAdd((unsigned long long *)p, (unsigned long long)v);
 }
 
 // ---- staged evaluation ---------------------------------------------------------------------------------------------
@@ -482,6 +424,309 @@ __global__ void __launch_bounds__(256, 1) probe_exchange_kernel(const __grid_con
   }
 }
 
+#include <string>
+#include "vdl_embedded.inc"
+
+// ---- run-time specialisation of the probe (NVRTC) ---------------------------------------------------------------------
+// probe_kernel above INTERPRETS the descriptor: per row and stage it walks parent chains through the leaf table, dispatches
+// on predicate kinds and reads bounds from the constant bank -- 160 thread-instructions per lineitem row on Q5, a handful of
+// them loads (profiles/r01e_q05_sf10_dominant_kernel.txt).  For tables of a few hundred thousand rows and up the descriptor
+// is instead PRINTED as CUDA C: one straight-line function per predicate stage (typed loads along the lookup chain, bounds
+// and constants as literals, out-of-range lookups turned into a flag and a clamped index so that no branch separates the
+// loads), one for the fold / emit of a surviving row, and the same tile loop around them.  The P_SUB rows a thread handles
+// per round are independent straight-line chains, so their loads overlap (memory-level parallelism instead of one
+// dependent chain per warp).  Same results as the interpreter (tests/test_gpu_probe.py and the fuzz plans run both).
+struct ProbeGen {
+  const PDesc &d;
+  std::string body;                 // statements of the function being generated
+  bool have[VDL_MAX_LEAVES];
+  int tmp = 0;
+  explicit ProbeGen(const PDesc &desc) : d(desc) { reset(); }
+  void reset() { body.clear(); memset(have, 0, sizeof have); tmp = 0; }
+  static std::string lit(i64 v) { char b[48]; snprintf(b, sizeof b, "((i64)0x%llxull)", (unsigned long long)v); return b; }
+  static std::string ulit(u64 v) { char b[48]; snprintf(b, sizeof b, "0x%llxull", (unsigned long long)v); return b; }
+  std::string leaf(int l) {
+    char nm[16], b[320];
+    snprintf(nm, sizeof nm, "L%d", l);
+    if (have[l]) return nm;
+    have[l] = true;
+    const PLeaf &L = d.leaf[l];
+    const char *ld = L.w4 ? "(i64)__ldg((const int *)d.leaf[%d].ptr + %s)" : "__ldg((const i64 *)d.leaf[%d].ptr + %s)";
+    char load[200];
+    if (L.parent < 0) {
+      snprintf(load, sizeof load, ld, l, "row");
+      snprintf(b, sizeof b, "  const i64 %s = %s;\n", nm, load);
+    } else {
+      const std::string p = leaf(L.parent);
+      char idx[64];
+      snprintf(idx, sizeof idx, "(in%d ? %s : 0)", l, p.c_str());
+      snprintf(load, sizeof load, ld, l, idx);
+      snprintf(b, sizeof b, "  const bool in%d = (u64)%s < (u64)d.leaf[%d].len; ok = ok && in%d;\n  const i64 %s = %s;\n", l, p.c_str(), l, l, nm, load);
+    }
+    body += b;
+    return nm;
+  }
+  std::string term(const PTerm &t) {
+    if (t.leaf == -1) return lit(t.a);
+    std::string v;
+    if (t.leaf == -2) v = "(d.row_base + row)";
+    else if (t.leaf <= -3) v = "(i64)(" + pred(d.ind[-3 - t.leaf]) + " ? 1 : 0)";
+    else {
+      v = leaf(t.leaf);
+      if (t.shr) v = "(" + v + " >> " + std::to_string(t.shr) + ")";
+    }
+    if (t.a == 0 && t.b == 1) return v;
+    return "(i64)((u64)" + lit(t.a) + " + (u64)" + lit(t.b) + " * (u64)" + v + ")";
+  }
+  std::string pred(const PPred &P) {
+    char nm[16];
+    snprintf(nm, sizeof nm, "T%d", tmp++);
+    body += std::string("  const i64 ") + nm + " = " + term(P.t) + ";\n";
+    if (P.kind == 0) {
+      std::string e = std::string("((u64)") + nm + " - (u64)" + lit(P.lo) + " <= " + ulit(P.span);
+      for (int k = 0; k < P.nmore; k++) e += std::string(" || (u64)") + nm + " - (u64)" + lit(P.lo_more[k]) + " <= " + ulit(P.span_more[k]);
+      return e + ")";
+    }
+    char un[16];
+    snprintf(un, sizeof un, "T%d", tmp++);
+    body += std::string("  const i64 ") + un + " = " + term(P.u) + ";\n";
+    static const char *CMP[] = {"==", "!=", ">", ">=", "<", "<="};
+    return std::string("(") + nm + " " + CMP[P.cmp] + " " + un + ")";
+  }
+  std::string product(const PProd &p) {
+    if (p.nfac == 0) return lit(1);
+    std::string e = "(i64)(";
+    for (int f = 0; f < p.nfac; f++) e += std::string(f ? " * " : "") + "(u64)" + term(p.f[f]);
+    return e + ")";
+  }
+};
+
+static const char *PROBE_JIT_TAIL = R"SKEL(
+#define STAGE_LOOP(Q, FN)                                                                                          \
+  if (n_in > 0) {                                                                                                  \
+    for (int j0 = 0; j0 < n_in; j0 += P_SUB * P_THREADS) {                                                         \
+      bool f[P_SUB];                                                                                               \
+      int r[P_SUB];                                                                                                \
+      _Pragma("unroll") for (int k = 0; k < P_SUB; k++) {                                                          \
+        const int j = j0 + k * P_THREADS + tid;                                                                    \
+        r[k] = j < n_in ? ((Q) == 0 ? j : (int)queue[cur][j]) : -1;                                                \
+      }                                                                                                            \
+      /* every slot evaluates a row (its own, or the tile's row 0 as a stand-in): straight-line, loads overlap */ \
+      _Pragma("unroll") for (int k = 0; k < P_SUB; k++) {                                                          \
+        bool okk = true;                                                                                           \
+        const bool pass = FN(d, base + (r[k] >= 0 ? r[k] : 0), okk);                                               \
+        f[k] = r[k] >= 0 && pass && okk;                                                                           \
+        if (r[k] >= 0 && !okk) ok = false;                                                                         \
+      }                                                                                                            \
+      unsigned m[P_SUB];                                                                                           \
+      int wtotal = 0;                                                                                              \
+      _Pragma("unroll") for (int k = 0; k < P_SUB; k++) { m[k] = __ballot_sync(0xffffffffu, f[k]); wtotal += __popc(m[k]); } \
+      if (wtotal) {                                                                                                \
+        int at = 0;                                                                                                \
+        if (lane == 0) at = atomicAdd(&s_cnt[((Q) + 1) % 3], wtotal);                                              \
+        at = __shfl_sync(0xffffffffu, at, 0);                                                                      \
+        _Pragma("unroll") for (int k = 0; k < P_SUB; k++) {                                                        \
+          if (f[k]) queue[cur ^ 1][at + __popc(m[k] & ((1u << lane) - 1))] = (uint16_t)r[k];                       \
+          at += __popc(m[k]);                                                                                      \
+        }                                                                                                          \
+      }                                                                                                            \
+    }                                                                                                              \
+  }                                                                                                                \
+  if (tid == 0) s_cnt[((Q) + 2) % 3] = 0;                                                                          \
+  __syncthreads();                                                                                                 \
+  n_in = s_cnt[((Q) + 1) % 3];                                                                                     \
+  cur ^= 1;
+
+extern "C" __global__ void __launch_bounds__(P_THREADS, P_JIT_BLOCKS) vdl_probe_jit(const __grid_constant__ PDesc d) {
+  extern __shared__ __align__(16) unsigned char psm[];
+  __shared__ uint16_t queue[2][P_TILE];
+  __shared__ int s_cnt[3];
+  __shared__ unsigned int s_bits[P_TILE / 32];
+  __shared__ int wsum[P_THREADS / 32];
+  __shared__ i64 s_off;
+  __shared__ unsigned int s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr bool folding = P_NEMITS == 0;
+  constexpr int nacc = P_NFOLDS + 2;
+  i64 *stab = (i64 *)psm;
+  if (folding && d.smem_table) {
+    for (i64 i = tid; i < (i64)nacc * d.domain; i += P_THREADS) {
+      int j = (int)(i / d.domain);
+      stab[i] = j < P_NFOLDS ? p_identity(d.fold_op[j]) : (j == P_NFOLDS ? 0 : INT64_MAX);
+    }
+  }
+  __syncthreads();
+  i64 *tab = (folding && d.smem_table) ? stab : d.table;
+  for (;;) {
+    if (tid == 0) { s_tile = atomicAdd(d.ticket, 1u); s_cnt[1] = 0; }
+    __syncthreads();
+    const i64 tile = s_tile;
+    if (tile >= d.ntiles) break;
+    const i64 base = tile * P_TILE;
+    if (d.npf) {
+      const i64 b2 = base + (i64)d.pf_dist * P_TILE;
+      const i64 n2 = min((i64)P_TILE, d.rows - b2);
+      for (int c = 0; c < d.npf && n2 > 0; c++) {
+        const unsigned char *p0 = d.pf_ptr[c] + (b2 << d.pf_shift[c]);
+        const i64 bytes = n2 << d.pf_shift[c];
+        for (i64 o = (i64)tid * 128; o < bytes; o += P_THREADS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+      }
+    }
+    bool ok = true;
+    int n_in = (int)min((i64)P_TILE, d.rows - base);
+    int cur = 0;
+    P_STAGES
+    constexpr bool implicit = P_NPREDS == 0;
+    if (folding) {
+      for (int j = tid; j < n_in; j += P_THREADS) probe_fold_row(d, base + (implicit ? j : (int)queue[cur][j]), tab, ok);
+    } else {
+      if (!implicit) {
+        s_bits[tid] = 0;
+        __syncthreads();
+        for (int j = tid; j < n_in; j += P_THREADS) { const unsigned rr = queue[cur][j]; atomicOr(&s_bits[rr >> 5], 1u << (rr & 31)); }
+        __syncthreads();
+        unsigned w = s_bits[tid];
+        const int c = __popc(w);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int at = incl - c;
+        for (int ww = 0; ww < warp; ww++) at += wsum[ww];
+        while (w) { const int b = __ffs(w) - 1; w &= w - 1; queue[cur ^ 1][at++] = (uint16_t)(tid * 32 + b); }
+        cur ^= 1;
+        __syncthreads();
+      }
+      if (tid == 0) {
+        const unsigned long long T = (unsigned long long)n_in;
+        i64 excl = 0;
+        if (tile == 0) {
+          atomicExch(d.tile_state, (2ull << 62) | T);
+        } else {
+          atomicExch(d.tile_state + tile, (1ull << 62) | T);
+          for (i64 j = tile - 1;; j--) {
+            unsigned long long st;
+            do { st = *((volatile unsigned long long *)(d.tile_state + j)); } while ((st >> 62) == 0);
+            excl += (i64)(st & ((1ull << 62) - 1));
+            if ((st >> 62) == 2) break;
+          }
+          atomicExch(d.tile_state + tile, (2ull << 62) | (unsigned long long)(excl + (i64)T));
+        }
+        s_off = excl;
+        if (tile == d.ntiles - 1) *d.total = excl + (i64)T;
+      }
+      __syncthreads();
+      const i64 off = s_off;
+      for (int j = tid; j < n_in; j += P_THREADS) probe_emit_row(d, base + (implicit ? j : (int)queue[cur][j]), off + j, ok);
+    }
+    if (!ok) atomicAdd(d.errflag, 1);
+    __syncthreads();
+  }
+  if (folding && d.smem_table) {
+    __syncthreads();
+    for (i64 i = tid; i < (i64)nacc * d.domain; i += P_THREADS) {
+      int j = (int)(i / d.domain);
+      const i64 v = stab[i];
+      if (j < P_NFOLDS) { if (v != p_identity(d.fold_op[j])) table_update(d.fold_op[j], d.table + i, v); }
+      else if (j == P_NFOLDS) { if (v) atomicAdd((unsigned long long *)(d.table + i), (unsigned long long)v); }
+      else if (v != INT64_MAX) atomicMin((long long *)(d.table + i), (long long)v);
+    }
+  }
+}
+)SKEL";
+
+static std::string probe_jit_source(const PDesc &d, int p_sub, int blocks) {
+  ProbeGen g(d);
+  char b[256];
+  snprintf(b, sizeof b, "#include \"vdl_probe_kernel.cuh\"\n#define P_SUB %d\n#define P_JIT_BLOCKS %d\n#define P_NPREDS %d\n#define P_NFOLDS %d\n#define P_NEMITS %d\n",
+           p_sub, blocks, d.npreds, d.nfolds, d.nemits);
+  std::string s = b, stages;
+  for (int q = 0; q < d.npreds; q++) {
+    g.reset();
+    const std::string e = g.pred(d.pred[q]);
+    snprintf(b, sizeof b, "__device__ __forceinline__ bool probe_stage_%d(const PDesc &d, const i64 row, bool &ok) {\n", q);
+    s += b + g.body + "  return " + e + ";\n}\n";
+    snprintf(b, sizeof b, "STAGE_LOOP(%d, probe_stage_%d) ", q, q);
+    stages += b;
+  }
+  // fold of one surviving row (fold mode) / its emitted expressions (emit mode)
+  g.reset();
+  s += "__device__ __forceinline__ void probe_fold_row(const PDesc &d, const i64 row, i64 *tab, bool &ok) {\n";
+  if (d.nemits == 0) {
+    std::string keyexpr = "  i64 key = 0;\n";
+    std::string pre;
+    for (int q = 0; q < d.nkeys; q++) {
+      const std::string t = g.term(d.key[q]);
+      keyexpr += "  key |= (i64)((u64)" + t + " << " + std::to_string(d.key_shl[q]) + ");\n";
+    }
+    std::string vals;
+    for (int j = 0; j < d.nfolds; j++) {
+      if (d.fold_op[j] == VDL_FOLD_CHOOSE || d.fold_op[j] == VDL_FOLD_COUNT) continue;
+      snprintf(b, sizeof b, "  table_update(%d, tab + (size_t)%d * d.domain + key, ", d.fold_op[j], j);
+      vals += b + g.product(d.fold[j]) + ");\n";
+    }
+    s += g.body + keyexpr + "  key &= d.key_mask;\n  if ((u64)key >= (u64)d.domain) { ok = false; return; }\n" + vals;
+    snprintf(b, sizeof b, "  atomicAdd((unsigned long long *)(tab + (size_t)%d * d.domain + key), 1ull);\n  atomicMin((long long *)(tab + (size_t)%d * d.domain + key), (long long)(d.row_base + row));\n",
+             d.nfolds, d.nfolds + 1);
+    s += b;
+  }
+  s += "}\n";
+  g.reset();
+  s += "__device__ __forceinline__ void probe_emit_row(const PDesc &d, const i64 row, const i64 at, bool &ok) {\n";
+  {
+    std::string st;
+    for (int e = 0; e < d.nemits; e++) { snprintf(b, sizeof b, "  d.emit_out[%d][at] = ", e); st += b + g.product(d.emit[e]) + ";\n"; }
+    s += g.body + st;
+  }
+  s += "}\n#define P_STAGES " + stages + "\n";
+  return s + PROBE_JIT_TAIL;
+}
+
+static cudaKernel_t probe_jit_compile(vdl_ctx *ctx, const PDesc &d, size_t smem, bool *ok, std::string *log) {
+  int p_sub = 4, blocks = 12;
+  if (const char *e = getenv("VDL_PROBE_JIT_SUB")) p_sub = std::max(1, std::min(16, atoi(e)));
+  if (const char *e = getenv("VDL_PROBE_JIT_BLOCKS")) blocks = std::max(1, std::min(16, atoi(e)));
+  const std::string src = probe_jit_source(d, p_sub, blocks);
+  static const char *const headers[] = {EMB_vdl_cuda_h, EMB_vdl_device_cuh, EMB_vdl_probe_kernel_cuh};
+  static const char *const names[] = {"vdl_cuda.h", "vdl_device.cuh", "vdl_probe_kernel.cuh"};
+  if (getenv("VDL_DEBUG_JIT")) fprintf(stderr, "[vdl jit] probe:\n%s\n", src.substr(0, src.find("#define STAGE_LOOP")).c_str());
+  cudaKernel_t kh = vdl_jit_kernel(ctx, "probe|" + src, src, "vdl_probe_jit", 3, headers, names, ok, log);
+  if (kh && smem > 48 * 1024 && cudaFuncSetAttribute((const void *)kh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return kh;
+}
+
+// Host-only check (no GPU): print a two-stage descriptor with a lookup chain, a range set, a column comparison, an
+// indicator and two folds as CUDA C and compile it with NVRTC for sm_100a; then an emit-mode one.
+extern "C" int vdl_probe_jit_selftest(char *log, int log_capacity) {
+  if (log && log_capacity > 0) log[0] = 0;
+  PDesc d;
+  memset(&d, 0, sizeof d);
+  d.nleaves = 4;
+  d.leaf[0] = PLeaf{nullptr, 10, 0, -1}; d.leaf[1] = PLeaf{nullptr, 10, 1, 0}; d.leaf[2] = PLeaf{nullptr, 10, 0, 1}; d.leaf[3] = PLeaf{nullptr, 10, 1, -1};
+  d.npreds = 2;
+  d.pred[0].kind = 0; d.pred[0].t = PTerm{1, 0, 0, 1}; d.pred[0].lo = 5; d.pred[0].span = 7; d.pred[0].nmore = 1; d.pred[0].lo_more[0] = 40; d.pred[0].span_more[0] = 0;
+  d.pred[1].kind = 1; d.pred[1].cmp = VDL_CMP_GE; d.pred[1].t = PTerm{2, 3, -1, 2}; d.pred[1].u = PTerm{3, 0, 0, 1};
+  d.nind = 1; d.ind[0] = d.pred[0];
+  d.nkeys = 1; d.key[0] = PTerm{2, 3, -2, 1}; d.key_shl[0] = 1; d.key_mask = 31; d.domain = 32;
+  d.nfolds = 3; d.fold_op[0] = VDL_FOLD_SUM; d.fold[0].nfac = 2; d.fold[0].f[0] = PTerm{3, 0, 0, 1}; d.fold[0].f[1] = PTerm{-3, 0, 0, 1};
+  d.fold_op[1] = VDL_FOLD_MIN; d.fold[1].nfac = 1; d.fold[1].f[0] = PTerm{-2, 0, 0, 1};
+  d.fold_op[2] = VDL_FOLD_COUNT;
+  std::string l;
+  bool ok1 = false, ok2 = false;
+  vdl_jit_kernel(nullptr, "", probe_jit_source(d, 4, 12), "vdl_probe_jit", 3, (const char *const[]){EMB_vdl_cuda_h, EMB_vdl_device_cuh, EMB_vdl_probe_kernel_cuh},
+                 (const char *const[]){"vdl_cuda.h", "vdl_device.cuh", "vdl_probe_kernel.cuh"}, &ok1, &l);
+  if (l == "NVRTC is not installed") return VDL_ENOTFOUND;
+  d.nfolds = 0; d.nkeys = 0; d.nemits = 2; d.emit[0] = d.fold[0]; d.emit[1].nfac = 1; d.emit[1].f[0] = PTerm{2, 0, 0, 1};
+  if (ok1) vdl_jit_kernel(nullptr, "", probe_jit_source(d, 4, 12), "vdl_probe_jit", 3, (const char *const[]){EMB_vdl_cuda_h, EMB_vdl_device_cuh, EMB_vdl_probe_kernel_cuh},
+                          (const char *const[]){"vdl_cuda.h", "vdl_device.cuh", "vdl_probe_kernel.cuh"}, &ok2, &l);
+  if (log && log_capacity > 1) snprintf(log, (size_t)log_capacity, "%s", l.c_str());
+  return ok1 && ok2 ? VDL_OK : VDL_ECUDA;
+}
+
 struct vdl_probe {
   vdl_ctx *ctx = nullptr;
   PDesc pd;
@@ -498,6 +743,7 @@ struct vdl_probe {
   int grid = 1;
   size_t smem = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaKernel_t jit_kernel = nullptr;   // the descriptor printed as CUDA C and compiled at run time (probe_jit_source)
   // identity of the leaf columns at prepare time (device pointers and lengths are baked into the descriptor)
   int nleaves = 0;
   vdl_vec leaf_handle[VDL_MAX_LEAVES] = {0};
@@ -654,6 +900,14 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
   int per_sm = P_BLOCKS;
   p->grid = (int)std::max<i64>(1, std::min<i64>((i64)ctx->sm_count * per_sm, d.ntiles));
   if (p->smem > 48 * 1024) cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+  {   // run-time specialisation (VDL_PROBE_JIT=0 switches it off; VDL_PROBE_JIT_MIN_ROWS, default 262144)
+    const char *e = getenv("VDL_PROBE_JIT");
+    i64 min_rows = 1 << 18;
+    if (const char *m = getenv("VDL_PROBE_JIT_MIN_ROWS")) min_rows = atoll(m);
+    bool lens_ok = true;             // the generated code clamps a failed lookup to index 0: every looked-up column needs a row
+    for (int l = 0; l < d.nleaves; l++) if (d.leaf[l].parent >= 0 && d.leaf[l].len < 1) lens_ok = false;
+    if (!(e && !strcmp(e, "0")) && d.rows >= min_rows && lens_ok) p->jit_kernel = probe_jit_compile(ctx, d, p->smem, nullptr, nullptr);
+  }
   *out = p;
   return VDL_OK;
 }
@@ -740,7 +994,12 @@ extern "C" int vdl_probe_run_ex(vdl_probe *p, int finalize) {
   }
   VDL_CUDA(ctx, cudaEventRecord(p->ev0, ctx->stream));
   if (d.rows > 0) {
-    probe_kernel<<<p->grid, P_THREADS, p->smem, ctx->stream>>>(d);
+    if (p->jit_kernel) {
+      void *args[] = {(void *)&d};
+      VDL_CUDA(ctx, cudaLaunchKernel((const void *)p->jit_kernel, dim3(p->grid), dim3(P_THREADS), args, p->smem, ctx->stream));
+    } else {
+      probe_kernel<<<p->grid, P_THREADS, p->smem, ctx->stream>>>(d);
+    }
     ctx->launches++;
   }
   VDL_CUDA(ctx, cudaEventRecord(p->ev1, ctx->stream));

@@ -133,6 +133,7 @@ SYMBOLS = [
     ("vdl_abi_sizeof_map_desc", _I, []),
     ("vdl_jit_selftest", _I, [C.c_char_p, _I]),
     ("vdl_scan_jit_selftest", _I, [C.c_char_p, _I]),
+    ("vdl_probe_jit_selftest", _I, [C.c_char_p, _I]),
     ("vdl_op_like", _I, [_P, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_int32)]),
     ("vdl_op_fold_select", _I, [_P, C.c_int32, C.POINTER(C.c_int32)]),
     ("vdl_op_gather", _I, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),

@@ -88,3 +88,16 @@ def test_scan_specialisation_compiles_without_a_gpu():
     if rc == 3:
         pytest.skip("NVRTC not installed")
     assert rc == 0, log.value.decode(errors="replace")
+
+
+def test_probe_specialisation_compiles_without_a_gpu():
+    """The FK-join probe printed as CUDA C for one descriptor (lookup chains, range sets, column comparisons, indicator
+    terms; fold and emit mode) and compiled by NVRTC for sm_100a."""
+    import ctypes
+    from mplan2vdl_b200 import lib
+    L = lib.load()
+    log = ctypes.create_string_buffer(1 << 16)
+    rc = L.vdl_probe_jit_selftest(log, len(log))
+    if rc == 3:
+        pytest.skip("NVRTC not installed")
+    assert rc == 0, log.value.decode(errors="replace")

@@ -119,3 +119,33 @@ def test_runtime_compiled_scan_on_tpch_shapes(catalog, query, colnames, narrow, 
     got, stats = run_gpu(plan_text(query), cols)
     assert stats["shape"].startswith("jit:")
     assert_same(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(0, 40, 2))
+def test_random_fk_join_plans_through_the_runtime_compiled_probe(catalog, seed, monkeypatch):
+    """The probe descriptor printed as CUDA C and compiled at run time (forced for these small tables), fold and emit
+    modes, against the oracle; the interpreter kernel on the same plans is test_random_fk_join_plans."""
+    monkeypatch.setenv("VDL_PROBE_JIT_MIN_ROWS", "0")
+    for rel, sf in ((fuzz_plans.join_query(seed, catalog), 0.02), (fuzz_plans.single_table(seed), 0.02)):
+        text = vlite.translate(catalog, rel)
+        rows = {t: synth.table_rows(catalog, t, sf) for t in catalog.tables}
+        cols = host_columns(catalog, tpch.plan_columns(text), rows, sf=sf)
+        got, stats = run_gpu(text, cols, fuse=True)
+        assert_same(got, run_oracle(text, cols))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("q", ["q03", "q05", "q12", "q19", "q04", "q09", "q14", "q16"])
+def test_tpch_join_plans_through_the_runtime_compiled_probe(catalog, q, monkeypatch):
+    from util import plan_text, q19_columns
+    monkeypatch.setenv("VDL_PROBE_JIT_MIN_ROWS", "0")
+    sf = 0.05
+    if q == "q19":
+        text, cols = q19_columns(catalog, sf=sf)
+    else:
+        text = plan_text(q + ".vdl")
+        rows = {t: synth.table_rows(catalog, t, sf) for t in catalog.tables}
+        cols = host_columns(catalog, tpch.plan_columns(text), rows, sf=sf)
+    got, stats = run_gpu(text, cols, fuse=True)
+    assert_same(got, run_oracle(text, cols))
