@@ -632,6 +632,12 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   f->fd.hmirror = f->h_mapped;
   for (int j = 0; j < k.nacc; j++) f->fd.acc_op[j] = k.acc[j].op;
 
+  {   // load every kernel a step may launch now, not lazily behind a peer's spinning exchange (see vdl_probe_prepare)
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, fused_init_kernel); cudaFuncGetAttributes(&fa, fused_choose_kernel); cudaFuncGetAttributes(&fa, fused_finalize_kernel);
+    cudaFuncGetAttributes(&fa, fused_exchange_kernel);
+    cudaGetLastError();
+  }
   cudaError_t e = cudaFuncSetAttribute(f->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
   if (e != cudaSuccess) { vdl_fused_destroy(f); return vdl_cuda_fail(ctx, e, "cudaFuncSetAttribute(fused_scan_fold_kernel)"); }
   for (int g : rs_slot_counts)

@@ -684,7 +684,7 @@ static std::string probe_jit_source(const PDesc &d, int p_sub, int blocks) {
 }
 
 static cudaKernel_t probe_jit_compile(vdl_ctx *ctx, const PDesc &d, size_t smem, bool *ok, std::string *log) {
-  int p_sub = 4, blocks = 12;
+  int p_sub = 8, blocks = 8;       // measured on B200 (Q5 / Q3 / Q12 / Q19 SF10): 8 rows per thread and round, 8 blocks x 64 registers
   if (const char *e = getenv("VDL_PROBE_JIT_SUB")) p_sub = std::max(1, std::min(16, atoi(e)));
   if (const char *e = getenv("VDL_PROBE_JIT_BLOCKS")) blocks = std::max(1, std::min(16, atoi(e)));
   const std::string src = probe_jit_source(d, p_sub, blocks);
@@ -900,6 +900,14 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
   int per_sm = P_BLOCKS;
   p->grid = (int)std::max<i64>(1, std::min<i64>((i64)ctx->sm_count * per_sm, d.ntiles));
   if (p->smem > 48 * 1024) cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+  {   // load every kernel a step may launch NOW (CUDA loads lazily, and loading can wait for running kernels: a first
+      // launch of the finalize kernel behind a peer's spinning exchange kernel would stall the host until the exchange
+      // times out -- seen when one host thread drives several ranks)
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, probe_kernel); cudaFuncGetAttributes(&fa, probe_init_kernel); cudaFuncGetAttributes(&fa, probe_choose_kernel);
+    cudaFuncGetAttributes(&fa, probe_exchange_kernel); cudaFuncGetAttributes(&fa, probe_finalize_kernel);
+    cudaGetLastError();
+  }
   {   // run-time specialisation (VDL_PROBE_JIT=0 switches it off; VDL_PROBE_JIT_MIN_ROWS, default 262144)
     const char *e = getenv("VDL_PROBE_JIT");
     i64 min_rows = 1 << 18;
