@@ -277,6 +277,9 @@ int vdl_ipc_free(vdl_ctx *ctx, void *device_ptr);
 
 /* Duration of the last vdl_fused_launch's scan kernel alone, CUDA events on the context stream. */
 int vdl_fused_last_kernel_ms(vdl_fused *f, float *ms);
+/* Mean and minimum of the scan kernel's duration over the last n launches (n <= 64): the library records an event pair
+ * around every launch, so a timed loop reads the durations afterwards instead of synchronising every step. */
+int vdl_fused_kernel_ms_stats(vdl_fused *f, int n, float *mean_ms, float *min_ms);
 
 /* ---- fused FK-join probe ----------------------------------------------------------------
  * One pass over a fact-table shard that follows foreign-key index columns into dimension columns, applies
@@ -340,6 +343,7 @@ int vdl_probe_result_host(vdl_probe *p, int index, const int64_t **data, int64_t
 /* emit mode: take ownership of the k-th emitted vector (synchronises for its length) */
 int vdl_probe_emit_take(vdl_probe *p, int k, vdl_vec *out);
 int vdl_probe_last_kernel_ms(vdl_probe *p, float *ms);
+int vdl_probe_kernel_ms_stats(vdl_probe *p, int n, float *mean_ms, float *min_ms);
 int vdl_probe_destroy(vdl_probe *p);
 
 /* ---- whole plans: the text mplan2vdl prints (Vdl.hs:410-453) ---------------------------- */
@@ -359,6 +363,8 @@ int vdl_plan_probe_stats(vdl_plan *p, int *fold_groups, int *emit_groups, int *e
 /* Map clusters of the op-at-a-time remainder: how many vdl_op_map launches stand for how many plan nodes. */
 int vdl_plan_map_stats(vdl_plan *p, int *clusters, int *nodes_covered);
 int vdl_plan_probe_kernel_ms(vdl_plan *p, float *ms);   /* sum over the probe passes of the last run; synchronises */
+/* Dominant-kernel time of the last n runs (first fused scan, else the sum over the probe passes): mean and minimum. */
+int vdl_plan_kernel_ms_stats(vdl_plan *p, int n, float *mean_ms, float *min_ms);
 /* Phase 1: everything up to and including the fused scans (local shard). */
 /* Global row id of this shard's row 0 (row-range sharding of the fact table; default 0). */
 int vdl_plan_set_row_base(vdl_plan *p, int64_t row_base);

@@ -3,6 +3,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <chrono>
+
 #include "vdl_internal.h"
 
 int vdl_fail(vdl_ctx *ctx, int code, const char *fmt, ...) {
@@ -201,6 +204,21 @@ int read_scalar(vdl_ctx *ctx, const void *device_src, void *host_dst, int bytes)
   VDL_CUDA(ctx, cudaGetLastError());
   VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   memcpy(host_dst, ctx->h_mail, (size_t)bytes);
+  return VDL_OK;
+}
+
+int wait_published(vdl_ctx *ctx, const volatile i64 *word, i64 seq) {
+  if (!getenv("VDL_NO_SPIN_WAIT")) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int it = 0;; it++) {
+      if (*word == seq) { std::atomic_thread_fence(std::memory_order_acquire); return VDL_OK; }
+      if ((it & 1023) == 1023 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(20)) break;
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return VDL_OK;
 }
 

@@ -71,7 +71,9 @@ struct vdl_fused {
   int grid = 1, nc = 256, r = 4;
   scan_kernel_fn kernel = nullptr;
   const char *shape = "generic";
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // event pairs around the dominant kernel of the last VDL_EVENT_RING launches: durations are read AFTER a timed loop
+  cudaEvent_t ev0[VDL_EVENT_RING] = {nullptr}, ev1[VDL_EVENT_RING] = {nullptr};
+  long nlaunch = 0;
   bool timed = false;
   // run-time specialised kernels (vdl_jit_kernel): the shape-traits class generated from THIS descriptor
   bool jit = false;
@@ -593,7 +595,7 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
   if (rc) { delete f; return rc; }
   k.table = (i64 *)ctx->vecs[f->table].ptr;
   {
-    size_t nb = ((size_t)(f->nout + desc->nposts) * k.domain + 2) * sizeof(i64);
+    size_t nb = ((size_t)(f->nout + desc->nposts) * k.domain + 3) * sizeof(i64);
     if (cudaMalloc(&f->d_outbuf, nb) != cudaSuccess || cudaHostAlloc(&f->h_outbuf, nb, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(&f->h_mapped, f->h_outbuf, 0) != cudaSuccess || cudaMalloc(&f->d_done, sizeof(unsigned int)) != cudaSuccess ||
         cudaMemsetAsync(f->d_done, 0, sizeof(unsigned int), ctx->stream) != cudaSuccess) {
@@ -601,6 +603,7 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
       return vdl_fail(ctx, VDL_ENOMEM, "fused scan: result buffers");
     }
     k.done = f->d_done;
+    memset(f->h_outbuf, 0, nb);        // (the publication word must not start out looking like a finished step)
   }
   for (int i = 0; i < f->nout; i++) {   // the fold results are views into the one result buffer
     rc = vec_new_range(ctx, 0, 0, 0, &f->out[i]);
@@ -613,8 +616,7 @@ extern "C" int vdl_fused_prepare(vdl_ctx *ctx, const vdl_fused_desc *desc, vdl_f
     v.domain = -1;
     f->fd.out[i] = (i64 *)v.ptr;
   }
-  cudaEventCreate(&f->ev0);
-  cudaEventCreate(&f->ev1);
+  for (int i = 0; i < VDL_EVENT_RING; i++) { cudaEventCreate(&f->ev0[i]); cudaEventCreate(&f->ev1[i]); }
   f->fd.domain = k.domain;
   f->fd.nacc = k.nacc;
   f->fd.nchoose = k.nchoose;
@@ -667,7 +669,7 @@ extern "C" int vdl_fused_launch_ex(vdl_fused *f, int self_finalize) {
     ctx->launches++;
     f->table_clean = true;
   }
-  VDL_CUDA(ctx, cudaEventRecord(f->ev0, ctx->stream));
+  VDL_CUDA(ctx, cudaEventRecord(f->ev0[f->nlaunch % VDL_EVENT_RING], ctx->stream));
   cudaKernel_t jit_launch = f->jit ? f->jit_kernel : nullptr;
   if (f->rs) {
     int g = f->rs_gmax;
@@ -693,6 +695,7 @@ extern "C" int vdl_fused_launch_ex(vdl_fused *f, int self_finalize) {
   f->fd.parts = f->kd.table;
   f->fd.nranks = 1;
   f->fd.reset_table = f->kd.table;
+  if (self_finalize) f->fd.seq++;
   if (scan) {
     f->kd.epilogue = self_finalize == 2 ? 3 : (self_finalize ? 2 : 1);
     if (jit_launch) {
@@ -710,7 +713,8 @@ extern "C" int vdl_fused_launch_ex(vdl_fused *f, int self_finalize) {
     fused_finalize_kernel<<<1, 256, 0, ctx->stream>>>(f->fd);
     ctx->launches++;
   }
-  VDL_CUDA(ctx, cudaEventRecord(f->ev1, ctx->stream));
+  VDL_CUDA(ctx, cudaEventRecord(f->ev1[f->nlaunch % VDL_EVENT_RING], ctx->stream));
+  f->nlaunch++;
   f->timed = true;
   VDL_CUDA(ctx, cudaGetLastError());
   if (self_finalize) f->finalized = true;
@@ -759,6 +763,7 @@ extern "C" int vdl_fused_finalize(vdl_fused *f, const void *all_partials, int nr
   f->fd.parts = all_partials ? (const i64 *)all_partials : f->kd.table;
   f->fd.nranks = nranks;
   f->fd.reset_table = f->kd.table;      // the gathered copies (or this one launch) are the last readers of the table
+  f->fd.seq++;
   fused_finalize_kernel<<<1, 256, 0, ctx->stream>>>(f->fd);
   ctx->launches++;
   VDL_CUDA(ctx, cudaGetLastError());
@@ -774,7 +779,7 @@ static int fused_fetch(vdl_fused *f) {
   if (!f->finalized) return vdl_fail(ctx, VDL_EINVAL, "fused scan not finalized");
   if (f->ngroups >= 0) return VDL_OK;
   size_t n = (size_t)(f->nout + f->fd.npost) * f->kd.domain + 2;
-  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // the finalize wrote the results straight into h_outbuf (mapped)
+  VDL_TRY(wait_published(ctx, f->h_outbuf + n, f->fd.seq));   // the finalize wrote the results straight into h_outbuf (mapped)
   i64 ng = f->h_outbuf[n - 2], err = f->h_outbuf[n - 1];
   if (err) {
     cudaMemsetAsync(ctx->d_errflag, 0, sizeof(int), ctx->stream);
@@ -822,8 +827,30 @@ extern "C" int vdl_fused_result(vdl_fused *f, int fold_index, vdl_vec *out) {
 extern "C" int vdl_fused_last_kernel_ms(vdl_fused *f, float *ms) {
   if (!f || !ms) return VDL_EINVAL;
   if (!f->timed) return vdl_fail(f->ctx, VDL_EINVAL, "fused scan not launched yet");
-  VDL_CUDA(f->ctx, cudaEventSynchronize(f->ev1));
-  VDL_CUDA(f->ctx, cudaEventElapsedTime(ms, f->ev0, f->ev1));
+  const int i = (int)((f->nlaunch - 1) % VDL_EVENT_RING);
+  VDL_CUDA(f->ctx, cudaEventSynchronize(f->ev1[i]));
+  VDL_CUDA(f->ctx, cudaEventElapsedTime(ms, f->ev0[i], f->ev1[i]));
+  return VDL_OK;
+}
+
+// Mean / minimum duration of the scan kernel over the last `n` launches (n <= VDL_EVENT_RING), from event pairs recorded
+// around each launch: a timed loop reads them afterwards instead of synchronising on an event every step.
+extern "C" int vdl_fused_kernel_ms_stats(vdl_fused *f, int n, float *mean_ms, float *min_ms) {
+  if (!f || n < 1) return VDL_EINVAL;
+  if (!f->timed) return vdl_fail(f->ctx, VDL_EINVAL, "fused scan not launched yet");
+  n = (int)std::min<long>(std::min<long>(n, VDL_EVENT_RING), f->nlaunch);
+  double sum = 0;
+  float mn = 1e30f;
+  for (int k = 1; k <= n; k++) {
+    const int i = (int)((f->nlaunch - k) % VDL_EVENT_RING);
+    float ms = 0;
+    VDL_CUDA(f->ctx, cudaEventSynchronize(f->ev1[i]));
+    VDL_CUDA(f->ctx, cudaEventElapsedTime(&ms, f->ev0[i], f->ev1[i]));
+    sum += ms;
+    mn = std::min(mn, ms);
+  }
+  if (mean_ms) *mean_ms = (float)(sum / n);
+  if (min_ms) *min_ms = mn;
   return VDL_OK;
 }
 
@@ -840,8 +867,7 @@ extern "C" int vdl_fused_destroy(vdl_fused *f) {
   if (f->d_outbuf) cudaFree(f->d_outbuf);
   if (f->d_done) cudaFree(f->d_done);
   if (f->h_outbuf) cudaFreeHost(f->h_outbuf);
-  if (f->ev0) cudaEventDestroy(f->ev0);
-  if (f->ev1) cudaEventDestroy(f->ev1);
+  for (int i = 0; i < VDL_EVENT_RING; i++) { if (f->ev0[i]) cudaEventDestroy(f->ev0[i]); if (f->ev1[i]) cudaEventDestroy(f->ev1[i]); }
   delete f;
   return VDL_OK;
 }

@@ -45,7 +45,8 @@ struct FinDesc {
   int32_t npost, pad;
   vdl_post_op post[VDL_MAX_POSTS];
   i64 *post_out[VDL_MAX_POSTS];
-  i64 *ngroups;                  // [0] number of groups, [1] snapshot of the context's error counter
+  i64 *ngroups;                  // [0] number of groups, [1] snapshot of the context's error counter, [2] (host mirror only) seq
+  i64 seq;                       // number of this finalize: the last word the kernel publishes to the host mirror
   const int *errflag;
   i64 *hmirror;                  // mapped pinned host copy of the whole result buffer (same layout as out[0]...), or null
   i64 *reset_table;              // this rank's partial table, re-initialised for the next launch after the merge, or null
@@ -881,7 +882,11 @@ __device__ __forceinline__ void finalize_block(const FinDesc &f, const i64 *part
   if (tid == 0) {
     const i64 ng = *running, err = *f.errflag;
     f.ngroups[0] = ng; f.ngroups[1] = err;
-    if (f.hmirror) { mirror(f.ngroups)[0] = ng; mirror(f.ngroups)[1] = err; }
+    if (f.hmirror) {
+      mirror(f.ngroups)[0] = ng; mirror(f.ngroups)[1] = err;
+      __threadfence_system();                      // every result store of this block (barriers above) before the publication
+      ((volatile i64 *)mirror(f.ngroups))[2] = f.seq;
+    }
   }
   if (f.reset_table) {      // every thread has read what it needed (barriers above): identity-initialise for the next launch
     const i64 n = (i64)(f.nacc + f.nchoose) * f.domain;

@@ -31,6 +31,8 @@ struct Vec {
   std::string name;
 };
 
+#define VDL_EVENT_RING 64
+
 struct vdl_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -77,6 +79,11 @@ int check_errflag(vdl_ctx *ctx, const char *what);                        // syn
 // mapped host memory, so the read never queues on the copy engine behind a bulk device->host copy of another stream
 // (plan outputs); synchronises the context's stream.
 int read_scalar(vdl_ctx *ctx, const void *device_src, void *host_dst, int bytes);
+
+// Wait until a kernel has published `seq` in mapped pinned host memory (its last store, after a system-scope fence):
+// a short spin on the word instead of cudaStreamSynchronize, whose wake-up costs 10-20 us -- several percent of a
+// 0.3 ms step on 8 GPUs.  Falls back to synchronising the stream (errors surface there) after ~20 ms.
+int wait_published(vdl_ctx *ctx, const volatile i64 *word, i64 seq);
 
 // Operand as the per-op kernels see it.
 struct Operand {

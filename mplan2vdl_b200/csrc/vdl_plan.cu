@@ -1309,6 +1309,22 @@ extern "C" int vdl_plan_probe_kernel_ms(vdl_plan *p, float *ms) {
   return VDL_OK;
 }
 
+// Mean and minimum, over the last n runs, of the plan's dominant-kernel time: the first fused scan's kernel, or else the
+// sum over the probe passes -- from event pairs the library records around every launch, read after a timed loop.
+extern "C" int vdl_plan_kernel_ms_stats(vdl_plan *p, int n, float *mean_ms, float *min_ms) {
+  if (!p || n < 1) return VDL_EINVAL;
+  if (!p->groups.empty()) {
+    if (!p->groups[0].fused) return vdl_fail(p->ctx, VDL_EINVAL, "plan has not run yet");
+    return vdl_fused_kernel_ms_stats(p->groups[0].fused, n, mean_ms, min_ms);
+  }
+  float mean = 0, mn = 0;
+  for (auto *g : p->pgroups) if (g->probe) { float a = 0, b = 0; VDL_TRY(vdl_probe_kernel_ms_stats(g->probe, n, &a, &b)); mean += a; mn += b; }
+  for (auto *g : p->egroups) if (g->probe) { float a = 0, b = 0; VDL_TRY(vdl_probe_kernel_ms_stats(g->probe, n, &a, &b)); mean += a; mn += b; }
+  if (mean_ms) *mean_ms = mean;
+  if (min_ms) *min_ms = mn;
+  return VDL_OK;
+}
+
 extern "C" int vdl_plan_set_row_base(vdl_plan *p, int64_t row_base) {
   if (!p) return VDL_EINVAL;
   p->row_base = row_base;

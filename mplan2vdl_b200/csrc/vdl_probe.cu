@@ -394,7 +394,11 @@ __global__ void __launch_bounds__(256, 1) probe_finalize_kernel(const __grid_con
     const size_t tail = (size_t)(f.nfolds + f.npost) * f.domain;
     const i64 ng = running, err = *f.errflag;
     f.out[tail] = ng; f.out[tail + 1] = err;
-    if (f.hmirror) { f.hmirror[tail] = ng; f.hmirror[tail + 1] = err; }
+    if (f.hmirror) {
+      f.hmirror[tail] = ng; f.hmirror[tail + 1] = err;
+      __threadfence_system();
+      ((volatile i64 *)f.hmirror)[tail + 2] = f.seq;
+    }
   }
 }
 
@@ -742,7 +746,9 @@ struct vdl_probe {
   i64 ngroups = -1, nselected = -1;
   int grid = 1;
   size_t smem = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // event pairs around the dominant kernel of the last VDL_EVENT_RING launches: durations are read AFTER a timed loop
+  cudaEvent_t ev0[VDL_EVENT_RING] = {nullptr}, ev1[VDL_EVENT_RING] = {nullptr};
+  long nlaunch = 0;
   cudaKernel_t jit_kernel = nullptr;   // the descriptor printed as CUDA C and compiled at run time (probe_jit_source)
   // identity of the leaf columns at prepare time (device pointers and lengths are baked into the descriptor)
   int nleaves = 0;
@@ -866,10 +872,11 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
       if (P.op < 0 || P.op > VDL_MODULO || !okk(P.a_kind, P.a) || !okk(P.b_kind, P.b)) return fail(vdl_fail(ctx, VDL_EINVAL, "probe: bad post op %d", q));
       p->pf.post[q] = P;
     }
-    size_t nb = ((size_t)(d.nfolds + desc->nposts) * d.domain + 2) * sizeof(i64);
+    size_t nb = ((size_t)(d.nfolds + desc->nposts) * d.domain + 3) * sizeof(i64);
     if (cudaMalloc(&p->d_out, nb) != cudaSuccess || cudaHostAlloc(&p->h_out, nb, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(&p->h_mapped, p->h_out, 0) != cudaSuccess)
       return fail(vdl_fail(ctx, VDL_ENOMEM, "probe: result buffers"));
+    memset(p->h_out, 0, nb);
     p->pf.domain = d.domain; p->pf.nfolds = d.nfolds; p->pf.npost = desc->nposts;
     for (int j = 0; j < d.nfolds; j++) p->pf.fold_op[j] = d.fold_op[j];
     p->pf.table = d.table; p->pf.nranks = 1; p->pf.stride = (i64)(d.nfolds + 2) * d.domain; p->pf.out = p->d_out; p->pf.hmirror = p->h_mapped; p->pf.errflag = ctx->d_errflag;
@@ -895,8 +902,7 @@ extern "C" int vdl_probe_prepare(vdl_ctx *ctx, const vdl_probe_desc *desc, vdl_p
     for (int l = 0; l < desc->nleaves; l++)
       if (want[l] && d.leaf[l].ptr) { d.pf_ptr[d.npf] = (const unsigned char *)d.leaf[l].ptr; d.pf_shift[d.npf] = d.leaf[l].w4 ? 2 : 3; d.npf++; }
   }
-  cudaEventCreate(&p->ev0);
-  cudaEventCreate(&p->ev1);
+  for (int i = 0; i < VDL_EVENT_RING; i++) { cudaEventCreate(&p->ev0[i]); cudaEventCreate(&p->ev1[i]); }
   int per_sm = P_BLOCKS;
   p->grid = (int)std::max<i64>(1, std::min<i64>((i64)ctx->sm_count * per_sm, d.ntiles));
   if (p->smem > 48 * 1024) cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
@@ -965,6 +971,7 @@ extern "C" int vdl_probe_finalize(vdl_probe *p, const void *all_partials, int nr
   p->pf.nranks = nranks;
   p->pf.stride = (i64)(p->pd.nfolds + 2) * p->pd.domain;
   p->pf.precomputed_choose = 1;
+  p->pf.seq++;
   probe_finalize_kernel<<<1, 256, 0, ctx->stream>>>(p->pd, p->pf);
   ctx->launches++;
   VDL_CUDA(ctx, cudaGetLastError());
@@ -1000,7 +1007,7 @@ extern "C" int vdl_probe_run_ex(vdl_probe *p, int finalize) {
       d.emit_out[e] = (i64 *)ctx->vecs[p->emit_vec[e]].ptr;
     }
   }
-  VDL_CUDA(ctx, cudaEventRecord(p->ev0, ctx->stream));
+  VDL_CUDA(ctx, cudaEventRecord(p->ev0[p->nlaunch % VDL_EVENT_RING], ctx->stream));
   if (d.rows > 0) {
     if (p->jit_kernel) {
       void *args[] = {(void *)&d};
@@ -1010,7 +1017,8 @@ extern "C" int vdl_probe_run_ex(vdl_probe *p, int finalize) {
     }
     ctx->launches++;
   }
-  VDL_CUDA(ctx, cudaEventRecord(p->ev1, ctx->stream));
+  VDL_CUDA(ctx, cudaEventRecord(p->ev1[p->nlaunch % VDL_EVENT_RING], ctx->stream));
+  p->nlaunch++;
   p->finalized = !p->folding || finalize != 0;
   if (p->folding && finalize == 2) {       // peer-memory combine: every rank ends with the global result, no host round trip
     if (p->xd.world < 1) return vdl_fail(ctx, VDL_EINVAL, "probe: peer exchange requested before vdl_probe_set_peers");
@@ -1020,10 +1028,12 @@ extern "C" int vdl_probe_run_ex(vdl_probe *p, int finalize) {
     probe_exchange_kernel<<<1, 256, 0, ctx->stream>>>(p->xd, d.table, ctx->d_errflag);
     p->pf.table = p->xd.peer[p->xd.rank] + (size_t)(p->xd.epoch & 1) * p->xd.world * p->xd.stride;
     p->pf.nranks = p->xd.world; p->pf.stride = p->xd.stride; p->pf.precomputed_choose = 1;
+    p->pf.seq++;
     probe_finalize_kernel<<<1, 256, 0, ctx->stream>>>(d, p->pf);
     ctx->launches += 3;
   } else if (p->folding && finalize) {
     p->pf.table = d.table; p->pf.nranks = 1; p->pf.stride = (i64)(d.nfolds + 2) * d.domain; p->pf.precomputed_choose = 0;
+    p->pf.seq++;
     probe_finalize_kernel<<<1, 256, 0, ctx->stream>>>(d, p->pf);
     ctx->launches++;
   } else if (p->folding) {
@@ -1043,7 +1053,8 @@ static int probe_fetch(vdl_probe *p) {
   if (!p->ran) return vdl_fail(ctx, VDL_EINVAL, "probe has not run");
   if (!p->finalized) return vdl_fail(ctx, VDL_EINVAL, "probe ran for an external combine: call vdl_probe_finalize first");
   if (p->fetched) return VDL_OK;
-  VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (p->folding) VDL_TRY(wait_published(ctx, p->h_out + (size_t)(p->pd.nfolds + p->pf.npost) * p->pd.domain + 2, p->pf.seq));
+  else VDL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (p->folding) {
     size_t tail = (size_t)(p->pd.nfolds + p->pf.npost) * p->pd.domain;
     i64 err = p->h_out[tail + 1];
@@ -1084,8 +1095,27 @@ extern "C" int vdl_probe_emit_take(vdl_probe *p, int k, vdl_vec *out) {
 
 extern "C" int vdl_probe_last_kernel_ms(vdl_probe *p, float *ms) {
   if (!p || !ms || !p->ran) return VDL_EINVAL;
-  VDL_CUDA(p->ctx, cudaEventSynchronize(p->ev1));
-  VDL_CUDA(p->ctx, cudaEventElapsedTime(ms, p->ev0, p->ev1));
+  const int i = (int)((p->nlaunch - 1) % VDL_EVENT_RING);
+  VDL_CUDA(p->ctx, cudaEventSynchronize(p->ev1[i]));
+  VDL_CUDA(p->ctx, cudaEventElapsedTime(ms, p->ev0[i], p->ev1[i]));
+  return VDL_OK;
+}
+
+extern "C" int vdl_probe_kernel_ms_stats(vdl_probe *p, int n, float *mean_ms, float *min_ms) {
+  if (!p || n < 1 || !p->ran) return VDL_EINVAL;
+  n = (int)std::min<long>(std::min<long>(n, VDL_EVENT_RING), p->nlaunch);
+  double sum = 0;
+  float mn = 1e30f;
+  for (int k = 1; k <= n; k++) {
+    const int i = (int)((p->nlaunch - k) % VDL_EVENT_RING);
+    float ms = 0;
+    VDL_CUDA(p->ctx, cudaEventSynchronize(p->ev1[i]));
+    VDL_CUDA(p->ctx, cudaEventElapsedTime(&ms, p->ev0[i], p->ev1[i]));
+    sum += ms;
+    mn = std::min(mn, ms);
+  }
+  if (mean_ms) *mean_ms = (float)(sum / n);
+  if (min_ms) *min_ms = mn;
   return VDL_OK;
 }
 
@@ -1102,8 +1132,7 @@ extern "C" int vdl_probe_destroy(vdl_probe *p) {
   if (p->d_total) cudaFree(p->d_total);
   if (p->d_ticket) cudaFree(p->d_ticket);
   if (p->d_state) cudaFree(p->d_state);
-  if (p->ev0) cudaEventDestroy(p->ev0);
-  if (p->ev1) cudaEventDestroy(p->ev1);
+  for (int i = 0; i < VDL_EVENT_RING; i++) { if (p->ev0[i]) cudaEventDestroy(p->ev0[i]); if (p->ev1[i]) cudaEventDestroy(p->ev1[i]); }
   delete p;
   return VDL_OK;
 }

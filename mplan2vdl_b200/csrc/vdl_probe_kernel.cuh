@@ -53,7 +53,8 @@ struct PFin {
   const i64 *table;                 // nranks tables back to back (stride int64 each); one = this rank's own
   i64 stride;
   int32_t nranks, precomputed_choose;   // precomputed_choose: FoldChoose values already sit in the tables (multi-rank)
-  i64 *out;                         // [(nfolds + npost)][domain] then [ngroups, errors]
+  i64 *out;                         // [(nfolds + npost)][domain] then [ngroups, errors] (+ [seq] in the host mirror)
+  i64 seq;                          // number of this finalize: the last word published to the host mirror
   i64 *hmirror;
   const int *errflag;
 };

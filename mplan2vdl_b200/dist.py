@@ -121,9 +121,12 @@ class ShardedPlan:
         dist.barrier(group=self.group)
         return True
 
-    def step(self, copy: bool = True) -> dict:
-        """copy=False: the arrays are views of pinned host buffers owned by the library, valid until the next step."""
+    def step(self, copy: bool = True, fetch: bool = True) -> dict:
+        """copy=False: the arrays are views of pinned host buffers owned by the library, valid until the next step.
+        fetch=False: run the step only (the results are on the host when it returns; plan.outputs() reads them)."""
         if self.world == 1 or self.peer_mode:
+            if not fetch:
+                return self.plan.execute()
             return self.plan.run(copy)                  # one launch per fused scan: its last thread block finalizes
         out = self._step_all_gather(copy)
         if self._want_peer:                             # the scans exist now: switch to the peer-memory combine

@@ -294,6 +294,12 @@ class Plan:
         self.ctx.check(self.L.vdl_fused_last_kernel_ms(f, C.byref(ms)))
         return ms.value
 
+    def kernel_ms_stats(self, n: int):
+        """(mean, min) duration in ms of the plan's dominant kernel over the last n runs (events recorded by the library)."""
+        a, b = C.c_float(), C.c_float()
+        self.ctx.check(self.L.vdl_plan_kernel_ms_stats(self.h, n, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def probe_kernel_ms(self) -> float:
         ms = C.c_float()
         self.ctx.check(self.L.vdl_plan_probe_kernel_ms(self.h, C.byref(ms)))
@@ -309,6 +315,13 @@ class Plan:
     def run(self, copy: bool = True) -> dict:
         self.ctx.check(self.L.vdl_plan_run(self.h))
         return self.outputs(copy)
+
+    def execute(self):
+        """vdl_plan_run alone: when it returns the results are in the library's pinned host buffers (outputs() wraps them
+        as arrays).  What a host that steps a plan repeatedly calls -- no Python objects are built per step."""
+        rc = self.L.vdl_plan_run(self.h)
+        if rc:
+            self.ctx.check(rc)
 
     def outputs(self, copy: bool = True) -> dict:
         """{output name: int64 array}.  copy=False returns views of the library's pinned host buffers, valid until the

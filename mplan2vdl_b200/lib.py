@@ -152,6 +152,9 @@ SYMBOLS = [
     ("vdl_fused_shape_name", C.c_char_p, [_P]),
     ("vdl_fused_destroy", _I, [_P]),
     ("vdl_fused_last_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
+    ("vdl_fused_kernel_ms_stats", _I, [_P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    ("vdl_probe_kernel_ms_stats", _I, [_P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    ("vdl_plan_kernel_ms_stats", _I, [_P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("vdl_plan_load", _I, [_P, C.c_char_p, _I, C.POINTER(_P)]),
     ("vdl_plan_stats", _I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
     ("vdl_probe_exchange_bytes", _I, [_P, _I, C.POINTER(_L)]),
