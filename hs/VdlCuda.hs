@@ -151,3 +151,6 @@ foreign import ccall safe "vdl_comm_plan_load" c_vdl_comm_plan_load :: Ptr VdlCo
 foreign import ccall safe "vdl_comm_plan_rank" c_vdl_comm_plan_rank :: Ptr VdlCommPlan -> CInt -> IO (Ptr VdlPlan)
 foreign import ccall safe "vdl_comm_plan_run" c_vdl_comm_plan_run :: Ptr VdlCommPlan -> IO CInt
 foreign import ccall safe "vdl_comm_plan_destroy" c_vdl_comm_plan_destroy :: Ptr VdlCommPlan -> IO CInt
+foreign import ccall safe "vdl_fused_kernel_ms_stats" c_vdl_fused_kernel_ms_stats :: Ptr VdlFused -> CInt -> Ptr CFloat -> Ptr CFloat -> IO CInt
+foreign import ccall safe "vdl_probe_kernel_ms_stats" c_vdl_probe_kernel_ms_stats :: Ptr VdlProbe -> CInt -> Ptr CFloat -> Ptr CFloat -> IO CInt
+foreign import ccall safe "vdl_plan_kernel_ms_stats" c_vdl_plan_kernel_ms_stats :: Ptr VdlPlan -> CInt -> Ptr CFloat -> Ptr CFloat -> IO CInt
