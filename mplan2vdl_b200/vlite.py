@@ -412,6 +412,10 @@ class Lowering:
         raise NotImplementedError(rel)
 
     # ---- group by (Vlite.hs:624-669, 1033-1194) ------------------------------------------------
+    @staticmethod
+    def _same_name(a: str, b: str) -> bool:
+        return a == b or a.endswith("." + b) or b.endswith("." + a)
+
     def shift_to_zero(self, v: Vexp) -> Vexp:             # 1139-1144
         if v.bounds[0] == 0 and v.tz == 0:
             return v
@@ -466,13 +470,31 @@ class Lowering:
             out = alias
             if agg[0] == "FChoose" and isinstance(agg[1], Ref) and alias is None:
                 out = agg[1].name
-            acc.insert(0, v.replace(name=out))
+            # 646-660: with a single group-by key, the grouped copy of that key is unique, and so is its lineage mask
+            # ("Query 18 makes this reasoning necessary")
+            quant, lineage = v.quant, v.lineage
+            if len(rel.inputkeys) == 1 and agg[0] == "FChoose" and isinstance(agg[1], Ref) and self._same_name(agg[1].name, rel.inputkeys[0][0]):
+                quant = "Unique"
+            if lineage and quant == "Unique":
+                lineage = (lineage[0], lineage[1].replace(quant="Unique"))
+            acc.insert(0, v.replace(name=out, quant=quant, lineage=lineage))
         return acc
 
     # ---- joins (Vlite.hs:682-719, 764-903, 1199-1282) ------------------------------------------------
     def join(self, rel: Join) -> list:
         left, right = self.solve(rel.left), self.solve(rel.right)
         specs, extras = self.separate_fk_joinable(rel.conds, left, right)
+        if len(specs) == 1 and not extras and specs[0][0] == "Self":       # 690, 1234-1246: one side is the whole table
+            _, leftmask, rightmask = specs[0]
+            if _is_range(rightmask, 0, 1):
+                factcols, dimcols, gathermask = left.list, right.list, leftmask
+            elif _is_range(leftmask, 0, 1):
+                factcols, dimcols, gathermask = right.list, left.list, rightmask
+            else:
+                raise NotImplementedError("TODO: handle case where both children of this self join have been modified (Vlite.hs:1241)")
+            if rel.variant != "Plain":
+                raise NotImplementedError(f"TODO: not a plain selfjoin: {rel.variant} (Vlite.hs:1246)")
+            return factcols + [gather(c, gathermask) for c in dimcols]
         if len(specs) == 1 and not extras:                 # 686-690
             order = specs[0][0]
             if order == "FactDim":
@@ -543,7 +565,15 @@ class Lowering:
         present becomes a join spec, everything else is returned as a plain condition.  (Self joins over a primary key,
         PartialSelfJoinSpec, are not restated: they stay conditions.)"""
         partial, extras = {}, []
+        selfs = {}                      # (left mask, right mask, pk id) -> [columns matched, conditions]
         for c in conds:
+            sj = self._classify_self(c, left, right)
+            if sj is not None:
+                key, col = sj
+                acc = selfs.setdefault(key, [[], []])
+                acc[0].append(col)
+                acc[1].append(c)
+                continue
             hit = self._classify(c, left, right)
             if hit is None:
                 extras.append(c)
@@ -560,7 +590,44 @@ class Lowering:
                 specs.append((order, self._masks[fm].replace(comment="factmask"), self._masks[dm].replace(comment="dimmmask"), joinidx, quant))
             else:
                 extras = origs + extras
+        for (lm, rm, pk), (cols, origs) in selfs.items():       # 791-797: a self join needs the whole primary key
+            if sorted(cols) == sorted(pk):
+                specs.append(("Self", self._masks[lm], self._masks[rm]))
+            else:
+                extras = origs + extras
         return specs, extras
+
+    def _classify_self(self, cond, left: Env, right: Env):
+        """processPartials, leftcol == rightcol (Vlite.hs:884-889): both sides descend from the SAME column, which is part of
+        its table's primary key, and one of the two masks is unique."""
+        if not (isinstance(cond, Bin) and cond.op == "Eq" and isinstance(cond.left, Ref) and isinstance(cond.right, Ref)):
+            return None
+        try:
+            sides = []
+            for name in (cond.left.name, cond.right.name):
+                for which, env in (("L", left), ("R", right)):
+                    try:
+                        sides.append((which, env.lookup(name)))
+                        break
+                    except KeyError:
+                        continue
+                else:
+                    return None
+        except KeyError:
+            return None
+        (w1, v1), (w2, v2) = sides
+        if w1 == w2 or not v1.lineage or not v2.lineage or v1.lineage[0] != v2.lineage[0]:
+            return None
+        lv, rv = (v1, v2) if w1 == "L" else (v2, v1)
+        table, col = lv.lineage[0].split(".", 1)
+        pk = [f"{table}.{c}" for c in self.cat.tables[table].pkey]
+        if lv.lineage[0] not in pk:
+            return None
+        if lv.lineage[1].quant != "Unique" and rv.lineage[1].quant != "Unique":
+            return None
+        self._masks[lv.lineage[1].sid] = lv.lineage[1]
+        self._masks[rv.lineage[1].sid] = rv.lineage[1]
+        return (lv.lineage[1].sid, rv.lineage[1].sid, tuple(pk)), lv.lineage[0]
 
     def _classify(self, cond, left: Env, right: Env):
         if not (isinstance(cond, Bin) and cond.op == "Eq" and isinstance(cond.left, Ref) and isinstance(cond.right, Ref)):

@@ -244,7 +244,7 @@ def _is_fk(data, l, rt, c):
             oa, ob = a.origin_of(an), b.origin_of(bn)
             if oa is None or ob is None:
                 return False
-            return (_unique_origin(data, a, an) != _unique_origin(data, b, bn)) or oa.endswith("%TID%") or ob.endswith("%TID%")
+            return (_unique_origin(data, a, an) != _unique_origin(data, b, bn)) or oa.endswith("%TID%") or ob.endswith("%TID%") or oa == ob
     return False
 
 

@@ -13,7 +13,7 @@ needs_reference = pytest.mark.skipif(not os.path.isdir(FIXTURES), reason="refere
 
 @needs_reference
 @pytest.mark.parametrize("n,plan", [("06", "q06.vdl"), ("03", "q03.vdl"), ("05", "q05.vdl"), ("12", "q12.vdl"), ("19", "q19.vdl"),
-                                    ("04", "q04.vdl"), ("11", "q11.vdl"), ("15", "q15.vdl"), ("09", "q09.vdl"), ("14", "q14.vdl"), ("16", "q16.vdl"), ("20", "q20.vdl")])
+                                    ("04", "q04.vdl"), ("11", "q11.vdl"), ("15", "q15.vdl"), ("09", "q09.vdl"), ("14", "q14.vdl"), ("16", "q16.vdl"), ("20", "q20.vdl"), ("10", "q10.vdl"), ("18", "q18.vdl")])
 def test_reference_fixture_translates_to_the_checked_in_program(catalog, n, plan):
     text = open(os.path.join(FIXTURES, f"{n}.sql.mplan")).read()
     assert mplan.translate_mplan(catalog, text) == plan_text(plan)      # q06.vdl is pinned by the reference README
@@ -29,7 +29,8 @@ def test_q1_fixture_gives_the_same_ir_as_the_hand_built_one(catalog):
 
 @needs_reference
 def test_unsupported_fixtures_fail_loudly_with_the_construct_named(catalog):
-    for n, what in [("13", "plain joins"), ("22", "IN operator"), ("10", "single complete FK"), ("17", "not known to be unique")]:
+    for n, what in [("13", "plain joins"), ("22", "IN operator"), ("21", "single complete FK"), ("17", "not known to be unique"),
+                    ("02", "char literal"), ("07", "char literal"), ("08", "char literal")]:
         with pytest.raises((NotImplementedError, ValueError), match=what):
             mplan.translate_mplan(catalog, open(os.path.join(FIXTURES, f"{n}.sql.mplan")).read())
 

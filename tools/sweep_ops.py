@@ -61,6 +61,7 @@ def main():
         flag = col("s.flag", n, synth.UNIFORM, 0, 2)               # 50 % selectivity predicate
         key = col("s.key", n, synth.UNIFORM, 0, 32)                # 32 buckets
         runs = col("s.runs", n, synth.FKDENSE, 0, max(1, n // 4), p1=n)   # nondecreasing, runs of ~4
+        wide = col("s.wide", n, synth.UNIFORM, 0, 1 << 38)         # unsorted 38-bit keys (Q3's composite key width)
         perm = ctx.op_partition(key, 0, 1, 32)                     # a permutation to scatter / gather by
         ctx.synchronize()
         cases = {
@@ -71,6 +72,7 @@ def main():
             "Gather (by pos_: sequential)": (lambda: [ctx.op_gather(a, ctx_pos)], 16 * n),
             "Scatter (by permutation)": (lambda: [ctx.op_scatter(a, perm, n)], 24 * n),
             "Partition (32 buckets, unsorted)": (lambda: [ctx.op_partition(key, 0, 1, 32)], 16 * n),
+            "Partition (unsorted 38-bit keys: LSD radix, 8 bits per pass)": (lambda: [ctx.op_partition(wide, 0, 1, (1 << 38) - 1)], 16 * n),
             "Partition (sorted keys -> identity)": (lambda: [ctx.op_partition(runs, 0, 1, max(1, n // 4))], 8 * n),
             "FoldSum (runs of ~4)": (lambda: [ctx.op_fold("FoldSum", runs, a)], 16 * n + 8 * (n // 4)),
             "FoldSum (one run)": (lambda: [ctx.op_fold("FoldSum", ctx_zero, a)], 8 * n),
@@ -84,7 +86,7 @@ def main():
                               "gbs": round(nbytes / best / 1e6, 1), "frac_of_measured_hbm_peak": round(nbytes / best / 1e6 / peak, 3)}), flush=True)
         for v in (perm, ctx_const, ctx_pos, ctx_zero):
             ctx.free(v)
-        for c in ("s.a", "s.b", "s.flag", "s.key", "s.runs"):
+        for c in ("s.a", "s.b", "s.flag", "s.key", "s.runs", "s.wide"):
             ctx.drop_column(c)
     ctx.close()
 
