@@ -28,6 +28,10 @@ struct Vec {
   // library can see (creation, upload, synthetic fill, vdl_column_touch).  A prepared scan / probe records
   // (handle, generation) of its columns: a different pair means other data, another allocation or a recycled handle.
   u64 gen = 0;
+  // a Fold result remembers the groups vector it was folded by: a Fold over these results with row-space groups (level 2
+  // of a hierarchical fold, Vlite.hs:1181-1192) groups them by the groups value at each level-1 run's head
+  vdl_vec fold_groups = 0;
+  u64 fold_groups_gen = 0;
   std::string name;
 };
 

@@ -612,72 +612,49 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const u64 *__restric
 
 // One-pass variant for <= 256 buckets (every low-cardinality group-by: Q1's 32, Q5's 128): the same histogram / scan,
 // then the destination of row i is written straight to out[i] -- no key / index ping-pong, no inversion pass.
-// Counting partition for up to 256 buckets, one 4096-row tile per block.  Every warp owns a contiguous 512-row slice of the
-// tile and keeps a PRIVATE histogram in shared memory: the lanes that share a bucket are found with match_any and their
-// leader adds the group's size (plain read-modify-write: one writer per (warp, bucket) at a time, no atomics, no
-// contention on 32 hot counters).  hist[d * nblocks + block] = rows of bucket d in the tile.
 __global__ void __launch_bounds__(256) bucket_hist_kernel(Operand data, i64 n, i64 pfrom, i64 pstep, i64 pcount, i64 nblocks, i64 *__restrict__ hist) {
-  __shared__ int wh[8][256];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int w = 0; w < 8; w++) wh[w][tid] = 0;
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
   __syncthreads();
-  const i64 base = (i64)blockIdx.x * RDX_TILE + (i64)warp * (RDX_TILE / 8);
-#pragma unroll 4
+  i64 base = (i64)blockIdx.x * RDX_TILE;
   for (int s = 0; s < RDX_TILE / 256; s++) {
-    const i64 i = base + s * 32 + lane;
-    const bool valid = i < n;
-    const int d = valid ? (int)bucket_of(op_ld(data, i), pfrom, pstep, pcount) : 256 + lane;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    if (valid && (peers & ((1u << lane) - 1)) == 0) wh[warp][d] += __popc(peers);
-    __syncwarp();
+    i64 i = base + s * 256 + threadIdx.x;
+    if (i < n) atomicAdd(&h[(int)bucket_of(op_ld(data, i), pfrom, pstep, pcount)], 1);
   }
   __syncthreads();
-  int c = 0;
-#pragma unroll
-  for (int w = 0; w < 8; w++) c += wh[w][tid];
-  hist[(i64)tid * nblocks + blockIdx.x] = c;
+  hist[(i64)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
-
-// Second pass: destination = tile's offset of the bucket (exclusive scan of hist) + rows of the bucket in the warps before
-// this one + rows of the bucket this warp has placed so far + rank among the lanes of this step.  Stable: warps own
-// consecutive slices, steps and lanes go in row order.  Two block barriers per tile (the tile is re-read from L1/L2).
 __global__ void __launch_bounds__(256) bucket_place_kernel(Operand data, i64 n, i64 pfrom, i64 pstep, i64 pcount, i64 nblocks,
                                                            const i64 *__restrict__ offs, i64 *__restrict__ out) {
-  __shared__ int wh[8][256];          // per-warp counts, then per-warp running offsets
+  __shared__ int wcount[8][256];
+  __shared__ int wbase[8][256];
+  __shared__ int run[256];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int w = 0; w < 8; w++) wh[w][tid] = 0;
+  for (int w = 0; w < 8; w++) wcount[w][tid] = 0;
+  run[tid] = 0;
   __syncthreads();
-  const i64 base = (i64)blockIdx.x * RDX_TILE + (i64)warp * (RDX_TILE / 8);
-#pragma unroll 4
+  i64 base = (i64)blockIdx.x * RDX_TILE;
   for (int s = 0; s < RDX_TILE / 256; s++) {
-    const i64 i = base + s * 32 + lane;
-    const bool valid = i < n;
-    const int d = valid ? (int)bucket_of(op_ld(data, i), pfrom, pstep, pcount) : 256 + lane;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    if (valid && (peers & ((1u << lane) - 1)) == 0) wh[warp][d] += __popc(peers);
-    __syncwarp();
-  }
-  __syncthreads();
-  {   // thread tid = bucket tid: exclusive prefix over the warps
-    int off = 0;
+    i64 i = base + s * 256 + tid;
+    bool valid = i < n;
+    int d = valid ? (int)bucket_of(op_ld(data, i), pfrom, pstep, pcount) : 256 + lane;
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    int rank_in_warp = __popc(peers & ((1u << lane) - 1));
+    if (valid && rank_in_warp == 0) wcount[warp][d] = __popc(peers);
+    __syncthreads();
+    {
+      int off = run[tid];
 #pragma unroll
-    for (int w = 0; w < 8; w++) { const int c = wh[w][tid]; wh[w][tid] = off; off += c; }
-  }
-  __syncthreads();
-  const i64 *tile_off = offs + blockIdx.x;
-  for (int s = 0; s < RDX_TILE / 256; s++) {
-    const i64 i = base + s * 32 + lane;
-    const bool valid = i < n;
-    const int d = valid ? (int)bucket_of(op_ld(data, i), pfrom, pstep, pcount) : 256 + lane;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int rank = __popc(peers & ((1u << lane) - 1));
-    if (valid) {
-      const int before = wh[warp][d];
-      out[i] = tile_off[(i64)d * nblocks] + before + rank;
+      for (int w = 0; w < 8; w++) {
+        int c = wcount[w][tid];
+        wcount[w][tid] = 0;
+        wbase[w][tid] = off;
+        off += c;
+      }
+      run[tid] = off;
     }
-    __syncwarp();
-    if (valid && rank == 0) wh[warp][d] += __popc(peers);
-    __syncwarp();
+    __syncthreads();
+    if (valid) out[i] = offs[(i64)d * nblocks + blockIdx.x] + wbase[warp][d] + rank_in_warp;
   }
 }
 
@@ -692,13 +669,11 @@ __global__ void __launch_bounds__(256) descents_kernel(Operand data, i64 n, i64 
   const i64 stride = (i64)gridDim.x * blockDim.x * 4;
   int bad = 0;
   for (i64 i0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += stride) {
-    if (*(volatile int *)descents) break;       // somebody already found a descent: unsorted input costs almost nothing
     u64 b[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) b[k] = i0 + k < n ? bucket_of(op_ld(data, i0 + k), pfrom, pstep, pcount) : ~0ull;
 #pragma unroll
     for (int k = 0; k < 4; k++) bad |= b[k] > b[k + 1] && i0 + k + 1 < n;
-    if (bad) break;
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAdd(descents, 1);
 }
@@ -848,13 +823,29 @@ extern "C" int vdl_op_fold(vdl_ctx *ctx, int fold_op, vdl_vec groups, vdl_vec da
   if (fold_op < VDL_FOLD_SUM || fold_op > VDL_FOLD_COUNT) return vdl_fail(ctx, VDL_EINVAL, "fold op %d unknown", fold_op);
   Vec *vg = vec_get(ctx, groups), *vd = vec_get(ctx, data);
   if (!vg || !vd) return VDL_EINVAL;
-  if (vg->len != vd->len) return vdl_fail(ctx, VDL_EINVAL, "Fold: groups length %lld != data length %lld", (long long)vg->len, (long long)vd->len);
+  if (vg->len != vd->len) {
+    // Level 2 of a hierarchical fold (make2LevelFold, Vlite.hs:1181-1192): `data` holds one result per level-1 run and
+    // `groups` is still row-aligned.  Dense model: result k belongs to the group value at the first row of level-1 run k,
+    // i.e. FoldChoose(level-1 groups, groups).  Anything else of unequal lengths is an error.
+    const vdl_vec g1 = vd->fold_groups;
+    Vec *v1 = g1 > 0 && (size_t)g1 < ctx->vecs.size() && ctx->vecs[g1].live ? &ctx->vecs[g1] : nullptr;
+    if (!v1 || v1->gen != vd->fold_groups_gen || v1->len != vg->len)
+      return vdl_fail(ctx, VDL_EINVAL, "Fold: groups length %lld != data length %lld", (long long)vg->len, (long long)vd->len);
+    vdl_vec heads = 0;
+    VDL_TRY(vdl_op_fold(ctx, VDL_FOLD_CHOOSE, g1, groups, &heads));
+    int rc = vdl_op_fold(ctx, fold_op, heads, data, out);
+    vdl_vec_free(ctx, heads);
+    return rc;
+  }
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const u64 groups_gen = vg->gen;
   i64 n = vd->len;
   Operand og = operand_of(*vg), od = operand_of(*vd);
   i64 total = 0, *off = nullptr;
   if (n > 0) VDL_TRY(flag_scan(ctx, true, og, n, &off, &total));
   VDL_TRY(vec_new(ctx, VDL_I64, total, out));
+  ctx->vecs[*out].fold_groups = groups;
+  ctx->vecs[*out].fold_groups_gen = groups_gen;
   if (total == 0) return VDL_OK;
   i64 *o = (i64 *)ctx->vecs[*out].ptr;
   int grid = (int)std::max<i64>(1, std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16));

@@ -144,6 +144,72 @@ const char *BINOPS[] = {"LogicalAnd", "LogicalOr", "BitwiseAnd", "BitwiseOr", "B
                         "Add", "Subtract", "Greater", "Multiply", "Divide", "Modulo"};
 const char *FOLDS[] = {"FoldSum", "FoldMin", "FoldMax", "FoldChoose", "FoldCount"};
 
+// ---- two-level folds (--agghierarchical: make2LevelFold, Vlite.hs:1181-1192) -------------------------------------
+// Fold(op, G, Fold(op, G1, D)) equals Fold(op, G, D) for Sum / Min / Max / Choose whenever equal G1 values imply equal G
+// values (the level-1 runs then refine G's runs).  That is proven structurally, on the shapes composeKeys prints
+// (Vlite.hs:1162-1170): G1 = ((G [- c]) << k) | x with 0 <= x < 2^k, or anything at all over constant groups.  Unproven
+// pairs stay two Folds and vdl_op_fold evaluates level 2 literally (see there).
+bool const_value(const std::vector<Node> &nd, int ni, i64 *k) {
+  const Node &n = nd[ni];
+  if (n.op == N_RANGEV && n.k1 == 0) { *k = n.k0; return true; }
+  if (n.op == N_BINARY && (n.sub == VDL_ADD || n.sub == VDL_SUBTRACT)) {
+    i64 x, y;
+    if (!const_value(nd, n.a, &x) || !const_value(nd, n.b, &y)) return false;
+    *k = n.sub == VDL_ADD ? (i64)((u64)x + (u64)y) : (i64)((u64)x - (u64)y);
+    return true;
+  }
+  return false;
+}
+// the node a vector copies its length from, followed through the elementwise ops
+int length_class(const std::vector<Node> &nd, int ni) {
+  const Node &n = nd[ni];
+  if (n.op == N_RANGEV || n.op == N_BINARY) return length_class(nd, n.a);
+  if (n.op == N_GATHER) return length_class(nd, n.b);
+  return ni;
+}
+bool below_pow2(const std::vector<Node> &nd, int ni, i64 bits) {      // 0 <= value < 2^bits, structurally
+  const Node &n = nd[ni];
+  i64 k;
+  if (const_value(nd, ni, &k)) return k >= 0 && (bits >= 63 || k < ((i64)1 << bits));
+  if (n.op == N_BINARY && n.sub == VDL_BITWISE_AND) {
+    for (int side : {n.a, n.b})
+      if (const_value(nd, side, &k) && k >= 0 && (bits >= 63 || k < ((i64)1 << bits))) return true;
+  }
+  return false;
+}
+bool determines(const std::vector<Node> &nd, int x, int g, int depth = 0) {   // the value of x determines the value of g
+  if (x == g) return true;
+  if (depth > 16) return false;
+  const Node &n = nd[x];
+  if (n.op != N_BINARY) return false;
+  i64 k;
+  switch (n.sub) {
+    case VDL_ADD: case VDL_SUBTRACT:
+      return const_value(nd, n.b, &k) && determines(nd, n.a, g, depth + 1);
+    case VDL_BITSHIFT:                       // left shifts keep every bit while the key fits (composeKeys asserts < 65 bits)
+      return const_value(nd, n.b, &k) && k <= 0 && k > -63 && determines(nd, n.a, g, depth + 1);
+    case VDL_BITWISE_OR: {
+      for (int t = 0; t < 2; t++) {
+        const int hi = t ? n.b : n.a, lo = t ? n.a : n.b;
+        const Node &h = nd[hi];
+        if (h.op == N_BINARY && h.sub == VDL_BITSHIFT && const_value(nd, h.b, &k) && k <= 0 && k > -63 && below_pow2(nd, lo, -k) &&
+            determines(nd, h.a, g, depth + 1))
+          return true;
+      }
+      return false;
+    }
+    default: return false;
+  }
+}
+void collapse_two_level_fold(const std::vector<Node> &nd, Node *f) {
+  if (f->op != N_FOLD || f->sub == VDL_FOLD_COUNT || f->b < 0) return;
+  const Node &inner = nd[f->b];
+  if (inner.op != N_FOLD || inner.sub != f->sub) return;
+  if (length_class(nd, inner.a) != length_class(nd, f->a)) return;
+  i64 k;
+  if (const_value(nd, f->a, &k) || determines(nd, inner.a, f->a)) f->b = inner.b;
+}
+
 int parse_plan(vdl_plan *p, const char *text) {
   vdl_ctx *ctx = p->ctx;
   std::vector<int> canon;          // statement id -> node index (aliases resolved)
@@ -236,6 +302,7 @@ int parse_plan(vdl_plan *p, const char *text) {
     if (alias >= 0) {
       idx = alias;
     } else {
+      if (p->flags & VDL_PLAN_FUSE) collapse_two_level_fold(p->nodes, &n);
       char key[512];
       snprintf(key, sizeof key, "%d|%d|%d|%d|%d|%lld|%lld|%lld|%s", n.op, n.sub, n.a, n.b, n.c, (long long)n.k0, (long long)n.k1,
                (long long)n.k2, n.name.c_str());

@@ -396,12 +396,25 @@ def relexpr_from_mplan(catalog, text: str):
     return Front(catalog).solve(parse(text))
 
 
-def translate_mplan(catalog, text: str) -> str:
+def translate_mplan(catalog, text: str, agg_strategy="serial") -> str:
     """The whole translator (MainFuns.compile, 172-188) for the supported subset: mplan text -> Voodoo program text."""
     from . import vlite
-    return vlite.translate(catalog, relexpr_from_mplan(catalog, text))
+    return vlite.translate(catalog, relexpr_from_mplan(catalog, text), agg_strategy)
 
 
 if __name__ == "__main__":
+    import argparse
     from .meta import builtin_catalog
-    sys.stdout.write(translate_mplan(builtin_catalog(), open(sys.argv[1]).read() if len(sys.argv) > 1 else sys.stdin.read()))
+    ap = argparse.ArgumentParser(prog="python -m mplan2vdl_b200.mplan", description="mplan -> Voodoo program (the reference's tpchrun)")
+    ap.add_argument("mplanfile", nargs="?", default="-")
+    g = ap.add_mutually_exclusive_group()                  # MainFuns.hs:61-65
+    g.add_argument("--aggserial", action="store_true")
+    g.add_argument("--agghierarchical", action="store_true")
+    g.add_argument("--aggshuffle", action="store_true")
+    ap.add_argument("-g", "--grainsize", type=int, default=8192, help="power of 2; only with --agghierarchical")
+    a = ap.parse_args()
+    if a.grainsize < 1 or a.grainsize & (a.grainsize - 1):
+        sys.exit("grainsize must be a power of 2 (MainFuns.hs:112)")
+    strategy = ("hierarchical", a.grainsize.bit_length() - 1) if a.agghierarchical else ("shuffle" if a.aggshuffle else "serial")
+    src = sys.stdin.read() if a.mplanfile == "-" else open(a.mplanfile).read()
+    sys.stdout.write(translate_mplan(builtin_catalog(), src, strategy))

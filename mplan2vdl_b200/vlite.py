@@ -297,8 +297,11 @@ class Env:
 class Lowering:
     """vexpsFromMplan (Vlite.hs:522-523) over a catalogue (mplan2vdl_b200.meta.Catalog = the reference's Config)."""
 
-    def __init__(self, catalog):
+    def __init__(self, catalog, agg_strategy="serial"):
+        """agg_strategy: "serial" (--aggserial, the default), "shuffle" (--aggshuffle) or ("hierarchical", log2 of the grain
+        size) (--agghierarchical -g GRAIN; MainFuns.hs:61-65, 139-147)."""
         self.cat = catalog
+        self.agg = agg_strategy
         # makeFKEntries (Config.hs:200-218): every foreign key is known by its column pairs ("implicit": l_orderkey =
         # o_orderkey; composite keys need all their pairs) and by its index column against the dimension's row ids
         # ("explicit": lineitem.lineitem_orders = orders.%TID%), in both argument orders
@@ -434,12 +437,26 @@ class Lowering:
         hint = const_(max_for_width(out), out).replace(comment="size hint for voodoo backend")
         return binop("BitAnd", out, hint)
 
-    def scatter_mask(self, gkey: Vexp) -> Vexp:           # getScatterMask 1082-1098, AggSerial
+    def scatter_mask(self, gkey: Vexp):                   # getScatterMask 1082-1098 -> (mask, sparse?)
         lo, hi = gkey.bounds
         if lo == hi:
-            return pos_(gkey)
+            return pos_(gkey), False
         pivots = complete("RangeC", (), (lo, 1, hi - lo + 1))
-        return complete("Partition", (pivots, gkey))
+        sparse = hi - lo + 1 > 32000                       # getSparsity 1076-1079
+        pdata = gkey
+        if self.agg != "serial" and (self.agg == "shuffle" or sparse):
+            pdata = complete("VShuffle", (gkey,))          # 1093-1097
+        return complete("Partition", (pivots, pdata)), sparse
+
+    def make_2level_fold(self, sparse: bool, foldop: str, fgroups: Vexp, fdata: Vexp) -> Vexp:      # 1173-1194
+        if sparse or not (isinstance(self.agg, tuple) and self.agg[0] == "hierarchical"):
+            return fold(foldop, fgroups, fdata)
+        gsz = self.agg[1]
+        pos = pos_(fgroups)
+        level1par = binop("BitAnd", binop("BitShift", pos, const_(gsz, fgroups)), ones_(fgroups))     # (pos >> log2 grain) & 1
+        level1groups = self.compose_keys(fgroups, level1par)
+        level1 = fold(foldop, level1groups, fdata)         # runs of at most `grain` rows
+        return fold(foldop, fgroups, level1)               # ... folded again per group
 
     def solve_agg(self, env: Env, after: Env, gkey: Vexp, agg) -> Vexp:   # 1033-1070
         if agg[0] == "Avg":
@@ -453,8 +470,8 @@ class Lowering:
             except KeyError:
                 pass
         gdata = self.sc(env, expr)
-        mask = self.scatter_mask(gkey)
-        return fold(foldop, scattered_to(gkey, mask), scattered_to(gdata, mask))   # make2LevelFold, AggSerial: plain Fold
+        mask, sparse = self.scatter_mask(gkey)
+        return self.make_2level_fold(sparse, foldop, scattered_to(gkey, mask), scattered_to(gdata, mask))
 
     def group_by(self, rel: GroupBy) -> list:
         child = self.solve(rel.child)
@@ -836,6 +853,7 @@ def emit(vexps: list) -> str:
     return "\n".join(e.lines) + "\n"
 
 
-def translate(catalog, rel) -> str:
-    """compile (MainFuns.hs:172-188) with the default flags: cleanup passes on, no push-joins, VdlFormat, AggSerial."""
-    return emit(cleanup(Lowering(catalog).solve_list(rel)))
+def translate(catalog, rel, agg_strategy="serial") -> str:
+    """compile (MainFuns.hs:172-188) with the default flags: cleanup passes on, no push-joins, VdlFormat; the aggregation
+    strategy is --aggserial unless given (see Lowering)."""
+    return emit(cleanup(Lowering(catalog, agg_strategy).solve_list(rel)))

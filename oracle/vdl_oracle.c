@@ -39,6 +39,9 @@
  *   Fold{Sum,Min,Max,Choose,Count}    one output per run of equal consecutive `groups`
  *       ,val,Id groups,val,Id data    values, in run order; Choose = first of run (G6);
  *                                     empty input -> empty output (G14)                      Vlite.hs:1048-1070; Vdl.hs:255-264
+ *                                     2-level folds (--agghierarchical, Vlite.hs:1181-1192) fold the level-1 RESULTS by
+ *                                     the row-space groups: in the dense model the data then has one entry per
+ *                                     level-1 run and is grouped by the groups value at that run's first row
  *   Shuffle,Id n                      identity (order-destroying hint)                        Vdl.hs:449-450
  *   MaterializeCompact,Id n           query output; name = the Project's <out>               Vdl.hs:278-292,452-453
  *   Like,val,Id d,val,Id heap,val,pat out[i] = 1 if the NUL-terminated string at byte offset d[i] of the column's string
@@ -482,6 +485,17 @@ int orc_run(orc_env *e, const char *plan_text, int nthreads) {
   clear_outputs(e);
   if (parse_plan(e, plan_text, &st, &n)) return -1;
   e->nstmts = n;
+  /* a Fold over the results of a Fold (make2LevelFold, Vlite.hs:1181-1192) re-reads the inner Fold's groups */
+  for (int i = 0; i < n; i++) {
+    int op = st[i].op;
+    if ((op == OP_FCHOOSE || op == OP_FMAX || op == OP_FSUM || op == OP_FMIN || op == OP_FCOUNT) && st[i].b > 0) {
+      stmt *inner = &st[st[i].b - 1];
+      while (inner->op == OP_PROJECT || inner->op == OP_SHUFFLE) inner = &st[inner->a - 1];
+      int iop = inner->op;
+      if ((iop == OP_FCHOOSE || iop == OP_FMAX || iop == OP_FSUM || iop == OP_FMIN || iop == OP_FCOUNT) && inner->a > 0 && st[inner->a - 1].lastuse < i)
+        st[inner->a - 1].lastuse = i;
+    }
+  }
   if (nthreads > 0) omp_set_num_threads(nthreads);
   vec *val = (vec *)calloc((size_t)n + 1, sizeof(vec));
   e->outs = (output *)calloc((size_t)n + 1, sizeof(output));
@@ -525,7 +539,21 @@ int orc_run(orc_env *e, const char *plan_text, int nthreads) {
       case OP_SCATTER: rc = op_scatter(e, A, C, &r); break;
       case OP_PARTITION: rc = op_partition(e, A, B, &r); break;
       case OP_LIKE: rc = op_like(e, A, B, s->name, &r); break;
-      case OP_FCHOOSE: case OP_FMAX: case OP_FSUM: case OP_FMIN: case OP_FCOUNT: rc = op_fold(e, s->op, A, B, &r); break;
+      case OP_FCHOOSE: case OP_FMAX: case OP_FSUM: case OP_FMIN: case OP_FCOUNT: {
+        if (A->n != B->n) {   /* level 2 of a hierarchical fold: group the level-1 results by the groups at each run's head */
+          stmt *inner = &st[s->b - 1];
+          while (inner->op == OP_PROJECT || inner->op == OP_SHUFFLE) inner = &st[inner->a - 1];
+          int iop = inner->op;
+          vec *g1 = (iop == OP_FCHOOSE || iop == OP_FMAX || iop == OP_FSUM || iop == OP_FMIN || iop == OP_FCOUNT) ? &val[inner->a] : NULL;
+          if (g1 && g1->valid && g1->n == A->n) {
+            vec eff; memset(&eff, 0, sizeof eff);
+            rc = op_fold(e, OP_FCHOOSE, g1, A, &eff);
+            if (!rc) { rc = op_fold(e, s->op, &eff, B, &r); vfree(&eff); }
+            break;
+          }
+        }
+        rc = op_fold(e, s->op, A, B, &r); break;
+      }
       case OP_MATERIALIZE: {
         output *o = &e->outs[e->nouts++];
         const char *nm = st[s->a - 1].op == OP_PROJECT ? st[s->a - 1].name : "val";
