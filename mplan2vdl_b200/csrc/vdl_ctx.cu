@@ -127,6 +127,7 @@ int vec_new(vdl_ctx *ctx, int dtype, i64 len, vdl_vec *out) {
 void vec_written(vdl_ctx *ctx, Vec *v) {
   v->gen = ++ctx->gen_counter;
   v->has_stats = false;
+  v->is_perm = false;
 }
 
 bool vec_identity(vdl_ctx *ctx, vdl_vec h, u64 *gen) {

@@ -20,6 +20,7 @@ struct Vec {
   bool owned = false;
   bool live = false;
   bool is_range = false;
+  bool is_perm = false;        // a Partition result: a permutation of 0..len-1, so a Scatter by it writes every slot
   i64 from = 0, step = 0;
   i64 domain = -1;          // length of the vector these values index into; -1 unknown (App. G2)
   bool has_stats = false;   // vmin/vmax computed on the device by vdl_column_analyze (invalidated by writes)

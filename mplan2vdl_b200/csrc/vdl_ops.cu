@@ -8,6 +8,7 @@
 #include <memory>
 
 #include "vdl_internal.h"
+#include <type_traits>
 
 __device__ __forceinline__ i64 op_ld(const Operand &o, i64 i) {
   if (o.kind == 0) return ((const i64 *)o.p)[i];
@@ -304,75 +305,10 @@ static void device_exclusive_scan(vdl_ctx *ctx, i64 *data, i64 n) {
   ctx->launches += 2;
 }
 
-#define SEL_TILE 4096   // rows per block of the flag-count / compaction kernels (16 steps of 256)
-
-// flag(i): FoldSelect -> pred[i] != 0 ; Fold head -> i == 0 || g[i] != g[i-1]
-template <bool HEADS>
-__device__ __forceinline__ bool flag_at(const Operand &o, i64 i) {
-  if (!HEADS) return op_ld(o, i) != 0;
-  return i == 0 || op_ld(o, i) != op_ld(o, i - 1);
-}
-
-template <bool HEADS>
-__global__ void __launch_bounds__(256) flag_count_kernel(Operand o, i64 n, i64 *__restrict__ block_count) {
-  __shared__ int wsum[8];
-  i64 base = (i64)blockIdx.x * SEL_TILE;
-  int c = 0;
-  for (int s = 0; s < SEL_TILE / 256; s++) {
-    i64 i = base + s * 256 + threadIdx.x;
-    c += (i < n) && flag_at<HEADS>(o, i);
-  }
-#pragma unroll
-  for (int k = 16; k > 0; k >>= 1) c += __shfl_xor_sync(0xffffffffu, c, k);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int w = 0; w < 8; w++) t += wsum[w];
-    block_count[blockIdx.x] = t;
-  }
-}
-
-// Rank of every flagged element inside its block step, by warp ballots (stream compaction without atomics).
-struct StepRank {
-  int rank;    // number of flagged elements before this one in the block so far (valid when flagged)
-  int incl;    // flagged elements up to and including this one (valid for every element)
-};
-__device__ __forceinline__ StepRank step_rank(bool flag, int *wcnt /*[8]*/, int &run) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned m = __ballot_sync(0xffffffffu, flag);
-  if (lane == 0) wcnt[warp] = __popc(m);
-  __syncthreads();
-  int before = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < 8; w++) {
-    int c = wcnt[w];
-    if (w < warp) before += c;
-    total += c;
-  }
-  StepRank r;
-  r.rank = run + before + __popc(m & ((1u << lane) - 1));
-  r.incl = r.rank + (flag ? 1 : 0);
-  run += total;
-  __syncthreads();
-  return r;
-}
+#define SEL_TILE 4096   // rows per tile of the compaction kernel (16 steps of 256)
 
 // ---------------------------------------------------------------------------------- FoldSelect
 // Vlite.hs:721-730: idx = Fold FSel (pos_ p) p.  Dense model: global stable compaction of positions.
-static int flag_scan(vdl_ctx *ctx, bool heads, const Operand &o, i64 n, i64 **block_off, i64 *total) {
-  i64 nb = (n + SEL_TILE - 1) / SEL_TILE;
-  VDL_TRY(scratch_reserve(ctx, scan_elems(nb) * 8));
-  i64 *cnt = (i64 *)ctx->scratch;
-  if (heads) flag_count_kernel<true><<<(unsigned)nb, 256, 0, ctx->stream>>>(o, n, cnt);
-  else flag_count_kernel<false><<<(unsigned)nb, 256, 0, ctx->stream>>>(o, n, cnt);
-  ctx->launches++;
-  device_exclusive_scan(ctx, cnt, nb);
-  VDL_TRY(read_scalar(ctx, cnt + nb, total, 8));
-  *block_off = cnt;
-  return VDL_OK;
-}
-
 // Single pass: a block takes 4096-element tiles in ticket order, reads its predicates ONCE (16 flags per thread kept
 // as a bit mask), gets the tile's output offset by a decoupled look-back over one 64-bit status word per tile
 // ((status << 62) | count; 1 = tile aggregate, 2 = inclusive prefix) and writes the positions in order.
@@ -497,8 +433,20 @@ extern "C" int vdl_op_gather(vdl_ctx *ctx, vdl_vec src, vdl_vec pos, vdl_vec *ou
 // Scatter (Vlite.hs:1057-1059 group sort, 1268-1275 dim validity / inverse index): out[pos[i]] = src[i],
 // unwritten slots 0.  Positions are unique in every use the translator emits (permutations, Unique masks).
 __global__ void __launch_bounds__(256) scatter_kernel(Operand src, Operand pos, i64 n, i64 *__restrict__ out, i64 out_len, int *errflag) {
-  i64 stride = (i64)gridDim.x * blockDim.x;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  // 4 independent (position, value) pairs per thread and step: the stores are fire-and-forget, the loads are what waits
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    i64 p[4], v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { p[k] = op_ld(pos, i + k * stride); v[k] = op_ld(src, i + k * stride); }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if ((u64)p[k] >= (u64)out_len) atomicAdd(errflag, 1);
+      else out[p[k]] = v[k];
+    }
+  }
+  for (; i < n; i += stride) {
     i64 p = op_ld(pos, i);
     if ((u64)p >= (u64)out_len) atomicAdd(errflag, 1);
     else out[p] = op_ld(src, i);
@@ -512,13 +460,14 @@ extern "C" int vdl_op_scatter(vdl_ctx *ctx, vdl_vec src, vdl_vec pos, int64_t ou
   if (vs->len != vp->len) return vdl_fail(ctx, VDL_EINVAL, "Scatter: source length %lld != positions length %lld", (long long)vs->len, (long long)vp->len);
   if (out_len < 0) return vdl_fail(ctx, VDL_EINVAL, "Scatter: negative output length");
   i64 n = vs->len, dom = vs->domain;
+  const bool covers = vp->is_perm && out_len == n;      // a permutation of 0..n-1 leaves no slot unwritten: nothing to zero
   Operand os = operand_of(*vs), op = operand_of(*vp);
   VDL_TRY(vec_new(ctx, VDL_I64, out_len, out));
   ctx->vecs[*out].domain = dom;
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (out_len > 0) VDL_CUDA(ctx, cudaMemsetAsync(ctx->vecs[*out].ptr, 0, (size_t)out_len * 8, ctx->stream));
+  if (out_len > 0 && !covers) VDL_CUDA(ctx, cudaMemsetAsync(ctx->vecs[*out].ptr, 0, (size_t)out_len * 8, ctx->stream));
   if (n == 0) return VDL_OK;
-  int blocks = (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 16));
+  int blocks = (int)std::max<i64>(1, std::min<i64>((n + 1023) / 1024, (i64)ctx->sm_count * 16));
   scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(os, op, n, (i64 *)ctx->vecs[*out].ptr, out_len, ctx->d_errflag);
   ctx->launches++;
   VDL_CUDA(ctx, cudaGetLastError());
@@ -610,52 +559,179 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const u64 *__restric
   }
 }
 
-// One-pass variant for <= 256 buckets (every low-cardinality group-by: Q1's 32, Q5's 128): the same histogram / scan,
-// then the destination of row i is written straight to out[i] -- no key / index ping-pong, no inversion pass.
-__global__ void __launch_bounds__(256) bucket_hist_kernel(Operand data, i64 n, i64 pfrom, i64 pstep, i64 pcount, i64 nblocks, i64 *__restrict__ hist) {
-  __shared__ int h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  i64 base = (i64)blockIdx.x * RDX_TILE;
-  for (int s = 0; s < RDX_TILE / 256; s++) {
-    i64 i = base + s * 256 + threadIdx.x;
-    if (i < n) atomicAdd(&h[(int)bucket_of(op_ld(data, i), pfrom, pstep, pcount)], 1);
-  }
-  __syncthreads();
-  hist[(i64)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+// Counting partition for <= 256 buckets (every low-cardinality group-by: Q1's 32, Q5's 128): two passes over the keys, no
+// key / index ping-pong, no inversion.  The unit of work is a WARP: warp gw owns the contiguous rows [gw*chunk, (gw+1)*chunk)
+// and a private table in shared memory, so neither pass has a block barrier or an atomic (a shared-memory atomic costs
+// 32-64 cycles per warp instruction -- more than the whole per-row budget at HBM speed).  Per 32 rows the lanes that share
+// a bucket are found with one ballot per bucket-index bit; the first of them updates the warp's table with a plain
+// read-modify-write.
+//   pass 1 (bucket_count_kernel): hist[d * nwarps + gw] = rows of bucket d in warp gw's chunk; the same pass counts the
+//          descents, so keys that are already in bucket order cost ONE read (the Partition then stays an identity range);
+//   scan over hist (bucket-major = the global stable order);
+//   pass 2 (bucket_place_kernel): out[i] = running position of row i's bucket in its warp's table + rank among the 32.
+#define CP_UNROLL 8
+// bucket index of row i for unit-step pivots (every emitted Partition: Vlite.hs:1088-1091), operand kind fixed at compile time
+template <int KIND>
+__device__ __forceinline__ int bucket_at(const Operand &o, i64 i, i64 pfrom, i64 pcount) {
+  const i64 v = KIND == 0 ? __ldg((const i64 *)o.p + i) : (KIND == 1 ? (i64)__ldg((const int *)o.p + i) : (i64)((u64)o.from + (u64)i * (u64)o.step));
+  if (v <= pfrom) return 0;
+  const u64 d = (u64)v - (u64)pfrom;
+  return (int)(d > (u64)pcount ? (u64)pcount : d);
 }
-__global__ void __launch_bounds__(256) bucket_place_kernel(Operand data, i64 n, i64 pfrom, i64 pstep, i64 pcount, i64 nblocks,
-                                                           const i64 *__restrict__ offs, i64 *__restrict__ out) {
-  __shared__ int wcount[8][256];
-  __shared__ int wbase[8][256];
-  __shared__ int run[256];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int w = 0; w < 8; w++) wcount[w][tid] = 0;
-  run[tid] = 0;
-  __syncthreads();
-  i64 base = (i64)blockIdx.x * RDX_TILE;
-  for (int s = 0; s < RDX_TILE / 256; s++) {
-    i64 i = base + s * 256 + tid;
-    bool valid = i < n;
-    int d = valid ? (int)bucket_of(op_ld(data, i), pfrom, pstep, pcount) : 256 + lane;
-    unsigned peers = __match_any_sync(0xffffffffu, d);
-    int rank_in_warp = __popc(peers & ((1u << lane) - 1));
-    if (valid && rank_in_warp == 0) wcount[warp][d] = __popc(peers);
-    __syncthreads();
-    {
-      int off = run[tid];
-#pragma unroll
-      for (int w = 0; w < 8; w++) {
-        int c = wcount[w][tid];
-        wcount[w][tid] = 0;
-        wbase[w][tid] = off;
-        off += c;
-      }
-      run[tid] = off;
-    }
-    __syncthreads();
-    if (valid) out[i] = offs[(i64)d * nblocks + blockIdx.x] + wbase[warp][d] + rank_in_warp;
+// lanes whose bucket index has bit K set.  Written in PTX so that the test stays "and, compare with zero" (one LOP3 with a
+// predicate result): the compiler's own canonical form is shift, mask, compare -- three instructions of the pipe that bounds
+// these kernels, per bit and row.
+template <int K>
+__device__ __forceinline__ unsigned ballot_bit(int d) {
+  unsigned b;
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}"
+               : "=r"(b) : "r"(d), "n"(1 << K));
+  return b;
+}
+template <int NBITS, int K = 0>
+struct BucketBits {
+  static __device__ __forceinline__ unsigned same(int d, unsigned peers) {          // lanes that agree with mine on bits K..NBITS-1
+    const unsigned b = ballot_bit<K>(d);
+    return BucketBits<NBITS, K + 1>::same(d, peers & ((d & (1 << K)) ? b : ~b));
   }
+  static __device__ __forceinline__ unsigned owned(int d, unsigned a, const unsigned (&inv)[5]) {   // bits K..min(NBITS,5)-1 against the lane's own id
+    return BucketBits<NBITS, K + 1>::owned(d, a & (ballot_bit<K>(d) ^ inv[K]), inv);
+  }
+};
+template <int NBITS>
+struct BucketBits<NBITS, NBITS> {
+  static __device__ __forceinline__ unsigned same(int, unsigned peers) { return peers; }
+  static __device__ __forceinline__ unsigned owned(int, unsigned a, const unsigned (&)[5]) { return a; }
+};
+template <int NBITS>
+__device__ __forceinline__ unsigned same_bucket_lanes(int d, unsigned valid_lanes) { return BucketBits<NBITS>::same(d, valid_lanes); }
+// Up to 64 buckets: lane l OWNS buckets l and l + 32.  m0 / m1 = the rows (lanes) of this step that fall into them: one
+// ballot per bucket-index bit, combined with masks that depend on the lane id only -- the kernels are bound by the integer
+// pipe, and this costs a third of the selects and compares of asking "who shares MY row's bucket" in every lane.
+template <int NBITS, bool FULL>
+__device__ __forceinline__ void owned_bucket_rows(int d, bool valid, const unsigned (&inv)[5], unsigned *m0, unsigned *m1) {
+  const unsigned a = BucketBits<(NBITS < 5 ? NBITS : 5)>::owned(d, FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid), inv);
+  if (NBITS > 5) {
+    const unsigned b5 = ballot_bit<5>(d);
+    *m0 = a & ~b5; *m1 = a & b5;
+  } else {
+    *m0 = a; *m1 = 0;
+  }
+}
+
+template <int NBITS, int KIND>
+__global__ void __launch_bounds__(256, 5) bucket_count_kernel(Operand data, i64 n, i64 pfrom, i64 pcount, i64 chunk, i64 nwarps,
+                                                              i64 *__restrict__ hist, int *descents) {
+  __shared__ unsigned wh[8][NBITS > 6 ? 1 << NBITS : 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const i64 gw = (i64)blockIdx.x * 8 + w;
+  if (gw >= nwarps) return;
+  unsigned *h = wh[w];
+  if (NBITS > 6) {
+    for (int d = lane; d < (1 << NBITS); d += 32) h[d] = 0;
+    __syncwarp();
+  }
+  unsigned inv[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) inv[k] = (lane >> k & 1) ? 0u : ~0u;
+  unsigned cnt0 = 0, cnt1 = 0;
+  const i64 r0 = gw * chunk, r1 = r0 + chunk < n ? r0 + chunk : n;
+  const unsigned lt = (1u << lane) - 1;
+  int bad = 0;
+  int prev = r0 > 0 && r0 < n ? bucket_at<KIND>(data, r0 - 1, pfrom, pcount) : 0;
+  auto step = [&](const i64 base, auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;          // all 32 * CP_UNROLL rows exist: no bounds tests, no validity ballot
+    int d[CP_UNROLL];
+#pragma unroll
+    for (int u = 0; u < CP_UNROLL; u++) {
+      const i64 i = base + u * 32 + lane;
+      d[u] = FULL || i < r1 ? bucket_at<KIND>(data, i, pfrom, pcount) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < CP_UNROLL; u++) {
+      const bool valid = FULL || d[u] >= 0;
+      int left = __shfl_up_sync(0xffffffffu, d[u], 1);
+      if (lane == 0) left = prev;
+      bad |= valid && left > d[u];
+      prev = __shfl_sync(0xffffffffu, d[u], 31);
+      if (NBITS <= 6) {
+        unsigned m0, m1;
+        owned_bucket_rows<NBITS, FULL>(valid ? d[u] : 0, valid, inv, &m0, &m1);
+        cnt0 += __popc(m0);
+        if (NBITS > 5) cnt1 += __popc(m1);
+      } else {
+        const unsigned peers = same_bucket_lanes<NBITS>(d[u], FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid));
+        if (valid && (peers & lt) == 0) h[d[u]] += __popc(peers);
+        __syncwarp();
+      }
+    }
+  };
+  i64 base = r0;
+  for (; base + 32 * CP_UNROLL <= r1; base += 32 * CP_UNROLL) step(base, std::true_type());
+  if (base < r1) step(base, std::false_type());
+  if (NBITS <= 6) {
+    if (lane <= pcount) hist[(i64)lane * nwarps + gw] = cnt0;
+    if (NBITS > 5 && lane + 32 <= pcount) hist[(i64)(lane + 32) * nwarps + gw] = cnt1;
+  } else {
+    for (int d = lane; d <= pcount; d += 32) hist[(i64)d * nwarps + gw] = h[d];
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(descents, 1);
+}
+
+template <int NBITS, int KIND>
+__global__ void __launch_bounds__(256, 5) bucket_place_kernel(Operand data, i64 n, i64 pfrom, i64 pcount, i64 chunk, i64 nwarps,
+                                                              const i64 *__restrict__ offs, i64 *__restrict__ out) {
+  __shared__ i64 wpos[8][1 << NBITS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const i64 gw = (i64)blockIdx.x * 8 + w;
+  if (gw >= nwarps) return;
+  i64 *pos = wpos[w];
+  for (int d = lane; d <= pcount; d += 32) pos[d] = offs[(i64)d * nwarps + gw];
+  __syncwarp();
+  unsigned inv[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) inv[k] = (lane >> k & 1) ? 0u : ~0u;
+  unsigned cnt0 = 0, cnt1 = 0;            // rows of this warp's chunk so far in the buckets this lane owns
+  const i64 r0 = gw * chunk, r1 = r0 + chunk < n ? r0 + chunk : n;
+  const unsigned lt = (1u << lane) - 1;
+  auto step = [&](const i64 base, auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
+    int d[CP_UNROLL];
+#pragma unroll
+    for (int u = 0; u < CP_UNROLL; u++) {
+      const i64 i = base + u * 32 + lane;
+      d[u] = FULL || i < r1 ? bucket_at<KIND>(data, i, pfrom, pcount) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < CP_UNROLL; u++) {
+      const bool valid = FULL || d[u] >= 0;
+      if (NBITS <= 6) {
+        const int dd = valid ? d[u] : 0;
+        unsigned m0, m1;
+        owned_bucket_rows<NBITS, FULL>(dd, valid, inv, &m0, &m1);
+        // what the owner of my row's bucket knows: the rows of this step in it, and the rows before this step
+        unsigned peers = __shfl_sync(0xffffffffu, m0, dd & 31), before = __shfl_sync(0xffffffffu, cnt0, dd & 31);
+        if (NBITS > 5) {
+          const unsigned peers1 = __shfl_sync(0xffffffffu, m1, dd & 31), before1 = __shfl_sync(0xffffffffu, cnt1, dd & 31);
+          if (dd & 32) { peers = peers1; before = before1; }
+        }
+        if (valid) out[base + u * 32 + lane] = pos[dd] + (i64)(before + __popc(peers & lt));
+        cnt0 += __popc(m0);
+        if (NBITS > 5) cnt1 += __popc(m1);
+      } else {
+        const unsigned peers = same_bucket_lanes<NBITS>(d[u], FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid));
+        const int rank = __popc(peers & lt);
+        const i64 at = valid ? pos[d[u]] : 0;
+        if (valid) out[base + u * 32 + lane] = at + rank;
+        __syncwarp();
+        if (valid && rank == 0) pos[d[u]] = at + __popc(peers);
+        __syncwarp();
+      }
+    }
+  };
+  i64 base = r0;
+  for (; base + 32 * CP_UNROLL <= r1; base += 32 * CP_UNROLL) step(base, std::true_type());
+  if (base < r1) step(base, std::false_type());
 }
 
 __global__ void __launch_bounds__(256) invert_perm_kernel(const i64 *__restrict__ order, i64 n, i64 *__restrict__ out) {
@@ -686,6 +762,51 @@ extern "C" int vdl_op_partition(vdl_ctx *ctx, vdl_vec data, int64_t pfrom, int64
   i64 n = vd->len;
   Operand od = operand_of(*vd);
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  int bits = 0;
+  while (bits < 63 && ((u64)pcount >> bits)) bits++;
+  if (n > 0 && pcount < 256 && pstep == 1) {   // buckets 0..pcount fit one digit: counting partition, sortedness checked by its first pass
+    const int nbits = bits <= 2 ? 2 : (bits <= 4 ? 4 : (bits <= 5 ? 5 : (bits <= 6 ? 6 : 8)));
+    const i64 step = 32 * CP_UNROLL;
+    i64 nwarps = std::min<i64>((n + step - 1) / step, (i64)ctx->sm_count * 5 * 8);      // one wave: 5 blocks of 8 warps per SM (48 registers)
+    const i64 chunk = ((n + nwarps - 1) / nwarps + step - 1) / step * step;
+    nwarps = (n + chunk - 1) / chunk;
+    const unsigned grid = (unsigned)((nwarps + 7) / 8);
+    const i64 nh = (pcount + 1) * nwarps;
+    VDL_TRY(scratch_reserve(ctx, (scan_elems(nh) + 8) * 8));
+    i64 *h = (i64 *)ctx->scratch;
+    int *d_desc = (int *)(h + scan_elems(nh)), h_desc = 1;
+    VDL_CUDA(ctx, cudaMemsetAsync(d_desc, 0, sizeof(int), ctx->stream));
+#define CP_LAUNCH_K(KERNEL, NB, ...)                                                                                  \
+    switch (od.kind) {                                                                                                \
+      case 0: KERNEL<NB, 0><<<grid, 256, 0, ctx->stream>>>(__VA_ARGS__); break;                                       \
+      case 1: KERNEL<NB, 1><<<grid, 256, 0, ctx->stream>>>(__VA_ARGS__); break;                                       \
+      default: KERNEL<NB, 2><<<grid, 256, 0, ctx->stream>>>(__VA_ARGS__); break;                                      \
+    }
+#define CP_LAUNCH(KERNEL, ...)                                                                                        \
+    switch (nbits) {                                                                                                  \
+      case 2: CP_LAUNCH_K(KERNEL, 2, __VA_ARGS__) break;                                                              \
+      case 4: CP_LAUNCH_K(KERNEL, 4, __VA_ARGS__) break;                                                              \
+      case 5: CP_LAUNCH_K(KERNEL, 5, __VA_ARGS__) break;                                                              \
+      case 6: CP_LAUNCH_K(KERNEL, 6, __VA_ARGS__) break;                                                              \
+      default: CP_LAUNCH_K(KERNEL, 8, __VA_ARGS__) break;                                                             \
+    }
+    CP_LAUNCH(bucket_count_kernel, od, n, pfrom, pcount, chunk, nwarps, h, d_desc)
+    ctx->launches++;
+    VDL_TRY(read_scalar(ctx, d_desc, &h_desc, sizeof(int)));
+    // keys already in bucket order sort to the identity permutation, which stays a virtual range -- a Scatter by it is the
+    // source vector itself (its domain is n: positions 0..n-1)
+    if (h_desc == 0) return vec_new_range(ctx, 0, 1, n, out);
+    VDL_TRY(vec_new(ctx, VDL_I64, n, out));
+    ctx->vecs[*out].domain = n;
+    ctx->vecs[*out].is_perm = true;
+    device_exclusive_scan(ctx, h, nh);
+    CP_LAUNCH(bucket_place_kernel, od, n, pfrom, pcount, chunk, nwarps, h, (i64 *)ctx->vecs[*out].ptr)
+#undef CP_LAUNCH
+#undef CP_LAUNCH_K
+    ctx->launches++;
+    VDL_CUDA(ctx, cudaGetLastError());
+    return VDL_OK;
+  }
   if (n > 0) {
     // one cheap pass first: keys that are already in bucket order sort to the identity permutation, which stays a
     // virtual range -- no radix passes, and a Scatter by it is the source vector itself
@@ -700,20 +821,9 @@ extern "C" int vdl_op_partition(vdl_ctx *ctx, vdl_vec data, int64_t pfrom, int64
   }
   VDL_TRY(vec_new(ctx, VDL_I64, n, out));
   ctx->vecs[*out].domain = n;
+  ctx->vecs[*out].is_perm = true;
   if (n == 0) return VDL_OK;
-  int bits = 0;
-  while (bits < 63 && ((u64)pcount >> bits)) bits++;
   i64 nb = (n + RDX_TILE - 1) / RDX_TILE;
-  if (pcount < 256) {                       // buckets 0..pcount fit one digit
-    VDL_TRY(scratch_reserve(ctx, scan_elems(256 * nb) * 8));
-    i64 *h = (i64 *)ctx->scratch;
-    bucket_hist_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(od, n, pfrom, pstep, pcount, nb, h);
-    device_exclusive_scan(ctx, h, 256 * nb);
-    bucket_place_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(od, n, pfrom, pstep, pcount, nb, h, (i64 *)ctx->vecs[*out].ptr);
-    ctx->launches += 2;
-    VDL_CUDA(ctx, cudaGetLastError());
-    return VDL_OK;
-  }
   // temporaries: key/idx ping-pong + histogram
   vdl_vec tk[2], ti[2];
   for (int k = 0; k < 2; k++) { VDL_TRY(vec_new(ctx, VDL_I64, n, &tk[k])); VDL_TRY(vec_new(ctx, VDL_I64, n, &ti[k])); }
@@ -740,83 +850,7 @@ extern "C" int vdl_op_partition(vdl_ctx *ctx, vdl_vec data, int64_t pfrom, int64
 }
 
 // ---------------------------------------------------------------------------------- Fold by runs
-// FoldSum/Min/Max/Choose/Count (Vlite.hs:1048-1070, 1179; Vdl.hs:255-264): one output per run of equal
-// consecutive `groups` values, in run order.  Run id = (number of run heads up to the element) - 1; inside a
-// warp equal run ids are contiguous, so a segmented shuffle reduction leaves one global atomic per
-// (warp, run) -- long runs (the common case after a Partition sort) cost almost no atomics.
-__device__ __forceinline__ i64 fold_identity(int op) { return op == VDL_FOLD_MIN ? INT64_MAX : (op == VDL_FOLD_MAX ? INT64_MIN : 0); }
-__device__ __forceinline__ i64 fold_combine(int op, i64 a, i64 b) {
-  if (op == VDL_FOLD_MIN) return b < a ? b : a;
-  if (op == VDL_FOLD_MAX) return b > a ? b : a;
-  return (i64)((u64)a + (u64)b);
-}
-
-__global__ void __launch_bounds__(256) fold_init_kernel(i64 *out, i64 n, i64 v) {
-  i64 stride = (i64)gridDim.x * blockDim.x;
-  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
-}
-
-__global__ void __launch_bounds__(256) fold_runs_kernel(int op, Operand groups, Operand data, i64 n, const i64 *__restrict__ block_off, i64 *__restrict__ out) {
-  __shared__ int wcnt[8];
-  const int lane = threadIdx.x & 31;
-  i64 base = (i64)blockIdx.x * SEL_TILE;
-  i64 off = block_off[blockIdx.x];   // run heads before this block
-  if (block_off[blockIdx.x + 1] == off && op != VDL_FOLD_CHOOSE) {
-    // no run starts inside this tile: all of it continues run off-1 (long runs: a single-group fold, a sorted low-
-    // cardinality key) -> plain block reduction, ONE atomic per tile instead of one per warp and step
-    __shared__ i64 wred[8];
-    i64 v = fold_identity(op);
-    for (int s = 0; s < SEL_TILE / 256; s++) {
-      i64 i = base + s * 256 + threadIdx.x;
-      if (i < n) v = fold_combine(op, v, op == VDL_FOLD_COUNT ? 1 : op_ld(data, i));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fold_combine(op, v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (lane == 0) wred[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < 8; w++) v = fold_combine(op, v, wred[w]);
-      i64 *dst = &out[off - 1];
-      if (op == VDL_FOLD_MIN) atomicMin((long long *)dst, (long long)v);
-      else if (op == VDL_FOLD_MAX) atomicMax((long long *)dst, (long long)v);
-      else atomicAdd((unsigned long long *)dst, (unsigned long long)v);
-    }
-    return;
-  }
-  int run = 0;
-  for (int s = 0; s < SEL_TILE / 256; s++) {
-    i64 i = base + s * 256 + threadIdx.x;
-    bool valid = i < n;
-    bool head = valid && flag_at<true>(groups, i);
-    StepRank r = step_rank(head, wcnt, run);
-    i64 rid = off + r.incl - 1;        // run id of this element
-    if (op == VDL_FOLD_CHOOSE) {
-      if (head) out[rid] = op_ld(data, i);
-      continue;
-    }
-    i64 v = valid ? (op == VDL_FOLD_COUNT ? 1 : op_ld(data, i)) : fold_identity(op);
-    if (!valid) rid = -1 - lane;       // never equal to a neighbour
-    // segmented inclusive scan over lanes with equal rid (contiguous)
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      i64 pv = __shfl_up_sync(0xffffffffu, v, o);
-      i64 pr = __shfl_up_sync(0xffffffffu, rid, o);
-      if (lane >= o && pr == rid) v = fold_combine(op, v, pv);
-    }
-    i64 nr = __shfl_down_sync(0xffffffffu, rid, 1);
-    bool last = lane == 31 || nr != rid;
-    // a run whose head AND end are inside this warp's 32 elements belongs to this lane alone: plain store
-    const unsigned heads = __ballot_sync(0xffffffffu, head);
-    const int head_lane = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));     // lane of this element's run head, -1 if in an earlier warp
-    const bool own = valid && last && lane < 31 && nr != rid && head_lane >= 0;
-    if (own) { out[rid] = v; continue; }
-    if (valid && last) {
-      if (op == VDL_FOLD_MIN) atomicMin((long long *)&out[rid], (long long)v);
-      else if (op == VDL_FOLD_MAX) atomicMax((long long *)&out[rid], (long long)v);
-      else atomicAdd((unsigned long long *)&out[rid], (unsigned long long)v);
-    }
-  }
-}
+#include "vdl_fold_kernel.cuh"
 
 extern "C" int vdl_op_fold(vdl_ctx *ctx, int fold_op, vdl_vec groups, vdl_vec data, vdl_vec *out) {
   if (!ctx || !out) return VDL_EINVAL;
@@ -841,17 +875,50 @@ extern "C" int vdl_op_fold(vdl_ctx *ctx, int fold_op, vdl_vec groups, vdl_vec da
   const u64 groups_gen = vg->gen;
   i64 n = vd->len;
   Operand og = operand_of(*vg), od = operand_of(*vd);
-  i64 total = 0, *off = nullptr;
-  if (n > 0) VDL_TRY(flag_scan(ctx, true, og, n, &off, &total));
-  VDL_TRY(vec_new(ctx, VDL_I64, total, out));
-  ctx->vecs[*out].fold_groups = groups;
-  ctx->vecs[*out].fold_groups_gen = groups_gen;
-  if (total == 0) return VDL_OK;
+  if (n == 0) {
+    VDL_TRY(vec_new(ctx, VDL_I64, 0, out));
+    ctx->vecs[*out].fold_groups = groups;
+    ctx->vecs[*out].fold_groups_gen = groups_gen;
+    return VDL_OK;
+  }
+  if (vg->is_range && vg->step == 0) {           // constant groups: one run
+    VDL_TRY(vec_new(ctx, VDL_I64, 1, out));
+    i64 *o = (i64 *)ctx->vecs[*out].ptr;
+    ctx->vecs[*out].fold_groups = groups;
+    ctx->vecs[*out].fold_groups_gen = groups_gen;
+    fold_all_init_kernel<<<1, 1, 0, ctx->stream>>>(fold_op, od, n, o);
+    ctx->launches++;
+    const int grid = (int)std::max<i64>(1, std::min<i64>((n + 2047) / 2048, (i64)ctx->sm_count * 8));
+    if (fold_op == VDL_FOLD_SUM) fold_all_kernel<VDL_FOLD_SUM><<<grid, 256, 0, ctx->stream>>>(od, n, o);
+    else if (fold_op == VDL_FOLD_MIN) fold_all_kernel<VDL_FOLD_MIN><<<grid, 256, 0, ctx->stream>>>(od, n, o);
+    else if (fold_op == VDL_FOLD_MAX) fold_all_kernel<VDL_FOLD_MAX><<<grid, 256, 0, ctx->stream>>>(od, n, o);
+    if (fold_op == VDL_FOLD_SUM || fold_op == VDL_FOLD_MIN || fold_op == VDL_FOLD_MAX) ctx->launches++;
+    VDL_CUDA(ctx, cudaGetLastError());
+    return VDL_OK;
+  }
+  const i64 ntiles = (n + FL_TILE - 1) / FL_TILE;
+  VDL_TRY(scratch_reserve(ctx, (size_t)ntiles * sizeof(FoldTileState) + 64));
+  FoldTileState *state = (FoldTileState *)ctx->scratch;
+  i64 *d_total = (i64 *)(state + ntiles);
+  unsigned int *ticket = (unsigned int *)(d_total + 1);
+  VDL_CUDA(ctx, cudaMemsetAsync(state, 0, (size_t)ntiles * sizeof(FoldTileState) + 16, ctx->stream));
+  VDL_TRY(vec_new(ctx, VDL_I64, n, out));                                   // capacity n; the run count is known after the pass
   i64 *o = (i64 *)ctx->vecs[*out].ptr;
-  int grid = (int)std::max<i64>(1, std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16));
-  fold_init_kernel<<<grid, 256, 0, ctx->stream>>>(o, total, fold_op == VDL_FOLD_MIN ? INT64_MAX : (fold_op == VDL_FOLD_MAX ? INT64_MIN : 0));
-  fold_runs_kernel<<<(unsigned)((n + SEL_TILE - 1) / SEL_TILE), 256, 0, ctx->stream>>>(fold_op, og, od, n, off, o);
-  ctx->launches += 2;
+  const int grid = (int)std::min<i64>(ntiles, (i64)ctx->sm_count * (1024 / FL_THREADS));
+  switch (fold_op) {
+    case VDL_FOLD_SUM: fold_lookback_kernel<VDL_FOLD_SUM><<<grid, FL_THREADS, 0, ctx->stream>>>(og, od, n, ntiles, state, ticket, o, d_total); break;
+    case VDL_FOLD_MIN: fold_lookback_kernel<VDL_FOLD_MIN><<<grid, FL_THREADS, 0, ctx->stream>>>(og, od, n, ntiles, state, ticket, o, d_total); break;
+    case VDL_FOLD_MAX: fold_lookback_kernel<VDL_FOLD_MAX><<<grid, FL_THREADS, 0, ctx->stream>>>(og, od, n, ntiles, state, ticket, o, d_total); break;
+    case VDL_FOLD_CHOOSE: fold_lookback_kernel<VDL_FOLD_CHOOSE><<<grid, FL_THREADS, 0, ctx->stream>>>(og, od, n, ntiles, state, ticket, o, d_total); break;
+    default: fold_lookback_kernel<VDL_FOLD_COUNT><<<grid, FL_THREADS, 0, ctx->stream>>>(og, od, n, ntiles, state, ticket, o, d_total); break;
+  }
+  ctx->launches++;
   VDL_CUDA(ctx, cudaGetLastError());
+  i64 total = 0;
+  VDL_TRY(read_scalar(ctx, d_total, &total, 8));
+  Vec &v = ctx->vecs[*out];
+  v.len = total;
+  v.fold_groups = groups;
+  v.fold_groups_gen = groups_gen;
   return VDL_OK;
 }

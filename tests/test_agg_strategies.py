@@ -87,13 +87,15 @@ def test_gpu_non_refining_level_one_matches_the_oracle(fuse):
 @pytest.mark.parametrize("strategy", ["shuffle", ("hierarchical", 0), ("hierarchical", 2), ("hierarchical", 13)])
 def test_gpu_runs_every_strategy(catalog, q, strategy):
     text = program(catalog, q, strategy)
-    rows = {"lineitem": 300_007}
+    rows = {"lineitem": 300_007} if q in ("q06", "q01") else None      # the join plans keep the FK columns inside their tables
     cols = columns(catalog, text, rows_override=rows)
     want = run_oracle(text, cols)
     fused, fstats = run_gpu(text, cols, fuse=True)
     assert_same(fused, want)
     plain, _ = run_gpu(text, cols, fuse=False)
     assert_same(plain, want)
-    if q in ("q06", "q01") and (strategy == "shuffle" or strategy[1] != 0 or q == "q06"):
-        # Shuffle is an alias; a level 1 that provably refines the groups collapses: the plan is ONE fused scan again
+    if q == "q06" or (q == "q01" and (strategy == "shuffle" or strategy[1] < 13)):
+        # Shuffle is an alias; a level 1 that provably refines the groups collapses: the plan is ONE fused scan again.  (Q1 with
+        # a grain above the 32 slots the reference's metadata gives the sorted vector: level1par is inferred constant, the keys
+        # are OR-ed without a shift, nothing is provable and both Folds run op-at-a-time -- literally.)
         assert fstats["fused_scans"] == 1, fstats
