@@ -320,7 +320,8 @@ def main():
         result = plan.outputs(False)
         kern_mean, kern_min = statistics.mean(kernel_ms), min(kernel_ms)
     wall_ms = 1e3 * (time.perf_counter() - t0)
-    result = {k: np.array(v, copy=True) for k, v in result.items()}     # the views die with the next step
+    # the views die with the next step; a sharded-tail plan's result is spread over the ranks: gathered here, outside the timing
+    result = sharded.global_result() if sharded.tail_mode else {k: np.array(v, copy=True) for k, v in result.items()}
     launches = ctx.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else {}
     if world > 1:
@@ -396,6 +397,8 @@ def main():
                 t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 e2e_s = float(t[0])
+            if sharded.tail_mode:
+                r2 = sharded.global_result()
             for k in result:
                 assert np.array_equal(r2[k], result[k]), f"e2e ({label}) result differs from the device-resident result"
             d2h = sum(8 * len(v) for v in result.values())
@@ -452,7 +455,10 @@ def main():
             "dtype": "int64", "data": "synthetic", "config": workload_config(args),
             "combine": "none (single GPU)" if world == 1 else (("peer-memory exchange fused into the scan kernel's last thread block (NVLink stores + epoch flags), no collective"
                                                                   if plan.num_fused else "peer-memory exchange kernel after the probe pass (NVLink stores + epoch flags) + finalize, no collective")
-                                                                 if sharded.peer_mode else "NCCL all-gather of the partial tables / survivors + finalize"),
+                                                                 if sharded.peer_mode else
+                                                                 ("sharded tail: every rank keeps the result slice of its rows; one all-gather of a boundary record per rank "
+                                                                  "(run count, first / last key, first / last row of each output) merges the groups that straddle shards"
+                                                                  if sharded.tail_mode else "NCCL all-gather of the partial tables / survivors + finalize")),
             "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "e2e_reference_storage": e2e_ref, "gpu_launches": launches, "clocks": clocks,
             "wall_ms_per_step": wall_ms / args.steps, "result": {k: [int(x) for x in v[:8]] for k, v in result.items()},

@@ -99,6 +99,10 @@ foreign import ccall safe "vdl_plan_partials" c_vdl_plan_partials :: Ptr VdlPlan
 foreign import ccall safe "vdl_plan_num_emits" c_vdl_plan_num_emits :: Ptr VdlPlan -> IO CInt
 foreign import ccall safe "vdl_plan_emit" c_vdl_plan_emit :: Ptr VdlPlan -> CInt -> Ptr (Ptr ()) -> Ptr Int64 -> IO CInt
 foreign import ccall safe "vdl_plan_emit_replace" c_vdl_plan_emit_replace :: Ptr VdlPlan -> CInt -> Ptr () -> Int64 -> IO CInt
+foreign import ccall safe "vdl_plan_tail_info" c_vdl_plan_tail_info :: Ptr VdlPlan -> Ptr CInt -> Ptr CInt -> CInt -> IO CInt
+foreign import ccall safe "vdl_plan_tail_enable" c_vdl_plan_tail_enable :: Ptr VdlPlan -> CInt -> IO CInt
+foreign import ccall safe "vdl_plan_tail_boundary" c_vdl_plan_tail_boundary :: Ptr VdlPlan -> Ptr Int64 -> CInt -> IO CInt
+foreign import ccall safe "vdl_plan_tail_apply" c_vdl_plan_tail_apply :: Ptr VdlPlan -> CInt -> Ptr Int64 -> IO CInt
 
 -- fused scan / FK-join probe / remaining context, column and plan entry points (tools/gen_hs_imports.py keeps this list
 -- in step with include/vdl_cuda.h; tests/test_abi.py checks that every declaration has an import)

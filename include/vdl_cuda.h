@@ -358,6 +358,21 @@ int vdl_plan_stats(vdl_plan *p, int *statements, int *nodes, int *fused_scans, i
 int vdl_plan_num_emits(vdl_plan *p);
 int vdl_plan_emit(vdl_plan *p, int i, void **device_ptr, int64_t *len);              /* synchronises */
 int vdl_plan_emit_replace(vdl_plan *p, int i, void *device_ptr, int64_t len);        /* caller-owned device memory */
+/* Sharded TAIL: when every output of the plan is an op-at-a-time Fold by runs of ONE groups vector -- a constant (a single
+ * SUM over a join's survivors: Q19) or keys sorted by their own Partition (Vlite.hs:1057-1060, the high-cardinality
+ * group-by of Q3) -- a rank can run the whole plan on its row-range shard (vdl_plan_run): its outputs are the slice of the
+ * global result that belongs to its rows, except that its first group may continue the previous rank's last one.
+ * vdl_plan_tail_info: is the plan of that shape, and the fold op of every output (VDL_FOLD_*).  After vdl_plan_tail_enable,
+ * every vdl_plan_run also records what vdl_plan_tail_boundary returns: rec = { keys were in order (Partition = identity) or
+ * constant, number of runs, first key, last key, first row of every output ..., last row of every output ... } (4 + 2 x
+ * outputs values).  Exchanging these records lets the ranks merge the straddling groups -- SUM adds, MIN / MAX compare,
+ * FoldChoose keeps the earlier rank's value -- without moving the survivors (mplan2vdl_b200/dist.py
+ * merge_tail_boundaries); vdl_plan_tail_apply writes the merged last row and / or gives up the first row (a group that
+ * starts on an earlier rank), after which vdl_plan_output returns this rank's slice of the global result. */
+int vdl_plan_tail_info(vdl_plan *p, int *mergeable, int *fold_ops, int cap);
+int vdl_plan_tail_enable(vdl_plan *p, int on);
+int vdl_plan_tail_boundary(vdl_plan *p, int64_t *rec, int cap);
+int vdl_plan_tail_apply(vdl_plan *p, int drop_first, const int64_t *last_row);
 /* FK-join plans: Folds run by the probe kernel, probe passes in emit mode, vectors those materialise. */
 int vdl_plan_probe_stats(vdl_plan *p, int *fold_groups, int *emit_groups, int *emitted_vectors);
 /* Map clusters of the op-at-a-time remainder: how many vdl_op_map launches stand for how many plan nodes. */

@@ -111,6 +111,11 @@ struct vdl_plan {
   std::vector<MapCluster> clusters;
   std::vector<int> cluster_of_root;     // node -> index into clusters when it is the root of one, else -1
   i64 row_base = 0;
+  // Sharded tail (vdl_plan_tail_*): every output is a Fold by runs of ONE groups vector, so a row-range shard's result is a
+  // slice of the global one up to the groups that straddle shard boundaries
+  bool tail_ok = false, tail_on = false;
+  int tail_groups = -1, tail_partition = -1;     // groups node; its Partition (-1: constant groups)
+  i64 tail_rec[4] = {0, 0, 0, 0};                // of the last run: sorted, runs, first key, last key
   // run state
   std::vector<vdl_vec> val;
   std::vector<vdl_vec> temps;
@@ -1298,6 +1303,62 @@ int eval(vdl_plan *p, int ni, vdl_vec *out) {
   return VDL_OK;
 }
 
+// A plan whose outputs are ALL op-at-a-time Folds (Sum / Min / Max / Choose / Count) by runs of one groups vector -- a
+// constant (one run: Q19's single SUM over the join's survivors) or keys sorted by their own Partition (Vlite.hs:1057-1060:
+// Q3's group-by on the 38-bit composite key) -- can run its whole tail on a row-range shard: rank r's result is the slice of
+// the global result for its rows, except that the last group of rank r and the first of rank r+1 may be the same group.
+void detect_mergeable_tail(vdl_plan *p) {
+  int G = -1;
+  for (auto &o : p->outputs) {
+    const Node &n = p->nodes[o.node];
+    if (n.op != N_FOLD || p->group_of_node[o.node] >= 0 || p->pgroup_of_node[o.node] >= 0) return;
+    if (G >= 0 && n.a != G) return;
+    G = n.a;
+  }
+  if (G < 0) return;
+  const Node &g = p->nodes[G];
+  int P = -1;
+  if (g.op == N_RANGEV && g.k1 == 0) P = -1;
+  else if (g.op == N_SCATTER && p->nodes[g.c].op == N_PARTITION && p->nodes[g.c].a == g.a) P = g.c;
+  else return;
+  for (auto &o : p->outputs) {              // the data of every Fold rides the same sort
+    const Node &d = p->nodes[p->nodes[o.node].b];
+    if (P >= 0 && !(d.op == N_SCATTER && d.c == P)) return;
+    if (p->nodes[d.op == N_SCATTER ? d.a : p->nodes[o.node].b].op == N_FOLD) return;    // no second level
+  }
+  p->tail_ok = true; p->tail_groups = G; p->tail_partition = P;
+}
+
+int capture_tail_boundary(vdl_plan *p) {
+  vdl_ctx *ctx = p->ctx;
+  i64 *r = p->tail_rec;
+  r[0] = r[1] = r[2] = r[3] = 0;
+  r[1] = p->outputs.empty() ? 0 : p->outputs[0].len;
+  const vdl_vec gh = p->val[p->tail_groups];
+  Vec *g = gh ? vec_get(ctx, gh) : nullptr;
+  if (!g) return vdl_fail(ctx, VDL_EINVAL, "sharded tail: the groups vector was not evaluated");
+  bool sorted = true;
+  if (p->tail_partition >= 0) {
+    Vec *pv = p->val[p->tail_partition] ? vec_get(ctx, p->val[p->tail_partition]) : nullptr;
+    sorted = pv && pv->is_range && pv->from == 0 && pv->step == 1;     // the local keys were already in order
+  }
+  r[0] = sorted;
+  const i64 n = g->len;
+  if (n > 0) {
+    if (g->is_range) { r[2] = g->from; r[3] = (i64)((u64)g->from + (u64)(n - 1) * (u64)g->step); }
+    else if (g->dtype == VDL_I64) {
+      VDL_TRY(read_scalar(ctx, (const i64 *)g->ptr, &r[2], 8));
+      VDL_TRY(read_scalar(ctx, (const i64 *)g->ptr + (n - 1), &r[3], 8));
+    } else {
+      int a = 0, b = 0;
+      VDL_TRY(read_scalar(ctx, (const int *)g->ptr, &a, 4));
+      VDL_TRY(read_scalar(ctx, (const int *)g->ptr + (n - 1), &b, 4));
+      r[2] = a; r[3] = b;
+    }
+  }
+  return VDL_OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------- ABI
@@ -1311,6 +1372,7 @@ extern "C" int vdl_plan_load(vdl_ctx *ctx, const char *vdl_text, int flags, vdl_
   if (!rc) rc = fuse(p);
   if (rc) { delete p; return rc; }
   p->val.assign(p->nodes.size(), 0);
+  detect_mergeable_tail(p);
   if (getenv("VDL_DEBUG_PLAN")) {
     fprintf(stderr, "[vdl plan] %d statements, %zu nodes: %zu fused scans, %zu probe fold groups, %zu probe emit groups\n", p->statements, p->nodes.size(),
             p->groups.size(), p->pgroups.size(), p->egroups.size());
@@ -1599,10 +1661,54 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
   }
   if (copies_pending) VDL_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));     // before the temporaries are released
   int rc = ran_ops ? check_errflag(ctx, "plan") : VDL_OK;
+  if (!rc && p->tail_on && p->tail_ok) rc = capture_tail_boundary(p);
   p->launches_last += ctx->launches - l0;
   free_temps(p);
   p->local_done = false;
   return rc;
+}
+
+// ---- sharded tail ---------------------------------------------------------------------------------------------------
+extern "C" int vdl_plan_tail_info(vdl_plan *p, int *mergeable, int *fold_ops, int cap) {
+  if (!p || !mergeable) return VDL_EINVAL;
+  *mergeable = p->tail_ok ? 1 : 0;
+  if (p->tail_ok && fold_ops)
+    for (int i = 0; i < cap && i < (int)p->outputs.size(); i++) fold_ops[i] = p->nodes[p->outputs[i].node].sub;
+  return VDL_OK;
+}
+extern "C" int vdl_plan_tail_enable(vdl_plan *p, int on) {
+  if (!p) return VDL_EINVAL;
+  if (on && !p->tail_ok) return vdl_fail(p->ctx, VDL_EUNSUPPORTED, "the plan's outputs are not Folds by runs of one groups vector");
+  p->tail_on = on != 0;
+  return VDL_OK;
+}
+extern "C" int vdl_plan_tail_boundary(vdl_plan *p, int64_t *rec, int cap) {
+  if (!p || !rec) return VDL_EINVAL;
+  if (!p->tail_on) return vdl_fail(p->ctx, VDL_EINVAL, "vdl_plan_tail_enable first");
+  const int k = (int)p->outputs.size();
+  if (cap < 4 + 2 * k) return vdl_fail(p->ctx, VDL_EINVAL, "tail record needs %d values", 4 + 2 * k);
+  for (int i = 0; i < 4; i++) rec[i] = p->tail_rec[i];
+  const i64 runs = p->tail_rec[1];
+  for (int i = 0; i < k; i++) {
+    const Output &o = p->outputs[i];
+    if ((i64)o.len != runs) return vdl_fail(p->ctx, VDL_EINVAL, "sharded tail: output %d has %lld values, the first has %lld", i, (long long)o.len, (long long)runs);
+    rec[4 + i] = runs ? o.data[0] : 0;
+    rec[4 + k + i] = runs ? o.data[runs - 1] : 0;
+  }
+  return VDL_OK;
+}
+// The outcome of the boundary merge for this rank: replace the last row of every output (last_row != NULL) and / or give
+// up the first row (it continues a group that starts on an earlier rank).  vdl_plan_output then returns the rank's slice.
+extern "C" int vdl_plan_tail_apply(vdl_plan *p, int drop_first, const int64_t *last_row) {
+  if (!p) return VDL_EINVAL;
+  if (!p->tail_on) return vdl_fail(p->ctx, VDL_EINVAL, "vdl_plan_tail_enable first");
+  for (size_t i = 0; i < p->outputs.size(); i++) {
+    Output &o = p->outputs[i];
+    if (o.len == 0 || o.data != o.pinned) continue;
+    if (last_row) o.pinned[o.len - 1] = last_row[i];
+    if (drop_first) { o.data = o.pinned + 1; o.len -= 1; }
+  }
+  return VDL_OK;
 }
 
 extern "C" int vdl_plan_run(vdl_plan *p) {

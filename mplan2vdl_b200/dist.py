@@ -13,6 +13,13 @@ domain] int64, a few bytes to a few KB -- are all-gathered (NCCL over NVLink on 
 the finalize kernel (vdl_plan_finish): SUM/MIN/MAX accumulators combine by their op, FoldChoose takes the value
 from the rank that holds the smallest first row, empty groups are dropped after the merge.  There is no other
 data-path collective: the scan itself never leaves the GPU that owns the rows.
+
+Plans that EMIT survivors (Q3, Q19) and whose outputs are all Folds by runs of one groups vector run their whole tail on
+the shard (vdl_plan_tail_*): every rank keeps the slice of the result that belongs to its rows, and only a boundary record
+per rank -- run count, first / last key, first / last row of every output, a few dozen int64 -- is all-gathered so that the
+groups straddling shard boundaries are merged into the rank where they start (merge_tail_boundaries).  The survivors never
+move; the result stays sharded (ShardedPlan.global_result concatenates it when somebody wants it in one place).  Anything
+else that emits falls back to all-gathering the survivors and evaluating the tail on every rank.
 """
 from __future__ import annotations
 
@@ -62,6 +69,47 @@ def gather_partial_tables(local: torch.Tensor, world: int, group=None) -> torch.
     return out
 
 
+FOLD_SUM, FOLD_MIN, FOLD_MAX, FOLD_CHOOSE, FOLD_COUNT = range(5)
+
+
+def merge_tail_boundaries(recs, ops, rank):
+    """recs[r] = [sorted, runs, first key, last key, first row of every output ..., last row of every output ...] of rank
+    r's local result.  Returns None when the shards' keys are not globally in order (the caller falls back to moving the
+    survivors), else (drop_first, last_row): drop_first -- this rank's first group continues a group that starts on an
+    earlier rank; last_row -- the values of this rank's last group after merging the following ranks' share of it, or
+    None when nothing changes.  FoldChoose keeps the value of the rank where the group starts (first of the run, G6)."""
+    k = len(ops)
+    live = [r for r in range(len(recs)) if recs[r][1] > 0]
+    if any(not recs[r][0] for r in live):
+        return None
+    for a, b in zip(live, live[1:]):
+        if recs[a][3] > recs[b][2]:
+            return None
+    if rank not in live:
+        return False, None
+    at = live.index(rank)
+    me = recs[rank]
+    drop_first = at > 0 and recs[live[at - 1]][3] == me[2]
+    if me[1] == 1 and drop_first:                      # my only group belongs to an earlier rank
+        return True, None
+    last, changed = list(me[4 + k:4 + 2 * k]), False
+    for r in live[at + 1:]:
+        if recs[r][2] != me[3]:
+            break
+        first = recs[r][4:4 + k]
+        for i, op in enumerate(ops):
+            if op in (FOLD_SUM, FOLD_COUNT):
+                last[i] = (last[i] + first[i] + 2 ** 63) % 2 ** 64 - 2 ** 63      # int64 wrap-around, as the kernels add
+            elif op == FOLD_MIN:
+                last[i] = min(last[i], first[i])
+            elif op == FOLD_MAX:
+                last[i] = max(last[i], first[i])
+        changed = True
+        if recs[r][1] > 1:                             # the group ends inside rank r
+            break
+    return drop_first, (last if changed else None)
+
+
 class ShardedPlan:
     """A plan executed over this rank's shard; step() returns the global result on every rank."""
 
@@ -75,6 +123,63 @@ class ShardedPlan:
         self.peer_mode = False
         self.peer_fallback = None          # why the peer-memory combine is not in use (None: it is, or was never wanted)
         self._mine, self._opened = [], []
+        # sharded tail: decided from the plan's shape alone, so every rank decides alike
+        self.tail_ops = plan.tail_info() if world > 1 and plan.num_emits > 0 and not os.environ.get("VDL_NO_TAIL") else None
+        self.tail_mode = self.tail_ops is not None
+        if self.tail_mode:
+            plan.tail_enable(True)
+        self._tail_slice, self._tb = None, None
+
+    def _tail_buffers(self):
+        """Allocated once: the record as a ctypes array over a pinned tensor, its device copy, the gathered records."""
+        import ctypes
+        import torch.distributed as dist
+        n = 4 + 2 * len(self.tail_ops)
+        cuda = torch.cuda.is_available() and dist.get_backend(self.group) == "nccl"
+        host = torch.zeros(n, dtype=torch.int64, pin_memory=cuda)
+        rec = (ctypes.c_int64 * n).from_address(host.data_ptr())
+        allhost = torch.zeros(self.world * n, dtype=torch.int64, pin_memory=cuda)
+        dev = torch.zeros(n, dtype=torch.int64, device=f"cuda:{self.ctx.device}") if cuda else None
+        alldev = torch.zeros(self.world * n, dtype=torch.int64, device=f"cuda:{self.ctx.device}") if cuda else None
+        self._tb = (n, cuda, host, rec, allhost, dev, alldev)
+        return self._tb
+
+    def _step_tail(self):
+        """Whole plan on the shard, then the boundary records of all ranks; returns False when the shards turn out not to be
+        globally ordered (every rank sees the same records, so every rank falls back together)."""
+        import torch.distributed as dist
+        n, cuda, host, rec, allhost, dev, alldev = self._tb or self._tail_buffers()
+        self.plan.execute()                              # probe pass + tail on this rank's rows, outputs in pinned memory
+        self.plan.tail_boundary(rec)                     # straight into the pinned tensor
+        if cuda:
+            dev.copy_(host, non_blocking=True)
+            dist.all_gather_into_tensor(alldev, dev, group=self.group)
+            allhost.copy_(alldev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            parts = list(allhost.view(self.world, n).unbind(0))
+            dist.all_gather(parts, host, group=self.group)
+        merged = merge_tail_boundaries(allhost.view(self.world, n).tolist(), self.tail_ops, self.rank)
+        if merged is None:
+            return False
+        self.plan.tail_apply(*merged)
+        self._tail_slice = None                          # wrapped on demand (outputs())
+        return True
+
+    def outputs(self) -> dict:
+        """This rank's share of the last step's result: the global result when the plan combines partial tables, the slice
+        for this rank's rows in sharded-tail mode (views of the library's pinned buffers, valid until the next step)."""
+        return self.plan.outputs(False)
+
+    def global_result(self) -> dict:
+        """The whole result on every rank (copies).  Sharded-tail plans gather their slices in rank order."""
+        import numpy as np
+        if not self.tail_mode:
+            return {k: np.array(v, copy=True) for k, v in self.plan.outputs(False).items()}
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, {k: np.array(v, copy=True) for k, v in self.plan.outputs(False).items()}, group=self.group)
+        return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
 
     def _setup_peers(self) -> bool:
         """Allocate / exchange / map the exchange buffers (after the scans exist, i.e. after one step).  Collective:
@@ -128,6 +233,11 @@ class ShardedPlan:
             if not fetch:
                 return self.plan.execute()
             return self.plan.run(copy)                  # one launch per fused scan: its last thread block finalizes
+        if self.tail_mode:
+            if self._step_tail():
+                return self.plan.outputs(copy) if fetch else None
+            self.tail_mode = False                      # shards not globally ordered: move the survivors instead
+            self.plan.tail_enable(False)
         out = self._step_all_gather(copy)
         if self._want_peer:                             # the scans exist now: switch to the peer-memory combine
             self._want_peer = False                     # (plans that emit survivors keep the all-gather path)

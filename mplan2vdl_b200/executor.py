@@ -270,6 +270,32 @@ class Plan:
     def emit_replace(self, i: int, ptr: int, n: int):
         self.ctx.check(self.L.vdl_plan_emit_replace(self.h, i, C.c_void_p(ptr), n))
 
+    def tail_info(self):
+        """None, or the fold op (VDL_FOLD_*: 0 Sum, 1 Min, 2 Max, 3 Choose, 4 Count) of every output when all of them are
+        Folds by runs of one groups vector: the plan's tail can then run on a row-range shard (vdl_plan_tail_info)."""
+        n = self.L.vdl_plan_num_outputs(self.h)
+        ok, ops = C.c_int(), (C.c_int * max(n, 1))()
+        self.ctx.check(self.L.vdl_plan_tail_info(self.h, C.byref(ok), ops, n))
+        return [ops[i] for i in range(n)] if ok.value else None
+
+    def tail_enable(self, on: bool = True):
+        self.ctx.check(self.L.vdl_plan_tail_enable(self.h, int(on)))
+
+    def tail_boundary(self, into=None):
+        """[keys in order, runs, first key, last key, first row of every output ..., last row of every output ...] of the
+        last run (after tail_enable).  `into`: a ctypes int64 array to fill instead of building a list."""
+        n = 4 + 2 * self.L.vdl_plan_num_outputs(self.h)
+        rec = into if into is not None else (C.c_int64 * n)()
+        self.ctx.check(self.L.vdl_plan_tail_boundary(self.h, rec, len(rec)))
+        return rec if into is not None else list(rec)
+
+    def tail_apply(self, drop_first: bool, last_row=None):
+        """The boundary merge's verdict for this rank (vdl_plan_tail_apply): outputs() then returns the rank's slice."""
+        arr = None
+        if last_row is not None:
+            arr = (C.c_int64 * len(last_row))(*last_row)
+        self.ctx.check(self.L.vdl_plan_tail_apply(self.h, int(drop_first), arr))
+
     @property
     def num_partials(self) -> int:
         """Partial aggregate tables of a sharded run: the fused scans, then the probe fold groups."""

@@ -169,6 +169,10 @@ SYMBOLS = [
     ("vdl_plan_num_emits", _I, [_P]),
     ("vdl_plan_emit", _I, [_P, _I, C.POINTER(_P), C.POINTER(_L)]),
     ("vdl_plan_emit_replace", _I, [_P, _I, _P, _L]),
+    ("vdl_plan_tail_info", _I, [_P, _P, _P, _I]),
+    ("vdl_plan_tail_enable", _I, [_P, _I]),
+    ("vdl_plan_tail_boundary", _I, [_P, _P, _I]),
+    ("vdl_plan_tail_apply", _I, [_P, _I, _P]),
     ("vdl_plan_num_partials", _I, [_P]),
     ("vdl_plan_partials", _I, [_P, _I, C.POINTER(_P), C.POINTER(_L)]),
     ("vdl_probe_run_ex", _I, [_P, _I]),
