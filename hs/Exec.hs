@@ -101,4 +101,7 @@ evalVexp ctx vexp@V.Vexp { V.vx, V.info = ColInfo { count } } = do
       h <- out $ \p -> withCString (show lcol ++ ".heap") $ \s -> c_vdl_column_lookup ctx s p
       out (\p -> C.useAsCString lpattern $ \pat -> c_vdl_op_like ctx d h pat p)
     go V.VShuffle { V.varg } = evalVexp ctx varg
+    go V.CrossProduct { V.left, V.right, V.variant } = do      -- joins under --use_cross_product (Vlite.hs:89-93, 672-680)
+      l <- evalVexp ctx left; r <- evalVexp ctx right
+      out (c_vdl_op_cross_product ctx l r (case variant of { V.COuter -> 0; V.CInner -> 1 }))
     go other = error ("Exec: op outside the supported vocabulary: " ++ show other)

@@ -55,6 +55,7 @@ foreign import ccall safe "vdl_vec_free" c_vdl_vec_free :: Ptr VdlCtx -> VdlVec 
 foreign import ccall safe "vdl_op_range" c_vdl_op_range :: Ptr VdlCtx -> Int64 -> Int64 -> Int64 -> Ptr VdlVec -> IO CInt
 foreign import ccall safe "vdl_op_binary" c_vdl_op_binary :: Ptr VdlCtx -> CInt -> VdlVec -> VdlVec -> Ptr VdlVec -> IO CInt
 foreign import ccall safe "vdl_op_like" c_vdl_op_like :: Ptr VdlCtx -> VdlVec -> VdlVec -> CString -> Ptr VdlVec -> IO CInt
+foreign import ccall safe "vdl_op_cross_product" c_vdl_op_cross_product :: Ptr VdlCtx -> VdlVec -> VdlVec -> CInt -> Ptr VdlVec -> IO CInt
 foreign import ccall safe "vdl_op_fold_select" c_vdl_op_fold_select :: Ptr VdlCtx -> VdlVec -> Ptr VdlVec -> IO CInt
 foreign import ccall safe "vdl_op_map" c_vdl_op_map :: Ptr VdlCtx -> Ptr VdlMapDesc -> Ptr VdlVec -> Ptr VdlVec -> Ptr VdlVec -> IO CInt
 foreign import ccall safe "vdl_jit_selftest" c_vdl_jit_selftest :: CString -> CInt -> IO CInt

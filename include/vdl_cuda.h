@@ -165,6 +165,11 @@ int vdl_jit_selftest(char *log, int log_capacity);
  * case-sensitive), else 0.  An offset outside the heap raises the context's range error (VDL_ERANGE at the next check). */
 #define VDL_LIKE_MAX_PATTERN 128
 int vdl_op_like(vdl_ctx *ctx, vdl_vec data, vdl_vec heap, const char *pattern, vdl_vec *out);
+/* CrossProductOuter (inner = 0) / CrossProductInner (inner = 1): Vlite.hs:89-93 `crossp`, 283-292; printed by Vdl.hs:412-416;
+ * joins under --use_cross_product (Mplan.hs:309-313).  The positions into `left` resp. `right` of the |left| x |right|
+ * pairs, left-major: out[i] = i / |right| resp. i % |right|.  Only the lengths of the arguments matter.  Quadratic by
+ * definition: refused above 2^33 pairs. */
+int vdl_op_cross_product(vdl_ctx *ctx, vdl_vec left, vdl_vec right, int inner, vdl_vec *out);
 /* FoldSelect with fold = pos_ pred (Vlite.hs:721-730): ascending positions of non-zero pred. */
 int vdl_op_fold_select(vdl_ctx *ctx, vdl_vec pred, vdl_vec *out);
 /* Gather (Vdl.hs:438): out[i] = src[pos[i]]. */

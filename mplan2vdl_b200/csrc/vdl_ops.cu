@@ -474,6 +474,31 @@ extern "C" int vdl_op_scatter(vdl_ctx *ctx, vdl_vec src, vdl_vec pos, int64_t ou
   return VDL_OK;
 }
 
+// ---------------------------------------------------------------------------------- CrossProduct
+// Vlite.hs:89-93, 283-292: "0,1,2,3 X 0,1 = 0,0,1,1,2,2,3,3 (outer), 0,1,0,1,0,1,0,1 (inner)".
+__global__ void __launch_bounds__(256) cross_kernel(i64 n, i64 nr, int inner, i64 *__restrict__ out) {
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = inner ? i % nr : i / nr;
+}
+
+extern "C" int vdl_op_cross_product(vdl_ctx *ctx, vdl_vec left, vdl_vec right, int inner, vdl_vec *out) {
+  if (!ctx || !out) return VDL_EINVAL;
+  Vec *vl = vec_get(ctx, left), *vr = vec_get(ctx, right);
+  if (!vl || !vr) return VDL_EINVAL;
+  const i64 nl = vl->len, nr = vr->len;
+  if (nr > 0 && nl > ((i64)1 << 33) / nr) return vdl_fail(ctx, VDL_EUNSUPPORTED, "CrossProduct of %lld x %lld rows", (long long)nl, (long long)nr);
+  const i64 n = nl * nr;
+  VDL_TRY(vec_new(ctx, VDL_I64, n, out));
+  ctx->vecs[*out].domain = inner ? nr : nl;          // positions into that side (App. G2)
+  if (n == 0) return VDL_OK;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int blocks = (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 16));
+  cross_kernel<<<blocks, 256, 0, ctx->stream>>>(n, nr, inner, (i64 *)ctx->vecs[*out].ptr);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaGetLastError());
+  return VDL_OK;
+}
+
 // ---------------------------------------------------------------------------------- Partition
 // Vlite.hs:1082-1098 emits Partition(key, RangeC(min,1,max-min+1)); its result is the scatter position that
 // sorts rows stably by key (1057-1060, 1172).  bucket(v) = number of pivots below v (App. G3); the

@@ -27,7 +27,7 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 
 namespace {
 
-enum NodeOp { N_LOAD, N_RANGEV, N_RANGEC, N_BINARY, N_FSELECT, N_GATHER, N_SCATTER, N_PARTITION, N_FOLD, N_LIKE };
+enum NodeOp { N_LOAD, N_RANGEV, N_RANGEC, N_BINARY, N_FSELECT, N_GATHER, N_SCATTER, N_PARTITION, N_FOLD, N_LIKE, N_CROSS };
 
 struct Node {
   int op = 0, sub = 0;         // sub: binary op / fold op
@@ -291,7 +291,11 @@ int parse_plan(vdl_plan *p, const char *text) {
       n.op = N_LIKE;
       n.name = f[7];
       for (size_t k = 8; k < f.size(); k++) n.name += "," + f[k];
-    } else if (op == "CrossProductOuter" || op == "CrossProductInner" || op == "Semisort") {
+    } else if (op == "CrossProductOuter" || op == "CrossProductInner") {   // id,CrossProductOuter,Id left,Id right (Vdl.hs:412-416)
+      if (f.size() != 4 || !arg(f[2], &n.a) || !arg(f[3], &n.b)) return bad();
+      n.op = N_CROSS;
+      n.sub = op == "CrossProductInner";
+    } else if (op == "Semisort") {
       return vdl_fail(ctx, VDL_EUNSUPPORTED, "plan line %d: op %s is outside the supported vocabulary", lineno, op.c_str());
     } else {
       if (f.size() != 7 || f[2] != "val" || f[4] != "val" || f[6] != "val" || !arg(f[3], &n.a) || !arg(f[5], &n.b)) return bad();
@@ -828,6 +832,7 @@ void mark_emits(vdl_plan *p, int ni, std::vector<char> &seen) {
     case N_BINARY: case N_GATHER: case N_FOLD: mark_emits(p, n.a, seen); mark_emits(p, n.b, seen); break;
     case N_FSELECT: mark_emits(p, n.b, seen); break;
     case N_LIKE: mark_emits(p, n.a, seen); break;
+    case N_CROSS: mark_emits(p, n.a, seen); mark_emits(p, n.b, seen); break;
     case N_SCATTER: mark_emits(p, n.a, seen); mark_emits(p, n.c, seen); break;
     case N_PARTITION: mark_emits(p, n.a, seen); break;
     default: break;
@@ -897,6 +902,7 @@ void live_walk(vdl_plan *p, int ni, std::vector<char> &live, std::vector<int> &c
     case N_BINARY: if (!fused) { use(n.a); use(n.b); } break;
     case N_FSELECT: use(n.b); break;
     case N_LIKE: use(n.a); use(n.b); break;
+    case N_CROSS: use(n.a); use(n.b); break;
     case N_GATHER: use(n.a); use(n.b); break;
     case N_SCATTER: use(n.a); use(n.c); break;
     case N_PARTITION: use(n.a); break;
@@ -1237,6 +1243,7 @@ int eval(vdl_plan *p, int ni, vdl_vec *out) {
     }
     case N_GATHER: VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.b, &b)); VDL_TRY(vdl_op_gather(ctx, a, b, &r)); break;
     case N_LIKE: VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.b, &b)); VDL_TRY(vdl_op_like(ctx, a, b, n.name.c_str(), &r)); break;
+    case N_CROSS: VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.b, &b)); VDL_TRY(vdl_op_cross_product(ctx, a, b, n.sub, &r)); break;
     case N_SCATTER: {
       VDL_TRY(eval(p, n.a, &a)); VDL_TRY(eval(p, n.c, &c));
       Vec *pv = vec_get(ctx, c), *sv = vec_get(ctx, a);

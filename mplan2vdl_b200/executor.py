@@ -152,6 +152,9 @@ class Context:
     def op_like(self, data: int, heap: int, pattern: str) -> int:
         return self._out(self.L.vdl_op_like, data, heap, pattern.encode())
 
+    def op_cross_product(self, left: int, right: int, inner: bool) -> int:
+        return self._out(self.L.vdl_op_cross_product, left, right, int(inner))
+
     def op_fold_select(self, pred: int) -> int:
         return self._out(self.L.vdl_op_fold_select, pred)
 

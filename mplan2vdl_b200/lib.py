@@ -135,6 +135,7 @@ SYMBOLS = [
     ("vdl_scan_jit_selftest", _I, [C.c_char_p, _I]),
     ("vdl_probe_jit_selftest", _I, [C.c_char_p, _I]),
     ("vdl_op_like", _I, [_P, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_int32)]),
+    ("vdl_op_cross_product", _I, [_P, C.c_int32, C.c_int32, _I, C.POINTER(C.c_int32)]),
     ("vdl_op_fold_select", _I, [_P, C.c_int32, C.POINTER(C.c_int32)]),
     ("vdl_op_gather", _I, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     ("vdl_op_scatter", _I, [_P, C.c_int32, C.c_int32, _L, C.POINTER(C.c_int32)]),

@@ -15,7 +15,7 @@ import datetime
 import re
 import sys
 
-from .vlite import Bin, Cast, GroupBy, Identity, IfThenElse, In, Join, Like, Lit, Project, Ref, Select, Table, Unary
+from .vlite import Bin, CartesianProduct, Cast, GroupBy, Identity, IfThenElse, In, Join, Like, Lit, Project, Ref, Select, Table, Unary
 
 DATE = ("date",)
 
@@ -236,8 +236,9 @@ def add_months_rollover(date: datetime.date, months: int) -> datetime.date:     
 
 
 class Front:
-    def __init__(self, catalog):
+    def __init__(self, catalog, cross_product=False):
         self.cat = catalog
+        self.cross_product = cross_product                  # Config.cross_product (Config.hs:150, 223)
 
     def _dtype_of_ref(self, name: str):
         """display type of a column reference, for typing char literals (Mplan.hs:441-446, 489-493)"""
@@ -387,19 +388,21 @@ class Front:
         if relop in ("join", "semijoin", "antijoin", "left outer join"):
             variant = {"join": "Plain", "semijoin": "LeftSemi", "antijoin": "LeftAnti", "left outer join": "LeftOuter"}[relop]   # classify_join (Mplan.hs:334-356)
             l, r = children
+            if self.cross_product and relop == "join":      # --use_cross_product (Mplan.hs:309-313): plain joins only
+                return Select(CartesianProduct(self.solve(l), self.solve(r)), self.conjunction(lists[0]))
             return Join(self.solve(l), self.solve(r), [self.sc(e) for e, _ in lists[0]], variant)
         raise NotImplementedError(f"relational operator {relop!r} (Mplan.hs:332)")
 
 
-def relexpr_from_mplan(catalog, text: str):
+def relexpr_from_mplan(catalog, text: str, cross_product=False):
     """mplanFromParseTree (Mplan.hs:567-568) after Parser.fromString (Parser.y:301-304)."""
-    return Front(catalog).solve(parse(text))
+    return Front(catalog, cross_product).solve(parse(text))
 
 
-def translate_mplan(catalog, text: str, agg_strategy="serial") -> str:
+def translate_mplan(catalog, text: str, agg_strategy="serial", cross_product=False) -> str:
     """The whole translator (MainFuns.compile, 172-188) for the supported subset: mplan text -> Voodoo program text."""
     from . import vlite
-    return vlite.translate(catalog, relexpr_from_mplan(catalog, text), agg_strategy)
+    return vlite.translate(catalog, relexpr_from_mplan(catalog, text, cross_product), agg_strategy)
 
 
 if __name__ == "__main__":
@@ -411,10 +414,11 @@ if __name__ == "__main__":
     g.add_argument("--aggserial", action="store_true")
     g.add_argument("--agghierarchical", action="store_true")
     g.add_argument("--aggshuffle", action="store_true")
+    ap.add_argument("--use_cross_product", action="store_true", help="plain joins as a selection over the cross product (MainFuns.hs:72)")
     ap.add_argument("-g", "--grainsize", type=int, default=8192, help="power of 2; only with --agghierarchical")
     a = ap.parse_args()
     if a.grainsize < 1 or a.grainsize & (a.grainsize - 1):
         sys.exit("grainsize must be a power of 2 (MainFuns.hs:112)")
     strategy = ("hierarchical", a.grainsize.bit_length() - 1) if a.agghierarchical else ("shuffle" if a.aggshuffle else "serial")
     src = sys.stdin.read() if a.mplanfile == "-" else open(a.mplanfile).read()
-    sys.stdout.write(translate_mplan(builtin_catalog(), src, strategy))
+    sys.stdout.write(translate_mplan(builtin_catalog(), src, strategy, a.use_cross_product))

@@ -159,6 +159,10 @@ def complete(op: str, args: tuple, params: tuple = ()) -> Vexp:
         pivots, pdata = args
         info = dict(bounds=(0, pivots.count - 1), count=pdata.count, tz=0, dtype=("dec", 0))
         quant = "Unique"
+    elif op == "CrossProduct":                             # 283-292: bounds of pos_ of the side it points into
+        left, right = args
+        side = left if params[0] == "COuter" else right
+        info = dict(bounds=(0, side.count), count=left.count * right.count, tz=0, dtype=("dec", 0))
     elif op == "Like":                                     # 296-297
         info = dict(bounds=(0, 1), count=args[0].count, tz=0, dtype=("dec", 0))
     elif op == "VShuffle":
@@ -272,6 +276,12 @@ class Join:
     right: object
     conds: list
     variant: str = "Plain"
+
+
+@dataclass
+class CartesianProduct:        # a plain join under --use_cross_product (Mplan.hs:211, 309-313)
+    left: object
+    right: object
 
 
 class Env:
@@ -412,6 +422,11 @@ class Lowering:
             return self.group_by(rel)
         if isinstance(rel, Join):
             return self.join(rel)
+        if isinstance(rel, CartesianProduct):              # 672-680: every column gathered by the pair positions
+            left, right = self.solve_list(rel.left), self.solve_list(rel.right)
+            outer = complete("CrossProduct", (left[0], right[0]), ("COuter",))
+            inner = complete("CrossProduct", (left[0], right[0]), ("CInner",))
+            return [gather(c, outer).replace(name=c.name) for c in left] + [gather(c, inner).replace(name=c.name) for c in right]
         raise NotImplementedError(rel)
 
     # ---- group by (Vlite.hs:624-669, 1033-1194) ------------------------------------------------
@@ -820,6 +835,10 @@ class Emitter:
         if v.op == "VShuffle":
             a = self.node(v.args[0])
             return self._emit(("Shuffle", a), ["Shuffle", f"Id {a}"])
+        if v.op == "CrossProduct":                         # Vdl.hs:184-187, 412-416
+            l, r = self.node(v.args[0]), self.node(v.args[1])
+            name = "CrossProductOuter" if v.params[0] == "COuter" else "CrossProductInner"
+            return self._emit((name, l, r), [name, f"Id {l}", f"Id {r}"])
         if v.op == "Like":                                 # 244-247: the dictionary is the column's string heap, `<table>.<col>.heap`
             d = self.node(v.args[0])
             pattern, col = v.params

@@ -44,10 +44,11 @@
  *                                     level-1 run and is grouped by the groups value at that run's first row
  *   Shuffle,Id n                      identity (order-destroying hint)                        Vdl.hs:449-450
  *   MaterializeCompact,Id n           query output; name = the Project's <out>               Vdl.hs:278-292,452-453
+ *   CrossProductOuter / Inner,Id l,Id r   positions into l (i / |r|) resp. r (i % |r|) of the |l| x |r| pairs                Vlite.hs:89-93,283-292
  *   Like,val,Id d,val,Id heap,val,pat out[i] = 1 if the NUL-terminated string at byte offset d[i] of the column's string
  *                                     heap (`Load,<table>.<col>.heap`, a byte vector) matches the SQL LIKE pattern
  *                                     (% any run, _ any one byte, no escape, case-sensitive), else 0          Vdl.hs:244-247,444-447
- *   CrossProduct* / Semisort          rejected (out of scope: SURVEY.md section 8 f3)
+ *   Semisort                          rejected (VliteFormat only: Vlite.hs:1061-1064)
  *
  * Threads: OpenMP, row-range split per op, deterministic combine.
  */
@@ -89,7 +90,7 @@ enum {
   OP_LOAD, OP_PROJECT, OP_RANGEV, OP_RANGEC,
   OP_LAND, OP_LOR, OP_BAND, OP_BOR, OP_SHIFT, OP_EQ, OP_ADD, OP_SUB, OP_GT, OP_MUL, OP_DIV, OP_MOD,
   OP_FCHOOSE, OP_FSELECT, OP_FMAX, OP_FSUM, OP_FMIN, OP_FCOUNT,
-  OP_GATHER, OP_SCATTER, OP_PARTITION, OP_SHUFFLE, OP_MATERIALIZE, OP_LIKE, OP_UNSUPPORTED
+  OP_GATHER, OP_SCATTER, OP_PARTITION, OP_SHUFFLE, OP_MATERIALIZE, OP_LIKE, OP_CROSS_OUTER, OP_CROSS_INNER, OP_UNSUPPORTED
 };
 static const struct { const char *name; int op; } OPNAMES[] = {
   {"Load", OP_LOAD}, {"Project", OP_PROJECT}, {"RangeV", OP_RANGEV}, {"RangeC", OP_RANGEC},
@@ -100,8 +101,8 @@ static const struct { const char *name; int op; } OPNAMES[] = {
   {"FoldSum", OP_FSUM}, {"FoldMin", OP_FMIN}, {"FoldCount", OP_FCOUNT},
   {"Gather", OP_GATHER}, {"Scatter", OP_SCATTER}, {"Partition", OP_PARTITION},
   {"Shuffle", OP_SHUFFLE}, {"MaterializeCompact", OP_MATERIALIZE},
-  {"Like", OP_LIKE}, {"CrossProductOuter", OP_UNSUPPORTED},
-  {"CrossProductInner", OP_UNSUPPORTED}, {"Semisort", OP_UNSUPPORTED}, {NULL, 0}};
+  {"Like", OP_LIKE}, {"CrossProductOuter", OP_CROSS_OUTER},
+  {"CrossProductInner", OP_CROSS_INNER}, {"Semisort", OP_UNSUPPORTED}, {NULL, 0}};
 
 typedef struct {
   int id, op;
@@ -210,6 +211,8 @@ static int parse_plan(orc_env *e, const char *text, stmt **out_stmts, int *out_n
       case OP_SCATTER: /* id,Scatter,src,fold,val,pos,val (Vdl.hs:441-442) */
         NEED(7); VAL(4); VAL(6); bad = parse_ref(f[2], &s->a) | parse_ref(f[3], &s->b) | parse_ref(f[5], &s->c); break;
       case OP_SHUFFLE: case OP_MATERIALIZE: NEED(3); bad = parse_ref(f[2], &s->a); break;
+      case OP_CROSS_OUTER: case OP_CROSS_INNER: /* id,CrossProductOuter,Id left,Id right (Vdl.hs:412-416) */
+        NEED(4); bad = parse_ref(f[2], &s->a) | parse_ref(f[3], &s->b); break;
       case OP_LIKE: { /* id,Like,val,Id data,val,Id heap,val,pattern (Vdl.hs:444-447); a pattern may contain commas */
         if (nf < 8) { bad = 1; goto done; }
         VAL(2); VAL(4); VAL(6); bad = parse_ref(f[3], &s->a) | parse_ref(f[5], &s->b);
@@ -342,6 +345,21 @@ static int op_scatter(orc_env *e, const vec *src, const vec *pos, vec *out) {
     if (p < 0 || p >= len) bad++; else o[p] = vget(src, i);
   }
   if (bad) { vfree(out); return fail(e, "Scatter: %lld positions out of range [0,%lld)", (long long)bad, (long long)len); }
+  return 0;
+}
+
+/* CrossProductOuter / CrossProductInner (Vlite.hs:89-93, 283-292; joins under --use_cross_product, Mplan.hs:309-313): the
+ * positions into `left` resp. `right` of the |left| x |right| pairs, left-major: "0,1,2,3 X 0,1 = 0,0,1,1,2,2,3,3 (outer),
+ * 0,1,0,1,0,1,0,1 (inner)".  Their index space is the side they point into. */
+static int op_cross(orc_env *e, const vec *left, const vec *right, int inner, vec *out) {
+  i64 nl = left->n, nr = right->n;
+  if (nl < 0 || nr < 0 || (nr > 0 && nl > (((i64)1 << 33) / nr))) return fail(e, "CrossProduct: %lld x %lld rows", (long long)nl, (long long)nr);
+  i64 n = nl * nr;
+  *out = new_dense(n);
+  out->domain = inner ? nr : nl;
+  i64 *o = out->d;
+#pragma omp parallel for schedule(static)
+  for (i64 i = 0; i < n; i++) o[i] = inner ? i % nr : i / nr;
   return 0;
 }
 
@@ -539,6 +557,7 @@ int orc_run(orc_env *e, const char *plan_text, int nthreads) {
       case OP_SCATTER: rc = op_scatter(e, A, C, &r); break;
       case OP_PARTITION: rc = op_partition(e, A, B, &r); break;
       case OP_LIKE: rc = op_like(e, A, B, s->name, &r); break;
+      case OP_CROSS_OUTER: case OP_CROSS_INNER: rc = op_cross(e, A, B, s->op == OP_CROSS_INNER, &r); break;
       case OP_FCHOOSE: case OP_FMAX: case OP_FSUM: case OP_FMIN: case OP_FCOUNT: {
         if (A->n != B->n) {   /* level 2 of a hierarchical fold: group the level-1 results by the groups at each run's head */
           stmt *inner = &st[s->b - 1];
