@@ -75,6 +75,8 @@ foreign import ccall safe "vdl_plan_run_local" c_vdl_plan_run_local :: Ptr VdlPl
 foreign import ccall safe "vdl_plan_finish" c_vdl_plan_finish :: Ptr VdlPlan -> Ptr (Ptr ()) -> CInt -> IO CInt
 foreign import ccall safe "vdl_plan_num_outputs" c_vdl_plan_num_outputs :: Ptr VdlPlan -> IO CInt
 foreign import ccall safe "vdl_plan_output" c_vdl_plan_output :: Ptr VdlPlan -> CInt -> Ptr CString -> Ptr (Ptr Int64) -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_plan_set_typed_outputs" c_vdl_plan_set_typed_outputs :: Ptr VdlPlan -> CInt -> IO CInt
+foreign import ccall safe "vdl_plan_output_typed" c_vdl_plan_output_typed :: Ptr VdlPlan -> CInt -> Ptr CString -> Ptr (Ptr ()) -> Ptr Int64 -> Ptr CInt -> IO CInt
 foreign import ccall safe "vdl_plan_destroy" c_vdl_plan_destroy :: Ptr VdlPlan -> IO CInt
 
 -- multi-GPU combine over peer memory (vdl_cuda.h "multi-GPU combine over peer memory"): after vdl_plan_set_peers,

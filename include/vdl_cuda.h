@@ -412,6 +412,13 @@ int vdl_plan_launch(vdl_plan *p);
 int vdl_plan_num_outputs(vdl_plan *p);
 /* Output i in MaterializeCompact order: name (the Project's <out>, Vdl.hs:278-292), host int64 data. */
 int vdl_plan_output(vdl_plan *p, int i, const char **name, const int64_t **data, int64_t *len);
+/* Typed result columns.  The reference's result is text (the server's JSON, resolve.py:8-32), so the width a column
+ * crosses PCIe in is the executor's choice: with typed outputs on, an op-at-a-time output whose every value is a value of
+ * a 4-byte column -- by provenance: a probe pass emitting a plain column, Gather, Scatter, FoldChoose / FoldMin / FoldMax of
+ * such a vector -- is narrowed on the device and copied as int32 (Q3 SF10: 28 instead of 44 MB per run).
+ * vdl_plan_output_typed returns dtype 4 (int32 data) or 8 (int64); vdl_plan_output fails for a column delivered as int32. */
+int vdl_plan_set_typed_outputs(vdl_plan *p, int on);
+int vdl_plan_output_typed(vdl_plan *p, int i, const char **name, const void **data, int64_t *len, int *dtype);
 int vdl_plan_destroy(vdl_plan *p);
 
 /* ---- several GPUs of one box driven from ONE process (SURVEY.md section 8 b, e) ----------------------------------------

@@ -128,6 +128,7 @@ void vec_written(vdl_ctx *ctx, Vec *v) {
   v->gen = ++ctx->gen_counter;
   v->has_stats = false;
   v->is_perm = false;
+  v->narrow32 = false;
 }
 
 bool vec_identity(vdl_ctx *ctx, vdl_vec h, u64 *gen) {

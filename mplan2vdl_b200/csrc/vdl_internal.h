@@ -21,6 +21,8 @@ struct Vec {
   bool live = false;
   bool is_range = false;
   bool is_perm = false;        // a Partition result: a permutation of 0..len-1, so a Scatter by it writes every slot
+  bool narrow32 = false;       // every value is a value of a 4-byte column (provenance: probe emit of a plain leaf, Gather,
+                               // Scatter, FoldChoose / Min / Max of such a vector): a result column can travel as int32
   i64 from = 0, step = 0;
   i64 domain = -1;          // length of the vector these values index into; -1 unknown (App. G2)
   bool has_stats = false;   // vmin/vmax computed on the device by vdl_column_analyze (invalidated by writes)
@@ -84,6 +86,7 @@ int check_errflag(vdl_ctx *ctx, const char *what);                        // syn
 // mapped host memory, so the read never queues on the copy engine behind a bulk device->host copy of another stream
 // (plan outputs); synchronises the context's stream.
 int read_scalar(vdl_ctx *ctx, const void *device_src, void *host_dst, int bytes);
+int vec_narrow_copy(vdl_ctx *ctx, vdl_vec src, vdl_vec *out);   // vdl_ops.cu: int64 -> int32 copy of a vector whose values fit
 
 // Wait until a kernel has published `seq` in mapped pinned host memory (its last store, after a system-scope fence):
 // a short spin on the word instead of cudaStreamSynchronize, whose wake-up costs 10-20 us -- several percent of a
@@ -97,6 +100,7 @@ struct Operand {
   i64 from, step;
 };
 Operand operand_of(const Vec &v);
+inline bool vec_is_narrow(const Vec &v) { return v.narrow32 || (v.dtype == VDL_I32 && !v.is_range); }
 
 // vdl_op_map's kernel arguments (interpreter in vdl_ops.cu, run-time specialisation in vdl_jit.cu)
 struct MapArgs {

@@ -418,9 +418,11 @@ extern "C" int vdl_op_gather(vdl_ctx *ctx, vdl_vec src, vdl_vec pos, vdl_vec *ou
   Vec *vs = vec_get(ctx, src), *vp = vec_get(ctx, pos);
   if (!vs || !vp) return VDL_EINVAL;
   i64 n = vp->len, m = vs->len, dom = vs->domain;
+  const bool narrow = vec_is_narrow(*vs);
   Operand os = operand_of(*vs), op = operand_of(*vp);
   VDL_TRY(vec_new(ctx, VDL_I64, n, out));
   ctx->vecs[*out].domain = dom;   // gathering positions keeps their index space
+  ctx->vecs[*out].narrow32 = narrow;
   if (n == 0) return VDL_OK;
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   int blocks = (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, (i64)ctx->sm_count * 16));
@@ -461,14 +463,40 @@ extern "C" int vdl_op_scatter(vdl_ctx *ctx, vdl_vec src, vdl_vec pos, int64_t ou
   if (out_len < 0) return vdl_fail(ctx, VDL_EINVAL, "Scatter: negative output length");
   i64 n = vs->len, dom = vs->domain;
   const bool covers = vp->is_perm && out_len == n;      // a permutation of 0..n-1 leaves no slot unwritten: nothing to zero
+  const bool narrow = vec_is_narrow(*vs);
   Operand os = operand_of(*vs), op = operand_of(*vp);
   VDL_TRY(vec_new(ctx, VDL_I64, out_len, out));
   ctx->vecs[*out].domain = dom;
+  ctx->vecs[*out].narrow32 = narrow;
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   if (out_len > 0 && !covers) VDL_CUDA(ctx, cudaMemsetAsync(ctx->vecs[*out].ptr, 0, (size_t)out_len * 8, ctx->stream));
   if (n == 0) return VDL_OK;
   int blocks = (int)std::max<i64>(1, std::min<i64>((n + 1023) / 1024, (i64)ctx->sm_count * 16));
   scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(os, op, n, (i64 *)ctx->vecs[*out].ptr, out_len, ctx->d_errflag);
+  ctx->launches++;
+  VDL_CUDA(ctx, cudaGetLastError());
+  return VDL_OK;
+}
+
+// ---------------------------------------------------------------------------------- int64 -> int32 (typed result columns)
+__global__ void __launch_bounds__(256) narrow_kernel(const i64 *__restrict__ in, i64 n, int *__restrict__ out) {
+  const i64 stride = (i64)gridDim.x * blockDim.x * 2;
+  for (i64 i = ((i64)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride) {
+    if (i + 1 < n) { const longlong2 v = *(const longlong2 *)(in + i); *(int2 *)(out + i) = make_int2((int)v.x, (int)v.y); }
+    else out[i] = (int)in[i];
+  }
+}
+// the low words of an int64 vector as a new VDL_I32 vector (the caller knows that every value fits)
+int vec_narrow_copy(vdl_ctx *ctx, vdl_vec src, vdl_vec *out) {
+  Vec *vs = vec_get(ctx, src);
+  if (!vs || vs->is_range || vs->dtype != VDL_I64) return vdl_fail(ctx, VDL_EINVAL, "narrow copy of a vector that is not a stored int64 vector");
+  const i64 n = vs->len;
+  const i64 *in = (const i64 *)vs->ptr;
+  VDL_TRY(vec_new(ctx, VDL_I32, n, out));
+  if (n == 0) return VDL_OK;
+  VDL_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int blocks = (int)std::max<i64>(1, std::min<i64>((n + 511) / 512, (i64)ctx->sm_count * 16));
+  narrow_kernel<<<blocks, 256, 0, ctx->stream>>>(in, n, (int *)ctx->vecs[*out].ptr);
   ctx->launches++;
   VDL_CUDA(ctx, cudaGetLastError());
   return VDL_OK;
@@ -898,6 +926,7 @@ extern "C" int vdl_op_fold(vdl_ctx *ctx, int fold_op, vdl_vec groups, vdl_vec da
   }
   VDL_CUDA(ctx, cudaSetDevice(ctx->device));
   const u64 groups_gen = vg->gen;
+  const bool narrow = (fold_op == VDL_FOLD_CHOOSE || fold_op == VDL_FOLD_MIN || fold_op == VDL_FOLD_MAX) && vec_is_narrow(*vd);
   i64 n = vd->len;
   Operand og = operand_of(*vg), od = operand_of(*vd);
   if (n == 0) {
@@ -911,6 +940,7 @@ extern "C" int vdl_op_fold(vdl_ctx *ctx, int fold_op, vdl_vec groups, vdl_vec da
     i64 *o = (i64 *)ctx->vecs[*out].ptr;
     ctx->vecs[*out].fold_groups = groups;
     ctx->vecs[*out].fold_groups_gen = groups_gen;
+    ctx->vecs[*out].narrow32 = narrow;
     fold_all_init_kernel<<<1, 1, 0, ctx->stream>>>(fold_op, od, n, o);
     ctx->launches++;
     const int grid = (int)std::max<i64>(1, std::min<i64>((n + 2047) / 2048, (i64)ctx->sm_count * 8));
@@ -945,5 +975,6 @@ extern "C" int vdl_op_fold(vdl_ctx *ctx, int fold_op, vdl_vec groups, vdl_vec da
   v.len = total;
   v.fold_groups = groups;
   v.fold_groups_gen = groups_gen;
+  v.narrow32 = narrow;
   return VDL_OK;
 }

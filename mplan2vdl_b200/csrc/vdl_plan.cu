@@ -37,7 +37,9 @@ struct Node {
 };
 
 // data points at the result's host copy: the fused scan's / probe's mapped result buffer, or this output's own pinned buffer
-struct Output { std::string name; int node; const i64 *data = nullptr; i64 len = 0; i64 *pinned = nullptr; size_t cap = 0; };
+// dtype 4: the values travelled as int32 (typed outputs: vdl_plan_set_typed_outputs); data then points at int32 values
+struct Output { std::string name; int node; const i64 *data = nullptr; i64 len = 0; i64 *pinned = nullptr; size_t cap = 0; int dtype = 8; };
+inline i64 out_get(const Output &o, i64 i) { return o.dtype == 4 ? (i64)((const int *)o.data)[i] : o.data[i]; }
 
 // ---- symbolic normal forms ------------------------------------------------------------------
 struct Aff { int col = -1; int shr = 0; i64 a = 0, b = 0; };   // a + b*(col >> shr); col = Load node, -1: constant a
@@ -113,6 +115,7 @@ struct vdl_plan {
   i64 row_base = 0;
   // Sharded tail (vdl_plan_tail_*): every output is a Fold by runs of ONE groups vector, so a row-range shard's result is a
   // slice of the global one up to the groups that straddle shard boundaries
+  bool typed_outputs = false;                    // result columns whose values provably fit travel as int32
   bool tail_ok = false, tail_on = false;
   int tail_groups = -1, tail_partition = -1;     // groups node; its Partition (-1: constant groups)
   i64 tail_rec[4] = {0, 0, 0, 0};                // of the last run: sorted, runs, first key, last key
@@ -1630,14 +1633,14 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
       const int64_t *data; int64_t len;
       const int idx = p->nodes[o.node].op == N_FOLD ? g.fold_of_node[o.node] : g.b.desc.nfolds + g.post_of_node[o.node];
       VDL_TRY(vdl_probe_result_host(g.probe, idx, &data, &len));
-      o.data = data; o.len = len;
+      o.data = data; o.len = len; o.dtype = 8;
       continue;
     }
     if (gi >= 0) {   // the output IS a fused fold or a post op of one: it arrived with the scan's single result copy
       const int64_t *data; int64_t len;
       if (p->nodes[o.node].op == N_FOLD) VDL_TRY(vdl_fused_result_host(p->groups[gi].fused, p->groups[gi].fold_of_node[o.node], &data, &len));
       else VDL_TRY(vdl_fused_post_host(p->groups[gi].fused, p->groups[gi].post_of_node[o.node], &data, &len));
-      o.data = data; o.len = len;
+      o.data = data; o.len = len; o.dtype = 8;
       continue;
     }
     ran_ops = true;
@@ -1654,7 +1657,19 @@ extern "C" int vdl_plan_finish(vdl_plan *p, const void *const *all_partials, int
       o.cap = want;
     }
     Vec *vv = vec_get(ctx, v);
-    if (vv && !vv->is_range && vv->dtype == VDL_I64 && len > 0) {
+    o.dtype = 8;
+    if (p->typed_outputs && vv && !vv->is_range && vv->dtype == VDL_I64 && vv->narrow32 && len > 0) {
+      // every value is a value of a 4-byte column: half the bytes over PCIe (a narrowing kernel, then the same async copy)
+      vdl_vec nv;
+      rc = vec_narrow_copy(ctx, v, &nv);
+      if (rc) { if (copies_pending) cudaStreamSynchronize(ctx->copy_stream); free_temps(p); return rc; }
+      p->temps.push_back(nv);
+      VDL_CUDA(ctx, cudaEventRecord(ctx->copy_event, ctx->stream));
+      VDL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
+      VDL_CUDA(ctx, cudaMemcpyAsync(o.pinned, vec_get(ctx, nv)->ptr, (size_t)len * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      copies_pending = true;
+      o.dtype = 4;
+    } else if (vv && !vv->is_range && vv->dtype == VDL_I64 && len > 0) {
       // the copy runs on its own stream behind an event, so the next output's kernels overlap it; one wait at the end
       VDL_CUDA(ctx, cudaEventRecord(ctx->copy_event, ctx->stream));
       VDL_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
@@ -1699,8 +1714,8 @@ extern "C" int vdl_plan_tail_boundary(vdl_plan *p, int64_t *rec, int cap) {
   for (int i = 0; i < k; i++) {
     const Output &o = p->outputs[i];
     if ((i64)o.len != runs) return vdl_fail(p->ctx, VDL_EINVAL, "sharded tail: output %d has %lld values, the first has %lld", i, (long long)o.len, (long long)runs);
-    rec[4 + i] = runs ? o.data[0] : 0;
-    rec[4 + k + i] = runs ? o.data[runs - 1] : 0;
+    rec[4 + i] = runs ? out_get(o, 0) : 0;
+    rec[4 + k + i] = runs ? out_get(o, runs - 1) : 0;
   }
   return VDL_OK;
 }
@@ -1712,8 +1727,11 @@ extern "C" int vdl_plan_tail_apply(vdl_plan *p, int drop_first, const int64_t *l
   for (size_t i = 0; i < p->outputs.size(); i++) {
     Output &o = p->outputs[i];
     if (o.len == 0 || o.data != o.pinned) continue;
-    if (last_row) o.pinned[o.len - 1] = last_row[i];
-    if (drop_first) { o.data = o.pinned + 1; o.len -= 1; }
+    if (last_row) {
+      if (o.dtype == 4) ((int *)o.pinned)[o.len - 1] = (int)last_row[i];      // CHOOSE / MIN / MAX of int32 values stay int32
+      else o.pinned[o.len - 1] = last_row[i];
+    }
+    if (drop_first) { o.data = o.dtype == 4 ? (const i64 *)((const int *)o.pinned + 1) : o.pinned + 1; o.len -= 1; }
   }
   return VDL_OK;
 }
@@ -1726,9 +1744,23 @@ extern "C" int vdl_plan_run(vdl_plan *p) {
 extern "C" int vdl_plan_num_outputs(vdl_plan *p) { return p ? (int)p->outputs.size() : 0; }
 extern "C" int vdl_plan_output(vdl_plan *p, int i, const char **name, const int64_t **data, int64_t *len) {
   if (!p || i < 0 || i >= (int)p->outputs.size()) return VDL_EINVAL;
+  if (data && p->outputs[i].dtype != 8) return vdl_fail(p->ctx, VDL_EINVAL, "output %d was delivered as int32 (typed outputs are on): read it with vdl_plan_output_typed", i);
   if (name) *name = p->outputs[i].name.c_str();
   if (data) *data = p->outputs[i].data;
   if (len) *len = (int64_t)p->outputs[i].len;
+  return VDL_OK;
+}
+extern "C" int vdl_plan_set_typed_outputs(vdl_plan *p, int on) {
+  if (!p) return VDL_EINVAL;
+  p->typed_outputs = on != 0;
+  return VDL_OK;
+}
+extern "C" int vdl_plan_output_typed(vdl_plan *p, int i, const char **name, const void **data, int64_t *len, int *dtype) {
+  if (!p || i < 0 || i >= (int)p->outputs.size()) return VDL_EINVAL;
+  if (name) *name = p->outputs[i].name.c_str();
+  if (data) *data = p->outputs[i].data;
+  if (len) *len = (int64_t)p->outputs[i].len;
+  if (dtype) *dtype = p->outputs[i].dtype;
   return VDL_OK;
 }
 

@@ -352,13 +352,22 @@ class Plan:
         if rc:
             self.ctx.check(rc)
 
+    def set_typed_outputs(self, on: bool = True):
+        """Result columns whose values provably fit travel as int32 (vdl_plan_set_typed_outputs); outputs() then returns
+        int32 arrays for them."""
+        self.ctx.check(self.L.vdl_plan_set_typed_outputs(self.h, int(on)))
+
     def outputs(self, copy: bool = True) -> dict:
-        """{output name: int64 array}.  copy=False returns views of the library's pinned host buffers, valid until the
-        plan runs again or is closed."""
+        """{output name: int64 (or, with typed outputs, int32) array}.  copy=False returns views of the library's pinned host
+        buffers, valid until the plan runs again or is closed."""
         out = {}
         for i in range(self.L.vdl_plan_num_outputs(self.h)):
-            name, data, n = C.c_char_p(), C.POINTER(C.c_int64)(), C.c_int64()
-            self.ctx.check(self.L.vdl_plan_output(self.h, i, C.byref(name), C.byref(data), C.byref(n)))
-            arr = np.ctypeslib.as_array(data, shape=(n.value,)) if n.value else np.zeros(0, np.int64)
+            name, data, n, dt = C.c_char_p(), C.c_void_p(), C.c_int64(), C.c_int()
+            self.ctx.check(self.L.vdl_plan_output_typed(self.h, i, C.byref(name), C.byref(data), C.byref(n), C.byref(dt)))
+            if n.value:
+                ctype = C.c_int32 if dt.value == 4 else C.c_int64
+                arr = np.ctypeslib.as_array(C.cast(data, C.POINTER(ctype)), shape=(n.value,))
+            else:
+                arr = np.zeros(0, np.int64)
             out[name.value.decode()] = arr.copy() if copy and n.value else arr
         return out

@@ -209,6 +209,8 @@ SYMBOLS = [
     ("vdl_comm_plan_destroy", _I, [_P]),
     ("vdl_plan_num_outputs", _I, [_P]),
     ("vdl_plan_output", _I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(_L)), C.POINTER(_L)]),
+    ("vdl_plan_set_typed_outputs", _I, [_P, _I]),
+    ("vdl_plan_output_typed", _I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(_L), C.POINTER(_I)]),
     ("vdl_plan_destroy", _I, [_P]),
 ]
 
