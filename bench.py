@@ -350,22 +350,25 @@ def main():
                 "kernel_ms": kern_mean, "kernel_ms_min": kern_min,
                 "frac_of_8TBs_spec": achieved / 8000.0, "bytes_per_launch": bytes_here}
     # DRAM bytes ncu counted for one launch of this kernel (profiles/traffic.json, tools/update_traffic.py) -- reported only
-    # while the kernel sources still hash to what the capture was taken from, so a stale figure cannot ride along
+    # while the sources that define THIS kernel's device code (mplan2vdl_b200.build.KERNEL_FAMILIES: the fused scan's or the
+    # probe's .cu + .cuh files) still hash to what the capture was taken from, so a stale figure cannot ride along
     try:
         from mplan2vdl_b200.build import source_hash
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
         tr = tj.get("workloads", {}).get(f"{args.query}_sf{args.sf:g}")
         if tr and world == 1:
-            if tj.get("source_hash") == source_hash():
+            fam = tr.get("family", "scan" if plan.num_fused else "probe")
+            if tj.get("family_hashes", {}).get(fam) == source_hash(fam):
                 roofline["traffic"] = tr["dram_bytes"]
-                roofline["traffic_source"] = f"ncu --set full, profiles/{tj.get('prefix')}_{args.query}_sf{args.sf:g}_dominant_kernel.txt ({tr.get('kernel')})"
+                roofline["traffic_source"] = (f"ncu --set full, profiles/{tj.get('prefix')}_{args.query}_sf{args.sf:g}_dominant_kernel.txt ({tr.get('kernel')}); "
+                                              f"the {fam} kernel's sources are unchanged since that capture (hash {source_hash(fam)})")
                 # a selective plan (probe kernel) never touches most columns of the rows it rejects: the DRAM bytes ncu
                 # counted are then the honest numerator, the all-columns algorithmic figure an upper bound
                 roofline["dram_gbs_by_traffic"] = tr["dram_bytes"] / (kern_mean / 1e3) / 1e9
                 roofline["frac_by_traffic"] = roofline["dram_gbs_by_traffic"] / peak
             else:
-                roofline["traffic_source"] = "profiles/traffic.json is older than the kernel sources (source hash differs): not reported"
+                roofline["traffic_source"] = f"profiles/traffic.json is older than the {fam} kernel's sources (hash differs): not reported"
     except Exception:
         pass
 

@@ -1203,6 +1203,12 @@ int run_emit_group(vdl_plan *p, EmitGroup &g) {
     VDL_TRY(vdl_probe_emit_take(g.probe, (int)k, &v));
     p->val[g.nodes[k]] = v;
     p->temps.push_back(v);
+    // a plain leaf of a 4-byte column: every emitted value fits int32 (typed result columns, vdl_plan_set_typed_outputs)
+    const vdl_product &e = g.b.desc.emit[k];
+    if (e.nfactors == 1 && e.factor[0].leaf >= 0 && e.factor[0].shr == 0 && e.factor[0].a == 0 && e.factor[0].b == 1) {
+      Vec *col = vec_get(p->ctx, g.b.desc.leaf[e.factor[0].leaf].column), *ev = vec_get(p->ctx, v);
+      if (col && ev && col->dtype == VDL_I32) ev->narrow32 = true;
+    }
   }
   g.ran = true;
   return VDL_OK;

@@ -1090,10 +1090,6 @@ extern "C" int vdl_probe_emit_take(vdl_probe *p, int k, vdl_vec *out) {
   if (!p->emit_vec[k]) return vdl_fail(p->ctx, VDL_EINVAL, "probe: emitted vector %d already taken", k);
   *out = p->emit_vec[k];
   p->emit_vec[k] = 0;
-  // a plain leaf of a 4-byte column: every value fits int32 (typed result columns, vdl_plan_set_typed_outputs)
-  const PProd &e = p->pd.emit[k];
-  if (e.nfac == 1 && e.f[0].leaf >= 0 && e.f[0].shr == 0 && e.f[0].a == 0 && e.f[0].b == 1 && p->pd.leaf[e.f[0].leaf].w4)
-    p->ctx->vecs[*out].narrow32 = true;
   return VDL_OK;
 }
 
