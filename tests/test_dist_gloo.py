@@ -222,3 +222,95 @@ def test_peer_setup_stays_collective_when_one_rank_fails():
             assert not ok and npeers == 0 and why
             assert len(freed) >= 1                      # its own buffers were freed again
     assert len(got[0][1][3]) >= 1                       # rank 0 had opened rank 1's first buffer: closed again
+
+
+class _FakeTailPlan:
+    """Stands for executor.Plan in the sharded-tail test: `execute` folds this rank's shard of a sorted key vector in numpy,
+    the tail_* methods do what vdl_plan_tail_boundary / vdl_plan_tail_apply do in the library."""
+    num_partials, num_emits = 0, 1
+    OPS = [3, 0, 1, 2]            # FoldChoose, FoldSum, FoldMin, FoldMax
+
+    def __init__(self, keys, vals):
+        self.keys, self.vals, self.outs = keys, vals, None
+
+    def tail_info(self):
+        return list(self.OPS)
+
+    def tail_enable(self, on):
+        self.on = on
+
+    def execute(self):
+        k, v = self.keys, self.vals
+        if len(k) == 0:
+            self.outs = [np.zeros(0, np.int64) for _ in self.OPS]
+            return
+        heads = np.flatnonzero(np.r_[True, k[1:] != k[:-1]])
+        self.outs = [v[heads].copy(), np.add.reduceat(v, heads), np.minimum.reduceat(v, heads), np.maximum.reduceat(v, heads)]
+
+    def tail_boundary(self, into):
+        runs = len(self.outs[0])
+        rec = [1, runs, int(self.keys[0]) if runs else 0, int(self.keys[-1]) if runs else 0] + \
+              [int(o[0]) if runs else 0 for o in self.outs] + [int(o[-1]) if runs else 0 for o in self.outs]
+        for i, x in enumerate(rec):
+            into[i] = x
+        return into
+
+    def tail_apply(self, drop_first, last_row=None):
+        if last_row is not None:
+            for o, x in zip(self.outs, last_row):
+                o[-1] = x
+        if drop_first:
+            self.outs = [o[1:] for o in self.outs]
+
+    def outputs(self, copy=True):
+        return {f"out{i}": (o.copy() if copy else o) for i, o in enumerate(self.outs)}
+
+
+TAIL_KEYS = np.sort(np.random.default_rng(7).integers(0, 40, 500)).astype(np.int64)
+TAIL_VALS = np.random.default_rng(8).integers(-50, 50, 500).astype(np.int64)
+
+
+def tail_worker(rank, world, port, q, cuts):
+    from mplan2vdl_b200.dist import ShardedPlan
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = []
+    for cut in cuts:
+        bounds = [0] + list(cut) + [len(TAIL_KEYS)]
+        plan = _FakeTailPlan(TAIL_KEYS[bounds[rank]:bounds[rank + 1]], TAIL_VALS[bounds[rank]:bounds[rank + 1]])
+        sp = ShardedPlan.__new__(ShardedPlan)
+        sp.ctx, sp.plan, sp.rank, sp.world, sp.group = _FakeCtx(rank, ("none", -1, 0)), plan, rank, world, None
+        sp.peer_mode, sp._want_peer, sp.tail_ops, sp.tail_mode, sp._tb, sp._tail_slice = False, False, plan.tail_info(), True, None, None
+        mine = sp.step()                                   # this rank's slice
+        whole = sp.global_result()                         # every rank: the concatenation
+        res.append(({k: v.tolist() for k, v in mine.items()}, {k: v.tolist() for k, v in whole.items()}))
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,cuts", [(2, [(250,), (0,), (500,), (251,)]), (3, [(100, 300), (10, 11), (200, 200)])])
+def test_gloo_sharded_tail_merges_the_groups_that_straddle_ranks(world, cuts):
+    """The N>1 host path of emit plans (dist.ShardedPlan._step_tail): every rank folds its own rows, one all-gather of the
+    boundary records, the straddling groups merged into the rank where they start; the concatenated slices are the fold of
+    the whole vector.  Cuts include empty shards and cuts inside a run."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=tail_worker, args=(r, world, port, q, cuts)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    whole_plan = _FakeTailPlan(TAIL_KEYS, TAIL_VALS)
+    whole_plan.execute()
+    want = {k: v.tolist() for k, v in whole_plan.outputs().items()}
+    for c in range(len(cuts)):
+        for rank in range(world):
+            assert got[rank][c][1] == want, (cuts[c], rank)
+        glued = {k: sum((got[r][c][0][k] for r in range(world)), []) for k in want}
+        assert glued == want
