@@ -132,6 +132,22 @@ def test_partition_is_a_stable_sort_permutation():
     np.testing.assert_array_equal(r["sorted"], [0, 1, 1, 1, 2, 3, 3])
 
 
+@pytest.mark.parametrize("domain", [7, 5000, 1 << 30])
+def test_large_partition_in_parallel_is_the_stable_argsort(domain):
+    """Above 65536 rows every radix pass runs on all threads (per-thread digit counts of contiguous slices): same permutation
+    as numpy's stable sort, also over several 11-bit passes; keys that are already in order take the identity shortcut."""
+    rng = np.random.default_rng(domain)
+    k = rng.integers(0, domain, 300_001).astype(I64)
+    plan = PART.replace("3,RangeC,val,0,4,1", f"3,RangeC,val,0,{domain},1")
+    for keys in (k, np.sort(k)):
+        r = run(plan, k=keys)
+        order = np.argsort(keys, kind="stable")
+        want = np.empty_like(order)
+        want[order] = np.arange(len(keys))
+        np.testing.assert_array_equal(r["perm"], want)
+        np.testing.assert_array_equal(r["sorted"], keys[order])
+
+
 def test_partition_clamps_to_pivot_range():
     # bucket = number of pivots below the value: values under the first pivot share bucket 0, above the last share bucket n
     r = run(PART, k=np.array([9, -5, 2, 100, 0], I64))
