@@ -188,9 +188,16 @@ def read_schema(path: str) -> dict:
 
 def load_metadata(directory: str) -> Catalog:
     """Read the four files of a metadata directory such as the reference's tests/tpch10noorder/."""
+    dpath = os.path.join(directory, "dictionary.csv")
+    return load_metadata_files(os.path.join(directory, "bounds.csv"), os.path.join(directory, "storage.csv"),
+                               os.path.join(directory, "schema.msqldump"), dpath if os.path.exists(dpath) else None)
+
+
+def load_metadata_files(bounds: str, storage_path: str, schema: str, dictionary: str | None) -> Catalog:
+    """makeConfig (Config.hs:149-170) from the reference's four inputs: -b bounds, -t storage, -s schema, --dictionary."""
     cat = Catalog()
-    storage = read_storage(os.path.join(directory, "storage.csv"))
-    for col in read_bounds(os.path.join(directory, "bounds.csv")):
+    storage = read_storage(storage_path)
+    for col in read_bounds(bounds):
         tab = cat.tables.setdefault(col.table, Table(col.table))
         st = storage.get((col.table, col.name))
         if st:
@@ -200,15 +207,14 @@ def load_metadata(directory: str) -> Catalog:
             col.width = _WIDTH[col.mtype]
         tab.columns[col.name] = col
         tab.rows = max(tab.rows, col.count)
-    for t, (pk_name, pk_cols, fks, scales) in read_schema(os.path.join(directory, "schema.msqldump")).items():
+    for t, (pk_name, pk_cols, fks, scales) in read_schema(schema).items():
         if t in cat.tables:
             cat.tables[t].pkey_name, cat.tables[t].pkey, cat.tables[t].fkeys = pk_name, pk_cols, fks
             for c, sc in scales.items():
                 if c in cat.tables[t].columns:
                     cat.tables[t].columns[c].scale = sc
-    dpath = os.path.join(directory, "dictionary.csv")
-    if os.path.exists(dpath):
-        cat.dictionary = read_dictionary(dpath)
+    if dictionary:
+        cat.dictionary = read_dictionary(dictionary)
     return cat
 
 

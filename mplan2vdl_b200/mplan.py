@@ -399,10 +399,10 @@ def relexpr_from_mplan(catalog, text: str, cross_product=False):
     return Front(catalog, cross_product).solve(parse(text))
 
 
-def translate_mplan(catalog, text: str, agg_strategy="serial", cross_product=False) -> str:
+def translate_mplan(catalog, text: str, agg_strategy="serial", cross_product=False, goffset=0, apply_cleanup_passes=True) -> str:
     """The whole translator (MainFuns.compile, 172-188) for the supported subset: mplan text -> Voodoo program text."""
     from . import vlite
-    return vlite.translate(catalog, relexpr_from_mplan(catalog, text, cross_product), agg_strategy)
+    return vlite.translate(catalog, relexpr_from_mplan(catalog, text, cross_product), agg_strategy, goffset, apply_cleanup_passes)
 
 
 if __name__ == "__main__":
@@ -414,6 +414,13 @@ if __name__ == "__main__":
     g.add_argument("--aggserial", action="store_true")
     g.add_argument("--agghierarchical", action="store_true")
     g.add_argument("--aggshuffle", action="store_true")
+    ap.add_argument("-b", "--boundsfile", help="(table,col,min,max,count,trailing zeros) csv; with -t -s --dictionary replaces the built-in SF10 catalogue")
+    ap.add_argument("-t", "--storagefile", help="output of 'select * from storage' in csv format")
+    ap.add_argument("-s", "--schemafile", help="output of msqldump -D -d <dbname>")
+    ap.add_argument("--dictionary", dest="dictionaryfile", help="dictionary to encode literal strings")
+    ap.add_argument("--goffset", type=int, default=0, help="offset for synthesized group-by keys (MainFuns.hs:67)")
+    ap.add_argument("-c", "--apply_cleanup_passes", type=lambda v: v.lower() not in ("false", "0", "no"), default=True,
+                    help="after generating vdl identify and clean up known no-op patterns (default true)")
     ap.add_argument("--use_cross_product", action="store_true", help="plain joins as a selection over the cross product (MainFuns.hs:72)")
     ap.add_argument("-g", "--grainsize", type=int, default=8192, help="power of 2; only with --agghierarchical")
     a = ap.parse_args()
@@ -421,4 +428,9 @@ if __name__ == "__main__":
         sys.exit("grainsize must be a power of 2 (MainFuns.hs:112)")
     strategy = ("hierarchical", a.grainsize.bit_length() - 1) if a.agghierarchical else ("shuffle" if a.aggshuffle else "serial")
     src = sys.stdin.read() if a.mplanfile == "-" else open(a.mplanfile).read()
-    sys.stdout.write(translate_mplan(builtin_catalog(), src, strategy, a.use_cross_product))
+    files = (a.boundsfile, a.storagefile, a.schemafile, a.dictionaryfile)
+    if any(files) and not all(files):
+        sys.exit("usage: need a column bounds csv, a storage file, a schema file and a dictionary file, or none of them (MainFuns.hs:101-112)")
+    from .meta import load_metadata_files
+    catalog = load_metadata_files(*files) if all(files) else builtin_catalog()
+    sys.stdout.write(translate_mplan(catalog, src, strategy, a.use_cross_product, a.goffset, a.apply_cleanup_passes))

@@ -307,11 +307,13 @@ class Env:
 class Lowering:
     """vexpsFromMplan (Vlite.hs:522-523) over a catalogue (mplan2vdl_b200.meta.Catalog = the reference's Config)."""
 
-    def __init__(self, catalog, agg_strategy="serial"):
+    def __init__(self, catalog, agg_strategy="serial", goffset=0):
         """agg_strategy: "serial" (--aggserial, the default), "shuffle" (--aggshuffle) or ("hierarchical", log2 of the grain
-        size) (--agghierarchical -g GRAIN; MainFuns.hs:61-65, 139-147)."""
+        size) (--agghierarchical -g GRAIN; MainFuns.hs:61-65, 139-147).  goffset: --goffset, an offset added to every
+        synthesized group-by key (Config.gboffset, makeCompositeKey 1125-1131)."""
         self.cat = catalog
         self.agg = agg_strategy
+        self.goffset = goffset
         # makeFKEntries (Config.hs:200-218): every foreign key is known by its column pairs ("implicit": l_orderkey =
         # o_orderkey; composite keys need all their pairs) and by its index column against the dimension's row ids
         # ("explicit": lineitem.lineitem_orders = orders.%TID%), in both argument orders
@@ -444,10 +446,12 @@ class Lowering:
         sl, sr = self.shift_to_zero(l), self.shift_to_zero(r)
         return binop("BitOr", shl(sl, const_(get_bit_width(sr), sl)), sr)
 
-    def make_composite_key(self, keys: list) -> Vexp:     # 1123-1136 (gboffset 0, VdlFormat: addSizeHint 1111-1115)
+    def make_composite_key(self, keys: list) -> Vexp:     # 1123-1136 (VdlFormat: addSizeHint 1111-1115)
         out = self.shift_to_zero(keys[0])
         for k in keys[1:]:
             out = self.compose_keys(out, k)
+        if self.goffset > 0:
+            out = binop("Add", out, const_(self.goffset, out)).replace(comment="offset added by goffset")
         out = out.replace(bounds=(0, out.bounds[1]))
         hint = const_(max_for_width(out), out).replace(comment="size hint for voodoo backend")
         return binop("BitAnd", out, hint)
@@ -872,7 +876,8 @@ def emit(vexps: list) -> str:
     return "\n".join(e.lines) + "\n"
 
 
-def translate(catalog, rel, agg_strategy="serial") -> str:
-    """compile (MainFuns.hs:172-188) with the default flags: cleanup passes on, no push-joins, VdlFormat; the aggregation
+def translate(catalog, rel, agg_strategy="serial", goffset=0, apply_cleanup_passes=True) -> str:
+    """compile (MainFuns.hs:172-188) with the default flags: cleanup passes on (-c), no push-joins, VdlFormat; the aggregation
     strategy is --aggserial unless given (see Lowering)."""
-    return emit(cleanup(Lowering(catalog, agg_strategy).solve_list(rel)))
+    vexps = Lowering(catalog, agg_strategy, goffset).solve_list(rel)
+    return emit(cleanup(vexps) if apply_cleanup_passes else vexps)

@@ -99,3 +99,35 @@ def test_gpu_runs_every_strategy(catalog, q, strategy):
         # a grain above the 32 slots the reference's metadata gives the sorted vector: level1par is inferred constant, the keys
         # are OR-ed without a shift, nothing is provable and both Folds run op-at-a-time -- literally.)
         assert fstats["fused_scans"] == 1, fstats
+
+
+@pytest.mark.parametrize("q", ["q01", "q05"])
+def test_goffset_shifts_the_group_key_and_nothing_else(catalog, q):
+    """--goffset (MainFuns.hs:67; makeCompositeKey Vlite.hs:1125-1131): the synthesized key gets an offset before its size
+    hint; the groups, their order and every aggregate stay what they were."""
+    rel = tpch_queries.QUERIES[q](catalog)
+    serial, shifted = vlite.translate(catalog, rel), vlite.translate(catalog, rel, goffset=3)
+    assert shifted != serial and "Add" in [l.split(",")[1] for l in shifted.splitlines()]
+    cols = columns(catalog, serial)
+    assert_same(run_oracle(shifted, cols), run_oracle(serial, cols))
+
+
+def test_without_the_cleanup_passes_the_program_is_longer_and_means_the_same(catalog):
+    rel = tpch_queries.QUERIES["q06"](catalog)
+    clean, raw = vlite.translate(catalog, rel), vlite.translate(catalog, rel, apply_cleanup_passes=False)
+    assert len(raw.splitlines()) > len(clean.splitlines())
+    cols = columns(catalog, clean)
+    assert_same(run_oracle(raw, cols), run_oracle(clean, cols))
+
+
+def test_catalogue_from_the_four_metadata_files_is_the_built_in_one(catalog):
+    import os
+    from mplan2vdl_b200 import mplan
+    from mplan2vdl_b200.meta import load_metadata_files
+    d = "/root/reference/tests/tpch10noorder"
+    if not os.path.isdir(d):
+        pytest.skip("reference fixtures not mounted (GPU box)")
+    cat = load_metadata_files(f"{d}/bounds.csv", f"{d}/storage.csv", f"{d}/schema.msqldump", f"{d}/dictionary.csv")
+    for n in ("01", "05", "16"):
+        src = open(f"{d}/{n}.sql.mplan").read()
+        assert mplan.translate_mplan(cat, src) == mplan.translate_mplan(catalog, src)
