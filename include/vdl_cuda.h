@@ -42,7 +42,7 @@ enum {
   VDL_EINVAL = 1,      /* bad argument / malformed plan text */
   VDL_ECUDA = 2,       /* CUDA runtime error (message has the cudaError string) */
   VDL_ENOTFOUND = 3,   /* Load of a column that is not registered */
-  VDL_EUNSUPPORTED = 4,/* op outside the supported vocabulary (CrossProduct*, Semisort) */
+  VDL_EUNSUPPORTED = 4,/* op or plan shape outside what is supported (Semisort; a cross product beyond 2^33 pairs) */
   VDL_ERANGE = 5,      /* Gather/Scatter position out of range */
   VDL_ENOMEM = 6,
   VDL_ESTALE = 7       /* a prepared scan / probe was launched after one of its columns was rewritten or dropped */
