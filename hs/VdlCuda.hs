@@ -100,6 +100,7 @@ foreign import ccall safe "vdl_plan_probe_stats" c_vdl_plan_probe_stats :: Ptr V
 foreign import ccall safe "vdl_plan_num_partials" c_vdl_plan_num_partials :: Ptr VdlPlan -> IO CInt
 foreign import ccall safe "vdl_plan_partials" c_vdl_plan_partials :: Ptr VdlPlan -> CInt -> Ptr (Ptr ()) -> Ptr Int64 -> IO CInt
 foreign import ccall safe "vdl_plan_num_emits" c_vdl_plan_num_emits :: Ptr VdlPlan -> IO CInt
+foreign import ccall safe "vdl_plan_emit_group_table" c_vdl_plan_emit_group_table :: Ptr VdlPlan -> CInt -> Ptr CString -> IO CInt
 foreign import ccall safe "vdl_plan_emit" c_vdl_plan_emit :: Ptr VdlPlan -> CInt -> Ptr (Ptr ()) -> Ptr Int64 -> IO CInt
 foreign import ccall safe "vdl_plan_emit_replace" c_vdl_plan_emit_replace :: Ptr VdlPlan -> CInt -> Ptr () -> Int64 -> IO CInt
 foreign import ccall safe "vdl_plan_tail_info" c_vdl_plan_tail_info :: Ptr VdlPlan -> Ptr CInt -> Ptr CInt -> CInt -> IO CInt

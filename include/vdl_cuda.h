@@ -361,6 +361,10 @@ int vdl_plan_stats(vdl_plan *p, int *statements, int *nodes, int *fused_scans, i
  * rank holds its shard's survivors; concatenate them over the ranks in rank order (= global row order; any transport) and
  * substitute the result before vdl_plan_finish, which then evaluates the remaining ops on the global vectors. */
 int vdl_plan_num_emits(vdl_plan *p);
+/* The table whose rows probe emit group `group` (0 .. emit_groups - 1 of vdl_plan_probe_stats) walks.  Sharding by row range
+ * is only meaningful when that is the sharded fact table: a pass over a replicated dimension table emits the same survivors on
+ * every rank (mplan2vdl_b200/dist.py refuses such plans instead of miscomputing them). */
+int vdl_plan_emit_group_table(vdl_plan *p, int group, const char **table);
 int vdl_plan_emit(vdl_plan *p, int i, void **device_ptr, int64_t *len);              /* synchronises */
 int vdl_plan_emit_replace(vdl_plan *p, int i, void *device_ptr, int64_t len);        /* caller-owned device memory */
 /* Sharded TAIL: when every output of the plan is an op-at-a-time Fold by runs of ONE groups vector -- a constant (a single

@@ -1436,6 +1436,18 @@ extern "C" int vdl_plan_probe_stats(vdl_plan *p, int *fold_groups, int *emit_gro
   return VDL_OK;
 }
 
+// The table whose rows probe emit group `group` walks (its fact side).  A row-range sharded run is only meaningful when that
+// is the sharded table: a pass over a replicated dimension table would emit the same survivors on every rank.
+extern "C" int vdl_plan_emit_group_table(vdl_plan *p, int group, const char **table) {
+  if (!p || !table || group < 0 || group >= (int)p->egroups.size() || !p->join) return VDL_EINVAL;
+  const int space = p->egroups[group]->space;
+  if (space < 0 || space >= (int)p->join->spaces.size()) return VDL_EINVAL;
+  const int t = p->join->spaces[space].table;
+  if (t < 0 || t >= (int)p->tables.size()) return VDL_EINVAL;
+  *table = p->tables[t].c_str();
+  return VDL_OK;
+}
+
 extern "C" int vdl_plan_map_stats(vdl_plan *p, int *clusters, int *nodes_covered) {
   if (!p) return VDL_EINVAL;
   if (clusters) *clusters = (int)p->clusters.size();

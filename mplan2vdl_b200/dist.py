@@ -110,11 +110,23 @@ def merge_tail_boundaries(recs, ops, rank):
     return drop_first, (last if changed else None)
 
 
+def check_shardable(plan, world: int, fact_table: str):
+    """Row-range sharding of a plan that emits survivors is implemented for ONE probe pass over the sharded fact table
+    (Q3, Q19).  A pass over a replicated dimension table would emit the same rows on every rank, and a semijoin's dimension
+    side needs matches from every rank's fact rows (Q4, Q20): refused loudly rather than miscomputed."""
+    if world > 1 and plan.num_emits > 0:
+        tables = plan.emit_tables()
+        if len(tables) != 1 or tables[0] != fact_table:
+            raise NotImplementedError(f"plan with probe emit passes over {tables} cannot be row-range sharded on {fact_table!r}: "
+                                      "run it on one GPU")
+
+
 class ShardedPlan:
     """A plan executed over this rank's shard; step() returns the global result on every rank."""
 
-    def __init__(self, ctx, plan, rank: int, world: int, row_base: int, group=None, peer: bool | None = None):
+    def __init__(self, ctx, plan, rank: int, world: int, row_base: int, group=None, peer: bool | None = None, fact_table: str = "lineitem"):
         import os
+        check_shardable(plan, world, fact_table)
         self.ctx, self.plan, self.rank, self.world, self.group = ctx, plan, rank, world, group
         plan.set_row_base(row_base)
         self._stream = torch.cuda.ExternalStream(ctx.stream, device=ctx.device) if world > 1 else None

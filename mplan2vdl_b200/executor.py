@@ -273,6 +273,15 @@ class Plan:
     def emit_replace(self, i: int, ptr: int, n: int):
         self.ctx.check(self.L.vdl_plan_emit_replace(self.h, i, C.c_void_p(ptr), n))
 
+    def emit_tables(self) -> list:
+        """The table each probe emit group walks (vdl_plan_emit_group_table)."""
+        out = []
+        for g in range(self.stats()["probe_emits"]):
+            name = C.c_char_p()
+            self.ctx.check(self.L.vdl_plan_emit_group_table(self.h, g, C.byref(name)))
+            out.append(name.value.decode())
+        return out
+
     def tail_info(self):
         """None, or the fold op (VDL_FOLD_*: 0 Sum, 1 Min, 2 Max, 3 Choose, 4 Count) of every output when all of them are
         Folds by runs of one groups vector: the plan's tail can then run on a row-range shard (vdl_plan_tail_info)."""

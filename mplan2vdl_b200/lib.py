@@ -168,6 +168,7 @@ SYMBOLS = [
     ("vdl_probe_last_kernel_ms", _I, [_P, C.POINTER(C.c_float)]),
     ("vdl_probe_destroy", _I, [_P]),
     ("vdl_plan_num_emits", _I, [_P]),
+    ("vdl_plan_emit_group_table", _I, [_P, _I, C.POINTER(C.c_char_p)]),
     ("vdl_plan_emit", _I, [_P, _I, C.POINTER(_P), C.POINTER(_L)]),
     ("vdl_plan_emit_replace", _I, [_P, _I, _P, _L]),
     ("vdl_plan_tail_info", _I, [_P, _P, _P, _I]),

@@ -141,3 +141,41 @@ def test_plans_of_another_shape_are_not_offered_the_sharded_tail(catalog):
         plan.tail_enable(True)
     plan.close()
     ctx.close()
+
+
+def test_emit_plans_over_a_dimension_table_are_refused_not_miscomputed():
+    """A probe pass over a replicated table would emit the same survivors on every rank, and a semijoin's dimension side needs
+    matches from every rank (Q4, Q20): dist.ShardedPlan refuses them before anything runs."""
+    from mplan2vdl_b200.dist import check_shardable
+
+    class P:
+        def __init__(self, tables):
+            self.num_emits, self._t = len(tables), tables
+
+        def emit_tables(self):
+            return self._t
+    check_shardable(P([]), 8, "lineitem")                      # scans / probe folds: nothing emitted
+    check_shardable(P(["lineitem"]), 8, "lineitem")            # Q3, Q19
+    check_shardable(P(["orders", "lineitem"]), 1, "lineitem")  # one GPU: anything goes
+    for tables in (["orders"], ["orders", "lineitem"], ["lineitem", "lineitem"]):
+        with pytest.raises(NotImplementedError, match="one GPU"):
+            check_shardable(P(tables), 2, "lineitem")
+
+
+@pytest.mark.gpu
+def test_emit_group_tables_are_reported(catalog):
+    from mplan2vdl_b200 import synth
+    from mplan2vdl_b200.executor import Context
+    ctx = Context(0)
+    for q, want in (("q03.vdl", ["lineitem"]), ("q06.vdl", [])):
+        text = plan_text(q)
+        rows = {t: synth.table_rows(catalog, t, 0.002) for t in catalog.tables}
+        for k, v in host_columns(catalog, tpch.plan_columns(text), rows, sf=0.002).items():
+            try:
+                ctx.lookup(k)
+            except Exception:
+                ctx.upload_column(k, v)
+        plan = ctx.plan(text)
+        assert plan.emit_tables() == want
+        plan.close()
+    ctx.close()
