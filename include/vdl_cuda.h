@@ -377,7 +377,8 @@ int vdl_plan_emit_replace(vdl_plan *p, int i, void *device_ptr, int64_t len);   
  * outputs values).  Exchanging these records lets the ranks merge the straddling groups -- SUM adds, MIN / MAX compare,
  * FoldChoose keeps the earlier rank's value -- without moving the survivors (mplan2vdl_b200/dist.py
  * merge_tail_boundaries); vdl_plan_tail_apply writes the merged last row and / or gives up the first row (a group that
- * starts on an earlier rank), after which vdl_plan_output returns this rank's slice of the global result. */
+ * starts on an earlier rank), after which vdl_plan_output returns this rank's slice of the global result.  (Only meaningful
+ * when the plan's one probe emit pass walks the sharded table: vdl_plan_emit_group_table.) */
 int vdl_plan_tail_info(vdl_plan *p, int *mergeable, int *fold_ops, int cap);
 int vdl_plan_tail_enable(vdl_plan *p, int on);
 int vdl_plan_tail_boundary(vdl_plan *p, int64_t *rec, int cap);
