@@ -91,6 +91,7 @@ foreign import ccall safe "vdl_ipc_free" c_vdl_ipc_free :: Ptr VdlCtx -> Ptr () 
 
 -- what the fusion passes did with a loaded program (Folds on the fused scan; FK-join Folds / vectors on the probe kernel)
 foreign import ccall safe "vdl_plan_stats" c_vdl_plan_stats :: Ptr VdlPlan -> Ptr CInt -> Ptr CInt -> Ptr CInt -> Ptr Int64 -> IO CInt
+foreign import ccall safe "vdl_plan_explain" c_vdl_plan_explain :: CString -> CInt -> CString -> CInt -> IO CInt
 foreign import ccall safe "vdl_probe_exchange_bytes" c_vdl_probe_exchange_bytes :: Ptr VdlProbe -> CInt -> Ptr Int64 -> IO CInt
 foreign import ccall safe "vdl_probe_set_peers" c_vdl_probe_set_peers :: Ptr VdlProbe -> CInt -> CInt -> Ptr (Ptr ()) -> IO CInt
 foreign import ccall safe "vdl_plan_map_stats" c_vdl_plan_map_stats :: Ptr VdlPlan -> Ptr CInt -> Ptr CInt -> IO CInt

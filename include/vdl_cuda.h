@@ -354,6 +354,11 @@ int vdl_probe_destroy(vdl_probe *p);
 /* ---- whole plans: the text mplan2vdl prints (Vdl.hs:410-453) ---------------------------- */
 enum { VDL_PLAN_FUSE = 1 };           /* flags: run the select->map->fold fusion pass */
 int vdl_plan_load(vdl_ctx *ctx, const char *vdl_text, int flags, vdl_plan **out);
+/* EXPLAIN: what the planner makes of a program, as JSON in `out` -- statements, nodes after CSE, the fused scans (table,
+ * columns, predicates, key parts, domain, folds, post ops), probe fold and emit groups, map clusters, Folds left for
+ * op-at-a-time evaluation, whether the tail is mergeable across shards.  Needs no context, no column and no device: binding
+ * happens at run time.  A program the parser or the planner rejects gives {"error": code, "message": ...} and that code. */
+int vdl_plan_explain(const char *vdl_text, int flags, char *out, int capacity);
 /* Statements parsed, distinct nodes after structural CSE (App. G10), fused scans, kernel launches
  * of the last run. */
 int vdl_plan_stats(vdl_plan *p, int *statements, int *nodes, int *fused_scans, int64_t *launches);

@@ -1417,6 +1417,62 @@ extern "C" int vdl_plan_load(vdl_ctx *ctx, const char *vdl_text, int flags, vdl_
   return VDL_OK;
 }
 
+// What the planner makes of a program, without a device: parse, CSE, both fusion passes, map clusters, the tail check -- as
+// JSON.  No column is looked up and nothing is compiled or launched (binding happens at run time), so this runs on a host
+// without a GPU: the planner's decisions are testable where the kernels are not.
+extern "C" int vdl_plan_explain(const char *vdl_text, int flags, char *out, int capacity) {
+  if (!vdl_text || !out || capacity < 2) return VDL_EINVAL;
+  vdl_ctx *ctx = new vdl_ctx();          // a message sink only: never touches CUDA, never passed to anything that does
+  ctx->device = -1;
+  vdl_plan *p = new vdl_plan();
+  p->ctx = ctx;
+  p->flags = flags;
+  int rc = parse_plan(p, vdl_text);
+  if (!rc) rc = fuse(p);
+  std::string js;
+  char b[512];
+  auto add = [&](const char *fmt, auto... a) { snprintf(b, sizeof b, fmt, a...); js += b; };
+  if (rc) {
+    std::string msg = ctx->err;
+    for (auto &c : msg) if (c == '"' || c == '\\' || (unsigned char)c < 32) c = ' ';
+    add("{\"error\": %d, \"message\": \"%s\"}", rc, msg.c_str());
+  } else {
+    detect_mergeable_tail(p);
+    add("{\"statements\": %d, \"nodes\": %d, \"outputs\": %d, \"fused_scans\": [", p->statements, (int)p->nodes.size(), (int)p->outputs.size());
+    for (size_t i = 0; i < p->groups.size(); i++) {
+      const FusedGroup &g = p->groups[i];
+      add("%s{\"table\": \"%s\", \"columns\": %d, \"predicates\": %d, \"key_parts\": %d, \"domain\": %lld, \"folds\": %d, \"posts\": %d}", i ? ", " : "",
+          p->tables[g.table].c_str(), g.desc.ncolumns, g.desc.npreds, g.desc.nkeys, (long long)g.desc.domain, g.desc.nfolds, g.desc.nposts);
+    }
+    js += "], \"probe_folds\": [";
+    for (size_t i = 0; i < p->pgroups.size(); i++) {
+      const vdl_probe_desc &d = p->pgroups[i]->b.desc;
+      add("%s{\"table\": \"%s\", \"leaves\": %d, \"predicates\": %d, \"key_parts\": %d, \"domain\": %lld, \"folds\": %d, \"posts\": %d}", i ? ", " : "",
+          p->tables[p->join->spaces[p->pgroups[i]->space].table].c_str(), d.nleaves, d.npreds, d.nkeys, (long long)d.domain, d.nfolds, d.nposts);
+    }
+    js += "], \"probe_emits\": [";
+    for (size_t i = 0; i < p->egroups.size(); i++) {
+      const vdl_probe_desc &d = p->egroups[i]->b.desc;
+      add("%s{\"table\": \"%s\", \"leaves\": %d, \"predicates\": %d, \"vectors\": %d}", i ? ", " : "",
+          p->tables[p->join->spaces[p->egroups[i]->space].table].c_str(), d.nleaves, d.npreds, d.nemits);
+    }
+    js += "], \"map_clusters\": [";
+    for (size_t i = 0; i < p->clusters.size(); i++) {
+      const MapCluster &c = p->clusters[i];
+      add("%s{\"nodes\": %d, \"inputs\": %d, \"tables\": %d, \"instructions\": %d}", i ? ", " : "", (int)c.members.size(), c.desc.ninputs, c.desc.ntables, c.desc.ninstrs);
+    }
+    int folds_left = 0;
+    for (size_t i = 0; i < p->nodes.size(); i++)
+      if (p->nodes[i].op == N_FOLD && p->group_of_node[i] < 0 && p->pgroup_of_node[i] < 0) folds_left++;
+    add("], \"folds_op_at_a_time\": %d, \"mergeable_tail\": %s}", folds_left, p->tail_ok ? "true" : "false");
+  }
+  vdl_plan_destroy(p);
+  delete ctx;
+  if ((int)js.size() + 1 > capacity) return VDL_ENOMEM;
+  memcpy(out, js.c_str(), js.size() + 1);
+  return rc;
+}
+
 extern "C" int vdl_plan_stats(vdl_plan *p, int *statements, int *nodes, int *fused_scans, int64_t *launches) {
   if (!p) return VDL_EINVAL;
   if (statements) *statements = p->statements;

@@ -208,6 +208,19 @@ class Context:
         return Plan(self, text, fuse)
 
 
+def explain(text: str, fuse: bool = True) -> dict:
+    """What the planner makes of a program (vdl_plan_explain): no GPU, no columns needed.  Raises VdlError for a program
+    the parser or the planner rejects."""
+    import json
+    L = _lib.load()
+    buf = C.create_string_buffer(1 << 16)
+    rc = L.vdl_plan_explain(text.encode(), VDL_PLAN_FUSE if fuse else 0, buf, len(buf))
+    doc = json.loads(buf.value.decode()) if buf.value else {}
+    if rc:
+        raise VdlError(rc, doc.get("message", "vdl_plan_explain failed"))
+    return doc
+
+
 class Plan:
     """A loaded Voodoo program (vdl_plan)."""
 

@@ -158,6 +158,7 @@ SYMBOLS = [
     ("vdl_plan_kernel_ms_stats", _I, [_P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("vdl_plan_load", _I, [_P, C.c_char_p, _I, C.POINTER(_P)]),
     ("vdl_plan_stats", _I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_L)]),
+    ("vdl_plan_explain", _I, [C.c_char_p, _I, C.c_char_p, _I]),
     ("vdl_probe_exchange_bytes", _I, [_P, _I, C.POINTER(_L)]),
     ("vdl_probe_set_peers", _I, [_P, _I, _I, C.POINTER(_P)]),
     ("vdl_abi_sizeof_probe_desc", _I, []),
