@@ -16,9 +16,15 @@ def main(argv=None) -> int:
     ap.add_argument("--sf", type=float, default=1.0, help="scale factor of the synthetic tables")
     ap.add_argument("--csv", action="store_true", help="decode dictionary-coded outputs and print CSV (resolve.py)")
     ap.add_argument("--no-fuse", action="store_true", help="op-at-a-time execution only")
+    ap.add_argument("--explain", action="store_true", help="print what the planner makes of the program (JSON) and stop: needs no GPU")
     args = ap.parse_args(argv)
     text = sys.stdin.read() if args.plan == "-" else open(args.plan).read()
     text = re.sub(r" ;;.*", "", text)          # the pipeline strips the --metadata suffix with sed (eval_query.sh:20)
+    if args.explain:
+        import json
+        from .executor import explain
+        sys.stdout.write(json.dumps(explain(text, fuse=not args.no_fuse), indent=1) + "\n")
+        return 0
 
     from . import resolve, tpch
     from .executor import Context
