@@ -87,3 +87,20 @@ def test_rejected_programs_report_the_planner_message():
                        ("1,Load,t.a\n2,Frobnicate,val,Id 1,val,Id 1,val\n", "unknown op"), ("1,Load,t.a\n", "MaterializeCompact")):
         with pytest.raises(VdlError, match=what):
             explain(text)
+
+
+def test_random_queries_are_planned_and_mostly_fused(catalog):
+    """The 80 random shapes of tests/fuzz_plans.py (the GPU fuzz tests run them for results): every program is accepted and
+    claimed by a fused scan or a probe pass (the probe also takes single-table plans whose predicates are IN sets or compare two
+    columns); at most two Folds of a plan stay op-at-a-time."""
+    import fuzz_plans
+    pure_scans = one_probe_fold = 0
+    for seed in range(40):
+        d = explain(vlite.translate(catalog, fuzz_plans.single_table(seed)))
+        assert d["fused_scans"] or d["probe_folds"] or d["probe_emits"], seed
+        assert d["folds_op_at_a_time"] <= 2, seed
+        pure_scans += len(d["fused_scans"]) == 1 and not d["probe_folds"] and not d["probe_emits"] and d["folds_op_at_a_time"] == 0
+        j = explain(vlite.translate(catalog, fuzz_plans.join_query(seed, catalog)))
+        assert j["nodes"] <= j["statements"] and (j["probe_folds"] or j["probe_emits"]), seed
+        one_probe_fold += len(j["probe_folds"]) == 1 and not j["probe_emits"] and j["folds_op_at_a_time"] == 0
+    assert pure_scans >= 20 and one_probe_fold >= 30
